@@ -1,0 +1,493 @@
+// C ABI (include/dfd_b200.h, include/dfd_b200_kernels.h): weight packing (BN fold, repack), the
+// EfficientNet-B0 layer schedule, workspace planning, error reporting.  Host code only; the kernels are in
+// preprocess.cu / stem.cu / dwconv.cu / se.cu / gemm_tc.cu / poolhead.cu.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dfd_b200.h"
+#include "../../include/dfd_b200_kernels.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return DFD_ECUDA;
+}
+#define DFD_CUDA(call, what)                                   \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        if (_e != cudaSuccess) return cuda_fail(_e, what);     \
+    } while (0)
+#define DFD_LAUNCH(call, what)                                 \
+    do {                                                       \
+        cudaError_t _e = (call);                               \
+        ++g_launches;                                          \
+        if (_e != cudaSuccess) return cuda_fail(_e, what);     \
+    } while (0)
+
+// timm efficientnet_b0 stage spec: (repeats, kernel, stride, expand, out_channels)  — SURVEY.md §8c
+const int kStages[7][5] = {{1, 3, 1, 1, 16}, {2, 3, 2, 6, 24}, {2, 5, 2, 6, 40}, {3, 3, 2, 6, 80},
+                           {3, 5, 1, 6, 112}, {4, 5, 2, 6, 192}, {1, 3, 1, 6, 320}};
+constexpr int kNumBlocks = 16;
+constexpr float kBnEps = 1e-5f;
+
+struct BlockW {
+    int cin, mid, cout, k, stride, rd;
+    bool has_expand, has_skip;
+    void* exp_w; float* exp_b;                         // [mid][cin] 16-bit, [mid]
+    float* dw_w; float* dw_b;                          // [k*k][mid], [mid]
+    float *se_w1, *se_b1, *se_w2t, *se_b2;             // [rd][mid], [rd], [rd][mid], [mid]
+    void* proj_w; float* proj_b;                       // [cout][mid] 16-bit, [cout]
+};
+
+bool use_simt_gemm() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DFD_GEMM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
+    return v == 1;
+}
+int64_t chunk_frames() {
+    const char* e = getenv("DFD_CHUNK_FRAMES");
+    long v = e ? atol(e) : 0;
+    return v > 0 ? v : 256;
+}
+
+}  // namespace
+
+struct dfd_weights {
+    int dtype;
+    float *stem_w, *stem_b;                            // [27][32], [32]
+    BlockW blocks[kNumBlocks];
+    void* head_w; float* head_b;                       // [1280][320] 16-bit, [1280]
+    dfd::HeadWeights hw;
+    void* arena;
+    size_t arena_bytes;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// packing
+// ---------------------------------------------------------------------------------------------------
+struct HostArena {
+    std::vector<uint8_t> bytes;
+    size_t alloc(size_t n) {                           // 256-byte aligned offsets
+        size_t off = (bytes.size() + 255) & ~size_t(255);
+        bytes.resize(off + n, 0);
+        return off;
+    }
+};
+
+struct Tensors {
+    std::unordered_map<std::string, std::pair<const float*, int64_t>> map;
+    std::string missing;
+    const float* get(const std::string& key, int64_t numel) {
+        auto it = map.find(key);
+        if (it == map.end() || it->second.second != numel || it->second.first == nullptr) {
+            if (missing.empty()) missing = key + (it == map.end() ? " (absent)" : " (wrong element count)");
+            return nullptr;
+        }
+        return it->second.first;
+    }
+};
+
+uint16_t to_h16(float v, int dtype) {
+    if (dtype == DFD_DTYPE_FP16) {
+        if (v > 65504.f) v = 65504.f;
+        if (v < -65504.f) v = -65504.f;
+        __half h = __float2half_rn(v);
+        uint16_t u; memcpy(&u, &h, 2); return u;
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    uint16_t u; memcpy(&u, &h, 2); return u;
+}
+
+// BN fold factors: scale = gamma / sqrt(var + eps), shift = beta - mean * scale   (fp32)
+bool bn_fold(Tensors& t, const std::string& p, int c, std::vector<float>& scale, std::vector<float>& shift) {
+    const float* g = t.get(p + ".weight", c);
+    const float* b = t.get(p + ".bias", c);
+    const float* m = t.get(p + ".running_mean", c);
+    const float* v = t.get(p + ".running_var", c);
+    if (!g || !b || !m || !v) return false;
+    scale.resize(c); shift.resize(c);
+    for (int i = 0; i < c; ++i) {
+        scale[i] = g[i] / sqrtf(v[i] + kBnEps);
+        shift[i] = b[i] - m[i] * scale[i];
+    }
+    return true;
+}
+
+// pointwise conv [N][K] + BN -> 16-bit [N][K] (K-major) + fp32 bias
+bool pack_pw(Tensors& t, const std::string& conv, const std::string& bn, int N, int K, int dtype,
+             HostArena& a, size_t& w_off, size_t& b_off) {
+    const float* w = t.get(conv + ".weight", (int64_t)N * K);
+    std::vector<float> sc, sh;
+    if (!w || !bn_fold(t, bn, N, sc, sh)) return false;
+    w_off = a.alloc((size_t)N * K * 2);
+    b_off = a.alloc((size_t)N * 4);
+    uint16_t* wd = reinterpret_cast<uint16_t*>(a.bytes.data() + w_off);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) wd[(size_t)n * K + k] = to_h16(w[(size_t)n * K + k] * sc[n], dtype);
+    memcpy(a.bytes.data() + b_off, sh.data(), (size_t)N * 4);
+    return true;
+}
+
+size_t pack_f32(HostArena& a, const float* src, size_t n) {
+    size_t off = a.alloc(n * 4);
+    memcpy(a.bytes.data() + off, src, n * 4);
+    return off;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int dfd_abi_version(void) { return DFD_ABI_VERSION; }
+const char* dfd_last_error(void) { return g_err.c_str(); }
+int dfd_last_launch_count(void) { return g_launches; }
+int dfd_weights_dtype(const dfd_weights_t* w) { return w ? w->dtype : DFD_EINVAL; }
+
+int dfd_pack_weights(int n_tensors, const char* const* names, const float* const* data, const int64_t* numel,
+                     int dtype, dfd_weights_t** out) {
+    if (!names || !data || !numel || !out || n_tensors <= 0) return fail(DFD_EINVAL, "dfd_pack_weights: null argument");
+    if (dtype != DFD_DTYPE_BF16 && dtype != DFD_DTYPE_FP16) return fail(DFD_EINVAL, "dfd_pack_weights: unknown dtype");
+    Tensors t;
+    for (int i = 0; i < n_tensors; ++i)
+        if (names[i]) t.map[names[i]] = {data[i], numel[i]};
+
+    HostArena a;
+    struct Off { size_t exp_w, exp_b, dw_w, dw_b, se_w1, se_b1, se_w2t, se_b2, proj_w, proj_b; } off[kNumBlocks];
+    dfd_weights W{};
+    W.dtype = dtype;
+
+    // stem: [32][3][3][3] + BN -> fp32 [(ky*3+kx)*3+c][32]
+    size_t stem_w_off = 0, stem_b_off = 0;
+    {
+        const float* w = t.get("backbone.0.weight", 32 * 27);
+        std::vector<float> sc, sh;
+        if (w && bn_fold(t, "backbone.1", 32, sc, sh)) {
+            std::vector<float> p(27 * 32);
+            for (int o = 0; o < 32; ++o)
+                for (int c = 0; c < 3; ++c)
+                    for (int ky = 0; ky < 3; ++ky)
+                        for (int kx = 0; kx < 3; ++kx)
+                            p[((ky * 3 + kx) * 3 + c) * 32 + o] = w[((o * 3 + c) * 3 + ky) * 3 + kx] * sc[o];
+            stem_w_off = pack_f32(a, p.data(), p.size());
+            stem_b_off = pack_f32(a, sh.data(), 32);
+        }
+    }
+    int bi = 0, cin = 32;
+    for (int s = 0; s < 7; ++s) {
+        for (int b = 0; b < kStages[s][0]; ++b, ++bi) {
+            BlockW& B = W.blocks[bi];
+            B.cin = cin; B.k = kStages[s][1]; B.stride = (b == 0) ? kStages[s][2] : 1;
+            B.mid = cin * kStages[s][3]; B.cout = kStages[s][4];
+            B.has_expand = kStages[s][3] != 1;
+            B.has_skip = (B.stride == 1 && B.cin == B.cout);
+            B.rd = std::max(1, (int)lrintf(cin * 0.25f));
+            const std::string p = "backbone.2." + std::to_string(s) + "." + std::to_string(b);
+            const std::string bn_dw = p + (B.has_expand ? ".bn2" : ".bn1");
+            const std::string bn_pr = p + (B.has_expand ? ".bn3" : ".bn2");
+            const std::string conv_pr = p + (B.has_expand ? ".conv_pwl" : ".conv_pw");
+            Off& o = off[bi];
+            memset(&o, 0, sizeof(o));
+            if (B.has_expand) pack_pw(t, p + ".conv_pw", p + ".bn1", B.mid, B.cin, dtype, a, o.exp_w, o.exp_b);
+            {   // depthwise [mid][1][k][k] + BN -> fp32 [k*k][mid]
+                const int kk = B.k * B.k;
+                const float* w = t.get(p + ".conv_dw.weight", (int64_t)B.mid * kk);
+                std::vector<float> sc, sh;
+                if (w && bn_fold(t, bn_dw, B.mid, sc, sh)) {
+                    std::vector<float> pw((size_t)kk * B.mid);
+                    for (int c = 0; c < B.mid; ++c)
+                        for (int i = 0; i < kk; ++i) pw[(size_t)i * B.mid + c] = w[(size_t)c * kk + i] * sc[c];
+                    o.dw_w = pack_f32(a, pw.data(), pw.size());
+                    o.dw_b = pack_f32(a, sh.data(), B.mid);
+                }
+            }
+            {   // squeeze-excite: conv_reduce [rd][mid], conv_expand [mid][rd] -> transposed [rd][mid]
+                const float* w1 = t.get(p + ".se.conv_reduce.weight", (int64_t)B.rd * B.mid);
+                const float* b1 = t.get(p + ".se.conv_reduce.bias", B.rd);
+                const float* w2 = t.get(p + ".se.conv_expand.weight", (int64_t)B.mid * B.rd);
+                const float* b2 = t.get(p + ".se.conv_expand.bias", B.mid);
+                if (w1 && b1 && w2 && b2) {
+                    std::vector<float> w2t((size_t)B.rd * B.mid);
+                    for (int c = 0; c < B.mid; ++c)
+                        for (int j = 0; j < B.rd; ++j) w2t[(size_t)j * B.mid + c] = w2[(size_t)c * B.rd + j];
+                    o.se_w1 = pack_f32(a, w1, (size_t)B.rd * B.mid);
+                    o.se_b1 = pack_f32(a, b1, B.rd);
+                    o.se_w2t = pack_f32(a, w2t.data(), w2t.size());
+                    o.se_b2 = pack_f32(a, b2, B.mid);
+                }
+            }
+            pack_pw(t, conv_pr, bn_pr, B.cout, B.mid, dtype, a, o.proj_w, o.proj_b);
+            cin = B.cout;
+        }
+    }
+    size_t head_w_off = 0, head_b_off = 0;
+    pack_pw(t, "backbone.3", "backbone.4", 1280, 320, dtype, a, head_w_off, head_b_off);
+    size_t hoff[8] = {0};
+    {
+        const char* keys[8] = {"temporal_attention.0.weight", "temporal_attention.0.bias", "temporal_attention.2.weight",
+                               "temporal_attention.2.bias", "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias"};
+        const int64_t n[8] = {64 * 1280, 64, 64, 1, 256 * 1280, 256, 2 * 256, 2};
+        for (int i = 0; i < 8; ++i) {
+            const float* p = t.get(keys[i], n[i]);
+            if (p) hoff[i] = pack_f32(a, p, (size_t)n[i]);
+        }
+    }
+    if (!t.missing.empty()) return fail(DFD_EKEY, "dfd_pack_weights: state_dict tensor " + t.missing);
+
+    void* dev = nullptr;
+    DFD_CUDA(cudaMalloc(&dev, a.bytes.size()), "cudaMalloc(weights)");
+    cudaError_t e = cudaMemcpy(dev, a.bytes.data(), a.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); return cuda_fail(e, "cudaMemcpy(weights)"); }
+    uint8_t* d = reinterpret_cast<uint8_t*>(dev);
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(d + o); };
+    W.arena = dev; W.arena_bytes = a.bytes.size();
+    W.stem_w = F(stem_w_off); W.stem_b = F(stem_b_off);
+    for (int i = 0; i < kNumBlocks; ++i) {
+        BlockW& B = W.blocks[i]; const Off& o = off[i];
+        B.exp_w = B.has_expand ? d + o.exp_w : nullptr; B.exp_b = B.has_expand ? F(o.exp_b) : nullptr;
+        B.dw_w = F(o.dw_w); B.dw_b = F(o.dw_b);
+        B.se_w1 = F(o.se_w1); B.se_b1 = F(o.se_b1); B.se_w2t = F(o.se_w2t); B.se_b2 = F(o.se_b2);
+        B.proj_w = d + o.proj_w; B.proj_b = F(o.proj_b);
+    }
+    W.head_w = d + head_w_off; W.head_b = F(head_b_off);
+    W.hw.att_w1 = F(hoff[0]); W.hw.att_b1 = F(hoff[1]); W.hw.att_w2 = F(hoff[2]); W.hw.att_b2 = F(hoff[3]);
+    W.hw.fc1_w = F(hoff[4]); W.hw.fc1_b = F(hoff[5]); W.hw.fc2_w = F(hoff[6]); W.hw.fc2_b = F(hoff[7]);
+    *out = new dfd_weights(W);
+    return DFD_OK;
+}
+
+void dfd_free_weights(dfd_weights_t* w) {
+    if (!w) return;
+    if (w->arena) cudaFree(w->arena);
+    delete w;
+}
+
+int dfd_preprocess_u8hwc_to_nchw(const uint8_t* d_in, void* d_out, int64_t frames, int H, int W, int dtype, void* stream) {
+    if (!d_in || !d_out) return fail(DFD_EINVAL, "dfd_preprocess: null pointer");
+    if (frames < 0 || H <= 0 || W <= 0 || ((int64_t)H * W) % 16 != 0) return fail(DFD_EINVAL, "dfd_preprocess: H*W must be a positive multiple of 16");
+    if (dtype != DFD_DTYPE_BF16 && dtype != DFD_DTYPE_FP16) return fail(DFD_EINVAL, "dfd_preprocess: unknown dtype");
+    g_launches = 0;
+    DFD_LAUNCH(dfd::launch_preprocess(d_in, d_out, frames, H, W, dtype, (cudaStream_t)stream), "preprocess kernel");
+    return DFD_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// workspace plan + layer schedule
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct Plan {
+    size_t io_elems, e_elems, d_elems, part_floats, gate_floats;     // per frame
+    size_t per_frame_bytes() const {
+        auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+        return 2 * up(io_elems * 2) + up(e_elems * 2) + up(d_elems * 2) + up(part_floats * 4) + up(gate_floats * 4);
+    }
+};
+
+bool shape_ok(int H, int W) {
+    return H > 0 && W > 0 && (H % 32) == 0 && (W % 32) == 0 && (H / 32) * (W / 32) <= 128 && 128 / ((H / 32) * (W / 32)) <= 4;
+}
+
+Plan make_plan(int H, int W) {
+    Plan p{};
+    int h = H / 2, w = W / 2, cin = 32;
+    p.io_elems = (size_t)h * w * 32;
+    for (int s = 0; s < 7; ++s)
+        for (int b = 0; b < kStages[s][0]; ++b) {
+            const int k = kStages[s][1], st = (b == 0) ? kStages[s][2] : 1, mid = cin * kStages[s][3], cout = kStages[s][4];
+            const int oh = (h + 2 * (k / 2) - k) / st + 1, ow = (w + 2 * (k / 2) - k) / st + 1;
+            if (kStages[s][3] != 1) p.e_elems = std::max(p.e_elems, (size_t)h * w * mid);
+            p.d_elems = std::max(p.d_elems, (size_t)oh * ow * mid);
+            p.part_floats = std::max(p.part_floats, (size_t)dfd::dw_num_partials(oh, ow, mid) * mid);
+            p.gate_floats = std::max(p.gate_floats, (size_t)mid);
+            p.io_elems = std::max(p.io_elems, (size_t)oh * ow * cout);
+            h = oh; w = ow; cin = cout;
+        }
+    return p;
+}
+
+int run_gemm(const void* A, const void* Wt, const float* bias, const float* gate, const void* R, void* D,
+             int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s) {
+    if (use_simt_gemm()) DFD_LAUNCH(dfd::launch_gemm_simt(A, Wt, bias, gate, R, D, nullptr, M, K, N, HW, act, dtype, s), "gemm (simt)");
+    else DFD_LAUNCH(dfd::launch_gemm_tc(A, Wt, bias, gate, R, D, M, K, N, HW, act, dtype, s), "gemm (tcgen05)");
+    return DFD_OK;
+}
+
+int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t frames, int H, int W,
+                    float* feat, uint8_t* ws, const Plan& plan, cudaStream_t s) {
+    auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+    uint8_t* io[2];
+    io[0] = ws;                                  ws += up(plan.io_elems * 2) * frames;
+    io[1] = ws;                                  ws += up(plan.io_elems * 2) * frames;
+    uint8_t* bufE = ws;                          ws += up(plan.e_elems * 2) * frames;
+    uint8_t* bufD = ws;                          ws += up(plan.d_elems * 2) * frames;
+    float* part = reinterpret_cast<float*>(ws);  ws += up(plan.part_floats * 4) * frames;
+    float* gate = reinterpret_cast<float*>(ws);
+    const int dt = w->dtype;
+
+    int h = H / 2, wd = W / 2, cur = 0;
+    DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
+    for (int i = 0; i < kNumBlocks; ++i) {
+        const BlockW& B = w->blocks[i];
+        const void* x = io[cur];
+        const void* e = x;
+        if (B.has_expand) {
+            int rc = run_gemm(x, B.exp_w, B.exp_b, nullptr, nullptr, bufE, frames * h * wd, B.cin, B.mid, h * wd, 1, dt, s);
+            if (rc) return rc;
+            e = bufE;
+        }
+        const int pad = B.k / 2;
+        const int oh = (h + 2 * pad - B.k) / B.stride + 1, ow = (wd + 2 * pad - B.k) / B.stride + 1;
+        DFD_LAUNCH(dfd::launch_dwconv(e, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.mid, B.k, B.stride, dt, s), "depthwise kernel");
+        const int nparts = dfd::dw_num_partials(oh, ow, B.mid);
+        DFD_LAUNCH(dfd::launch_se(part, nparts, 1.0f / (float)(oh * ow), B.se_w1, B.se_b1, B.se_w2t, B.se_b2, gate,
+                                  frames, B.mid, B.rd, s), "squeeze-excite kernel");
+        int rc = run_gemm(bufD, B.proj_w, B.proj_b, gate, B.has_skip ? x : nullptr, io[cur ^ 1],
+                          frames * oh * ow, B.mid, B.cout, oh * ow, 0, dt, s);
+        if (rc) return rc;
+        cur ^= 1; h = oh; wd = ow;
+    }
+    if (use_simt_gemm())
+        DFD_LAUNCH(dfd::launch_gemm_simt(io[cur], w->head_w, w->head_b, nullptr, nullptr, nullptr, feat, frames * h * wd, 320, 1280, h * wd, 1, dt, s), "head (simt)");
+    else
+        DFD_LAUNCH(dfd::launch_gemm_tc_pool(io[cur], w->head_w, w->head_b, feat, frames * h * wd, 320, 1280, h * wd, dt, s), "head (tcgen05)");
+    return DFD_OK;
+}
+
+size_t in_frame_bytes(int in_kind, int H, int W) {
+    const size_t px = (size_t)H * W * 3;
+    return in_kind == DFD_IN_U8_HWC ? px : (in_kind == DFD_IN_F32_NCHW ? px * 4 : px * 2);
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int dfd_workspace_bytes(int64_t frames, int H, int W, size_t* bytes) {
+    if (!bytes || frames < 0) return fail(DFD_EINVAL, "dfd_workspace_bytes: bad argument");
+    if (!shape_ok(H, W)) return fail(DFD_EINVAL, "unsupported crop size: H and W must be multiples of 32 with 32 <= (H/32)*(W/32) <= 128 (224x224 is the supported size)");
+    const Plan p = make_plan(H, W);
+    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(frames, 1), chunk_frames());
+    *bytes = p.per_frame_bytes() * (size_t)chunk + 256;
+    return DFD_OK;
+}
+
+int dfd_effnet_b0_features(const dfd_weights_t* w, const void* d_in, int in_kind, int64_t frames, int H, int W,
+                           float* d_features, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!w || !d_in || !d_features || !d_workspace) return fail(DFD_EINVAL, "dfd_effnet_b0_features: null pointer");
+    if (in_kind < 0 || in_kind > 2) return fail(DFD_EINVAL, "dfd_effnet_b0_features: unknown input layout");
+    if (frames < 0) return fail(DFD_EINVAL, "dfd_effnet_b0_features: negative frame count");
+    size_t need = 0;
+    int rc = dfd_workspace_bytes(frames, H, W, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return fail(DFD_ENOMEM, "dfd_effnet_b0_features: workspace too small (" + std::to_string(workspace_bytes) + " < " + std::to_string(need) + ")");
+    g_launches = 0;
+    const Plan p = make_plan(H, W);
+    const int64_t chunk = chunk_frames();
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255));
+    const size_t fb = in_frame_bytes(in_kind, H, W);
+    for (int64_t f0 = 0; f0 < frames; f0 += chunk) {
+        const int64_t n = std::min(chunk, frames - f0);
+        rc = run_trunk_chunk(w, reinterpret_cast<const uint8_t*>(d_in) + (size_t)f0 * fb, in_kind, n, H, W,
+                             d_features + (size_t)f0 * DFD_FEATURE_DIM, ws, p, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return DFD_OK;
+}
+
+int dfd_attn_pool_head(const dfd_weights_t* w, const float* d_features, const int32_t* d_offsets, int64_t videos,
+                       int64_t frames, int use_attention, float* d_logits, float* d_frame_scores, void* stream) {
+    (void)frames;
+    if (!w || !d_features || !d_offsets || !d_logits) return fail(DFD_EINVAL, "dfd_attn_pool_head: null pointer");
+    if (videos < 0) return fail(DFD_EINVAL, "dfd_attn_pool_head: negative video count");
+    g_launches = 0;
+    DFD_LAUNCH(dfd::launch_pool_head(w->hw, d_features, d_offsets, videos, use_attention, d_logits, d_frame_scores,
+                                     (cudaStream_t)stream), "pool+head kernel");
+    return DFD_OK;
+}
+
+int dfd_score_workspace_bytes(int64_t frames, int H, int W, size_t* bytes) {
+    size_t b = 0;
+    int rc = dfd_workspace_bytes(frames, H, W, &b);
+    if (rc) return rc;
+    *bytes = b + (size_t)std::max<int64_t>(frames, 1) * DFD_FEATURE_DIM * 4 + 256;
+    return DFD_OK;
+}
+
+int dfd_score_videos(const dfd_weights_t* w, const void* d_in, int in_kind, const int32_t* d_offsets, int64_t videos,
+                     int64_t frames, int H, int W, int use_attention, float* d_logits, float* d_frame_scores,
+                     float* d_features_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!w || !d_in || !d_offsets || !d_logits || !d_workspace) return fail(DFD_EINVAL, "dfd_score_videos: null pointer");
+    size_t need = 0, trunk = 0;
+    int rc = dfd_score_workspace_bytes(frames, H, W, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return fail(DFD_ENOMEM, "dfd_score_videos: workspace too small (" + std::to_string(workspace_bytes) + " < " + std::to_string(need) + ")");
+    dfd_workspace_bytes(frames, H, W, &trunk);
+    uint8_t* ws = reinterpret_cast<uint8_t*>(d_workspace);
+    float* feat = d_features_out;
+    if (!feat) feat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws + trunk) + 255) & ~uintptr_t(255));
+    rc = dfd_effnet_b0_features(w, d_in, in_kind, frames, H, W, feat, d_workspace, trunk, stream);
+    if (rc) return rc;
+    const int n = g_launches;
+    rc = dfd_attn_pool_head(w, feat, d_offsets, videos, frames, use_attention, d_logits, d_frame_scores, stream);
+    g_launches += n;
+    return rc;
+}
+
+// ---- kernel-level entry points (include/dfd_b200_kernels.h) ------------------------------------------
+int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_bias, void* d_out, int64_t frames,
+               int H, int W, int dtype, void* stream) {
+    g_launches = 0;
+    DFD_LAUNCH(dfd::launch_stem(d_in, in_kind, d_w, d_bias, d_out, frames, H, W, dtype, (cudaStream_t)stream), "stem kernel");
+    return DFD_OK;
+}
+int dfd_k_dw_num_partials(int OH, int OW, int C) { return dfd::dw_num_partials(OH, OW, C); }
+int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,
+                 int64_t frames, int H, int W, int C, int k, int stride, int dtype, void* stream) {
+    g_launches = 0;
+    DFD_LAUNCH(dfd::launch_dwconv(d_in, d_w, d_bias, d_out, d_partials, frames, H, W, C, k, stride, dtype, (cudaStream_t)stream), "depthwise kernel");
+    return DFD_OK;
+}
+int dfd_k_se(const float* d_partials, int nparts, float inv_hw, const float* d_w1, const float* d_b1, const float* d_w2t,
+             const float* d_b2, float* d_gate, int64_t frames, int C, int rd, void* stream) {
+    g_launches = 0;
+    DFD_LAUNCH(dfd::launch_se(d_partials, nparts, inv_hw, d_w1, d_b1, d_w2t, d_b2, d_gate, frames, C, rd, (cudaStream_t)stream), "squeeze-excite kernel");
+    return DFD_OK;
+}
+int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const float* d_gate, const void* d_R, void* d_D,
+               int64_t M, int K, int N, int HW, int act, int dtype, int impl, void* stream) {
+    g_launches = 0;
+    if (impl == 1) DFD_LAUNCH(dfd::launch_gemm_simt(d_A, d_W, d_bias, d_gate, d_R, d_D, nullptr, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (simt)");
+    else DFD_LAUNCH(dfd::launch_gemm_tc(d_A, d_W, d_bias, d_gate, d_R, d_D, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (tcgen05)");
+    return DFD_OK;
+}
+int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K, int N,
+                    int HW, int dtype, int impl, void* stream) {
+    g_launches = 0;
+    if (impl == 1) DFD_LAUNCH(dfd::launch_gemm_simt(d_A, d_W, d_bias, nullptr, nullptr, nullptr, d_feat, M, K, N, HW, 1, dtype, (cudaStream_t)stream), "head (simt)");
+    else DFD_LAUNCH(dfd::launch_gemm_tc_pool(d_A, d_W, d_bias, d_feat, M, K, N, HW, dtype, (cudaStream_t)stream), "head (tcgen05)");
+    return DFD_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,194 @@
+// Shared device helpers for the sm_100a kernels: 16-bit storage traits, SiLU, vector ld/st,
+// mbarrier / tcgen05 / TMEM PTX wrappers.  Everything here is inline device code.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace dfd {
+
+// ------------------------------------------------------------------------------------------
+// 16-bit storage types.  Activations and GEMM operands are stored as fp16 (default) or bf16;
+// all accumulation is fp32.  dtype codes match include/dfd_b200.h (DFD_DTYPE_*).
+// ------------------------------------------------------------------------------------------
+enum : int { kDtypeBF16 = 0, kDtypeFP16 = 1 };
+
+template <typename T> struct Half16;
+template <> struct Half16<__half> {
+    using T2 = __half2;
+    static constexpr int kCode = kDtypeFP16;
+    static constexpr uint32_t kUmmaFormat = 0;   // F16F32Format::F16
+    __device__ __forceinline__ static float2 unpack(uint32_t v) {
+        return __half22float2(*reinterpret_cast<const __half2*>(&v));
+    }
+    __device__ __forceinline__ static uint32_t pack(float a, float b) {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __device__ __forceinline__ static float to_float(__half v) { return __half2float(v); }
+    __device__ __forceinline__ static __half from_float(float v) { return __float2half_rn(v); }
+    // d = a*b + c with a, b 16-bit and fp32 accumulate (single FHFMA, no unpack)
+    __device__ __forceinline__ static float fma_mixed(uint16_t a, uint16_t b, float c) {
+        float d;
+        asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+        return d;
+    }
+};
+template <> struct Half16<__nv_bfloat16> {
+    using T2 = __nv_bfloat162;
+    static constexpr int kCode = kDtypeBF16;
+    static constexpr uint32_t kUmmaFormat = 1;   // F16F32Format::BF16
+    __device__ __forceinline__ static float2 unpack(uint32_t v) {
+        return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+    }
+    __device__ __forceinline__ static uint32_t pack(float a, float b) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __device__ __forceinline__ static float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+    __device__ __forceinline__ static __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+    __device__ __forceinline__ static float fma_mixed(uint16_t a, uint16_t b, float c) {
+        float d;
+        asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+        return d;
+    }
+};
+
+// ImageNet statistics of app.py:1774-1775 and the reference's exact fp32 prep arithmetic
+// (`u8/255` then `(x-mean)/std`, IEEE divides).
+__device__ __forceinline__ float imagenet_mean(int c) { return c == 0 ? 0.485f : (c == 1 ? 0.456f : 0.406f); }
+__device__ __forceinline__ float imagenet_std(int c) { return c == 0 ? 0.229f : (c == 1 ? 0.224f : 0.225f); }
+__device__ __forceinline__ float prep_value(int c, int v) {
+    const float x = __fdiv_rn((float)v, 255.0f);
+    return __fdiv_rn(__fsub_rn(x, imagenet_mean(c)), imagenet_std(c));
+}
+
+// x * sigmoid(x), fp32.  ex2.approx (2 ulp) + rcp.approx (1 ulp): well below 16-bit storage error.
+__device__ __forceinline__ float silu_f(float x) {
+    return __fdividef(x, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+    return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+
+// ------------------------------------------------------------------------------------------
+// vector global access
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg16(const void* p) {      // read-only 128-bit
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ uint4 ldg16_stream(const void* p) {   // streaming: do not allocate in L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg16(void* p, const uint4& v) {
+    *reinterpret_cast<uint4*>(p) = v;
+}
+struct alignas(32) U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ void stg32(void* p, const U32x8& r) {   // 256-bit store (sm_100+)
+    asm volatile("st.global.v8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};"
+                 :: "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]), "r"(r.v[3]),
+                    "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7]), "l"(p) : "memory");
+}
+__device__ __forceinline__ U32x8 ldg32(const void* p) {            // 256-bit read-only load (sm_100+)
+    U32x8 r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]),
+                   "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier (shared::cta)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    printf("dfd: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (UMMA operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {    // same warp as alloc
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] · B[smem]^T, 16-bit inputs, fp32 accumulate, issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+// TMEM → registers: this thread's lane, 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, no swizzle ("interleave"): core matrix = 8 rows x 16 B,
+// rows 16 B apart; 8-row groups `sbo` bytes apart; the two 16-byte K chunks of one MMA `lbo` bytes apart.
+// Bit layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor), version field = 1 on sm_100.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;   // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// Instruction descriptor for kind::f16: fp32 accumulate, K-major A and B, M x N tile.
+__device__ __host__ constexpr uint32_t umma_idesc(uint32_t ab_format, uint32_t m, uint32_t n) {
+    return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+}  // namespace dfd

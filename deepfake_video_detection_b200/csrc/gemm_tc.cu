@@ -1,0 +1,351 @@
+// K3 — pointwise (1x1) convolutions of EfficientNet-B0 as tcgen05 / TMEM GEMMs (sm_100a).
+//
+//   D[M,N] = act( (A .* gate)[M,K] · W[N,K]^T + bias[N] ) (+ R[M,N])
+//
+//   A   NHWC activations viewed as [M = frames*H*W, K = Cin], 16-bit, K contiguous (K-major)
+//   W   conv weight [N = Cout, K = Cin] with BatchNorm folded, 16-bit, K-major (timm conv_pw / conv_pwl /
+//       conv_head; reference call site pretrained_detector.py:116)
+//   gate  squeeze-excite gate fp32 [frames][K], applied to the A operand while it is staged (project convs)
+//   R   residual input of the block (stride-1, Cin == Cout blocks)
+//   pool variant: conv_head + BN + SiLU + global average pool -> features fp32 [frames][N]
+//
+// Structure (one persistent CTA per SM, 17 warps, warp-specialised):
+//   warps 9..16  producers: global -> registers -> (x gate) -> shared memory in the UMMA canonical
+//                K-major no-swizzle layout (8-row x 16-byte core matrices), `fence.proxy.async`, mbarrier arrive
+//   warp  8      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=NBp, K=16) per 16-wide K step,
+//                accumulators in TMEM (double buffered), tcgen05.commit releases smem stages / signals epilogue
+//   warps 0..7   epilogue: tcgen05.ld (32 lanes x 16 columns), +bias, SiLU, +residual, pack, store
+// Almost every layer is HBM-bound: the design goal is "read A once, write D once, keep
+// enough bytes in flight", not tensor-pipe occupancy.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfd {
+
+constexpr int kBM = 128;            // rows per tile = TMEM lanes
+constexpr int kKB = 64;             // K elements per pipeline stage (8 chunks of 8)
+constexpr int kMaxStages = 4;
+constexpr int kEpiWarps = 8;
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = kProdWarps * 32;
+constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps) * 32;     // 544
+constexpr int kMmaWarp = kEpiWarps;
+constexpr uint32_t kLboA = kBM * 16 + 16;                            // +16: bank-conflict-free staging stores
+constexpr uint32_t kAStageBytes = 8 * kLboA;
+
+struct GemmArgs {
+    const void* A; const void* W; const float* bias; const float* gate; const void* R; void* D; float* feat;
+    int64_t M; int K; int N; int HW;
+    int NB, NBp, n_chunks;          // columns per work unit, padded to 16, units along N
+    int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
+    int64_t m_tiles;
+    int stages;
+    uint32_t lbo_b, b_stage_bytes, tmem_cols;
+    float inv_hw;
+};
+
+template <typename T, bool GATE, bool ACT, bool RES, bool POOL>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // ---- shared memory carve-up ----------------------------------------------------------------
+    const uint32_t stage_bytes = kAStageBytes + p.b_stage_bytes;
+    uint8_t* sp = smem_raw + (size_t)p.stages * stage_bytes;
+    float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
+    float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += 4 * 4 * p.NBp * 4;
+    sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], tfull[2], tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const uint32_t smem_base = smem_u32(smem_raw);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = p.bias[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, kProdThreads); mbar_init(bar_empty + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiWarps * 32); }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), p.tmem_cols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int num_kb = (p.K + kKB - 1) / kKB;
+    const int64_t units = p.m_tiles * p.n_chunks;
+
+    if (warp > kMmaWarp) {
+        // =================================== PRODUCERS ===========================================
+        const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
+        const T* A = reinterpret_cast<const T*>(p.A);
+        const T* Wt = reinterpret_cast<const T*>(p.W);
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int64_t mt = u / p.n_chunks;
+            const int nc = (int)(u - mt * p.n_chunks);
+            const int64_t m0 = mt * p.rows_per_tile;
+            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            const int n0 = nc * p.NB;
+            const int nb_valid = min(p.NB, p.N - n0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int k0 = kb * kKB;
+                const int kc = min(8, (p.K - k0) >> 3);        // 16-byte chunks present in this block
+                const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
+                const int na = kBM * kcp, nb = p.NBp * kcp;
+                uint4 va[4], vb[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = tp + j * kProdThreads;
+                    va[j] = make_uint4(0, 0, 0, 0);
+                    if (i < na) {
+                        const int r = i / kcp, q = i - r * kcp;
+                        if (r < rows_valid && q < kc) va[j] = ldg16_stream(A + (size_t)(m0 + r) * p.K + k0 + q * 8);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = tp + j * kProdThreads;
+                    vb[j] = make_uint4(0, 0, 0, 0);
+                    if (i < nb) {
+                        const int r = i / kcp, q = i - r * kcp;
+                        if (r < nb_valid && q < kc) vb[j] = ldg16(Wt + (size_t)(n0 + r) * p.K + k0 + q * 8);
+                    }
+                }
+                if (GATE) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = tp + j * kProdThreads;
+                        if (i < na) {
+                            const int r = i / kcp, q = i - r * kcp;
+                            if (r < rows_valid && q < kc) {
+                                const uint32_t frame = (uint32_t)(m0 + r) / (uint32_t)p.HW;
+                                const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+                                float2 x0 = Half16<T>::unpack(va[j].x), x1 = Half16<T>::unpack(va[j].y);
+                                float2 x2 = Half16<T>::unpack(va[j].z), x3 = Half16<T>::unpack(va[j].w);
+                                va[j].x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y);
+                                va[j].y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
+                                va[j].z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y);
+                                va[j].w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
+                            }
+                        }
+                    }
+                }
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t a_base = smem_base + stage * stage_bytes;
+                const uint32_t b_base = a_base + kAStageBytes;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = tp + j * kProdThreads;
+                    if (i < na) { const int r = i / kcp, q = i - r * kcp; sts16(a_base + q * kLboA + r * 16, va[j]); }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int i = tp + j * kProdThreads;
+                    if (i < nb) { const int r = i / kcp, q = i - r * kcp; sts16(b_base + q * p.lbo_b + r * 16, vb[j]); }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(bar_full + 8 * stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // =================================== MMA ISSUER ==========================================
+        const uint32_t idesc = umma_idesc(Half16<T>::kUmmaFormat, kBM, (uint32_t)p.NBp);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NBp);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int kc = min(8, (p.K - kb * kKB) >> 3);
+                const int steps = (kc + 1) >> 1;
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_base + stage * stage_bytes;
+                    const uint32_t b_base = a_base + kAStageBytes;
+                    for (int j = 0; j < steps; ++j) {
+                        const uint64_t adesc = umma_smem_desc(a_base + 2 * j * kLboA, kLboA, 128);
+                        const uint64_t bdesc = umma_smem_desc(b_base + 2 * j * p.lbo_b, p.lbo_b, 128);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty + 8 * stage);                 // smem stage reusable once the MMAs retire
+                    if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // =================================== EPILOGUE ============================================
+        const int q = warp & 3, half = warp >> 2;
+        const int row = 32 * q + lane;
+        T* D = reinterpret_cast<T*>(p.D);
+        const T* R = reinterpret_cast<const T*>(p.R);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int64_t mt = u / p.n_chunks;
+            const int nc = (int)(u - mt * p.n_chunks);
+            const int64_t m0 = mt * p.rows_per_tile;
+            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            const int n0 = nc * p.NB;
+            const int nb_valid = min(p.NB, p.N - n0);
+            const bool valid = row < rows_valid;
+            const int64_t m = m0 + row;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after_sync();
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
+            const int slots = POOL ? rows_valid / p.HW : 0;
+            const int my_slot = POOL ? row / p.HW : 0;
+            for (int c16 = half; c16 * 16 < p.NBp; c16 += 2) {
+                uint32_t r[16];
+                tmem_ld16(t_row + c16 * 16, r);
+                tmem_ld_wait();
+                const int ncol = nb_valid - c16 * 16;               // valid columns in this chunk (>=16, 8 or <=0)
+                if (ncol <= 0) continue;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float x = __uint_as_float(r[i]) + s_bias[min(n0 + c16 * 16 + i, p.N - 1)];
+                    v[i] = ACT ? silu_f(x) : x;
+                }
+                if (POOL) {
+                    for (int s = 0; s < slots; ++s) {
+                        const bool mine = valid && (my_slot == s);
+                        float keep = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float x = mine ? v[i] : 0.f;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                            if (lane == i) keep = x;
+                        }
+                        if (lane < 16) s_pool[(q * 4 + s) * p.NBp + c16 * 16 + lane] = keep;
+                    }
+                } else if (valid) {
+                    T* dst = D + (size_t)m * p.N + n0 + c16 * 16;
+                    if (RES) {
+                        const T* rs = R + (size_t)m * p.N + n0 + c16 * 16;
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            if (h8 * 8 < ncol) {
+                                const uint4 rv = ldg16_stream(rs + h8 * 8);
+                                const float2 a0 = Half16<T>::unpack(rv.x), a1 = Half16<T>::unpack(rv.y);
+                                const float2 a2 = Half16<T>::unpack(rv.z), a3 = Half16<T>::unpack(rv.w);
+                                v[h8 * 8 + 0] += a0.x; v[h8 * 8 + 1] += a0.y; v[h8 * 8 + 2] += a1.x; v[h8 * 8 + 3] += a1.y;
+                                v[h8 * 8 + 4] += a2.x; v[h8 * 8 + 5] += a2.y; v[h8 * 8 + 6] += a3.x; v[h8 * 8 + 7] += a3.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        if (h8 * 8 < ncol) {
+                            uint4 o;
+                            o.x = Half16<T>::pack(v[h8 * 8 + 0], v[h8 * 8 + 1]); o.y = Half16<T>::pack(v[h8 * 8 + 2], v[h8 * 8 + 3]);
+                            o.z = Half16<T>::pack(v[h8 * 8 + 4], v[h8 * 8 + 5]); o.w = Half16<T>::pack(v[h8 * 8 + 6], v[h8 * 8 + 7]);
+                            stg16(dst + h8 * 8, o);
+                        }
+                    }
+                }
+            }
+            if (POOL) {
+                asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory");
+                const int64_t frame0 = m0 / p.HW;
+                for (int i = threadIdx.x; i < slots * nb_valid; i += kEpiWarps * 32) {
+                    const int s = i / nb_valid, col = i - s * nb_valid;
+                    float tot = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) tot += s_pool[(qq * 4 + s) * p.NBp + col];
+                    p.feat[(size_t)(frame0 + s) * p.N + n0 + col] = tot * p.inv_hw;
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory");
+            }
+            tc_fence_before_sync();
+            mbar_arrive(bar_tempty + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) { tc_fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+
+template <typename KernelT>
+static cudaError_t run(KernelT kernel, GemmArgs& a, cudaStream_t s) {
+    if (g_num_sms == 0) {
+        int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    }
+    // split N into equal chunks of <= 256 columns (multiple of 8)
+    int n_chunks = (a.N + 255) / 256;
+    while ((a.N % n_chunks) != 0 || ((a.N / n_chunks) & 7)) ++n_chunks;
+    a.n_chunks = n_chunks;
+    a.NB = a.N / n_chunks;
+    a.NBp = (a.NB + 15) & ~15;
+    a.lbo_b = (uint32_t)a.NBp * 16 + 16;
+    a.b_stage_bytes = 8 * a.lbo_b;
+    uint32_t cols = 32; while (cols < (uint32_t)(2 * a.NBp)) cols <<= 1;
+    a.tmem_cols = cols;
+    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)16 * a.NBp * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t budget = 227 * 1024;
+    const size_t stage_bytes = kAStageBytes + a.b_stage_bytes;
+    int stages = (int)((budget - fixed) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return cudaErrorInvalidValue;
+    a.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t units = a.m_tiles * a.n_chunks;
+    const unsigned grid = (unsigned)(units < g_num_sms ? units : g_num_sms);
+    kernel<<<grid, kGemmThreads, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
+    const bool gate = a.gate != nullptr, res = a.R != nullptr;
+    if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true>, a, s);
+    if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false>, a, s);
+    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false>, a, s);
+    if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false>, a, s);
+    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false>, a, s);
+    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false>, a, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, const float* gate, const void* R,
+                           void* D, int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((K & 7) || (N & 7) || K < 8 || N < 8 || HW <= 0) return cudaErrorInvalidValue;
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = bias; a.gate = gate; a.R = R; a.D = D; a.feat = nullptr;
+    a.M = M; a.K = K; a.N = N; a.HW = HW;
+    a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
+    if (dtype == kDtypeFP16) return launch_t<__half>(a, act, s);
+    return launch_t<__nv_bfloat16>(a, act, s);
+}
+
+cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
+                                int64_t M, int K, int N, int HW, int dtype, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((K & 7) || (N & 7) || HW <= 0 || HW > kBM || (M % HW) != 0 || kBM / HW > 4) return cudaErrorInvalidValue;
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = nullptr; a.D = nullptr; a.feat = feat;
+    a.M = M; a.K = K; a.N = N; a.HW = HW;
+    a.rows_per_tile = (kBM / HW) * HW; a.m_tiles = (M + a.rows_per_tile - 1) / a.rows_per_tile; a.inv_hw = 1.0f / (float)HW;
+    if (dtype == kDtypeFP16) return launch_t<__half>(a, 1, s);
+    return launch_t<__nv_bfloat16>(a, 1, s);
+}
+
+}  // namespace dfd

@@ -1,0 +1,49 @@
+// Host-side launchers of the sm_100a kernels (internal; the public surface is include/dfd_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace dfd {
+
+// K1 (preprocess.cu): uint8 HWC -> 16-bit NCHW, ImageNet normalisation (app.py:1772-1780, 2084-2085)
+cudaError_t launch_preprocess(const uint8_t* in, void* out, int64_t frames, int H, int W, int dtype, cudaStream_t s);
+
+// stem (stem.cu): conv3x3 s2 p1 3->32 + folded BN + SiLU -> NHWC.  w: fp32 [27][32] (tap-major: (ky*3+kx)*3+c), bias fp32 [32]
+cudaError_t launch_stem(const void* in, int in_kind, const float* w, const float* bias, void* out,
+                        int64_t frames, int H, int W, int dtype, cudaStream_t s);
+
+// K2 (dwconv.cu): depthwise kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU, NHWC, plus the
+// squeeze-excite spatial sums as per-block partials.  w: fp32 [k*k][C], bias fp32 [C].
+// partials: fp32 [frames][dw_num_partials][C] (sum of SiLU outputs over the block's pixels).
+int dw_num_partials(int OH, int OW, int C);
+cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, void* out, float* partials,
+                          int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
+
+// K2 tail (se.cu): mean -> FC(C->rd)+bias -> SiLU -> FC(rd->C)+bias -> sigmoid.  gate fp32 [frames][C].
+// w1 fp32 [rd][C], w2t fp32 [rd][C] (conv_expand transposed), b1 [rd], b2 [C].
+cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,
+                      const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s);
+
+// K3 (gemm_tc.cu): pointwise conv as tcgen05/TMEM GEMM.  D[M,N] = act((A .* gate)[M,K] * W[N,K]^T + bias) (+ R)
+// A, W, R, D 16-bit; bias fp32 [N]; gate fp32 [M/HW][K] or null; R [M,N] or null; act: 0 none, 1 SiLU.
+cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, const float* gate, const void* R,
+                           void* D, int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s);
+// conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
+cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
+                                int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
+// straightforward CUDA-core GEMM with the same contract; bring-up / bisecting aid (DFD_GEMM_IMPL=simt)
+cudaError_t launch_gemm_simt(const void* A, const void* W, const float* bias, const float* gate, const void* R,
+                             void* D, float* pool_feat, int64_t M, int K, int N, int HW, int act, int dtype,
+                             cudaStream_t s);
+
+// K4 (poolhead.cu): temporal attention pool + fc1/ReLU/fc2 per video (pretrained_detector.py:123-141)
+struct HeadWeights {
+    const float *att_w1, *att_b1, *att_w2, *att_b2;   // [64][1280], [64], [64], [1]
+    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;       // [256][1280], [256], [2][256], [2]
+};
+// a video that is empty or longer than 1024 frames gets NaN logits
+cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos,
+                             int use_attention, float* logits, float* frame_scores, cudaStream_t s);
+
+}  // namespace dfd

@@ -1,0 +1,111 @@
+// K4 — per-video temporal attention pool + classification head, fp32 throughout.
+// Reference: pretrained_detector.py:123-131 (sigmoid-MLP score -> softmax over T -> weighted FEATURE sum),
+// :132-135 (mean mode), :138-141 (fc1 / ReLU / fc2; dropout is the identity in eval).
+// One CTA per video (ragged T via offsets).  Segmented warp-level reductions: a warp owns whole frames for
+// the score MLP (1280-long dot products reduced with shuffles), then the softmax over the video's frames,
+// then the weighted sum and the two FCs.  No atomics: results are bit-reproducible.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfd {
+
+constexpr int kPhThreads = 256;
+constexpr int kFeat = 1280, kAttHidden = 64, kFc1 = 256;
+constexpr int kMaxT = 1024;
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+__global__ void __launch_bounds__(kPhThreads)
+pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int32_t* __restrict__ offsets,
+                 int use_attention, float* __restrict__ logits, float* __restrict__ frame_scores) {
+    __shared__ float s_w[kMaxT];
+    __shared__ float s_pooled[kFeat];
+    __shared__ float s_h1[kFc1];
+    const int v = blockIdx.x;
+    const int f0 = offsets[v];
+    const int T = offsets[v + 1] - f0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (T <= 0 || T > kMaxT) {      // empty / over-long video: poison the outputs instead of guessing
+        if (threadIdx.x < 2) logits[(size_t)v * 2 + threadIdx.x] = __int_as_float(0x7fc00000);
+        return;
+    }
+    const float* fv = feat + (size_t)f0 * kFeat;
+
+    if (use_attention) {
+        const float b2 = __ldg(hw.att_b2);
+        for (int t = warp; t < T; t += kPhThreads / 32) {
+            float x[kFeat / 32];
+#pragma unroll
+            for (int i = 0; i < kFeat / 32; ++i) x[i] = fv[(size_t)t * kFeat + lane + 32 * i];
+            float score = 0.f;
+            for (int h = 0; h < kAttHidden; ++h) {
+                const float* wr = hw.att_w1 + (size_t)h * kFeat;
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < kFeat / 32; ++i) acc = fmaf(x[i], __ldg(wr + lane + 32 * i), acc);
+                acc = warp_sum(acc) + __ldg(hw.att_b1 + h);
+                score = fmaf(fmaxf(acc, 0.f), __ldg(hw.att_w2 + h), score);
+            }
+            if (lane == 0) s_w[t] = 1.0f / (1.0f + expf(-(score + b2)));      // nn.Sigmoid, :70
+        }
+        __syncthreads();
+        if (warp == 0) {                                                      // F.softmax(dim=1), :127
+            float mx = -INFINITY;
+            for (int t = lane; t < T; t += 32) mx = fmaxf(mx, s_w[t]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int t = lane; t < T; t += 32) { const float e = expf(s_w[t] - mx); s_w[t] = e; sum += e; }
+            sum = warp_sum(sum);
+            for (int t = lane; t < T; t += 32) s_w[t] = s_w[t] / sum;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < kFeat; c += kPhThreads) {               // (features * w).sum(dim=1), :131
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c] * s_w[t];
+            s_pooled[c] = acc;
+        }
+    } else {
+        for (int t = threadIdx.x; t < T; t += kPhThreads) s_w[t] = 1.0f / (float)T;   // :135
+        for (int c = threadIdx.x; c < kFeat; c += kPhThreads) {               // features.mean(dim=1), :134
+            float acc = 0.f;
+            for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c];
+            s_pooled[c] = acc / (float)T;
+        }
+    }
+    __syncthreads();
+    if (frame_scores) for (int t = threadIdx.x; t < T; t += kPhThreads) frame_scores[f0 + t] = s_w[t];
+
+    for (int j = warp; j < kFc1; j += kPhThreads / 32) {                      // relu(fc1(.)), :139
+        const float* wr = hw.fc1_w + (size_t)j * kFeat;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kFeat / 32; ++i) acc = fmaf(s_pooled[lane + 32 * i], __ldg(wr + lane + 32 * i), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) s_h1[j] = fmaxf(acc + __ldg(hw.fc1_b + j), 0.f);
+    }
+    __syncthreads();
+    if (warp < 2) {                                                           // fc2, :141
+        float acc = 0.f;
+        for (int i = lane; i < kFc1; i += 32) acc = fmaf(s_h1[i], __ldg(hw.fc2_w + warp * kFc1 + i), acc);
+        acc = warp_sum(acc);
+        if (lane == 0) logits[(size_t)v * 2 + warp] = acc + __ldg(hw.fc2_b + warp);
+    }
+}
+
+cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos,
+                             int use_attention, float* logits, float* frame_scores, cudaStream_t s) {
+    if (videos <= 0) return cudaSuccess;
+    pool_head_kernel<<<(unsigned)videos, kPhThreads, 0, s>>>(hw, feat, offsets, use_attention, logits, frame_scores);
+    return cudaGetLastError();
+}
+
+}  // namespace dfd

@@ -1,0 +1,92 @@
+// K2 tail — squeeze-excite gate (timm SqueezeExcite inside every MBConv block, reached from
+// pretrained_detector.py:116):  gate = sigmoid(W2 · SiLU(W1 · mean_hw(x) + b1) + b2), all fp32.
+// Input: the per-block partial sums written by dwconv.cu.  One CTA handles 8 frames so each FC weight is
+// read once per 8 frames; partial rows are added in a fixed order (bit-reproducible).  The gate itself is
+// applied to the A operand inside the project GEMM (gemm_tc.cu), so the dw output is never re-written.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace dfd {
+
+constexpr int kSeFrames = 8;
+constexpr int kSeThreads = 256;
+
+__global__ void __launch_bounds__(kSeThreads)
+se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
+          const float* __restrict__ w1, const float* __restrict__ b1,
+          const float* __restrict__ w2t, const float* __restrict__ b2,
+          float* __restrict__ gate, int64_t frames, int C, int rd) {
+    extern __shared__ float smem[];
+    float* s_mean = smem;                         // [kSeFrames][C]
+    float* s_r = smem + kSeFrames * C;            // [kSeFrames][rd]
+    const int64_t f0 = (int64_t)blockIdx.x * kSeFrames;
+    const int nf = (int)min((int64_t)kSeFrames, frames - f0);
+
+    for (int i = threadIdx.x; i < kSeFrames * C; i += kSeThreads) {
+        const int f = i / C, c = i - f * C;
+        float acc = 0.f;
+        if (f < nf) {
+            const float* p = partials + ((size_t)(f0 + f) * nparts) * C + c;
+            for (int q = 0; q < nparts; ++q) acc += p[(size_t)q * C];
+        }
+        s_mean[i] = acc * inv_hw;
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < rd; j += kSeThreads / 32) {
+        float acc[kSeFrames];
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f) acc[f] = 0.f;
+        const float* wr = w1 + (size_t)j * C;
+        for (int c = lane; c < C; c += 32) {
+            const float wv = __ldg(wr + c);
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f) acc[f] = fmaf(wv, s_mean[f * C + c], acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[f] += __shfl_xor_sync(0xffffffffu, acc[f], o);
+        }
+        if (lane == 0) {
+            const float bj = __ldg(b1 + j);
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f) s_r[f * rd + j] = silu_f(acc[f] + bj);
+        }
+    }
+    __syncthreads();
+
+    for (int c = threadIdx.x; c < C; c += kSeThreads) {
+        float acc[kSeFrames];
+        const float bc = __ldg(b2 + c);
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f) acc[f] = bc;
+        for (int j = 0; j < rd; ++j) {
+            const float wv = __ldg(w2t + (size_t)j * C + c);
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f) acc[f] = fmaf(wv, s_r[f * rd + j], acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < kSeFrames; ++f)
+            if (f < nf) gate[(size_t)(f0 + f) * C + c] = sigmoid_f(acc[f]);
+    }
+}
+
+cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,
+                      const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s) {
+    if (frames <= 0) return cudaSuccess;
+    const size_t smem = (size_t)kSeFrames * (C + rd) * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    if (smem > 64 * 1024) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)((frames + kSeFrames - 1) / kSeFrames);
+    se_kernel<<<grid, kSeThreads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
+    return cudaGetLastError();
+}
+
+}  // namespace dfd

@@ -1,0 +1,50 @@
+"""Multi-GPU scoring: videos are independent, so whole videos are sharded over ranks (never split — the
+softmax over T in pretrained_detector.py:127 is per video) and the only exchange is one all-gather of the
+per-video logits (8 bytes per video).  One process per GPU, torch.distributed (NCCL on GPUs, gloo in the
+CPU tests of the host logic)."""
+from __future__ import annotations
+
+from typing import Callable, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_videos: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced split: rank r owns videos [lo, hi); sizes differ by at most one."""
+    base, rem = divmod(num_videos, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_video_logits(local_logits: torch.Tensor, num_videos: int, group=None) -> torch.Tensor:
+    """All-gather per-video logits of a `shard_bounds` partition back into global video order.
+
+    Ranks may own different counts, so every rank pads to the maximum shard size and the padding is
+    dropped after the collective (all_gather needs equal shapes)."""
+    world = dist.get_world_size(group)
+    max_local = (num_videos + world - 1) // world
+    buf = local_logits.new_zeros((max_local, local_logits.shape[1]))
+    buf[: local_logits.shape[0]] = local_logits
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(num_videos, world, r)
+        parts.append(out[r][: hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def score_videos_sharded(score_fn: Callable[[int, int], torch.Tensor], num_videos: int, group=None) -> torch.Tensor:
+    """`score_fn(lo, hi)` scores this rank's videos [lo, hi) and returns their logits (hi-lo, 2)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(num_videos, world, rank)
+    local = score_fn(lo, hi)
+    if local.shape[0] != hi - lo:
+        raise RuntimeError(f"score_fn returned {local.shape[0]} videos for shard [{lo},{hi})")
+    return gather_video_logits(local, num_videos, group)
+
+
+def frames_of_shard(offsets: Sequence[int], lo: int, hi: int) -> Tuple[int, int]:
+    """Frame range [a, b) covered by videos [lo, hi) of a global offsets array."""
+    return int(offsets[lo]), int(offsets[hi])

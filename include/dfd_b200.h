@@ -1,0 +1,101 @@
+/* dfd_b200 — C ABI of the B200 (sm_100a) EfficientNet-B0 frame-scoring path.
+ *
+ * The reference (SaiPranav1506/DeepFake-Video-Detection) is pure Python and has no FFI/plugin boundary
+ * (SURVEY.md §8b); its boundary is the nn.Module contract of
+ *     src/pretrained_detector.py:15-143   PretrainedBackboneDetector (ctor :21-29, forward :103-143)
+ *     app.py:1772-1780                    imagenet_normalize
+ *     app.py:2084-2094                    tensor prep + model call + softmax
+ * This header is what a binding for that path would bind: plain pointers and sizes, no torch types.
+ * Every pointer named `d_*` is DEVICE memory on the current CUDA device; `stream` is a cudaStream_t
+ * passed as void* (0 = legacy default stream).  All entry points are asynchronous on `stream` unless
+ * stated, re-entrant (no hidden mutable state besides the immutable packed weights), and return
+ * 0 on success or a negative DFD_E* code; dfd_last_error() gives the thread-local message.
+ * No exception crosses this boundary.
+ */
+#ifndef DFD_B200_H
+#define DFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFD_ABI_VERSION 1
+
+/* 16-bit storage type of activations and GEMM operands (accumulation is always fp32). */
+#define DFD_DTYPE_BF16 0
+#define DFD_DTYPE_FP16 1
+
+/* layout of the frames handed to dfd_effnet_b0_features / dfd_score_videos */
+#define DFD_IN_U8_HWC 0      /* uint8 (F,H,W,3) RGB crops: prep of app.py:2084-2085 is fused into the stem   */
+#define DFD_IN_F32_NCHW 1    /* float (F,3,H,W), already normalised: what forward() receives (:103-116)      */
+#define DFD_IN_H16_NCHW 2    /* fp16/bf16 (F,3,H,W), output of dfd_preprocess_u8hwc_to_nchw                   */
+
+#define DFD_OK 0
+#define DFD_EINVAL (-1)      /* bad argument (null pointer, unsupported shape, unknown dtype ...)             */
+#define DFD_ECUDA (-2)       /* a CUDA runtime call or kernel launch failed                                  */
+#define DFD_ENOMEM (-3)      /* workspace too small / allocation failed                                      */
+#define DFD_EKEY (-4)        /* a required state_dict tensor is missing or has the wrong element count       */
+
+#define DFD_FEATURE_DIM 1280 /* pretrained_detector.py:49                                                     */
+#define DFD_NUM_CLASSES 2
+
+typedef struct dfd_weights dfd_weights_t;   /* opaque: BN-folded, repacked weights resident in HBM */
+
+int dfd_abi_version(void);
+const char* dfd_last_error(void);
+
+/* ---- weights -------------------------------------------------------------------------------------
+ * Replaces `model.load_state_dict(state_dict)` + `model.to(DEVICE)` (app.py:1718,1760; agent_system.py:89-91).
+ * `names[i]` are reference state_dict keys (e.g. "backbone.2.1.0.conv_dw.weight"),
+ * `data[i]` HOST fp32 pointers with `numel[i]` elements (`num_batches_tracked` entries may be omitted).
+ * BatchNorm is folded in fp32 (w' = w*g/sqrt(var+1e-5), b' = beta - mean*g/sqrt(var+1e-5)), then cast
+ * to `dtype` and repacked K-major for the tensor-core GEMMs.  Synchronous.  Free with dfd_free_weights. */
+int dfd_pack_weights(int n_tensors, const char* const* names, const float* const* data,
+                     const int64_t* numel, int dtype, dfd_weights_t** out);
+void dfd_free_weights(dfd_weights_t* w);
+int dfd_weights_dtype(const dfd_weights_t* w);
+
+/* ---- K1: tensor prep (app.py:2084-2085 + imagenet_normalize app.py:1772-1780) ---------------------
+ * uint8 (F,H,W,3) -> `dtype` (F,3,H,W): y = ((u8/255) - mean[c]) / std[c], evaluated in fp32 exactly as
+ * the reference does, then rounded once to the 16-bit type.  H*W must be a multiple of 16. */
+int dfd_preprocess_u8hwc_to_nchw(const uint8_t* d_in, void* d_out, int64_t frames, int H, int W,
+                                 int dtype, void* stream);
+
+/* ---- trunk: `self.backbone(x_flat)` (pretrained_detector.py:116) ----------------------------------
+ * frames (layout `in_kind`) -> pooled features fp32 (F,1280).  H = W = 224 is the supported crop size
+ * (any H, W multiple of 32 with (H/32)*(W/32) <= 128 works).  `d_workspace` must hold at least
+ * dfd_workspace_bytes(frames, H, W) bytes and must not be shared between concurrent calls. */
+int dfd_workspace_bytes(int64_t frames, int H, int W, size_t* bytes);
+int dfd_effnet_b0_features(const dfd_weights_t* w, const void* d_in, int in_kind, int64_t frames,
+                           int H, int W, float* d_features, void* d_workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ---- pool + head: pretrained_detector.py:123-141 --------------------------------------------------
+ * `d_offsets` int32 (V+1): video v owns frames [offsets[v], offsets[v+1]) of `d_features` (ragged T,
+ * each video is scored exactly as one reference B=1 call; an empty video is an error).
+ * use_attention != 0: sigmoid-MLP scores -> softmax over T -> weighted feature sum (:123-131);
+ * use_attention == 0: feature mean, frame_scores = 1/T (:132-135).  Then fc1/ReLU/fc2 (:138-141).
+ * Outputs: d_logits fp32 (V,2), d_frame_scores fp32 (F,) in frame order (may be NULL). */
+int dfd_attn_pool_head(const dfd_weights_t* w, const float* d_features, const int32_t* d_offsets,
+                       int64_t videos, int64_t frames, int use_attention, float* d_logits,
+                       float* d_frame_scores, void* stream);
+
+/* ---- whole path: app.py:2084-2089 for a batch of videos -------------------------------------------
+ * = dfd_effnet_b0_features + dfd_attn_pool_head.  `d_features_out` (F,1280) may be NULL, in which case
+ * the features live in the workspace (dfd_score_workspace_bytes accounts for them). */
+int dfd_score_workspace_bytes(int64_t frames, int H, int W, size_t* bytes);
+int dfd_score_videos(const dfd_weights_t* w, const void* d_in, int in_kind, const int32_t* d_offsets,
+                     int64_t videos, int64_t frames, int H, int W, int use_attention, float* d_logits,
+                     float* d_frame_scores, float* d_features_out, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* number of kernel launches the last dfd_effnet_b0_features / dfd_score_videos call on this thread made */
+int dfd_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_B200_H */

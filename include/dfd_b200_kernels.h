@@ -1,0 +1,45 @@
+/* dfd_b200 — kernel-level C entry points (one launch each).  Same conventions as dfd_b200.h.
+ * These exist so that every kernel can be parity-tested and profiled on its own through the C ABI;
+ * a binding for the reference only needs dfd_b200.h.  Layouts:
+ *   activations   NHWC, 16-bit (DFD_DTYPE_*), i.e. a [frames*H*W, C] row-major matrix
+ *   BatchNorm     already folded into weight/bias by the caller (dfd_pack_weights does this)
+ */
+#ifndef DFD_B200_KERNELS_H
+#define DFD_B200_KERNELS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* timm conv_stem + bn1 (backbone.0/.1): conv3x3 s2 p1 3->32 + bias + SiLU.  d_w fp32 [(ky*3+kx)*3+c][32]. */
+int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_bias, void* d_out,
+               int64_t frames, int H, int W, int dtype, void* stream);
+
+/* timm conv_dw + bn: depthwise kxk (k 3|5, stride 1|2, pad k/2) + bias + SiLU, plus the squeeze-excite
+ * spatial sums as d_partials fp32 [frames][dfd_k_dw_num_partials(OH,OW,C)][C].  d_w fp32 [k*k][C]. */
+int dfd_k_dw_num_partials(int OH, int OW, int C);
+int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,
+                 int64_t frames, int H, int W, int C, int k, int stride, int dtype, void* stream);
+
+/* timm SqueezeExcite: gate = sigmoid(W2 * SiLU(W1 * mean + b1) + b2), fp32 [frames][C].
+ * d_w1 [rd][C], d_w2t [rd][C] (conv_expand transposed). */
+int dfd_k_se(const float* d_partials, int nparts, float inv_hw, const float* d_w1, const float* d_b1,
+             const float* d_w2t, const float* d_b2, float* d_gate, int64_t frames, int C, int rd, void* stream);
+
+/* pointwise conv: D[M,N] = act((A .* gate)[M,K] * W[N,K]^T + bias) (+ R).  gate fp32 [M/HW][K] or NULL,
+ * R [M,N] or NULL, act 0|1 (SiLU).  impl 0 = tcgen05/TMEM kernel (the product path), 1 = CUDA-core
+ * bring-up kernel with identical rounding points. */
+int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const float* d_gate, const void* d_R,
+               void* d_D, int64_t M, int K, int N, int HW, int act, int dtype, int impl, void* stream);
+
+/* conv_head + bn2 + SiLU + global average pool: feat fp32 [M/HW][N]. */
+int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K,
+                    int N, int HW, int dtype, int impl, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFD_B200_KERNELS_H */
