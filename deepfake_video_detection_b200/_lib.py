@@ -30,6 +30,8 @@ _SIGNATURES = {
     "dfd_attn_pool_head": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _vp, _vp, _vp]),
     "dfd_score_workspace_bytes": (_int, [_i64, _int, _int, C.POINTER(C.c_size_t)]),
     "dfd_score_videos": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "dfd_profile_enable": (_int, [_int]),
+    "dfd_profile_collect": (_int, [_vp, _int, C.POINTER(_int)]),
     # dfd_b200_kernels.h
     "dfd_k_stem": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "dfd_k_dw_num_partials": (_int, [_int, _int, _int]),
@@ -39,6 +41,10 @@ _SIGNATURES = {
     "dfd_k_gemm_pool": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int), ("ms", C.c_double), ("bytes", C.c_double), ("flops", C.c_double)]
 
 _lock = threading.Lock()
 _lib = None

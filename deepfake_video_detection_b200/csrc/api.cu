@@ -21,6 +21,28 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_launches = 0;
 
+// ---- optional per-launch profiling (dfd_profile_*): CUDA events around every launch on the launch stream
+enum KClass { KC_PREPROCESS = 0, KC_STEM, KC_DWCONV, KC_SE, KC_GEMM_EXPAND, KC_GEMM_PROJECT, KC_GEMM_HEAD_POOL, KC_POOL_HEAD, KC_COUNT };
+const char* const kClassNames[KC_COUNT] = {"preprocess", "stem", "dwconv_se_squeeze", "se_gate", "gemm_expand", "gemm_project",
+                                           "gemm_head_pool", "attn_pool_head"};
+struct ProfRec { int cls; cudaEvent_t a, b; double bytes, flops; };
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfRec> g_prof;
+thread_local int g_cls = 0;
+thread_local double g_bytes = 0, g_flops = 0;
+thread_local cudaStream_t g_prof_stream = nullptr;
+// declare what the NEXT launch is (class, algorithmic bytes = activations read once + written once, flops)
+inline void prof_next(int cls, double bytes, double flops, cudaStream_t s) { g_cls = cls; g_bytes = bytes; g_flops = flops; g_prof_stream = s; }
+struct ProfScope {
+    ProfRec r{}; bool on;
+    ProfScope() : on(g_prof_on) {
+        if (on) { cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, g_prof_stream); }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(r.b, g_prof_stream); r.cls = g_cls; r.bytes = g_bytes; r.flops = g_flops; g_prof.push_back(r); }
+    }
+};
+
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -33,7 +55,8 @@ int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 #define DFD_LAUNCH(call, what)                                 \
     do {                                                       \
-        cudaError_t _e = (call);                               \
+        cudaError_t _e;                                        \
+        { ProfScope _ps; _e = (call); }                        \
         ++g_launches;                                          \
         if (_e != cudaSuccess) return cuda_fail(_e, what);     \
     } while (0)
@@ -283,6 +306,7 @@ int dfd_preprocess_u8hwc_to_nchw(const uint8_t* d_in, void* d_out, int64_t frame
     if (frames < 0 || H <= 0 || W <= 0 || ((int64_t)H * W) % 16 != 0) return fail(DFD_EINVAL, "dfd_preprocess: H*W must be a positive multiple of 16");
     if (dtype != DFD_DTYPE_BF16 && dtype != DFD_DTYPE_FP16) return fail(DFD_EINVAL, "dfd_preprocess: unknown dtype");
     g_launches = 0;
+    prof_next(KC_PREPROCESS, (double)frames * H * W * 3 * 3, 0, (cudaStream_t)stream);
     DFD_LAUNCH(dfd::launch_preprocess(d_in, d_out, frames, H, W, dtype, (cudaStream_t)stream), "preprocess kernel");
     return DFD_OK;
 }
@@ -325,8 +349,14 @@ Plan make_plan(int H, int W) {
     return p;
 }
 
+size_t in_frame_bytes(int in_kind, int H, int W) {
+    const size_t px = (size_t)H * W * 3;
+    return in_kind == DFD_IN_U8_HWC ? px : (in_kind == DFD_IN_F32_NCHW ? px * 4 : px * 2);
+}
+
 int run_gemm(const void* A, const void* Wt, const float* bias, const float* gate, const void* R, void* D,
              int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s) {
+    prof_next(gate ? KC_GEMM_PROJECT : KC_GEMM_EXPAND, (double)M * (K + N + (R ? N : 0)) * 2, 2.0 * M * K * N, s);
     if (use_simt_gemm()) DFD_LAUNCH(dfd::launch_gemm_simt(A, Wt, bias, gate, R, D, nullptr, M, K, N, HW, act, dtype, s), "gemm (simt)");
     else DFD_LAUNCH(dfd::launch_gemm_tc(A, Wt, bias, gate, R, D, M, K, N, HW, act, dtype, s), "gemm (tcgen05)");
     return DFD_OK;
@@ -345,6 +375,7 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
     const int dt = w->dtype;
 
     int h = H / 2, wd = W / 2, cur = 0;
+    prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
     DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
     for (int i = 0; i < kNumBlocks; ++i) {
         const BlockW& B = w->blocks[i];
@@ -357,8 +388,10 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         }
         const int pad = B.k / 2;
         const int oh = (h + 2 * pad - B.k) / B.stride + 1, ow = (wd + 2 * pad - B.k) / B.stride + 1;
+        prof_next(KC_DWCONV, (double)frames * B.mid * ((double)h * wd + (double)oh * ow) * 2, 2.0 * frames * oh * ow * B.mid * B.k * B.k, s);
         DFD_LAUNCH(dfd::launch_dwconv(e, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.mid, B.k, B.stride, dt, s), "depthwise kernel");
         const int nparts = dfd::dw_num_partials(oh, ow, B.mid);
+        prof_next(KC_SE, (double)frames * B.mid * (nparts + 1) * 4, 4.0 * frames * B.mid * B.rd, s);
         DFD_LAUNCH(dfd::launch_se(part, nparts, 1.0f / (float)(oh * ow), B.se_w1, B.se_b1, B.se_w2t, B.se_b2, gate,
                                   frames, B.mid, B.rd, s), "squeeze-excite kernel");
         int rc = run_gemm(bufD, B.proj_w, B.proj_b, gate, B.has_skip ? x : nullptr, io[cur ^ 1],
@@ -366,16 +399,12 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         if (rc) return rc;
         cur ^= 1; h = oh; wd = ow;
     }
+    prof_next(KC_GEMM_HEAD_POOL, (double)frames * h * wd * 320 * 2 + (double)frames * 1280 * 4, 2.0 * frames * h * wd * 320 * 1280, s);
     if (use_simt_gemm())
         DFD_LAUNCH(dfd::launch_gemm_simt(io[cur], w->head_w, w->head_b, nullptr, nullptr, nullptr, feat, frames * h * wd, 320, 1280, h * wd, 1, dt, s), "head (simt)");
     else
         DFD_LAUNCH(dfd::launch_gemm_tc_pool(io[cur], w->head_w, w->head_b, feat, frames * h * wd, 320, 1280, h * wd, dt, s), "head (tcgen05)");
     return DFD_OK;
-}
-
-size_t in_frame_bytes(int in_kind, int H, int W) {
-    const size_t px = (size_t)H * W * 3;
-    return in_kind == DFD_IN_U8_HWC ? px : (in_kind == DFD_IN_F32_NCHW ? px * 4 : px * 2);
 }
 
 }  // namespace
@@ -421,6 +450,7 @@ int dfd_attn_pool_head(const dfd_weights_t* w, const float* d_features, const in
     if (!w || !d_features || !d_offsets || !d_logits) return fail(DFD_EINVAL, "dfd_attn_pool_head: null pointer");
     if (videos < 0) return fail(DFD_EINVAL, "dfd_attn_pool_head: negative video count");
     g_launches = 0;
+    prof_next(KC_POOL_HEAD, (double)frames * 1280 * 4 * 2, 2.0 * frames * 1280 * 64 + 2.0 * videos * 1280 * 256, (cudaStream_t)stream);
     DFD_LAUNCH(dfd::launch_pool_head(w->hw, d_features, d_offsets, videos, use_attention, d_logits, d_frame_scores,
                                      (cudaStream_t)stream), "pool+head kernel");
     return DFD_OK;
@@ -452,6 +482,29 @@ int dfd_score_videos(const dfd_weights_t* w, const void* d_in, int in_kind, cons
     rc = dfd_attn_pool_head(w, feat, d_offsets, videos, frames, use_attention, d_logits, d_frame_scores, stream);
     g_launches += n;
     return rc;
+}
+
+// ---- profiling ---------------------------------------------------------------------------------------
+int dfd_profile_enable(int on) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = on != 0;
+    return DFD_OK;
+}
+int dfd_profile_collect(dfd_profile_entry* out, int max_entries, int* n_out) {
+    if (!out || !n_out || max_entries < KC_COUNT) return fail(DFD_EINVAL, "dfd_profile_collect: need room for all kernel classes");
+    for (int c = 0; c < KC_COUNT; ++c) {
+        memset(&out[c], 0, sizeof(out[c]));
+        strncpy(out[c].name, kClassNames[c], sizeof(out[c].name) - 1);
+    }
+    for (auto& r : g_prof) {
+        DFD_CUDA(cudaEventSynchronize(r.b), "cudaEventSynchronize(profile)");
+        float ms = 0.f;
+        DFD_CUDA(cudaEventElapsedTime(&ms, r.a, r.b), "cudaEventElapsedTime(profile)");
+        out[r.cls].launches += 1; out[r.cls].ms += ms; out[r.cls].bytes += r.bytes; out[r.cls].flops += r.flops;
+    }
+    *n_out = KC_COUNT;
+    return DFD_OK;
 }
 
 // ---- kernel-level entry points (include/dfd_b200_kernels.h) ------------------------------------------

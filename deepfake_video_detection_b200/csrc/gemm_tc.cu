@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     const uint32_t stage_bytes = kAStageBytes + p.b_stage_bytes;
     uint8_t* sp = smem_raw + (size_t)p.stages * stage_bytes;
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
-    float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += 4 * 4 * p.NBp * 4;
+    float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += 2 * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], tfull[2], tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             tc_fence_after_sync();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
             const int slots = POOL ? rows_valid / p.HW : 0;
-            const int my_slot = POOL ? row / p.HW : 0;
             for (int c16 = half; c16 * 16 < p.NBp; c16 += 2) {
                 uint32_t r[16];
                 tmem_ld16(t_row + c16 * 16, r);
@@ -216,18 +215,28 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     v[i] = ACT ? silu_f(x) : x;
                 }
                 if (POOL) {
-                    for (int s = 0; s < slots; ++s) {
-                        const bool mine = valid && (my_slot == s);
-                        float keep = 0.f;
+                    // Batch-invariant average pool: stage the SiLU'd tile in shared memory, then add each frame's
+                    // HW rows in an order that depends only on the row index inside the frame (4 fixed row
+                    // quarters, combined as (p0+p1)+(p2+p3)), never on where the frame sits in the tile.
+                    float* tile = s_pool + half * (kBM * 17);
+                    if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = mine ? v[i] : 0.f;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-                            if (lane == i) keep = x;
-                        }
-                        if (lane < 16) s_pool[(q * 4 + s) * p.NBp + c16 * 16 + lane] = keep;
+                        for (int i = 0; i < 16; ++i) tile[row * 17 + i] = v[i];
                     }
+                    asm volatile("bar.sync %0, 128;" :: "r"(1 + half) : "memory");
+                    const int th = q * 32 + lane;
+                    const int rq = (p.HW + 3) >> 2;
+                    const int64_t frame0 = m0 / p.HW;
+                    for (int item = th; item < slots * 64; item += 128) {
+                        const int part = item & 3, col = (item >> 2) & 15, s = item >> 6;
+                        const int r0 = part * rq, r1 = min(p.HW, r0 + rq);
+                        float tot = 0.f;
+                        for (int r = r0; r < r1; ++r) tot += tile[(s * p.HW + r) * 17 + col];
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+                        if (part == 0 && col < ncol) p.feat[(size_t)(frame0 + s) * p.N + n0 + c16 * 16 + col] = tot * p.inv_hw;
+                    }
+                    asm volatile("bar.sync %0, 128;" :: "r"(1 + half) : "memory");
                 } else if (valid) {
                     T* dst = D + (size_t)m * p.N + n0 + c16 * 16;
                     if (RES) {
@@ -253,18 +262,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         }
                     }
                 }
-            }
-            if (POOL) {
-                asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory");
-                const int64_t frame0 = m0 / p.HW;
-                for (int i = threadIdx.x; i < slots * nb_valid; i += kEpiWarps * 32) {
-                    const int s = i / nb_valid, col = i - s * nb_valid;
-                    float tot = 0.f;
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) tot += s_pool[(qq * 4 + s) * p.NBp + col];
-                    p.feat[(size_t)(frame0 + s) * p.N + n0 + col] = tot * p.inv_hw;
-                }
-                asm volatile("bar.sync 1, %0;" :: "n"(kEpiWarps * 32) : "memory");
             }
             tc_fence_before_sync();
             mbar_arrive(bar_tempty + 8 * acc);
@@ -296,7 +293,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, cudaStream_t s) {
     a.b_stage_bytes = 8 * a.lbo_b;
     uint32_t cols = 32; while (cols < (uint32_t)(2 * a.NBp)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)16 * a.NBp * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)2 * kBM * 17 * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
     const size_t budget = 227 * 1024;
     const size_t stage_bytes = kAStageBytes + a.b_stage_bytes;
     int stages = (int)((budget - fixed) / stage_bytes);

@@ -95,6 +95,20 @@ int dfd_score_videos(const dfd_weights_t* w, const void* d_in, int in_kind, cons
 /* number of kernel launches the last dfd_effnet_b0_features / dfd_score_videos call on this thread made */
 int dfd_last_launch_count(void);
 
+/* ---- measurement aid --------------------------------------------------------------------------------
+ * dfd_profile_enable(1): from now on every kernel launched by this thread through this library is
+ * bracketed by CUDA events recorded on the launch stream.  dfd_profile_collect synchronises on them and
+ * returns one entry per kernel class: launches, summed device time, algorithmic bytes (activations read
+ * once + written once, weights excluded — SURVEY.md §8d) and flops.  dfd_profile_enable(0) stops and
+ * discards.  Not for use inside a timed region. */
+typedef struct dfd_profile_entry {
+    char name[32];
+    int launches;
+    double ms, bytes, flops;
+} dfd_profile_entry;
+int dfd_profile_enable(int on);
+int dfd_profile_collect(dfd_profile_entry* out, int max_entries, int* n_out);
+
 #ifdef __cplusplus
 }
 #endif

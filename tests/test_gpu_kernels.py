@@ -1,0 +1,193 @@
+"""Per-kernel parity through the C ABI (include/dfd_b200_kernels.h) against fp32 PyTorch ops on the same
+16-bit-rounded inputs.  Tolerances are one output rounding of the storage type plus accumulation noise:
+fp16 2^-10, bf16 2^-7 relative (written next to each check)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DT = {"fp16": (1, torch.float16, 2.0 ** -10), "bf16": (0, torch.bfloat16, 2.0 ** -7)}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from deepfake_video_detection_b200 import _lib
+    return _lib.load()
+
+
+def chk(lib, rc):
+    assert rc == 0, lib.dfd_last_error().decode()
+
+
+def stream():
+    return int(torch.cuda.current_stream().cuda_stream)
+
+
+def close(out, ref, rel, abs_=None):
+    out, ref = out.float(), ref.float()
+    scale = ref.abs().max().item() + 1e-6
+    err = (out - ref).abs().max().item()
+    tol = rel * scale if abs_ is None else max(rel * scale, abs_)
+    assert err <= tol, f"max abs err {err:.3e} > {tol:.3e} (scale {scale:.3e})"
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_preprocess_bit_exact(lib, prec):
+    from oracle import effnet_b0_oracle as O
+    code, tdt, _ = DT[prec]
+    g = torch.Generator().manual_seed(1)
+    u8 = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=g)
+    u8[0, 0, :, :] = torch.arange(224 * 3, dtype=torch.int64).remainder(256).to(torch.uint8).view(224, 3)   # every byte value, every channel
+    u8[0, 1, :, :] = torch.arange(224 * 3, dtype=torch.int64).add(85).remainder(256).to(torch.uint8).view(224, 3)
+    u8[0, 2, :, :] = torch.arange(224 * 3, dtype=torch.int64).add(170).remainder(256).to(torch.uint8).view(224, 3)
+    out = torch.empty((5, 3, 224, 224), dtype=tdt, device="cuda")
+    u8d = u8.cuda()
+    chk(lib, lib.dfd_preprocess_u8hwc_to_nchw(u8d.data_ptr(), out.data_ptr(), 5, 224, 224, code, stream()))
+    ref = O.prep_u8_hwc(u8).to(tdt)            # reference fp32 arithmetic, one rounding to the storage type
+    assert torch.equal(out.cpu().view(torch.int16), ref.view(torch.int16))
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_stem(lib, prec, kind):
+    from oracle import effnet_b0_oracle as O
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(2)
+    u8 = torch.randint(0, 256, (3, 64, 96, 3), dtype=torch.uint8, generator=g)
+    x32 = O.prep_u8_hwc(u8)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(32, generator=g) * 0.2
+    wp = w.permute(2, 3, 1, 0).reshape(27, 32).contiguous().cuda()
+    if kind == 0:
+        xin, xref = u8.cuda(), x32
+    elif kind == 1:
+        xin, xref = x32.cuda(), x32
+    else:
+        xin = x32.to(tdt).cuda(); xref = xin.float().cpu()
+    out = torch.empty((3, 32, 48, 32), dtype=tdt, device="cuda")
+    bd = b.cuda()
+    chk(lib, lib.dfd_k_stem(xin.data_ptr(), kind, wp.data_ptr(), bd.data_ptr(), out.data_ptr(), 3, 64, 96, code, stream()))
+    ref = F.silu(F.conv2d(xref, w, b, 2, 1)).permute(0, 2, 3, 1)
+    close(out.cpu(), ref, rel)
+
+
+DW_SHAPES = [(32, 3, 1, 112), (96, 3, 2, 112), (144, 3, 1, 56), (144, 5, 2, 56), (240, 5, 1, 28), (240, 3, 2, 28),
+             (480, 3, 1, 14), (480, 5, 1, 14), (672, 5, 1, 14), (672, 5, 2, 14), (1152, 5, 1, 7), (1152, 3, 1, 7)]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("C_,k,s,H", DW_SHAPES)
+def test_dwconv_and_squeeze(lib, prec, C_, k, s, H):
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(C_ + k + s)
+    frames = 3
+    x = torch.randn(frames, H, H, C_, generator=g).to(tdt)
+    w = torch.randn(C_, 1, k, k, generator=g) * (1.0 / k)
+    b = torch.randn(C_, generator=g) * 0.2
+    OH = (H + 2 * (k // 2) - k) // s + 1
+    nparts = lib.dfd_k_dw_num_partials(OH, OH, C_)
+    wp = w.reshape(C_, k * k).t().contiguous().cuda()
+    out = torch.empty((frames, OH, OH, C_), dtype=tdt, device="cuda")
+    parts = torch.full((frames, nparts, C_), float("nan"), device="cuda")
+    xd, bd = x.cuda(), b.cuda()
+    chk(lib, lib.dfd_k_dwconv(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), out.data_ptr(), parts.data_ptr(),
+                              frames, H, H, C_, k, s, code, stream()))
+    ref = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w, b, s, k // 2, 1, C_))
+    close(out.cpu(), ref.permute(0, 2, 3, 1), rel)
+    sums = parts.sum(1).cpu()
+    assert torch.isfinite(sums).all()
+    close(sums, ref.sum((2, 3)), 1e-5, abs_=1e-3)
+
+
+@pytest.mark.parametrize("C_,rd,nparts,frames", [(32, 8, 49, 3), (96, 4, 37, 9), (1152, 48, 8, 17), (672, 28, 19, 8)])
+def test_se_gate(lib, C_, rd, nparts, frames):
+    g = torch.Generator().manual_seed(C_)
+    parts = torch.randn(frames, nparts, C_, generator=g)
+    w1 = torch.randn(rd, C_, generator=g) * 0.1; b1 = torch.randn(rd, generator=g) * 0.1
+    w2 = torch.randn(C_, rd, generator=g) * 0.3; b2 = torch.randn(C_, generator=g) * 0.3
+    gate = torch.empty((frames, C_), device="cuda")
+    inv = 1.0 / 123.0
+    dev = [t.cuda() for t in (parts, w1, b1, w2.t().contiguous(), b2)]
+    chk(lib, lib.dfd_k_se(dev[0].data_ptr(), nparts, C.c_float(inv), dev[1].data_ptr(), dev[2].data_ptr(),
+                          dev[3].data_ptr(), dev[4].data_ptr(), gate.data_ptr(), frames, C_, rd, stream()))
+    mean = parts.sum(1) * inv
+    ref = torch.sigmoid(F.linear(F.silu(F.linear(mean, w1, b1)), w2, b2))
+    close(gate.cpu(), ref, 1e-5, abs_=2e-6)
+
+
+# (K, N, HW): the 19 distinct pointwise shapes of SURVEY.md App. A
+PW_SHAPES = [(32, 16, 12544), (16, 96, 12544), (96, 24, 3136), (24, 144, 3136), (144, 24, 3136), (144, 40, 784),
+             (40, 240, 784), (240, 40, 784), (240, 80, 196), (80, 480, 196), (480, 80, 196), (480, 112, 196),
+             (112, 672, 196), (672, 112, 196), (672, 192, 49), (192, 1152, 49), (1152, 192, 49), (1152, 320, 49)]
+
+
+def _gemm_case(lib, prec, K, N, HW, frames, gate, res, act, impl, seed=0):
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(seed + K * 7 + N)
+    M = frames * HW
+    A = (torch.randn(M, K, generator=g)).to(tdt)
+    Wt = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).to(tdt)
+    bias = torch.randn(N, generator=g) * 0.3
+    G = torch.rand(frames, K, generator=g) if gate else None
+    R = torch.randn(M, N, generator=g).to(tdt) if res else None
+    D = torch.full((M, N), float("nan"), dtype=tdt, device="cuda")
+    Ad, Wd, bd = A.cuda(), Wt.cuda(), bias.cuda()
+    Gd = G.cuda() if gate else None
+    Rd = R.cuda() if res else None
+    chk(lib, lib.dfd_k_gemm(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), Gd.data_ptr() if gate else None,
+                            Rd.data_ptr() if res else None, D.data_ptr(), M, K, N, HW, int(act), code, impl, stream()))
+    torch.cuda.synchronize()
+    a = A.float()
+    if gate:
+        a = (a.view(frames, HW, K) * G.view(frames, 1, K)).to(tdt).float().view(M, K)   # operand is re-rounded
+    ref = a.double() @ Wt.double().t() + bias.double()
+    if act:
+        ref = F.silu(ref)
+    if res:
+        ref = ref + R.double()
+    close(D.cpu(), ref.float(), rel)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("K,N,HW", PW_SHAPES)
+def test_gemm_tcgen05_all_shapes(lib, prec, K, N, HW):
+    frames = 2 if HW >= 3136 else 5          # M not a multiple of 128 for the small maps
+    is_project = K > N or (K, N) == (32, 16)
+    _gemm_case(lib, prec, K, N, HW, frames, gate=is_project, res=False, act=not is_project, impl=0)
+
+
+@pytest.mark.parametrize("K,N,HW", [(144, 24, 3136), (240, 40, 784), (480, 80, 196), (672, 112, 196), (1152, 192, 49)])
+def test_gemm_tcgen05_gate_residual(lib, K, N, HW):
+    _gemm_case(lib, "fp16", K, N, HW, 3, gate=True, res=True, act=False, impl=0)
+
+
+@pytest.mark.parametrize("M_frames,HW", [(1, 49), (1, 1), (3, 127), (2, 129)])
+def test_gemm_tcgen05_ragged_m(lib, M_frames, HW):
+    _gemm_case(lib, "fp16", 96, 24, HW, M_frames, gate=True, res=False, act=False, impl=0)
+    _gemm_case(lib, "fp16", 24, 144, HW, M_frames, gate=False, res=False, act=True, impl=0)
+
+
+def test_gemm_simt_matches(lib):
+    _gemm_case(lib, "fp16", 144, 40, 784, 2, gate=True, res=False, act=False, impl=1)
+    _gemm_case(lib, "bf16", 40, 240, 784, 2, gate=False, res=False, act=True, impl=1)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("frames", [1, 2, 7])
+def test_head_gemm_pool(lib, prec, impl, frames):
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(frames)
+    K, N, HW = 320, 1280, 49
+    A = torch.randn(frames * HW, K, generator=g).to(tdt)
+    Wt = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).to(tdt)
+    bias = torch.randn(N, generator=g) * 0.3
+    feat = torch.full((frames, N), float("nan"), device="cuda")
+    Ad, Wd, bd = A.cuda(), Wt.cuda(), bias.cuda()
+    chk(lib, lib.dfd_k_gemm_pool(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), feat.data_ptr(),
+                                 frames * HW, K, N, HW, code, impl, stream()))
+    ref = F.silu(A.double() @ Wt.double().t() + bias.double()).view(frames, HW, N).mean(1)
+    close(feat.cpu(), ref.float(), 1e-5, abs_=1e-5)
