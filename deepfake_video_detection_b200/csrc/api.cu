@@ -84,7 +84,7 @@ bool use_simt_gemm() {
 int64_t chunk_frames() {
     const char* e = getenv("DFD_CHUNK_FRAMES");
     long v = e ? atol(e) : 0;
-    return v > 0 ? v : 256;
+    return v > 0 ? v : 2048;
 }
 
 }  // namespace

@@ -64,9 +64,9 @@ def test_stem(lib, prec, kind):
     if kind == 0:
         xin, xref = u8.cuda(), x32
     elif kind == 1:
-        xin, xref = x32.cuda(), x32
+        xin, xref = x32.contiguous().cuda(), x32
     else:
-        xin = x32.to(tdt).cuda(); xref = xin.float().cpu()
+        xin = x32.contiguous().to(tdt).cuda(); xref = xin.float().cpu()
     out = torch.empty((3, 32, 48, 32), dtype=tdt, device="cuda")
     bd = b.cuda()
     chk(lib, lib.dfd_k_stem(xin.data_ptr(), kind, wp.data_ptr(), bd.data_ptr(), out.data_ptr(), 3, 64, 96, code, stream()))
