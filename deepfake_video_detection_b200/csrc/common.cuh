@@ -109,6 +109,20 @@ __device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS), L1 bypass; `valid == false` writes 16 zero bytes
+// without touching global memory (src must still be a mapped address).
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(saddr), "l"(gptr), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // mbarrier (shared::cta)
 // ------------------------------------------------------------------------------------------

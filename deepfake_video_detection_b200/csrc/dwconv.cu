@@ -4,12 +4,15 @@
 //
 // One thread owns 8 channels (one 128-bit vector) x TW consecutive output columns of one output row:
 // each input row of the window is loaded once as (TW-1)*stride+k vectors and reused from registers for the
-// TW outputs; vertical reuse is served by L1.  Consecutive threads walk channel groups first, so a warp's
-// loads are runs of contiguous 16-byte vectors (coalesced NHWC).  fp32 accumulation, fp32 weights.
+// TW outputs.  A CTA owns a compact 3-D tile (TR output rows x TS column strips x TC channel groups), so
+// the vertical and horizontal halo re-reads of neighbouring threads hit L1 instead of going back to L2
+// (a k x k window would otherwise pull every input row k times through L2).  Channel groups are the
+// fastest thread index, so a warp's loads are runs of contiguous 16-byte vectors (coalesced NHWC).
+// fp32 accumulation, fp32 weights.
 //
 // SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding) per channel; the
-// block combines them in a fixed order and writes one partial row per block — no atomics, so the result
-// is bit-reproducible.  se.cu adds the partial rows up in order.
+// CTA combines them in a fixed order and writes its channel slice of one partial row per spatial tile —
+// no atomics, so the result is bit-reproducible.  se.cu adds the partial rows up in order.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -18,34 +21,56 @@ namespace dfd {
 constexpr int kDwThreads = 256;
 constexpr int kDwTW = 4;
 
-static inline int dw_items(int OH, int OW, int C) { return OH * ((OW + kDwTW - 1) / kDwTW) * (C / 8); }
-int dw_num_partials(int OH, int OW, int C) { return (dw_items(OH, OW, C) + kDwThreads - 1) / kDwThreads; }
+struct DwPlan { int strips, TS, TR, TC, tiles_x, tiles_y, groups_c; };
+
+static DwPlan dw_plan(int OH, int OW, int C) {
+    DwPlan p;
+    const int C8 = C / 8;
+    p.strips = (OW + kDwTW - 1) / kDwTW;
+    const int nx = (p.strips + 3) / 4;               // <= 4 strips (16 output columns) per tile, balanced
+    p.TS = (p.strips + nx - 1) / nx;
+    const int ny = (OH + 7) / 8;                      // <= 8 output rows per tile, balanced
+    p.TR = (OH + ny - 1) / ny;
+    p.TC = C8 < kDwThreads / (p.TS * p.TR) ? C8 : kDwThreads / (p.TS * p.TR);
+    while (p.TC * p.TS * (p.TR * 2) <= kDwThreads && p.TR * 2 <= OH) p.TR *= 2;   // few channels: taller tiles
+    p.tiles_x = (p.strips + p.TS - 1) / p.TS;
+    p.tiles_y = (OH + p.TR - 1) / p.TR;
+    p.groups_c = (C8 + p.TC - 1) / p.TC;
+    return p;
+}
+int dw_num_partials(int OH, int OW, int C) { const DwPlan p = dw_plan(OH, OW, C); return p.tiles_x * p.tiles_y; }
 
 template <typename T, int KS, int STRIDE>
 __global__ void __launch_bounds__(kDwThreads, 2)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
-              int H, int W, int C, int OH, int OW, int strips, int items, int blocks_per_frame) {
+              int H, int W, int C, int OH, int OW, const DwPlan pl) {
     constexpr int TW = kDwTW;
     constexpr int PAD = KS / 2;
     constexpr int NCOL = (TW - 1) * STRIDE + KS;
     __shared__ float s_part[kDwThreads][9];     // +1 pad: conflict-free column walks
 
     const int C8 = C >> 3;
-    const int64_t frame = blockIdx.x / blocks_per_frame;
-    const int blk = blockIdx.x - (int)(frame * blocks_per_frame);
-    const int item = blk * kDwThreads + threadIdx.x;
-    const bool valid = item < items;
+    // block -> (frame, tile_y, tile_x, channel group); channel group fastest so co-resident CTAs share halos in L2
+    int bid = blockIdx.x;
+    const int gc = bid % pl.groups_c; bid /= pl.groups_c;
+    const int tx = bid % pl.tiles_x;  bid /= pl.tiles_x;
+    const int ty = bid % pl.tiles_y;
+    const int64_t frame = bid / pl.tiles_y;
+    // thread -> (row, strip, channel) inside the tile; channel fastest
+    const int cl = threadIdx.x % pl.TC;
+    const int sl = (threadIdx.x / pl.TC) % pl.TS;
+    const int rl = threadIdx.x / (pl.TC * pl.TS);
+    const int c8 = gc * pl.TC + cl;
+    const int strip = tx * pl.TS + sl;
+    const int oy = ty * pl.TR + rl;
+    const bool valid = (rl < pl.TR) && (c8 < C8) && (strip < pl.strips) && (oy < OH);
 
     float sums[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) sums[c] = 0.f;
 
     if (valid) {
-        const int c8 = item % C8;
-        const int t = item / C8;
-        const int strip = t % strips;
-        const int oy = t / strips;
         const int ox0 = strip * TW;
         const int iy0 = oy * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
         const T* in_f = in + (size_t)frame * H * W * C + c8 * 8;
@@ -106,22 +131,16 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
 
     // ---- deterministic block reduction of the SE sums --------------------------------------------
 #pragma unroll
-    for (int c = 0; c < 8; ++c) s_part[threadIdx.x][c] = sums[c];
+    for (int c = 0; c < 8; ++c) s_part[threadIdx.x][c] = sums[c];     // invalid threads contribute zeros
     __syncthreads();
-    if (threadIdx.x < C8) {
-        const int cg = threadIdx.x;
-        const int base = (blk * kDwThreads) % C8;          // channel group of thread 0 in this block
-        int t0 = cg - base; if (t0 < 0) t0 += C8;
-        float tot[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) tot[c] = 0.f;
-        for (int t = t0; t < kDwThreads; t += C8) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) tot[c] += s_part[t][c];
+    if (threadIdx.x < pl.TC * 8) {
+        const int tc = threadIdx.x >> 3, ch = threadIdx.x & 7;
+        if (gc * pl.TC + tc < C8) {
+            float tot = 0.f;
+            const int n = (kDwThreads / pl.TC) * pl.TC;
+            for (int t = tc; t < n; t += pl.TC) tot += s_part[t][ch];   // fixed order over (row, strip)
+            partials[((size_t)frame * (pl.tiles_x * pl.tiles_y) + ty * pl.tiles_x + tx) * C + (gc * pl.TC + tc) * 8 + ch] = tot;
         }
-        float* dst = partials + ((size_t)frame * blocks_per_frame + blk) * C + cg * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(tot[0], tot[1], tot[2], tot[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(tot[4], tot[5], tot[6], tot[7]);
     }
 }
 
@@ -130,13 +149,12 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
                                int64_t frames, int H, int W, int C, int k, int stride, cudaStream_t s) {
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
-    const int strips = (OW + kDwTW - 1) / kDwTW;
-    const int items = dw_items(OH, OW, C);
-    const int bpf = dw_num_partials(OH, OW, C);
+    const DwPlan pl = dw_plan(OH, OW, C);
     if (frames <= 0) return cudaSuccess;
-    if ((C & 7) || C / 8 > kDwThreads || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)(frames * bpf);
-#define DFD_DW(KS, ST) dwconv_kernel<T, KS, ST><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf)
+    const int64_t blocks = frames * pl.tiles_y * pl.tiles_x * pl.groups_c;
+    if ((C & 7) || pl.TC * 8 > kDwThreads || blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)blocks;
+#define DFD_DW(KS, ST) dwconv_kernel<T, KS, ST><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, pl)
     if (k == 3 && stride == 1) DFD_DW(3, 1);
     else if (k == 3 && stride == 2) DFD_DW(3, 2);
     else if (k == 5 && stride == 1) DFD_DW(5, 1);

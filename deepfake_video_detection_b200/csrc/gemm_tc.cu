@@ -10,8 +10,11 @@
 //   pool variant: conv_head + BN + SiLU + global average pool -> features fp32 [frames][N]
 //
 // Structure (one persistent CTA per SM, 17 warps, warp-specialised):
-//   warps 9..16  producers: global -> registers -> (x gate) -> shared memory in the UMMA canonical
-//                K-major no-swizzle layout (8-row x 16-byte core matrices), `fence.proxy.async`, mbarrier arrive
+//   warps 9..16  producers: cp.async (LDGSTS, 16 B, L1 bypass) global -> shared memory straight into the UMMA
+//                canonical K-major no-swizzle layout (8-row x 16-byte core matrices), 3 stages of look-ahead so
+//                ~50 KB per SM are in flight; gated layers rescale their own chunks in place (x gate) once they
+//                have landed; then `fence.proxy.async` + mbarrier arrive.  Weights that fit (<= 120 KB) are
+//                loaded once per CTA and stay resident; larger ones stream through the stage ring.
 //   warp  8      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=NBp, K=16) per 16-wide K step,
 //                accumulators in TMEM (double buffered), tcgen05.commit releases smem stages / signals epilogue
 //   warps 0..7   epilogue: tcgen05.ld (32 lanes x 16 columns), +bias, SiLU, +residual, pack, store
@@ -24,7 +27,8 @@ namespace dfd {
 
 constexpr int kBM = 128;            // rows per tile = TMEM lanes
 constexpr int kKB = 64;             // K elements per pipeline stage (8 chunks of 8)
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
+constexpr int kLook = 3;               // producer look-ahead (stages issued before the oldest is awaited)
 constexpr int kEpiWarps = 8;
 constexpr int kProdWarps = 8;
 constexpr int kProdThreads = kProdWarps * 32;
@@ -40,7 +44,9 @@ struct GemmArgs {
     int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
     int64_t m_tiles;
     int stages;
-    uint32_t lbo_b, b_stage_bytes, tmem_cols;
+    int b_resident;                 // whole W lives in shared memory for the CTA's lifetime
+    int kchunks_pad;                // K/8 rounded up to even
+    uint32_t lbo_b, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
 };
 
@@ -48,15 +54,16 @@ template <typename T, bool GATE, bool ACT, bool RES, bool POOL>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- shared memory carve-up ----------------------------------------------------------------
-    const uint32_t stage_bytes = kAStageBytes + p.b_stage_bytes;
-    uint8_t* sp = smem_raw + (size_t)p.stages * stage_bytes;
+    const uint32_t stage_bytes = kAStageBytes + (p.b_resident ? 0u : p.b_stage_bytes);
+    uint8_t* sp = smem_raw + p.b_res_bytes + (size_t)p.stages * stage_bytes;
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
     float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += 2 * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], tfull[2], tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
 
-    const uint32_t smem_base = smem_u32(smem_raw);
+    const uint32_t bres_base = smem_u32(smem_raw);
+    const uint32_t smem_base = bres_base + p.b_res_bytes;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
     const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + 2);
 
@@ -69,6 +76,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), p.tmem_cols);
+    if (warp > kMmaWarp && p.b_resident) {
+        const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
+        const T* Wt = reinterpret_cast<const T*>(p.W);
+        const int kch = p.K >> 3, per = p.NBp * p.kchunks_pad;
+        for (int c = 0; c < p.n_chunks; ++c) {
+            const int nbv = min(p.NB, p.N - c * p.NB);
+            for (int i = tp; i < per; i += kProdThreads) {
+                const int r = i / p.kchunks_pad, q = i - r * p.kchunks_pad;
+                const bool ok = r < nbv && q < kch;
+                cp_async16(bres_base + c * p.b_chunk_bytes + q * p.lbo_b + r * 16,
+                           ok ? Wt + (size_t)(c * p.NB + r) * p.K + q * 8 : Wt, ok);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -82,75 +106,74 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
         const T* A = reinterpret_cast<const T*>(p.A);
         const T* Wt = reinterpret_cast<const T*>(p.W);
-        int stage = 0; uint32_t phase = 0;
-        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const int64_t mt = u / p.n_chunks;
-            const int nc = (int)(u - mt * p.n_chunks);
-            const int64_t m0 = mt * p.rows_per_tile;
-            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
-            const int n0 = nc * p.NB;
-            const int nb_valid = min(p.NB, p.N - n0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int k0 = kb * kKB;
-                const int kc = min(8, (p.K - k0) >> 3);        // 16-byte chunks present in this block
+        const int64_t my_units = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int64_t n_iters = my_units * num_kb;
+        int64_t ui = blockIdx.x, ud = blockIdx.x;      // unit of the issue / completion cursor
+        int kbi = 0, kbd = 0, si = 0, sd = 0;
+        uint32_t pi = 0;
+        for (int64_t it = 0; it < n_iters + kLook; ++it) {
+            if (it < n_iters) {
+                const int64_t mt = ui / p.n_chunks;
+                const int nc = (int)(ui - mt * p.n_chunks);
+                const int64_t m0 = mt * p.rows_per_tile;
+                const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+                const int k0 = kbi * kKB;
+                const int kc = min(8, (p.K - k0) >> 3);        // 16-byte chunks present in this k-block
                 const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
-                const int na = kBM * kcp, nb = p.NBp * kcp;
-                uint4 va[4], vb[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = tp + j * kProdThreads;
-                    va[j] = make_uint4(0, 0, 0, 0);
-                    if (i < na) {
+                mbar_wait(bar_empty + 8 * si, pi ^ 1);
+                const uint32_t a_base = smem_base + si * stage_bytes;
+                for (int i = tp; i < kBM * kcp; i += kProdThreads) {
+                    const int r = i / kcp, q = i - r * kcp;
+                    const bool ok = r < rows_valid && q < kc;
+                    cp_async16(a_base + q * kLboA + r * 16, ok ? A + (size_t)(m0 + r) * p.K + k0 + q * 8 : A, ok);
+                }
+                if (!p.b_resident) {
+                    const int n0 = nc * p.NB;
+                    const int nb_valid = min(p.NB, p.N - n0);
+                    const uint32_t b_base = a_base + kAStageBytes;
+                    for (int i = tp; i < p.NBp * kcp; i += kProdThreads) {
                         const int r = i / kcp, q = i - r * kcp;
-                        if (r < rows_valid && q < kc) va[j] = ldg16_stream(A + (size_t)(m0 + r) * p.K + k0 + q * 8);
+                        const bool ok = r < nb_valid && q < kc;
+                        cp_async16(b_base + q * p.lbo_b + r * 16, ok ? Wt + (size_t)(n0 + r) * p.K + k0 + q * 8 : Wt, ok);
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = tp + j * kProdThreads;
-                    vb[j] = make_uint4(0, 0, 0, 0);
-                    if (i < nb) {
-                        const int r = i / kcp, q = i - r * kcp;
-                        if (r < nb_valid && q < kc) vb[j] = ldg16(Wt + (size_t)(n0 + r) * p.K + k0 + q * 8);
-                    }
-                }
+                if (++kbi == num_kb) { kbi = 0; ui += gridDim.x; }
+                if (++si == p.stages) { si = 0; pi ^= 1; }
+            }
+            cp_async_commit();
+            if (it >= kLook) {
+                cp_async_wait<kLook>();                        // this thread's chunks of iteration it-kLook have landed
                 if (GATE) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = tp + j * kProdThreads;
-                        if (i < na) {
-                            const int r = i / kcp, q = i - r * kcp;
-                            if (r < rows_valid && q < kc) {
-                                const uint32_t frame = (uint32_t)(m0 + r) / (uint32_t)p.HW;
-                                const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
-                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
-                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
-                                float2 x0 = Half16<T>::unpack(va[j].x), x1 = Half16<T>::unpack(va[j].y);
-                                float2 x2 = Half16<T>::unpack(va[j].z), x3 = Half16<T>::unpack(va[j].w);
-                                va[j].x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y);
-                                va[j].y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
-                                va[j].z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y);
-                                va[j].w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
-                            }
+                    const int64_t mt = ud / p.n_chunks;
+                    const int64_t m0 = mt * p.rows_per_tile;
+                    const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+                    const int k0 = kbd * kKB;
+                    const int kc = min(8, (p.K - k0) >> 3);
+                    const int kcp = (kc + 1) & ~1;
+                    const uint32_t a_base = smem_base + sd * stage_bytes;
+                    for (int i = tp; i < kBM * kcp; i += kProdThreads) {   // the same chunks this thread copied
+                        const int r = i / kcp, q = i - r * kcp;
+                        if (r < rows_valid && q < kc) {
+                            const uint32_t frame = (uint32_t)(m0 + r) / (uint32_t)p.HW;
+                            const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
+                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+                            const uint32_t addr = a_base + q * kLboA + r * 16;
+                            uint4 v = lds16(addr);
+                            const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
+                            const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
+                            v.x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y);
+                            v.y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
+                            v.z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y);
+                            v.w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
+                            sts16(addr, v);
                         }
                     }
                 }
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                const uint32_t a_base = smem_base + stage * stage_bytes;
-                const uint32_t b_base = a_base + kAStageBytes;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = tp + j * kProdThreads;
-                    if (i < na) { const int r = i / kcp, q = i - r * kcp; sts16(a_base + q * kLboA + r * 16, va[j]); }
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int i = tp + j * kProdThreads;
-                    if (i < nb) { const int r = i / kcp, q = i - r * kcp; sts16(b_base + q * p.lbo_b + r * 16, vb[j]); }
-                }
                 fence_proxy_async_smem();
-                mbar_arrive(bar_full + 8 * stage);
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                mbar_arrive(bar_full + 8 * sd);
+                if (++kbd == num_kb) { kbd = 0; ud += gridDim.x; }
+                if (++sd == p.stages) sd = 0;
             }
         }
     } else if (warp == kMmaWarp) {
@@ -158,6 +181,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         const uint32_t idesc = umma_idesc(Half16<T>::kUmmaFormat, kBM, (uint32_t)p.NBp);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int nc = (int)(u % p.n_chunks);
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NBp);
@@ -168,7 +192,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_base = smem_base + stage * stage_bytes;
-                    const uint32_t b_base = a_base + kAStageBytes;
+                    const uint32_t b_base = p.b_resident ? bres_base + nc * p.b_chunk_bytes + kb * 8 * p.lbo_b
+                                                         : a_base + kAStageBytes;
                     for (int j = 0; j < steps; ++j) {
                         const uint64_t adesc = umma_smem_desc(a_base + 2 * j * kLboA, kLboA, 128);
                         const uint64_t bdesc = umma_smem_desc(b_base + 2 * j * p.lbo_b, p.lbo_b, 128);
@@ -239,27 +264,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     asm volatile("bar.sync %0, 128;" :: "r"(1 + half) : "memory");
                 } else if (valid) {
                     T* dst = D + (size_t)m * p.N + n0 + c16 * 16;
+                    const bool wide = ((p.N & 15) == 0);              // every 16-column chunk is then 32-byte aligned
                     if (RES) {
                         const T* rs = R + (size_t)m * p.N + n0 + c16 * 16;
+                        uint32_t rr[8];
+                        if (wide) {
+                            const U32x8 t = ldg32(rs);
 #pragma unroll
-                        for (int h8 = 0; h8 < 2; ++h8) {
-                            if (h8 * 8 < ncol) {
-                                const uint4 rv = ldg16_stream(rs + h8 * 8);
-                                const float2 a0 = Half16<T>::unpack(rv.x), a1 = Half16<T>::unpack(rv.y);
-                                const float2 a2 = Half16<T>::unpack(rv.z), a3 = Half16<T>::unpack(rv.w);
-                                v[h8 * 8 + 0] += a0.x; v[h8 * 8 + 1] += a0.y; v[h8 * 8 + 2] += a1.x; v[h8 * 8 + 3] += a1.y;
-                                v[h8 * 8 + 4] += a2.x; v[h8 * 8 + 5] += a2.y; v[h8 * 8 + 6] += a3.x; v[h8 * 8 + 7] += a3.y;
-                            }
+                            for (int i = 0; i < 8; ++i) rr[i] = t.v[i];
+                        } else {
+                            const uint4 t0 = ldg16_stream(rs);
+                            const uint4 t1 = (ncol > 8) ? ldg16_stream(rs + 8) : make_uint4(0, 0, 0, 0);
+                            rr[0] = t0.x; rr[1] = t0.y; rr[2] = t0.z; rr[3] = t0.w; rr[4] = t1.x; rr[5] = t1.y; rr[6] = t1.z; rr[7] = t1.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 a = Half16<T>::unpack(rr[i]);
+                            v[2 * i] += a.x; v[2 * i + 1] += a.y;
                         }
                     }
+                    U32x8 o;
 #pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        if (h8 * 8 < ncol) {
-                            uint4 o;
-                            o.x = Half16<T>::pack(v[h8 * 8 + 0], v[h8 * 8 + 1]); o.y = Half16<T>::pack(v[h8 * 8 + 2], v[h8 * 8 + 3]);
-                            o.z = Half16<T>::pack(v[h8 * 8 + 4], v[h8 * 8 + 5]); o.w = Half16<T>::pack(v[h8 * 8 + 6], v[h8 * 8 + 7]);
-                            stg16(dst + h8 * 8, o);
-                        }
+                    for (int i = 0; i < 8; ++i) o.v[i] = Half16<T>::pack(v[2 * i], v[2 * i + 1]);
+                    if (wide) {
+                        stg32(dst, o);
+                    } else {
+                        stg16(dst, make_uint4(o.v[0], o.v[1], o.v[2], o.v[3]));
+                        if (ncol > 8) stg16(dst + 8, make_uint4(o.v[4], o.v[5], o.v[6], o.v[7]));
                     }
                 }
             }
@@ -291,16 +322,21 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, cudaStream_t s) {
     a.NBp = (a.NB + 15) & ~15;
     a.lbo_b = (uint32_t)a.NBp * 16 + 16;
     a.b_stage_bytes = 8 * a.lbo_b;
+    a.kchunks_pad = ((a.K >> 3) + 1) & ~1;
+    a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
     uint32_t cols = 32; while (cols < (uint32_t)(2 * a.NBp)) cols <<= 1;
     a.tmem_cols = cols;
     const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)2 * kBM * 17 * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
     const size_t budget = 227 * 1024;
-    const size_t stage_bytes = kAStageBytes + a.b_stage_bytes;
-    int stages = (int)((budget - fixed) / stage_bytes);
+    const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
+    a.b_resident = (bres <= 120 * 1024) ? 1 : 0;
+    a.b_res_bytes = a.b_resident ? (uint32_t)bres : 0u;
+    const size_t stage_bytes = kAStageBytes + (a.b_resident ? 0 : a.b_stage_bytes);
+    int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) return cudaErrorInvalidValue;
+    if (stages < kLook + 1) return cudaErrorInvalidValue;
     a.stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    const size_t smem = a.b_res_bytes + (size_t)stages * stage_bytes + fixed;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t units = a.m_tiles * a.n_chunks;
