@@ -73,6 +73,38 @@ __device__ __forceinline__ float sigmoid_f(float x) {
     return __fdividef(1.0f, 1.0f + __expf(-x));
 }
 
+// Packed fp32x2 arithmetic (sm_100: the full fp32 rate needs the .f32x2 forms) and a SiLU for register
+// pairs that spends ONE MUFU per element (ex2) instead of two: the reciprocal of 1+e^-x is a bit-trick seed
+// refined by three Newton steps on the FMA pipe (relative error ~1e-7).  Used where MUFU, not FMA, is the
+// scarce pipe (GEMM epilogues).  The result is returned NEGATED (-x*sigmoid(x)); callers flip the sign bits
+// of the packed 16-bit pair for free.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) { float2 v = make_float2(a, b); return *reinterpret_cast<uint64_t*>(&v); }
+__device__ __forceinline__ float2 f2_unpack(uint64_t v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint64_t neg_silu2(uint64_t x) {
+    const float2 t = f2_unpack(mul2(x, f2_pack(-1.4426950408889634f, -1.4426950408889634f)));
+    const uint64_t e = f2_pack(ex2_approx(fminf(t.x, 126.f)), ex2_approx(fminf(t.y, 126.f)));
+    const uint64_t d = add2(e, f2_pack(1.f, 1.f));                       // 1 + e^-x  in [1, 2^126]
+    const float2 df = f2_unpack(d);
+    // s = -(1/d): seed -(magic - bits(d)), then s <- s * (2 + d*s)  (Newton on the negated reciprocal)
+    uint64_t s = f2_pack(__int_as_float((0x7EF311C7 - __float_as_int(df.x)) | 0x80000000),
+                         __int_as_float((0x7EF311C7 - __float_as_int(df.y)) | 0x80000000));
+    const uint64_t two = f2_pack(2.f, 2.f);
+    s = mul2(s, fma2(d, s, two));
+    s = mul2(s, fma2(d, s, two));
+    s = mul2(s, fma2(d, s, two));
+    return mul2(x, s);                                                   // = -x * sigmoid(x)
+}
+
 // ------------------------------------------------------------------------------------------
 // vector global access
 // ------------------------------------------------------------------------------------------

@@ -2,17 +2,17 @@
 // fused with the squeeze-excite spatial reduction (timm `conv_dw` + `bn` + the `x.mean((2,3))` of
 // SqueezeExcite; reference call site pretrained_detector.py:116).
 //
-// One thread owns 8 channels (one 128-bit vector) x TW consecutive output columns of one output row:
-// each input row of the window is loaded once as (TW-1)*stride+k vectors and reused from registers for the
-// TW outputs.  A CTA owns a compact 3-D tile (TR output rows x TS column strips x TC channel groups), so
-// the vertical and horizontal halo re-reads of neighbouring threads hit L1 instead of going back to L2
-// (a k x k window would otherwise pull every input row k times through L2).  Channel groups are the
-// fastest thread index, so a warp's loads are runs of contiguous 16-byte vectors (coalesced NHWC).
-// fp32 accumulation, fp32 weights.
+// One thread owns ONE CHANNEL PAIR (a 32-bit half2/bf162) x a TH x TW tile of output pixels:
+//   * the k*k x 2 filter taps of its pair stay in registers as packed fp32x2 for the whole tile;
+//   * input rows are streamed once per thread ((TH-1)*s+k rows of (TW-1)*s+k values) and every loaded
+//     value feeds up to k x min(TH,k) packed FMAs (`fma.rn.f32x2`, the only way to reach the full fp32
+//     rate on sm_100) — L1 traffic per output drops ~5x against a one-row-per-thread mapping;
+//   * lanes walk channel pairs, so every warp load/store is one contiguous 128-byte NHWC run.
+// fp32 accumulation, fp32 weights, one rounding to the storage type at the store.
 //
-// SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding) per channel; the
-// CTA combines them in a fixed order and writes its channel slice of one partial row per spatial tile —
-// no atomics, so the result is bit-reproducible.  se.cu adds the partial rows up in order.
+// SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding); a CTA covers PG channel
+// pairs x TG neighbouring tiles and adds its TG tiles up in a fixed order, writing its channel slice of one
+// partial row per tile group — no atomics, bit-reproducible.  se.cu adds the partial rows up in order.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,126 +21,120 @@ namespace dfd {
 constexpr int kDwThreads = 256;
 constexpr int kDwTW = 4;
 
-struct DwPlan { int strips, TS, TR, TC, tiles_x, tiles_y, groups_c; };
+struct DwPlan { int TH, tiles_x, tiles, PG, TG, pair_groups, tile_groups; };
 
-static DwPlan dw_plan(int OH, int OW, int C) {
+static DwPlan dw_plan(int OH, int OW, int C, int k) {
     DwPlan p;
-    const int C8 = C / 8;
-    p.strips = (OW + kDwTW - 1) / kDwTW;
-    const int nx = (p.strips + 3) / 4;               // <= 4 strips (16 output columns) per tile, balanced
-    p.TS = (p.strips + nx - 1) / nx;
-    const int ny = (OH + 7) / 8;                      // <= 8 output rows per tile, balanced
-    p.TR = (OH + ny - 1) / ny;
-    p.TC = C8 < kDwThreads / (p.TS * p.TR) ? C8 : kDwThreads / (p.TS * p.TR);
-    while (p.TC * p.TS * (p.TR * 2) <= kDwThreads && p.TR * 2 <= OH) p.TR *= 2;   // few channels: taller tiles
-    p.tiles_x = (p.strips + p.TS - 1) / p.TS;
-    p.tiles_y = (OH + p.TR - 1) / p.TR;
-    p.groups_c = (C8 + p.TC - 1) / p.TC;
+    const int pairs = C / 2;
+    p.TH = (k == 3 && OH <= 14 && OH % 7 == 0) ? 7 : 4;
+    p.tiles_x = (OW + kDwTW - 1) / kDwTW;
+    p.tiles = p.tiles_x * ((OH + p.TH - 1) / p.TH);
+    p.pair_groups = (pairs + kDwThreads - 1) / kDwThreads;
+    while (pairs % p.pair_groups) ++p.pair_groups;
+    p.PG = pairs / p.pair_groups;
+    p.TG = kDwThreads / p.PG;
+    if (p.TG > p.tiles) p.TG = p.tiles;
+    p.tile_groups = (p.tiles + p.TG - 1) / p.TG;
     return p;
 }
-int dw_num_partials(int OH, int OW, int C) { const DwPlan p = dw_plan(OH, OW, C); return p.tiles_x * p.tiles_y; }
+int dw_num_partials(int OH, int OW, int C, int k) { return dw_plan(OH, OW, C, k).tile_groups; }
 
-template <typename T, int KS, int STRIDE>
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t pack_f2(float2 v) { return *reinterpret_cast<uint64_t*>(&v); }
+__device__ __forceinline__ float2 unpack_f2(uint64_t v) { return *reinterpret_cast<float2*>(&v); }
+
+template <typename T, int KS, int S, int TH>
 __global__ void __launch_bounds__(kDwThreads, 2)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
               int H, int W, int C, int OH, int OW, const DwPlan pl) {
     constexpr int TW = kDwTW;
     constexpr int PAD = KS / 2;
-    constexpr int NCOL = (TW - 1) * STRIDE + KS;
-    __shared__ float s_part[kDwThreads][9];     // +1 pad: conflict-free column walks
+    constexpr int NCOL = (TW - 1) * S + KS;
+    constexpr int NROW = (TH - 1) * S + KS;
+    __shared__ float2 s_part[kDwThreads];
 
-    const int C8 = C >> 3;
-    // block -> (frame, tile_y, tile_x, channel group); channel group fastest so co-resident CTAs share halos in L2
     int bid = blockIdx.x;
-    const int gc = bid % pl.groups_c; bid /= pl.groups_c;
-    const int tx = bid % pl.tiles_x;  bid /= pl.tiles_x;
-    const int ty = bid % pl.tiles_y;
-    const int64_t frame = bid / pl.tiles_y;
-    // thread -> (row, strip, channel) inside the tile; channel fastest
-    const int cl = threadIdx.x % pl.TC;
-    const int sl = (threadIdx.x / pl.TC) % pl.TS;
-    const int rl = threadIdx.x / (pl.TC * pl.TS);
-    const int c8 = gc * pl.TC + cl;
-    const int strip = tx * pl.TS + sl;
-    const int oy = ty * pl.TR + rl;
-    const bool valid = (rl < pl.TR) && (c8 < C8) && (strip < pl.strips) && (oy < OH);
+    const int pg = bid % pl.pair_groups; bid /= pl.pair_groups;
+    const int tg = bid % pl.tile_groups;
+    const int64_t frame = bid / pl.tile_groups;
+    const int pl_ = threadIdx.x % pl.PG, tl = threadIdx.x / pl.PG;
+    const int pair = pg * pl.PG + pl_;
+    const int tile = tg * pl.TG + tl;
+    const bool active = (tl < pl.TG) && (tile < pl.tiles);
 
-    float sums[8];
+    float2 sum = make_float2(0.f, 0.f);
+    if (active) {
+        const int ty = tile / pl.tiles_x, tx = tile - ty * pl.tiles_x;
+        const int oy0 = ty * TH, ox0 = tx * TW;
+        const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
+
+        uint64_t wreg[KS * KS];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sums[c] = 0.f;
-
-    if (valid) {
-        const int ox0 = strip * TW;
-        const int iy0 = oy * STRIDE - PAD, ix0 = ox0 * STRIDE - PAD;
-        const T* in_f = in + (size_t)frame * H * W * C + c8 * 8;
-        const float* wc = w + c8 * 8;
-
-        float acc[TW][8];
+        for (int i = 0; i < KS * KS; ++i) wreg[i] = pack_f2(__ldg(reinterpret_cast<const float2*>(w + (size_t)i * C + 2 * pair)));
+        uint64_t acc[TH][TW];
         {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+            const uint64_t b = pack_f2(__ldg(reinterpret_cast<const float2*>(bias + 2 * pair)));
 #pragma unroll
-            for (int j = 0; j < TW; ++j) {
-                acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b0.z; acc[j][3] = b0.w;
-                acc[j][4] = b1.x; acc[j][5] = b1.y; acc[j][6] = b1.z; acc[j][7] = b1.w;
-            }
+            for (int t = 0; t < TH; ++t)
+#pragma unroll
+                for (int j = 0; j < TW; ++j) acc[t][j] = b;
         }
+        const T* base = in + (size_t)frame * H * W * C + 2 * pair;
 #pragma unroll
-        for (int ky = 0; ky < KS; ++ky) {
-            const int iy = iy0 + ky;
-            if (iy < 0 || iy >= H) continue;
-            const T* row = in_f + (size_t)iy * W * C;
-            uint4 v[NCOL];
+        for (int r = 0; r < NROW; ++r) {
+            const int iy = iy0 + r;
+            if (iy < 0 || iy >= H) continue;                  // zero padding row: contributes nothing
+            const T* row = base + (size_t)iy * W * C;
+            uint64_t x[NCOL];
 #pragma unroll
             for (int j = 0; j < NCOL; ++j) {
                 const int ix = ix0 + j;
-                v[j] = (ix >= 0 && ix < W) ? ldg16(row + (size_t)ix * C) : make_uint4(0, 0, 0, 0);
+                uint32_t v = 0u;
+                if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)ix * C));
+                x[j] = pack_f2(Half16<T>::unpack(v));
             }
 #pragma unroll
-            for (int kx = 0; kx < KS; ++kx) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wc + (ky * KS + kx) * C));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wc + (ky * KS + kx) * C + 4));
+            for (int t = 0; t < TH; ++t) {
+                const int ky = r - t * S;                      // compile-time after unrolling
+                if (ky >= 0 && ky < KS) {
 #pragma unroll
-                for (int j = 0; j < TW; ++j) {
-                    const uint4 x = v[j * STRIDE + kx];
-                    const float2 x0 = Half16<T>::unpack(x.x), x1 = Half16<T>::unpack(x.y);
-                    const float2 x2 = Half16<T>::unpack(x.z), x3 = Half16<T>::unpack(x.w);
-                    acc[j][0] = fmaf(x0.x, w0.x, acc[j][0]); acc[j][1] = fmaf(x0.y, w0.y, acc[j][1]);
-                    acc[j][2] = fmaf(x1.x, w0.z, acc[j][2]); acc[j][3] = fmaf(x1.y, w0.w, acc[j][3]);
-                    acc[j][4] = fmaf(x2.x, w1.x, acc[j][4]); acc[j][5] = fmaf(x2.y, w1.y, acc[j][5]);
-                    acc[j][6] = fmaf(x3.x, w1.z, acc[j][6]); acc[j][7] = fmaf(x3.y, w1.w, acc[j][7]);
+                    for (int kx = 0; kx < KS; ++kx)
+#pragma unroll
+                        for (int j = 0; j < TW; ++j) acc[t][j] = ffma2(x[j * S + kx], wreg[ky * KS + kx], acc[t][j]);
                 }
             }
         }
-        T* orow = out + (((size_t)frame * OH + oy) * OW) * C + c8 * 8;
+        T* obase = out + (size_t)frame * OH * OW * C + 2 * pair;
 #pragma unroll
-        for (int j = 0; j < TW; ++j) {
-            const int ox = ox0 + j;
-            if (ox < OW) {
-                float y[8];
+        for (int t = 0; t < TH; ++t) {
+            const int oy = oy0 + t;
+            if (oy < OH) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) { y[c] = silu_f(acc[j][c]); sums[c] += y[c]; }
-                uint4 o;
-                o.x = Half16<T>::pack(y[0], y[1]); o.y = Half16<T>::pack(y[2], y[3]);
-                o.z = Half16<T>::pack(y[4], y[5]); o.w = Half16<T>::pack(y[6], y[7]);
-                stg16(orow + (size_t)ox * C, o);
+                for (int j = 0; j < TW; ++j) {
+                    const int ox = ox0 + j;
+                    if (ox < OW) {
+                        const float2 a = unpack_f2(acc[t][j]);
+                        const float y0 = silu_f(a.x), y1 = silu_f(a.y);
+                        sum.x += y0; sum.y += y1;
+                        *reinterpret_cast<uint32_t*>(obase + ((size_t)oy * OW + ox) * C) = Half16<T>::pack(y0, y1);
+                    }
+                }
             }
         }
     }
 
-    // ---- deterministic block reduction of the SE sums --------------------------------------------
-#pragma unroll
-    for (int c = 0; c < 8; ++c) s_part[threadIdx.x][c] = sums[c];     // invalid threads contribute zeros
+    // ---- deterministic CTA reduction of the SE sums over the CTA's tiles ----------------------------
+    s_part[threadIdx.x] = sum;                         // inactive threads contribute zeros
     __syncthreads();
-    if (threadIdx.x < pl.TC * 8) {
-        const int tc = threadIdx.x >> 3, ch = threadIdx.x & 7;
-        if (gc * pl.TC + tc < C8) {
-            float tot = 0.f;
-            const int n = (kDwThreads / pl.TC) * pl.TC;
-            for (int t = tc; t < n; t += pl.TC) tot += s_part[t][ch];   // fixed order over (row, strip)
-            partials[((size_t)frame * (pl.tiles_x * pl.tiles_y) + ty * pl.tiles_x + tx) * C + (gc * pl.TC + tc) * 8 + ch] = tot;
-        }
+    if (threadIdx.x < pl.PG) {
+        float2 tot = make_float2(0.f, 0.f);
+        for (int t = 0; t < pl.TG; ++t) { const float2 v = s_part[t * pl.PG + threadIdx.x]; tot.x += v.x; tot.y += v.y; }
+        *reinterpret_cast<float2*>(partials + ((size_t)frame * pl.tile_groups + tg) * C + 2 * pair) = tot;
     }
 }
 
@@ -149,17 +143,19 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
                                int64_t frames, int H, int W, int C, int k, int stride, cudaStream_t s) {
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
-    const DwPlan pl = dw_plan(OH, OW, C);
     if (frames <= 0) return cudaSuccess;
-    const int64_t blocks = frames * pl.tiles_y * pl.tiles_x * pl.groups_c;
-    if ((C & 7) || pl.TC * 8 > kDwThreads || blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if ((C & 7) || (k != 3 && k != 5) || (stride != 1 && stride != 2)) return cudaErrorInvalidValue;
+    const DwPlan pl = dw_plan(OH, OW, C, k);
+    const int64_t blocks = frames * pl.tile_groups * pl.pair_groups;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)blocks;
-#define DFD_DW(KS, ST) dwconv_kernel<T, KS, ST><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, pl)
-    if (k == 3 && stride == 1) DFD_DW(3, 1);
-    else if (k == 3 && stride == 2) DFD_DW(3, 2);
-    else if (k == 5 && stride == 1) DFD_DW(5, 1);
-    else if (k == 5 && stride == 2) DFD_DW(5, 2);
-    else return cudaErrorInvalidValue;
+#define DFD_DW(KS, ST, TH) dwconv_kernel<T, KS, ST, TH><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, pl)
+    if (k == 3 && stride == 1 && pl.TH == 4) DFD_DW(3, 1, 4);
+    else if (k == 3 && stride == 1) DFD_DW(3, 1, 7);
+    else if (k == 3 && stride == 2 && pl.TH == 4) DFD_DW(3, 2, 4);
+    else if (k == 3 && stride == 2) DFD_DW(3, 2, 7);
+    else if (k == 5 && stride == 1) DFD_DW(5, 1, 4);
+    else DFD_DW(5, 2, 4);
 #undef DFD_DW
     return cudaGetLastError();
 }

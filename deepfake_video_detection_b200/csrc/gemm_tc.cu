@@ -103,7 +103,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
 
     if (warp > kMmaWarp) {
         // =================================== PRODUCERS ===========================================
+        // Thread tp owns 16-byte chunk column q = tp % 8 of rows rb + 32*j: no divisions in the loop, a
+        // quarter-warp copies 128 contiguous bytes of one row, and its 8 shared-memory stores land in 8
+        // different bank groups (LBO is padded by 16 bytes).
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
+        const int q = tp & 7, rb = tp >> 3;
         const T* A = reinterpret_cast<const T*>(p.A);
         const T* Wt = reinterpret_cast<const T*>(p.W);
         const int64_t my_units = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -111,6 +115,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         int64_t ui = blockIdx.x, ud = blockIdx.x;      // unit of the issue / completion cursor
         int kbi = 0, kbd = 0, si = 0, sd = 0;
         uint32_t pi = 0;
+        const uint32_t a_off = q * kLboA + rb * 16, b_off = q * p.lbo_b + rb * 16;
         for (int64_t it = 0; it < n_iters + kLook; ++it) {
             if (it < n_iters) {
                 const int64_t mt = ui / p.n_chunks;
@@ -122,19 +127,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
                 mbar_wait(bar_empty + 8 * si, pi ^ 1);
                 const uint32_t a_base = smem_base + si * stage_bytes;
-                for (int i = tp; i < kBM * kcp; i += kProdThreads) {
-                    const int r = i / kcp, q = i - r * kcp;
-                    const bool ok = r < rows_valid && q < kc;
-                    cp_async16(a_base + q * kLboA + r * 16, ok ? A + (size_t)(m0 + r) * p.K + k0 + q * 8 : A, ok);
-                }
-                if (!p.b_resident) {
-                    const int n0 = nc * p.NB;
-                    const int nb_valid = min(p.NB, p.N - n0);
-                    const uint32_t b_base = a_base + kAStageBytes;
-                    for (int i = tp; i < p.NBp * kcp; i += kProdThreads) {
-                        const int r = i / kcp, q = i - r * kcp;
-                        const bool ok = r < nb_valid && q < kc;
-                        cp_async16(b_base + q * p.lbo_b + r * 16, ok ? Wt + (size_t)(n0 + r) * p.K + k0 + q * 8 : Wt, ok);
+                if (q < kcp) {
+                    const T* src = A + (size_t)(m0 + rb) * p.K + k0 + q * 8;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool ok = (rb + 32 * j < rows_valid) && (q < kc);
+                        cp_async16(a_base + a_off + j * 512, ok ? src + (size_t)(32 * j) * p.K : A, ok);
+                    }
+                    if (!p.b_resident) {
+                        const int n0 = nc * p.NB;
+                        const int nb_valid = min(p.NB, p.N - n0);
+                        const uint32_t b_base = a_base + kAStageBytes;
+                        const T* wsrc = Wt + (size_t)(n0 + rb) * p.K + k0 + q * 8;
+                        for (int r = rb; r < p.NBp; r += 32) {
+                            const bool ok = (r < nb_valid) && (q < kc);
+                            cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * p.K : Wt, ok);
+                        }
                     }
                 }
                 if (++kbi == num_kb) { kbi = 0; ui += gridDim.x; }
@@ -149,24 +157,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
                     const int k0 = kbd * kKB;
                     const int kc = min(8, (p.K - k0) >> 3);
-                    const int kcp = (kc + 1) & ~1;
-                    const uint32_t a_base = smem_base + sd * stage_bytes;
-                    for (int i = tp; i < kBM * kcp; i += kProdThreads) {   // the same chunks this thread copied
-                        const int r = i / kcp, q = i - r * kcp;
-                        if (r < rows_valid && q < kc) {
-                            const uint32_t frame = (uint32_t)(m0 + r) / (uint32_t)p.HW;
-                            const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
-                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
-                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
-                            const uint32_t addr = a_base + q * kLboA + r * 16;
-                            uint4 v = lds16(addr);
-                            const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
-                            const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
-                            v.x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y);
-                            v.y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
-                            v.z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y);
-                            v.w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
-                            sts16(addr, v);
+                    if (q < kc) {
+                        const uint32_t a_base = smem_base + sd * stage_bytes;
+                        // frame of row m0+rb without a per-row division: one division per tile-stage, then steps
+                        uint32_t frame = (uint32_t)(m0 + rb) / (uint32_t)p.HW;
+                        uint32_t rem = (uint32_t)(m0 + rb) - frame * (uint32_t)p.HW;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (rb + 32 * j < rows_valid) {
+                                const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+                                const uint32_t addr = a_base + a_off + j * 512;
+                                uint4 v = lds16(addr);
+                                const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
+                                const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
+                                v.x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y);
+                                v.y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
+                                v.z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y);
+                                v.w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
+                                sts16(addr, v);
+                            }
+                            rem += 32;
+                            while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++frame; }
                         }
                     }
                 }
@@ -235,9 +248,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 if (ncol <= 0) continue;
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float x = __uint_as_float(r[i]) + s_bias[min(n0 + c16 * 16 + i, p.N - 1)];
-                    v[i] = ACT ? silu_f(x) : x;
+                for (int i = 0; i < 16; i += 2) {
+                    const int col = min(n0 + c16 * 16 + i, p.N - 2);
+                    uint64_t x = add2(f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                      *reinterpret_cast<const uint64_t*>(&s_bias[col]));
+                    if (ACT) x = neg_silu2(x);                        // -silu(x); sign restored below
+                    const float2 xf = f2_unpack(x);
+                    v[i] = ACT ? -xf.x : xf.x; v[i + 1] = ACT ? -xf.y : xf.y;
                 }
                 if (POOL) {
                     // Batch-invariant average pool: stage the SiLU'd tile in shared memory, then add each frame's
