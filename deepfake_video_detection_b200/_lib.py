@@ -34,7 +34,7 @@ _SIGNATURES = {
     "dfd_profile_collect": (_int, [_vp, _int, C.POINTER(_int)]),
     # dfd_b200_kernels.h
     "dfd_k_stem": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
-    "dfd_k_dw_num_partials": (_int, [_int, _int, _int, _int]),
+    "dfd_k_dw_num_partials": (_int, [_int, _int, _int, _int, _int]),
     "dfd_k_dwconv": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp]),
     "dfd_k_se": (_int, [_vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "dfd_k_gemm": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp]),

@@ -341,7 +341,7 @@ Plan make_plan(int H, int W) {
             const int oh = (h + 2 * (k / 2) - k) / st + 1, ow = (w + 2 * (k / 2) - k) / st + 1;
             if (kStages[s][3] != 1) p.e_elems = std::max(p.e_elems, (size_t)h * w * mid);
             p.d_elems = std::max(p.d_elems, (size_t)oh * ow * mid);
-            p.part_floats = std::max(p.part_floats, (size_t)dfd::dw_num_partials(oh, ow, mid, k) * mid);
+            p.part_floats = std::max(p.part_floats, (size_t)dfd::dw_num_partials(oh, ow, mid, k, st) * mid);
             p.gate_floats = std::max(p.gate_floats, (size_t)mid);
             p.io_elems = std::max(p.io_elems, (size_t)oh * ow * cout);
             h = oh; w = ow; cin = cout;
@@ -390,7 +390,7 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         const int oh = (h + 2 * pad - B.k) / B.stride + 1, ow = (wd + 2 * pad - B.k) / B.stride + 1;
         prof_next(KC_DWCONV, (double)frames * B.mid * ((double)h * wd + (double)oh * ow) * 2, 2.0 * frames * oh * ow * B.mid * B.k * B.k, s);
         DFD_LAUNCH(dfd::launch_dwconv(e, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.mid, B.k, B.stride, dt, s), "depthwise kernel");
-        const int nparts = dfd::dw_num_partials(oh, ow, B.mid, B.k);
+        const int nparts = dfd::dw_num_partials(oh, ow, B.mid, B.k, B.stride);
         prof_next(KC_SE, (double)frames * B.mid * (nparts + 1) * 4, 4.0 * frames * B.mid * B.rd, s);
         DFD_LAUNCH(dfd::launch_se(part, nparts, 1.0f / (float)(oh * ow), B.se_w1, B.se_b1, B.se_w2t, B.se_b2, gate,
                                   frames, B.mid, B.rd, s), "squeeze-excite kernel");
@@ -514,7 +514,7 @@ int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_b
     DFD_LAUNCH(dfd::launch_stem(d_in, in_kind, d_w, d_bias, d_out, frames, H, W, dtype, (cudaStream_t)stream), "stem kernel");
     return DFD_OK;
 }
-int dfd_k_dw_num_partials(int OH, int OW, int C, int k) { return dfd::dw_num_partials(OH, OW, C, k); }
+int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride) { return dfd::dw_num_partials(OH, OW, C, k, stride); }
 int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,
                  int64_t frames, int H, int W, int C, int k, int stride, int dtype, void* stream) {
     g_launches = 0;

@@ -2,139 +2,150 @@
 // fused with the squeeze-excite spatial reduction (timm `conv_dw` + `bn` + the `x.mean((2,3))` of
 // SqueezeExcite; reference call site pretrained_detector.py:116).
 //
-// One thread owns ONE CHANNEL PAIR (a 32-bit half2/bf162) x a TH x TW tile of output pixels:
-//   * the k*k x 2 filter taps of its pair stay in registers as packed fp32x2 for the whole tile;
-//   * input rows are streamed once per thread ((TH-1)*s+k rows of (TW-1)*s+k values) and every loaded
-//     value feeds up to k x min(TH,k) packed FMAs (`fma.rn.f32x2`, the only way to reach the full fp32
-//     rate on sm_100) — L1 traffic per output drops ~5x against a one-row-per-thread mapping;
-//   * lanes walk channel pairs, so every warp load/store is one contiguous 128-byte NHWC run.
-// fp32 accumulation, fp32 weights, one rounding to the storage type at the store.
+// One thread owns 8 channels (one 128-bit vector) x TW = 4 consecutive output columns x kDwRPT consecutive
+// output rows (processed one after the other, so the rows it re-reads are still in L1).
+// Each input row of the window is loaded once as (TW-1)*stride+k vectors, unpacked once to packed fp32x2
+// and reused from registers for the TW outputs; vertical reuse is served by L1 (consecutive work items are
+// channel groups first, then columns, then rows, so the CTAs that share rows run next to each other).
+// All arithmetic is packed `fma.rn.f32x2` (the full-rate fp32 form on sm_100) with fp32 weights; address
+// and bounds work is amortised over 8 channels.  A warp's loads are runs of contiguous 16-byte vectors.
 //
-// SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding); a CTA covers PG channel
-// pairs x TG neighbouring tiles and adds its TG tiles up in a fixed order, writing its channel slice of one
-// partial row per tile group — no atomics, bit-reproducible.  se.cu adds the partial rows up in order.
+// SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding) per channel; the CTA
+// combines them in a fixed order and writes one partial row per CTA — no atomics, bit-reproducible.
+// se.cu adds the partial rows up in order.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace dfd {
 
 constexpr int kDwThreads = 256;
-constexpr int kDwTW = 4;
+constexpr int kDwTW = 4;              // output columns per thread (stride 1); stride-2 layers use 2 to fit registers
+constexpr int kDwRPT = 4;             // output rows per thread
 
-struct DwPlan { int TH, tiles_x, tiles, PG, TG, pair_groups, tile_groups; };
-
-static DwPlan dw_plan(int OH, int OW, int C, int k) {
-    DwPlan p;
-    const int pairs = C / 2;
-    p.TH = (k == 3 && OH <= 14 && OH % 7 == 0) ? 7 : 4;
-    p.tiles_x = (OW + kDwTW - 1) / kDwTW;
-    p.tiles = p.tiles_x * ((OH + p.TH - 1) / p.TH);
-    p.pair_groups = (pairs + kDwThreads - 1) / kDwThreads;
-    while (pairs % p.pair_groups) ++p.pair_groups;
-    p.PG = pairs / p.pair_groups;
-    p.TG = kDwThreads / p.PG;
-    if (p.TG > p.tiles) p.TG = p.tiles;
-    p.tile_groups = (p.tiles + p.TG - 1) / p.TG;
-    return p;
+static inline int dw_tw(int stride) { return stride == 1 ? kDwTW : 2; }
+static inline int dw_items(int OH, int OW, int C, int stride) {
+    const int tw = dw_tw(stride);
+    return ((OH + kDwRPT - 1) / kDwRPT) * ((OW + tw - 1) / tw) * (C / 8);
 }
-int dw_num_partials(int OH, int OW, int C, int k) { return dw_plan(OH, OW, C, k).tile_groups; }
+int dw_num_partials(int OH, int OW, int C, int /*k*/, int stride) { return (dw_items(OH, OW, C, stride) + kDwThreads - 1) / kDwThreads; }
 
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
+// x * sigmoid(x) with raw MUFU ex2 + rcp (no range fix-ups: e = inf -> rcp = 0 -> -0, which is the limit)
+__device__ __forceinline__ float silu_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(-1.4426950408889634f * x)));
+    return x * r;
 }
-__device__ __forceinline__ uint64_t pack_f2(float2 v) { return *reinterpret_cast<uint64_t*>(&v); }
-__device__ __forceinline__ float2 unpack_f2(uint64_t v) { return *reinterpret_cast<float2*>(&v); }
 
-template <typename T, int KS, int S, int TH>
+template <typename T, int KS, int STRIDE>
 __global__ void __launch_bounds__(kDwThreads, 2)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
-              int H, int W, int C, int OH, int OW, const DwPlan pl) {
-    constexpr int TW = kDwTW;
+              int H, int W, int C, int OH, int OW, int strips, int items, int blocks_per_frame) {
+    constexpr int TW = STRIDE == 1 ? kDwTW : 2;
     constexpr int PAD = KS / 2;
-    constexpr int NCOL = (TW - 1) * S + KS;
-    constexpr int NROW = (TH - 1) * S + KS;
-    __shared__ float2 s_part[kDwThreads];
+    constexpr int NCOL = (TW - 1) * STRIDE + KS;
+    __shared__ float s_part[kDwThreads][9];     // +1 pad: conflict-free column walks
 
-    int bid = blockIdx.x;
-    const int pg = bid % pl.pair_groups; bid /= pl.pair_groups;
-    const int tg = bid % pl.tile_groups;
-    const int64_t frame = bid / pl.tile_groups;
-    const int pl_ = threadIdx.x % pl.PG, tl = threadIdx.x / pl.PG;
-    const int pair = pg * pl.PG + pl_;
-    const int tile = tg * pl.TG + tl;
-    const bool active = (tl < pl.TG) && (tile < pl.tiles);
+    const int C8 = C >> 3;
+    const int64_t frame = blockIdx.x / blocks_per_frame;
+    const int blk = blockIdx.x - (int)(frame * blocks_per_frame);
+    const int item = blk * kDwThreads + threadIdx.x;
+    const bool valid = item < items;
 
-    float2 sum = make_float2(0.f, 0.f);
-    if (active) {
-        const int ty = tile / pl.tiles_x, tx = tile - ty * pl.tiles_x;
-        const int oy0 = ty * TH, ox0 = tx * TW;
-        const int iy0 = oy0 * S - PAD, ix0 = ox0 * S - PAD;
+    uint64_t sums[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sums[c] = 0ull;
 
-        uint64_t wreg[KS * KS];
+    if (valid) {
+        const int c8 = item % C8;
+        const int t = item / C8;
+        const int strip = t % strips;
+        const int oyb = t / strips;
+        const int ox0 = strip * TW;
+        const int ix0 = ox0 * STRIDE - PAD;
+        const T* in_f = in + (size_t)frame * H * W * C + c8 * 8;
+        const float* wc = w + c8 * 8;
+        const int WC = W * C;
+        int coloff[NCOL];                                   // element offset of each window column, -1 = padding
 #pragma unroll
-        for (int i = 0; i < KS * KS; ++i) wreg[i] = pack_f2(__ldg(reinterpret_cast<const float2*>(w + (size_t)i * C + 2 * pair)));
-        uint64_t acc[TH][TW];
-        {
-            const uint64_t b = pack_f2(__ldg(reinterpret_cast<const float2*>(bias + 2 * pair)));
+        for (int j = 0; j < NCOL; ++j) { const int ix = ix0 + j; coloff[j] = (ix >= 0 && ix < W) ? ix * C : -1; }
+        const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * 8));
+        const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * 8 + 4));
+
+        for (int rr = 0; rr < kDwRPT; ++rr) {
+            const int oy = oyb * kDwRPT + rr;
+            if (oy >= OH) break;
+            uint64_t acc[TW][4];
 #pragma unroll
-            for (int t = 0; t < TH; ++t)
+            for (int j = 0; j < TW; ++j) { acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b1.x; acc[j][3] = b1.y; }
 #pragma unroll
-                for (int j = 0; j < TW; ++j) acc[t][j] = b;
-        }
-        const T* base = in + (size_t)frame * H * W * C + 2 * pair;
+            for (int ky = 0; ky < KS; ++ky) {
+                const int iy = oy * STRIDE - PAD + ky;
+                const bool row_ok = (unsigned)iy < (unsigned)H;      // padding rows read as zeros (branch-free)
+                const T* row = in_f + (row_ok ? iy : 0) * WC;
+                uint64_t x[NCOL][4];
 #pragma unroll
-        for (int r = 0; r < NROW; ++r) {
-            const int iy = iy0 + r;
-            if (iy < 0 || iy >= H) continue;                  // zero padding row: contributes nothing
-            const T* row = base + (size_t)iy * W * C;
-            uint64_t x[NCOL];
+                for (int j = 0; j < NCOL; ++j) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (row_ok && coloff[j] >= 0) v = ldg16(row + coloff[j]);
+                    const float2 f0 = Half16<T>::unpack(v.x), f1 = Half16<T>::unpack(v.y);
+                    const float2 f2 = Half16<T>::unpack(v.z), f3 = Half16<T>::unpack(v.w);
+                    x[j][0] = f2_pack(f0.x, f0.y); x[j][1] = f2_pack(f1.x, f1.y);
+                    x[j][2] = f2_pack(f2.x, f2.y); x[j][3] = f2_pack(f3.x, f3.y);
+                }
 #pragma unroll
-            for (int j = 0; j < NCOL; ++j) {
-                const int ix = ix0 + j;
-                uint32_t v = 0u;
-                if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)ix * C));
-                x[j] = pack_f2(Half16<T>::unpack(v));
-            }
+                for (int kx = 0; kx < KS; ++kx) {
+                    const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * C));
+                    const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * C + 4));
 #pragma unroll
-            for (int t = 0; t < TH; ++t) {
-                const int ky = r - t * S;                      // compile-time after unrolling
-                if (ky >= 0 && ky < KS) {
-#pragma unroll
-                    for (int kx = 0; kx < KS; ++kx)
-#pragma unroll
-                        for (int j = 0; j < TW; ++j) acc[t][j] = ffma2(x[j * S + kx], wreg[ky * KS + kx], acc[t][j]);
+                    for (int j = 0; j < TW; ++j) {
+                        acc[j][0] = fma2(x[j * STRIDE + kx][0], w0.x, acc[j][0]);
+                        acc[j][1] = fma2(x[j * STRIDE + kx][1], w0.y, acc[j][1]);
+                        acc[j][2] = fma2(x[j * STRIDE + kx][2], w1.x, acc[j][2]);
+                        acc[j][3] = fma2(x[j * STRIDE + kx][3], w1.y, acc[j][3]);
+                    }
                 }
             }
-        }
-        T* obase = out + (size_t)frame * OH * OW * C + 2 * pair;
+            T* orow = out + (((size_t)frame * OH + oy) * OW) * C + c8 * 8;
 #pragma unroll
-        for (int t = 0; t < TH; ++t) {
-            const int oy = oy0 + t;
-            if (oy < OH) {
+            for (int j = 0; j < TW; ++j) {
+                const int ox = ox0 + j;
+                if (ox < OW) {
+                    uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < TW; ++j) {
-                    const int ox = ox0 + j;
-                    if (ox < OW) {
-                        const float2 a = unpack_f2(acc[t][j]);
-                        const float y0 = silu_f(a.x), y1 = silu_f(a.y);
-                        sum.x += y0; sum.y += y1;
-                        *reinterpret_cast<uint32_t*>(obase + ((size_t)oy * OW + ox) * C) = Half16<T>::pack(y0, y1);
+                    for (int c = 0; c < 4; ++c) {
+                        const float2 a = f2_unpack(acc[j][c]);
+                        const float y0 = silu_fast(a.x), y1 = silu_fast(a.y);
+                        sums[c] = add2(sums[c], f2_pack(y0, y1));
+                        o[c] = Half16<T>::pack(y0, y1);
                     }
+                    stg16(orow + (size_t)ox * C, make_uint4(o[0], o[1], o[2], o[3]));
                 }
             }
         }
     }
 
-    // ---- deterministic CTA reduction of the SE sums over the CTA's tiles ----------------------------
-    s_part[threadIdx.x] = sum;                         // inactive threads contribute zeros
+    // ---- deterministic block reduction of the SE sums --------------------------------------------
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float2 v = f2_unpack(sums[c]);
+        s_part[threadIdx.x][2 * c] = v.x; s_part[threadIdx.x][2 * c + 1] = v.y;
+    }
     __syncthreads();
-    if (threadIdx.x < pl.PG) {
-        float2 tot = make_float2(0.f, 0.f);
-        for (int t = 0; t < pl.TG; ++t) { const float2 v = s_part[t * pl.PG + threadIdx.x]; tot.x += v.x; tot.y += v.y; }
-        *reinterpret_cast<float2*>(partials + ((size_t)frame * pl.tile_groups + tg) * C + 2 * pair) = tot;
+    if (threadIdx.x < C8) {
+        const int cg = threadIdx.x;
+        const int base = (blk * kDwThreads) % C8;          // channel group of thread 0 in this block
+        int t0 = cg - base; if (t0 < 0) t0 += C8;
+        float tot[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) tot[c] = 0.f;
+        for (int t = t0; t < kDwThreads; t += C8) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) tot[c] += s_part[t][c];
+        }
+        float* dst = partials + ((size_t)frame * blocks_per_frame + blk) * C + cg * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(tot[0], tot[1], tot[2], tot[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(tot[4], tot[5], tot[6], tot[7]);
     }
 }
 
@@ -143,19 +154,18 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
                                int64_t frames, int H, int W, int C, int k, int stride, cudaStream_t s) {
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
+    const int strips = (OW + dw_tw(stride) - 1) / dw_tw(stride);
+    const int items = dw_items(OH, OW, C, stride);
+    const int bpf = dw_num_partials(OH, OW, C, k, stride);
     if (frames <= 0) return cudaSuccess;
-    if ((C & 7) || (k != 3 && k != 5) || (stride != 1 && stride != 2)) return cudaErrorInvalidValue;
-    const DwPlan pl = dw_plan(OH, OW, C, k);
-    const int64_t blocks = frames * pl.tile_groups * pl.pair_groups;
-    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)blocks;
-#define DFD_DW(KS, ST, TH) dwconv_kernel<T, KS, ST, TH><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, pl)
-    if (k == 3 && stride == 1 && pl.TH == 4) DFD_DW(3, 1, 4);
-    else if (k == 3 && stride == 1) DFD_DW(3, 1, 7);
-    else if (k == 3 && stride == 2 && pl.TH == 4) DFD_DW(3, 2, 4);
-    else if (k == 3 && stride == 2) DFD_DW(3, 2, 7);
-    else if (k == 5 && stride == 1) DFD_DW(5, 1, 4);
-    else DFD_DW(5, 2, 4);
+    if ((C & 7) || C / 8 > kDwThreads || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)(frames * bpf);
+#define DFD_DW(KS, ST) dwconv_kernel<T, KS, ST><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf)
+    if (k == 3 && stride == 1) DFD_DW(3, 1);
+    else if (k == 3 && stride == 2) DFD_DW(3, 2);
+    else if (k == 5 && stride == 1) DFD_DW(5, 1);
+    else if (k == 5 && stride == 2) DFD_DW(5, 2);
+    else return cudaErrorInvalidValue;
 #undef DFD_DW
     return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ cudaError_t launch_stem(const void* in, int in_kind, const float* w, const float
 // K2 (dwconv.cu): depthwise kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU, NHWC, plus the
 // squeeze-excite spatial sums as per-block partials.  w: fp32 [k*k][C], bias fp32 [C].
 // partials: fp32 [frames][dw_num_partials][C] (sums of SiLU outputs over groups of output tiles).
-int dw_num_partials(int OH, int OW, int C, int k);
+int dw_num_partials(int OH, int OW, int C, int k, int stride);
 cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, void* out, float* partials,
                           int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
 

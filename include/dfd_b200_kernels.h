@@ -19,8 +19,8 @@ int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_b
                int64_t frames, int H, int W, int dtype, void* stream);
 
 /* timm conv_dw + bn: depthwise kxk (k 3|5, stride 1|2, pad k/2) + bias + SiLU, plus the squeeze-excite
- * spatial sums as d_partials fp32 [frames][dfd_k_dw_num_partials(OH,OW,C,k)][C].  d_w fp32 [k*k][C]. */
-int dfd_k_dw_num_partials(int OH, int OW, int C, int k);
+ * spatial sums as d_partials fp32 [frames][dfd_k_dw_num_partials(OH,OW,C,k,stride)][C].  d_w fp32 [k*k][C]. */
+int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride);
 int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,
                  int64_t frames, int H, int W, int C, int k, int stride, int dtype, void* stream);
 

@@ -88,7 +88,7 @@ def test_dwconv_and_squeeze(lib, prec, C_, k, s, H):
     w = torch.randn(C_, 1, k, k, generator=g) * (1.0 / k)
     b = torch.randn(C_, generator=g) * 0.2
     OH = (H + 2 * (k // 2) - k) // s + 1
-    nparts = lib.dfd_k_dw_num_partials(OH, OH, C_, k)
+    nparts = lib.dfd_k_dw_num_partials(OH, OH, C_, k, s)
     wp = w.reshape(C_, k * k).t().contiguous().cuda()
     out = torch.empty((frames, OH, OH, C_), dtype=tdt, device="cuda")
     parts = torch.full((frames, nparts, C_), float("nan"), device="cuda")
