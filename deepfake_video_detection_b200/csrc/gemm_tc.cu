@@ -27,15 +27,12 @@ namespace dfd {
 
 constexpr int kBM = 128;            // rows per tile = TMEM lanes
 constexpr int kKB = 64;             // K elements per pipeline stage (8 chunks of 8)
-constexpr int kMaxStages = 8;
-constexpr int kLook = 3;               // producer look-ahead (stages issued before the oldest is awaited)
-constexpr int kEpiWarps = 8;
-constexpr int kProdWarps = 8;
-constexpr int kProdThreads = kProdWarps * 32;
-constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps) * 32;     // 544
-constexpr int kMmaWarp = kEpiWarps;
+constexpr int kMaxStages = 16;
+constexpr int kMaxLook = 12;           // producer look-ahead (stages in flight before the oldest is awaited)
+// Warp roles are a template parameter: D-heavy layers (expand, head: SiLU on every output) get 16 epilogue
+// and 4 producer warps, A-heavy gated project layers 8 + 8.  Epilogue warps come first so that
+// (warp index % 4) is the TMEM lane quarter a warp may access.
 constexpr uint32_t kLboA = kBM * 16 + 16;                            // +16: bank-conflict-free staging stores
-constexpr uint32_t kAStageBytes = 8 * kLboA;
 
 struct GemmArgs {
     const void* A; const void* W; const float* bias; const float* gate; const void* R; void* D; float* feat;
@@ -43,21 +40,29 @@ struct GemmArgs {
     int NB, NBp, n_chunks;          // columns per work unit, padded to 16, units along N
     int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
     int64_t m_tiles;
-    int stages;
+    int stages, look;
     int b_resident;                 // whole W lives in shared memory for the CTA's lifetime
     int kchunks_pad;                // K/8 rounded up to even
-    uint32_t lbo_b, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
+    uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
 };
 
-template <typename T, bool GATE, bool ACT, bool RES, bool POOL>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs p) {
+template <int N> struct WaitGroup { __device__ static void run(int look) { if (look == N) cp_async_wait<N>(); else WaitGroup<N - 1>::run(look); } };
+template <> struct WaitGroup<0> { __device__ static void run(int) { cp_async_wait<0>(); } };
+
+template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps>
+__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
+    constexpr int kProdThreads = kProdWarps * 32;
+    constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps) * 32;
+    constexpr int kMmaWarp = kEpiWarps;
+    constexpr int kColGroups = kEpiWarps / 4;       // epilogue warps sharing a TMEM lane quarter split the columns
+    constexpr int kRowStep = kProdWarps * 4;        // producer thread tp copies rows (tp >> 3) + kRowStep * j
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- shared memory carve-up ----------------------------------------------------------------
-    const uint32_t stage_bytes = kAStageBytes + (p.b_resident ? 0u : p.b_stage_bytes);
+    const uint32_t stage_bytes = p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes);
     uint8_t* sp = smem_raw + p.b_res_bytes + (size_t)p.stages * stage_bytes;
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
-    float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += 2 * kBM * 17 * 4;
+    float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += kColGroups * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], tfull[2], tempty[2]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
@@ -116,7 +121,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         int kbi = 0, kbd = 0, si = 0, sd = 0;
         uint32_t pi = 0;
         const uint32_t a_off = q * kLboA + rb * 16, b_off = q * p.lbo_b + rb * 16;
-        for (int64_t it = 0; it < n_iters + kLook; ++it) {
+        const int look = p.look;
+        for (int64_t it = 0; it < n_iters + look; ++it) {
             if (it < n_iters) {
                 const int64_t mt = ui / p.n_chunks;
                 const int nc = (int)(ui - mt * p.n_chunks);
@@ -130,16 +136,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 if (q < kcp) {
                     const T* src = A + (size_t)(m0 + rb) * p.K + k0 + q * 8;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool ok = (rb + 32 * j < rows_valid) && (q < kc);
-                        cp_async16(a_base + a_off + j * 512, ok ? src + (size_t)(32 * j) * p.K : A, ok);
+                    for (int j = 0; j < kBM / kRowStep; ++j) {
+                        const bool ok = (rb + kRowStep * j < rows_valid) && (q < kc);
+                        cp_async16(a_base + a_off + j * (kRowStep * 16), ok ? src + (size_t)(kRowStep * j) * p.K : A, ok);
                     }
                     if (!p.b_resident) {
                         const int n0 = nc * p.NB;
                         const int nb_valid = min(p.NB, p.N - n0);
-                        const uint32_t b_base = a_base + kAStageBytes;
+                        const uint32_t b_base = a_base + p.a_stage_bytes;
                         const T* wsrc = Wt + (size_t)(n0 + rb) * p.K + k0 + q * 8;
-                        for (int r = rb; r < p.NBp; r += 32) {
+                        for (int r = rb; r < p.NBp; r += kRowStep) {
                             const bool ok = (r < nb_valid) && (q < kc);
                             cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * p.K : Wt, ok);
                         }
@@ -149,8 +155,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 if (++si == p.stages) { si = 0; pi ^= 1; }
             }
             cp_async_commit();
-            if (it >= kLook) {
-                cp_async_wait<kLook>();                        // this thread's chunks of iteration it-kLook have landed
+            if (it >= look) {
+                WaitGroup<kMaxLook>::run(look);                // this thread's chunks of iteration it-look have landed
                 if (GATE) {
                     const int64_t mt = ud / p.n_chunks;
                     const int64_t m0 = mt * p.rows_per_tile;
@@ -163,12 +169,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         uint32_t frame = (uint32_t)(m0 + rb) / (uint32_t)p.HW;
                         uint32_t rem = (uint32_t)(m0 + rb) - frame * (uint32_t)p.HW;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (rb + 32 * j < rows_valid) {
+                        for (int j = 0; j < kBM / kRowStep; ++j) {
+                            if (rb + kRowStep * j < rows_valid) {
                                 const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
                                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
                                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
-                                const uint32_t addr = a_base + a_off + j * 512;
+                                const uint32_t addr = a_base + a_off + j * (kRowStep * 16);
                                 uint4 v = lds16(addr);
                                 const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
                                 const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                                 v.w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
                                 sts16(addr, v);
                             }
-                            rem += 32;
+                            rem += kRowStep;
                             while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++frame; }
                         }
                     }
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 if (lane == 0) {
                     const uint32_t a_base = smem_base + stage * stage_bytes;
                     const uint32_t b_base = p.b_resident ? bres_base + nc * p.b_chunk_bytes + kb * 8 * p.lbo_b
-                                                         : a_base + kAStageBytes;
+                                                         : a_base + p.a_stage_bytes;
                     for (int j = 0; j < steps; ++j) {
                         const uint64_t adesc = umma_smem_desc(a_base + 2 * j * kLboA, kLboA, 128);
                         const uint64_t bdesc = umma_smem_desc(b_base + 2 * j * p.lbo_b, p.lbo_b, 128);
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         }
     } else {
         // =================================== EPILOGUE ============================================
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, half = warp >> 2;      // half = column group of this warp
         const int row = 32 * q + lane;
         T* D = reinterpret_cast<T*>(p.D);
         const T* R = reinterpret_cast<const T*>(p.R);
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             tc_fence_after_sync();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
             const int slots = POOL ? rows_valid / p.HW : 0;
-            for (int c16 = half; c16 * 16 < p.NBp; c16 += 2) {
+            for (int c16 = half; c16 * 16 < p.NBp; c16 += kColGroups) {
                 uint32_t r[16];
                 tmem_ld16(t_row + c16 * 16, r);
                 tmem_ld_wait();
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
 static int g_num_sms = 0;
 
 template <typename KernelT>
-static cudaError_t run(KernelT kernel, GemmArgs& a, cudaStream_t s) {
+static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, cudaStream_t s) {
     if (g_num_sms == 0) {
         int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
@@ -338,39 +344,43 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, cudaStream_t s) {
     a.NB = a.N / n_chunks;
     a.NBp = (a.NB + 15) & ~15;
     a.lbo_b = (uint32_t)a.NBp * 16 + 16;
-    a.b_stage_bytes = 8 * a.lbo_b;
     a.kchunks_pad = ((a.K >> 3) + 1) & ~1;
+    const int kcp_max = a.kchunks_pad < 8 ? a.kchunks_pad : 8;       // 16-byte chunk columns a stage can hold
+    a.a_stage_bytes = (uint32_t)kcp_max * kLboA;
+    a.b_stage_bytes = (uint32_t)kcp_max * a.lbo_b;
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
     uint32_t cols = 32; while (cols < (uint32_t)(2 * a.NBp)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)2 * kBM * 17 * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
     const size_t budget = 227 * 1024;
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
     a.b_resident = (bres <= 120 * 1024) ? 1 : 0;
     a.b_res_bytes = a.b_resident ? (uint32_t)bres : 0u;
-    const size_t stage_bytes = kAStageBytes + (a.b_resident ? 0 : a.b_stage_bytes);
+    const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes);
     int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < kLook + 1) return cudaErrorInvalidValue;
+    if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
+    a.look = stages - 1 < kMaxLook ? stages - 1 : kMaxLook;
     const size_t smem = a.b_res_bytes + (size_t)stages * stage_bytes + fixed;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t units = a.m_tiles * a.n_chunks;
     const unsigned grid = (unsigned)(units < g_num_sms ? units : g_num_sms);
-    kernel<<<grid, kGemmThreads, smem, s>>>(a);
+    kernel<<<grid, (epi_warps + 1 + prod_warps) * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     const bool gate = a.gate != nullptr, res = a.R != nullptr;
-    if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true>, a, s);
-    if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false>, a, s);
-    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false>, a, s);
-    if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false>, a, s);
-    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false>, a, s);
-    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false>, a, s);
+    // <T, GATE, ACT, RES, POOL, epilogue warps, producer warps>
+    if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true, 16, 4>, a, 16, 4, s);
+    if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false, 8, 8>, a, 8, 8, s);
+    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false, 8, 8>, a, 8, 8, s);
+    if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false, 16, 4>, a, 16, 4, s);
+    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false, 8, 8>, a, 8, 8, s);
+    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false, 8, 8>, a, 8, 8, s);
     return cudaErrorInvalidValue;
 }
 
