@@ -152,6 +152,11 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, boo
     const uint32_t n = valid ? 16u : 0u;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(saddr), "l"(gptr), "r"(n) : "memory");
 }
+// Make the mbarrier track this thread's prior cp.async copies: its pending count is incremented now and
+// decremented when they have all landed (pair it with a normal arrive; CUTLASS cpasync_barrier_arrive).
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 

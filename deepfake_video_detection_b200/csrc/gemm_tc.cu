@@ -10,11 +10,14 @@
 //   pool variant: conv_head + BN + SiLU + global average pool -> features fp32 [frames][N]
 //
 // Structure (one persistent CTA per SM, 17 warps, warp-specialised):
-//   warps 9..16  producers: cp.async (LDGSTS, 16 B, L1 bypass) global -> shared memory straight into the UMMA
-//                canonical K-major no-swizzle layout (8-row x 16-byte core matrices), 3 stages of look-ahead so
-//                ~50 KB per SM are in flight; gated layers rescale their own chunks in place (x gate) once they
-//                have landed; then `fence.proxy.async` + mbarrier arrive.  Weights that fit (<= 120 KB) are
-//                loaded once per CTA and stay resident; larger ones stream through the stage ring.
+//   loaders      cp.async (LDGSTS, 16 B, L1 bypass) global -> shared memory straight into the UMMA canonical
+//                K-major no-swizzle layout (8-row x 16-byte core matrices).  Completion is tracked by the
+//                stage mbarrier itself (`cp.async.mbarrier.arrive`), so a loader never waits for data: up to
+//                16 stages are in flight.  Weights that fit (<= 120 KB) are loaded once per CTA and stay
+//                resident; larger ones stream through the stage ring.
+//   transformers (gated project layers only) wait for a landed stage, multiply it in place by the per-frame
+//                squeeze-excite gate (the gate slice travels with the stage), `fence.proxy.async`, then hand
+//                the stage to the MMA warp.  They hold no outstanding cp.async, so the proxy fence is cheap.
 //   warp  8      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=NBp, K=16) per 16-wide K step,
 //                accumulators in TMEM (double buffered), tcgen05.commit releases smem stages / signals epilogue
 //   warps 0..7   epilogue: tcgen05.ld (32 lanes x 16 columns), +bias, SiLU, +residual, pack, store
@@ -28,10 +31,9 @@ namespace dfd {
 constexpr int kBM = 128;            // rows per tile = TMEM lanes
 constexpr int kKB = 64;             // K elements per pipeline stage (8 chunks of 8)
 constexpr int kMaxStages = 16;
-constexpr int kMaxLook = 12;           // producer look-ahead (stages in flight before the oldest is awaited)
-// Warp roles are a template parameter: D-heavy layers (expand, head: SiLU on every output) get 16 epilogue
-// and 4 producer warps, A-heavy gated project layers 8 + 8.  Epilogue warps come first so that
-// (warp index % 4) is the TMEM lane quarter a warp may access.
+// Warp roles are template parameters: D-heavy layers (expand, head: SiLU on every output) get 16 epilogue
+// and 4 loader warps; A-heavy gated project layers 8 epilogue, 4 loader and 8 transformer warps.  Epilogue
+// warps come first so that (warp index % 4) is the TMEM lane quarter a warp may access.
 constexpr uint32_t kLboA = kBM * 16 + 16;                            // +16: bank-conflict-free staging stores
 
 struct GemmArgs {
@@ -40,48 +42,55 @@ struct GemmArgs {
     int NB, NBp, n_chunks;          // columns per work unit, padded to 16, units along N
     int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
     int64_t m_tiles;
-    int stages, look;
+    int stages;
+    int nf_max, total_frames;       // gated: frames a tile can touch, frames in the tensor
+    uint32_t g_stage_bytes;         // gated: bytes of the per-stage gate slice [nf_max][64] fp32
     int b_resident;                 // whole W lives in shared memory for the CTA's lifetime
     int kchunks_pad;                // K/8 rounded up to even
     uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
 };
 
-template <int N> struct WaitGroup { __device__ static void run(int look) { if (look == N) cp_async_wait<N>(); else WaitGroup<N - 1>::run(look); } };
-template <> struct WaitGroup<0> { __device__ static void run(int) { cp_async_wait<0>(); } };
-
-template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps>
-__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
+template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps>
+__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
+    static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
     constexpr int kProdThreads = kProdWarps * 32;
-    constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps) * 32;
+    constexpr int kXformThreads = kXformWarps * 32;
+    constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps + kXformWarps) * 32;
     constexpr int kMmaWarp = kEpiWarps;
     constexpr int kColGroups = kEpiWarps / 4;       // epilogue warps sharing a TMEM lane quarter split the columns
     constexpr int kRowStep = kProdWarps * 4;        // producer thread tp copies rows (tp >> 3) + kRowStep * j
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- shared memory carve-up ----------------------------------------------------------------
-    const uint32_t stage_bytes = p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes);
+    const uint32_t stage_bytes = p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes) + p.g_stage_bytes;
+    const uint32_t g_off = stage_bytes - p.g_stage_bytes;          // gate slice sits at the end of a stage
     uint8_t* sp = smem_raw + p.b_res_bytes + (size_t)p.stages * stage_bytes;
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
     float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += kColGroups * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], tfull[2], tempty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], raw[S], tfull[2], tempty[2]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
 
     const uint32_t bres_base = smem_u32(smem_raw);
     const uint32_t smem_base = bres_base + p.b_res_bytes;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
-    const uint32_t bar_tfull = smem_u32(bars + 2 * kMaxStages), bar_tempty = smem_u32(bars + 2 * kMaxStages + 2);
+    const uint32_t bar_raw = smem_u32(bars + 2 * kMaxStages);
+    const uint32_t bar_tfull = smem_u32(bars + 3 * kMaxStages), bar_tempty = smem_u32(bars + 3 * kMaxStages + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, kProdThreads); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full + 8 * s, GATE ? kXformThreads : kProdThreads);
+            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_raw + 8 * s, kProdThreads);
+        }
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiWarps * 32); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), p.tmem_cols);
-    if (warp > kMmaWarp && p.b_resident) {
+    if (warp > kMmaWarp && warp <= kMmaWarp + kProdWarps && p.b_resident) {
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
         const T* Wt = reinterpret_cast<const T*>(p.W);
         const int kch = p.K >> 3, per = p.NBp * p.kchunks_pad;
@@ -106,33 +115,31 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps) * 32, 1) gemm_tc_
     const int num_kb = (p.K + kKB - 1) / kKB;
     const int64_t units = p.m_tiles * p.n_chunks;
 
-    if (warp > kMmaWarp) {
-        // =================================== PRODUCERS ===========================================
-        // Thread tp owns 16-byte chunk column q = tp % 8 of rows rb + 32*j: no divisions in the loop, a
-        // quarter-warp copies 128 contiguous bytes of one row, and its 8 shared-memory stores land in 8
+    if (warp > kMmaWarp && warp <= kMmaWarp + kProdWarps) {
+        // =================================== LOADERS =============================================
+        // Thread tp owns 16-byte chunk column q = tp % 8 of rows rb + kRowStep*j: no divisions in the loop, a
+        // quarter-warp copies 128 contiguous bytes of one row, and its 8 shared-memory writes land in 8
         // different bank groups (LBO is padded by 16 bytes).
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
         const int q = tp & 7, rb = tp >> 3;
         const T* A = reinterpret_cast<const T*>(p.A);
         const T* Wt = reinterpret_cast<const T*>(p.W);
-        const int64_t my_units = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
-        const int64_t n_iters = my_units * num_kb;
-        int64_t ui = blockIdx.x, ud = blockIdx.x;      // unit of the issue / completion cursor
-        int kbi = 0, kbd = 0, si = 0, sd = 0;
-        uint32_t pi = 0;
         const uint32_t a_off = q * kLboA + rb * 16, b_off = q * p.lbo_b + rb * 16;
-        const int look = p.look;
-        for (int64_t it = 0; it < n_iters + look; ++it) {
-            if (it < n_iters) {
-                const int64_t mt = ui / p.n_chunks;
-                const int nc = (int)(ui - mt * p.n_chunks);
-                const int64_t m0 = mt * p.rows_per_tile;
-                const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
-                const int k0 = kbi * kKB;
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int64_t mt = u / p.n_chunks;
+            const int nc = (int)(u - mt * p.n_chunks);
+            const int64_t m0 = mt * p.rows_per_tile;
+            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            const int n0 = nc * p.NB;
+            const int nb_valid = min(p.NB, p.N - n0);
+            const uint32_t f0 = GATE ? (uint32_t)m0 / (uint32_t)p.HW : 0u;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int k0 = kb * kKB;
                 const int kc = min(8, (p.K - k0) >> 3);        // 16-byte chunks present in this k-block
                 const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
-                mbar_wait(bar_empty + 8 * si, pi ^ 1);
-                const uint32_t a_base = smem_base + si * stage_bytes;
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t a_base = smem_base + stage * stage_bytes;
                 if (q < kcp) {
                     const T* src = A + (size_t)(m0 + rb) * p.K + k0 + q * 8;
 #pragma unroll
@@ -141,8 +148,6 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps) * 32, 1) gemm_tc_
                         cp_async16(a_base + a_off + j * (kRowStep * 16), ok ? src + (size_t)(kRowStep * j) * p.K : A, ok);
                     }
                     if (!p.b_resident) {
-                        const int n0 = nc * p.NB;
-                        const int nb_valid = min(p.NB, p.N - n0);
                         const uint32_t b_base = a_base + p.a_stage_bytes;
                         const T* wsrc = Wt + (size_t)(n0 + rb) * p.K + k0 + q * 8;
                         for (int r = rb; r < p.NBp; r += kRowStep) {
@@ -151,48 +156,62 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps) * 32, 1) gemm_tc_
                         }
                     }
                 }
-                if (++kbi == num_kb) { kbi = 0; ui += gridDim.x; }
-                if (++si == p.stages) { si = 0; pi ^= 1; }
+                if (GATE) {                                    // gate slice [nf_max][64] fp32 for this k-block
+                    for (int i = tp; i < p.nf_max * 16; i += kProdThreads) {
+                        const uint32_t fl = i >> 4, c = i & 15;
+                        const bool ok = (f0 + fl < (uint32_t)p.total_frames) && (k0 + (int)c * 4 < p.K);
+                        cp_async16(a_base + g_off + fl * 256 + c * 16,
+                                   ok ? p.gate + (size_t)(f0 + fl) * p.K + k0 + c * 4 : p.gate, ok);
+                    }
+                }
+                const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
+                cp_async_mbar_arrive(bar);                     // completes when this thread's copies have landed
+                mbar_arrive(bar);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            cp_async_commit();
-            if (it >= look) {
-                WaitGroup<kMaxLook>::run(look);                // this thread's chunks of iteration it-look have landed
-                if (GATE) {
-                    const int64_t mt = ud / p.n_chunks;
-                    const int64_t m0 = mt * p.rows_per_tile;
-                    const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
-                    const int k0 = kbd * kKB;
-                    const int kc = min(8, (p.K - k0) >> 3);
-                    if (q < kc) {
-                        const uint32_t a_base = smem_base + sd * stage_bytes;
-                        // frame of row m0+rb without a per-row division: one division per tile-stage, then steps
-                        uint32_t frame = (uint32_t)(m0 + rb) / (uint32_t)p.HW;
-                        uint32_t rem = (uint32_t)(m0 + rb) - frame * (uint32_t)p.HW;
+        }
+    } else if (GATE && warp > kMmaWarp + kProdWarps) {
+        // =================================== TRANSFORMERS ========================================
+        const int tx = threadIdx.x - (kMmaWarp + 1 + kProdWarps) * 32;
+        constexpr int kXRowStep = kXformWarps > 0 ? kXformWarps * 4 : 1;
+        const int q = tx & 7, rb = tx >> 3;
+        const uint32_t a_off = q * kLboA + rb * 16;
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int64_t mt = u / p.n_chunks;
+            const int64_t m0 = mt * p.rows_per_tile;
+            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            const uint32_t f0 = (uint32_t)m0 / (uint32_t)p.HW;
+            const uint32_t rem0 = (uint32_t)m0 - f0 * (uint32_t)p.HW + rb;      // row rb relative to frame f0
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int kc = min(8, (p.K - kb * kKB) >> 3);
+                mbar_wait(bar_raw + 8 * stage, phase);
+                if (q < kc) {
+                    const uint32_t a_base = smem_base + stage * stage_bytes;
+                    uint32_t fl = 0, rem = rem0;
+                    while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
 #pragma unroll
-                        for (int j = 0; j < kBM / kRowStep; ++j) {
-                            if (rb + kRowStep * j < rows_valid) {
-                                const float* g = p.gate + (size_t)frame * p.K + k0 + q * 8;
-                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
-                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
-                                const uint32_t addr = a_base + a_off + j * (kRowStep * 16);
-                                uint4 v = lds16(addr);
-                                const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
-                                const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
-                                v.x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y);
-                                v.y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
-                                v.z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y);
-                                v.w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
-                                sts16(addr, v);
-                            }
-                            rem += kRowStep;
-                            while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++frame; }
+                    for (int j = 0; j < kBM / kXRowStep; ++j) {
+                        if (rb + kXRowStep * j < rows_valid) {
+                            const uint32_t gaddr = a_base + g_off + fl * 256 + q * 32;
+                            const uint4 gA = lds16(gaddr), gB = lds16(gaddr + 16);
+                            const uint32_t addr = a_base + a_off + j * (kXRowStep * 16);
+                            uint4 v = lds16(addr);
+                            const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
+                            const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
+                            v.x = Half16<T>::pack(x0.x * __uint_as_float(gA.x), x0.y * __uint_as_float(gA.y));
+                            v.y = Half16<T>::pack(x1.x * __uint_as_float(gA.z), x1.y * __uint_as_float(gA.w));
+                            v.z = Half16<T>::pack(x2.x * __uint_as_float(gB.x), x2.y * __uint_as_float(gB.y));
+                            v.w = Half16<T>::pack(x3.x * __uint_as_float(gB.z), x3.y * __uint_as_float(gB.w));
+                            sts16(addr, v);
                         }
+                        rem += kXRowStep;
+                        while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
                     }
                 }
                 fence_proxy_async_smem();
-                mbar_arrive(bar_full + 8 * sd);
-                if (++kbd == num_kb) { kbd = 0; ud += gridDim.x; }
-                if (++sd == p.stages) sd = 0;
+                mbar_arrive(bar_full + 8 * stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == kMmaWarp) {
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps) * 32, 1) gemm_tc_
 static int g_num_sms = 0;
 
 template <typename KernelT>
-static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, cudaStream_t s) {
+static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, int xform_warps, cudaStream_t s) {
     if (g_num_sms == 0) {
         int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
@@ -351,36 +370,38 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
     uint32_t cols = 32; while (cols < (uint32_t)(2 * a.NBp)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (2 * kMaxStages + 4) * 8 + 16;
+    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (3 * kMaxStages + 4) * 8 + 16;
+    a.nf_max = a.gate ? (kBM - 1) / a.HW + 2 : 0;
+    a.total_frames = (int)((a.M + a.HW - 1) / a.HW);
+    a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
     const size_t budget = 227 * 1024;
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
     a.b_resident = (bres <= 120 * 1024) ? 1 : 0;
     a.b_res_bytes = a.b_resident ? (uint32_t)bres : 0u;
-    const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes);
+    const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes;
     int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
-    a.look = stages - 1 < kMaxLook ? stages - 1 : kMaxLook;
     const size_t smem = a.b_res_bytes + (size_t)stages * stage_bytes + fixed;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t units = a.m_tiles * a.n_chunks;
     const unsigned grid = (unsigned)(units < g_num_sms ? units : g_num_sms);
-    kernel<<<grid, (epi_warps + 1 + prod_warps) * 32, smem, s>>>(a);
+    kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     const bool gate = a.gate != nullptr, res = a.R != nullptr;
-    // <T, GATE, ACT, RES, POOL, epilogue warps, producer warps>
-    if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true, 16, 4>, a, 16, 4, s);
-    if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false, 8, 8>, a, 8, 8, s);
-    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false, 8, 8>, a, 8, 8, s);
-    if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false, 16, 4>, a, 16, 4, s);
-    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false, 8, 8>, a, 8, 8, s);
-    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false, 8, 8>, a, 8, 8, s);
+    // <T, GATE, ACT, RES, POOL, epilogue warps, loader warps, transformer warps>
+    if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true, 16, 4, 0>, a, 16, 4, 0, s);
+    if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false, 8, 4, 8>, a, 8, 4, 8, s);
+    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false, 8, 4, 8>, a, 8, 4, 8, s);
+    if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false, 16, 4, 0>, a, 16, 4, 0, s);
+    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false, 8, 4, 0>, a, 8, 4, 0, s);
+    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false, 8, 4, 0>, a, 8, 4, 0, s);
     return cudaErrorInvalidValue;
 }
 
