@@ -36,16 +36,62 @@ __device__ __forceinline__ float silu_fast(float x) {
     return x * r;
 }
 
-template <typename T, int KS, int STRIDE>
+// One output row strip (TW columns x 8 channels) of the window.  XINT: every window column is inside the
+// image, so the loads need no column predicate; CC/WC are compile-time for the twelve layer shapes of the
+// 224x224 network (addresses become immediates) and 0 for the generic fallback.
+template <typename T, int KS, int STRIDE, int TW, bool XINT, int CC>
+__device__ __forceinline__ void dw_row(const T* __restrict__ in_f, const float* __restrict__ wc, int C, int WCs, int H,
+                                       int oy, int ix0, const int (&coloff)[(TW - 1) * STRIDE + KS],
+                                       const ulonglong2& b0, const ulonglong2& b1, uint64_t (&acc)[TW][4]) {
+    constexpr int PAD = KS / 2;
+    constexpr int NCOL = (TW - 1) * STRIDE + KS;
+    const int Cc = CC ? CC : C;
+#pragma unroll
+    for (int j = 0; j < TW; ++j) { acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b1.x; acc[j][3] = b1.y; }
+#pragma unroll
+    for (int ky = 0; ky < KS; ++ky) {
+        const int iy = oy * STRIDE - PAD + ky;
+        const bool row_ok = (unsigned)iy < (unsigned)H;          // padding rows read as zeros (branch-free)
+        const T* row = in_f + (size_t)((row_ok ? iy : 0) * WCs) + (XINT ? ix0 * Cc : 0);
+        uint64_t x[NCOL][4];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (XINT) { if (row_ok) v = ldg16(row + j * Cc); }
+            else      { if (row_ok && coloff[j] >= 0) v = ldg16(row + coloff[j]); }
+            const float2 f0 = Half16<T>::unpack(v.x), f1 = Half16<T>::unpack(v.y);
+            const float2 f2 = Half16<T>::unpack(v.z), f3 = Half16<T>::unpack(v.w);
+            x[j][0] = f2_pack(f0.x, f0.y); x[j][1] = f2_pack(f1.x, f1.y);
+            x[j][2] = f2_pack(f2.x, f2.y); x[j][3] = f2_pack(f3.x, f3.y);
+        }
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+            const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * Cc));
+            const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * Cc + 4));
+#pragma unroll
+            for (int j = 0; j < TW; ++j) {
+                acc[j][0] = fma2(x[j * STRIDE + kx][0], w0.x, acc[j][0]);
+                acc[j][1] = fma2(x[j * STRIDE + kx][1], w0.y, acc[j][1]);
+                acc[j][2] = fma2(x[j * STRIDE + kx][2], w1.x, acc[j][2]);
+                acc[j][3] = fma2(x[j * STRIDE + kx][3], w1.y, acc[j][3]);
+            }
+        }
+    }
+}
+
+template <typename T, int KS, int STRIDE, int CC, int WW>
 __global__ void __launch_bounds__(kDwThreads, 2)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
-              int H, int W, int C, int OH, int OW, int strips, int items, int blocks_per_frame) {
+              int H_, int W_, int C_, int OH_, int OW_, int strips, int items, int blocks_per_frame) {
     constexpr int TW = STRIDE == 1 ? kDwTW : 2;
     constexpr int PAD = KS / 2;
     constexpr int NCOL = (TW - 1) * STRIDE + KS;
     __shared__ float s_part[kDwThreads][9];     // +1 pad: conflict-free column walks
 
+    // compile-time geometry for the specialised instantiations (square maps), run-time otherwise
+    const int C = CC ? CC : C_, W = WW ? WW : W_, H = WW ? WW : H_;
+    const int OW = WW ? (WW + 2 * PAD - KS) / STRIDE + 1 : OW_, OH = WW ? OW : OH_;
     const int C8 = C >> 3;
     const int64_t frame = blockIdx.x / blocks_per_frame;
     const int blk = blockIdx.x - (int)(frame * blocks_per_frame);
@@ -65,7 +111,8 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
         const int ix0 = ox0 * STRIDE - PAD;
         const T* in_f = in + (size_t)frame * H * W * C + c8 * 8;
         const float* wc = w + c8 * 8;
-        const int WC = W * C;
+        const int WCs = W * C;
+        const bool x_interior = (ix0 >= 0) && (ix0 + NCOL <= W) && (ox0 + TW <= OW);
         int coloff[NCOL];                                   // element offset of each window column, -1 = padding
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) { const int ix = ix0 + j; coloff[j] = (ix >= 0 && ix < W) ? ix * C : -1; }
@@ -76,36 +123,8 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
             const int oy = oyb * kDwRPT + rr;
             if (oy >= OH) break;
             uint64_t acc[TW][4];
-#pragma unroll
-            for (int j = 0; j < TW; ++j) { acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b1.x; acc[j][3] = b1.y; }
-#pragma unroll
-            for (int ky = 0; ky < KS; ++ky) {
-                const int iy = oy * STRIDE - PAD + ky;
-                const bool row_ok = (unsigned)iy < (unsigned)H;      // padding rows read as zeros (branch-free)
-                const T* row = in_f + (row_ok ? iy : 0) * WC;
-                uint64_t x[NCOL][4];
-#pragma unroll
-                for (int j = 0; j < NCOL; ++j) {
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (row_ok && coloff[j] >= 0) v = ldg16(row + coloff[j]);
-                    const float2 f0 = Half16<T>::unpack(v.x), f1 = Half16<T>::unpack(v.y);
-                    const float2 f2 = Half16<T>::unpack(v.z), f3 = Half16<T>::unpack(v.w);
-                    x[j][0] = f2_pack(f0.x, f0.y); x[j][1] = f2_pack(f1.x, f1.y);
-                    x[j][2] = f2_pack(f2.x, f2.y); x[j][3] = f2_pack(f3.x, f3.y);
-                }
-#pragma unroll
-                for (int kx = 0; kx < KS; ++kx) {
-                    const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * C));
-                    const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * C + 4));
-#pragma unroll
-                    for (int j = 0; j < TW; ++j) {
-                        acc[j][0] = fma2(x[j * STRIDE + kx][0], w0.x, acc[j][0]);
-                        acc[j][1] = fma2(x[j * STRIDE + kx][1], w0.y, acc[j][1]);
-                        acc[j][2] = fma2(x[j * STRIDE + kx][2], w1.x, acc[j][2]);
-                        acc[j][3] = fma2(x[j * STRIDE + kx][3], w1.y, acc[j][3]);
-                    }
-                }
-            }
+            if (x_interior) dw_row<T, KS, STRIDE, TW, true, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, b1, acc);
+            else            dw_row<T, KS, STRIDE, TW, false, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, b1, acc);
             T* orow = out + (((size_t)frame * OH + oy) * OW) * C + c8 * 8;
 #pragma unroll
             for (int j = 0; j < TW; ++j) {
@@ -160,12 +179,18 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
     if (frames <= 0) return cudaSuccess;
     if ((C & 7) || C / 8 > kDwThreads || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(frames * bpf);
-#define DFD_DW(KS, ST) dwconv_kernel<T, KS, ST><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf)
-    if (k == 3 && stride == 1) DFD_DW(3, 1);
-    else if (k == 3 && stride == 2) DFD_DW(3, 2);
-    else if (k == 5 && stride == 1) DFD_DW(5, 1);
-    else if (k == 5 && stride == 2) DFD_DW(5, 2);
+#define DFD_DW(KS, ST, CC, WW) dwconv_kernel<T, KS, ST, CC, WW><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf)
+    // the twelve depthwise shapes of EfficientNet-B0 at 224x224 get compile-time geometry
+#define DFD_DW_CASE(KS, ST, CC, WW) if (k == KS && stride == ST && C == CC && W == WW && H == WW) { DFD_DW(KS, ST, CC, WW); return cudaGetLastError(); }
+    DFD_DW_CASE(3, 1, 32, 112) DFD_DW_CASE(3, 2, 96, 112) DFD_DW_CASE(3, 1, 144, 56) DFD_DW_CASE(5, 2, 144, 56)
+    DFD_DW_CASE(5, 1, 240, 28) DFD_DW_CASE(3, 2, 240, 28) DFD_DW_CASE(3, 1, 480, 14) DFD_DW_CASE(5, 1, 480, 14)
+    DFD_DW_CASE(5, 1, 672, 14) DFD_DW_CASE(5, 2, 672, 14) DFD_DW_CASE(5, 1, 1152, 7) DFD_DW_CASE(3, 1, 1152, 7)
+    if (k == 3 && stride == 1) DFD_DW(3, 1, 0, 0);
+    else if (k == 3 && stride == 2) DFD_DW(3, 2, 0, 0);
+    else if (k == 5 && stride == 1) DFD_DW(5, 1, 0, 0);
+    else if (k == 5 && stride == 2) DFD_DW(5, 2, 0, 0);
     else return cudaErrorInvalidValue;
+#undef DFD_DW_CASE
 #undef DFD_DW
     return cudaGetLastError();
 }
