@@ -2,7 +2,7 @@
 // fused with the squeeze-excite spatial reduction (timm `conv_dw` + `bn` + the `x.mean((2,3))` of
 // SqueezeExcite; reference call site pretrained_detector.py:116).
 //
-// One thread owns 8 channels (one 128-bit vector) x TW = 4 consecutive output columns x kDwRPT consecutive
+// One thread owns 8 channels (one 128-bit vector) x TW = 4 consecutive output columns x 7-8 consecutive
 // output rows (processed one after the other, so the rows it re-reads are still in L1).
 // Each input row of the window is loaded once as (TW-1)*stride+k vectors, unpacked once to packed fp32x2
 // and reused from registers for the TW outputs; vertical reuse is served by L1 (consecutive work items are
@@ -10,9 +10,10 @@
 // All arithmetic is packed `fma.rn.f32x2` (the full-rate fp32 form on sm_100) with fp32 weights; address
 // and bounds work is amortised over 8 channels.  A warp's loads are runs of contiguous 16-byte vectors.
 //
-// SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding) per channel; the CTA
-// combines them in a fixed order and writes one partial row per CTA — no atomics, bit-reproducible.
-// se.cu adds the partial rows up in order.
+// SE squeeze: every thread sums its SiLU outputs (fp32, before the 16-bit rounding) per channel over its
+// rows and writes its own 8-channel slice of a partial row (one partial row per (row group, column strip)):
+// no atomics, no CTA barrier (early warps never wait for late ones), bit-reproducible.  se.cu adds the
+// partial rows up in a fixed order.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -20,14 +21,14 @@ namespace dfd {
 
 constexpr int kDwThreads = 256;
 constexpr int kDwTW = 4;              // output columns per thread (stride 1); stride-2 layers use 2 to fit registers
-constexpr int kDwRPT = 4;             // output rows per thread
 
 static inline int dw_tw(int stride) { return stride == 1 ? kDwTW : 2; }
-static inline int dw_items(int OH, int OW, int C, int stride) {
-    const int tw = dw_tw(stride);
-    return ((OH + kDwRPT - 1) / kDwRPT) * ((OW + tw - 1) / tw) * (C / 8);
+static inline int dw_rpt(int OH) { return OH >= 56 ? 8 : 7; }          // output rows per thread
+static inline int dw_slots(int OH, int OW, int stride) {                 // (row group, column strip) pairs per frame
+    const int tw = dw_tw(stride), rpt = dw_rpt(OH);
+    return ((OH + rpt - 1) / rpt) * ((OW + tw - 1) / tw);
 }
-int dw_num_partials(int OH, int OW, int C, int /*k*/, int stride) { return (dw_items(OH, OW, C, stride) + kDwThreads - 1) / kDwThreads; }
+int dw_num_partials(int OH, int OW, int /*C*/, int /*k*/, int stride) { return dw_slots(OH, OW, stride); }
 
 // x * sigmoid(x) with raw MUFU ex2 + rcp (no range fix-ups: e = inf -> rcp = 0 -> -0, which is the limit)
 __device__ __forceinline__ float silu_fast(float x) {
@@ -83,12 +84,10 @@ template <typename T, int KS, int STRIDE, int CC, int WW>
 __global__ void __launch_bounds__(kDwThreads, 2)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
-              int H_, int W_, int C_, int OH_, int OW_, int strips, int items, int blocks_per_frame) {
+              int H_, int W_, int C_, int OH_, int OW_, int strips, int items, int blocks_per_frame, int rpt, int slots) {
     constexpr int TW = STRIDE == 1 ? kDwTW : 2;
     constexpr int PAD = KS / 2;
     constexpr int NCOL = (TW - 1) * STRIDE + KS;
-    __shared__ float s_part[kDwThreads][9];     // +1 pad: conflict-free column walks
-
     // compile-time geometry for the specialised instantiations (square maps), run-time otherwise
     const int C = CC ? CC : C_, W = WW ? WW : W_, H = WW ? WW : H_;
     const int OW = WW ? (WW + 2 * PAD - KS) / STRIDE + 1 : OW_, OH = WW ? OW : OH_;
@@ -96,13 +95,12 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
     const int64_t frame = blockIdx.x / blocks_per_frame;
     const int blk = blockIdx.x - (int)(frame * blocks_per_frame);
     const int item = blk * kDwThreads + threadIdx.x;
-    const bool valid = item < items;
+    if (item >= items) return;
 
     uint64_t sums[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) sums[c] = 0ull;
-
-    if (valid) {
+    {
         const int c8 = item % C8;
         const int t = item / C8;
         const int strip = t % strips;
@@ -119,8 +117,8 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
         const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * 8));
         const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * 8 + 4));
 
-        for (int rr = 0; rr < kDwRPT; ++rr) {
-            const int oy = oyb * kDwRPT + rr;
+        for (int rr = 0; rr < rpt; ++rr) {
+            const int oy = oyb * rpt + rr;
             if (oy >= OH) break;
             uint64_t acc[TW][4];
             if (x_interior) dw_row<T, KS, STRIDE, TW, true, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, b1, acc);
@@ -142,29 +140,12 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
                 }
             }
         }
-    }
 
-    // ---- deterministic block reduction of the SE sums --------------------------------------------
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float2 v = f2_unpack(sums[c]);
-        s_part[threadIdx.x][2 * c] = v.x; s_part[threadIdx.x][2 * c + 1] = v.y;
-    }
-    __syncthreads();
-    if (threadIdx.x < C8) {
-        const int cg = threadIdx.x;
-        const int base = (blk * kDwThreads) % C8;          // channel group of thread 0 in this block
-        int t0 = cg - base; if (t0 < 0) t0 += C8;
-        float tot[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) tot[c] = 0.f;
-        for (int t = t0; t < kDwThreads; t += C8) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) tot[c] += s_part[t][c];
-        }
-        float* dst = partials + ((size_t)frame * blocks_per_frame + blk) * C + cg * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(tot[0], tot[1], tot[2], tot[3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(tot[4], tot[5], tot[6], tot[7]);
+        // this thread is the only writer of its (frame, slot, channel group) slice
+        float* dst = partials + ((size_t)frame * slots + t) * C + c8 * 8;
+        const float2 s0 = f2_unpack(sums[0]), s1 = f2_unpack(sums[1]), s2 = f2_unpack(sums[2]), s3 = f2_unpack(sums[3]);
+        *reinterpret_cast<float4*>(dst) = make_float4(s0.x, s0.y, s1.x, s1.y);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(s2.x, s2.y, s3.x, s3.y);
     }
 }
 
@@ -174,12 +155,13 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     const int strips = (OW + dw_tw(stride) - 1) / dw_tw(stride);
-    const int items = dw_items(OH, OW, C, stride);
-    const int bpf = dw_num_partials(OH, OW, C, k, stride);
+    const int rpt = dw_rpt(OH), slots = dw_slots(OH, OW, stride);
+    const int items = slots * (C / 8);
+    const int bpf = (items + kDwThreads - 1) / kDwThreads;
     if (frames <= 0) return cudaSuccess;
     if ((C & 7) || C / 8 > kDwThreads || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(frames * bpf);
-#define DFD_DW(KS, ST, CC, WW) dwconv_kernel<T, KS, ST, CC, WW><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf)
+#define DFD_DW(KS, ST, CC, WW) dwconv_kernel<T, KS, ST, CC, WW><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf, rpt, slots)
     // the twelve depthwise shapes of EfficientNet-B0 at 224x224 get compile-time geometry
 #define DFD_DW_CASE(KS, ST, CC, WW) if (k == KS && stride == ST && C == CC && W == WW && H == WW) { DFD_DW(KS, ST, CC, WW); return cudaGetLastError(); }
     DFD_DW_CASE(3, 1, 32, 112) DFD_DW_CASE(3, 2, 96, 112) DFD_DW_CASE(3, 1, 144, 56) DFD_DW_CASE(5, 2, 144, 56)
