@@ -2,8 +2,11 @@
 // fused with the squeeze-excite spatial reduction (timm `conv_dw` + `bn` + the `x.mean((2,3))` of
 // SqueezeExcite; reference call site pretrained_detector.py:116).
 //
-// One thread owns 8 channels (one 128-bit vector) x TW = 4 consecutive output columns x 7-8 consecutive
-// output rows (processed one after the other, so the rows it re-reads are still in L1).
+// One thread owns 4 channels (one 64-bit vector) x TW = 8 consecutive output columns (4 for stride 2) x 7-8
+// consecutive output rows (processed one after the other, so the rows it re-reads are still in L1).
+// The kernel is bound by the L1/shared-memory pipe (ncu: l1tex throughput > 60 %, every other pipe < 40 %),
+// so the tile shape is chosen to minimise L1 bytes per output: wide strips amortise both the window halo
+// and the per-tap weight loads.
 // Each input row of the window is loaded once as (TW-1)*stride+k vectors, unpacked once to packed fp32x2
 // and reused from registers for the TW outputs; vertical reuse is served by L1 (consecutive work items are
 // channel groups first, then columns, then rows, so the CTAs that share rows run next to each other).
@@ -20,9 +23,10 @@
 namespace dfd {
 
 constexpr int kDwThreads = 256;
-constexpr int kDwTW = 4;              // output columns per thread (stride 1); stride-2 layers use 2 to fit registers
+constexpr int kDwTW = 8;              // output columns per thread (stride 1); stride-2 layers use 4 to fit registers
+constexpr int kDwCH = 4;              // channels per thread
 
-static inline int dw_tw(int stride) { return stride == 1 ? kDwTW : 2; }
+static inline int dw_tw(int stride) { return stride == 1 ? kDwTW : 4; }
 static inline int dw_rpt(int OH) { return OH >= 56 ? 8 : 7; }          // output rows per thread
 static inline int dw_slots(int OH, int OW, int stride) {                 // (row group, column strip) pairs per frame
     const int tw = dw_tw(stride), rpt = dw_rpt(OH);
@@ -43,38 +47,33 @@ __device__ __forceinline__ float silu_fast(float x) {
 template <typename T, int KS, int STRIDE, int TW, bool XINT, int CC>
 __device__ __forceinline__ void dw_row(const T* __restrict__ in_f, const float* __restrict__ wc, int C, int WCs, int H,
                                        int oy, int ix0, const int (&coloff)[(TW - 1) * STRIDE + KS],
-                                       const ulonglong2& b0, const ulonglong2& b1, uint64_t (&acc)[TW][4]) {
+                                       const ulonglong2& b0, uint64_t (&acc)[TW][2]) {
     constexpr int PAD = KS / 2;
     constexpr int NCOL = (TW - 1) * STRIDE + KS;
     const int Cc = CC ? CC : C;
 #pragma unroll
-    for (int j = 0; j < TW; ++j) { acc[j][0] = b0.x; acc[j][1] = b0.y; acc[j][2] = b1.x; acc[j][3] = b1.y; }
+    for (int j = 0; j < TW; ++j) { acc[j][0] = b0.x; acc[j][1] = b0.y; }
 #pragma unroll
     for (int ky = 0; ky < KS; ++ky) {
         const int iy = oy * STRIDE - PAD + ky;
         const bool row_ok = (unsigned)iy < (unsigned)H;          // padding rows read as zeros (branch-free)
         const T* row = in_f + (size_t)((row_ok ? iy : 0) * WCs) + (XINT ? ix0 * Cc : 0);
-        uint64_t x[NCOL][4];
+        uint64_t x[NCOL][2];
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (XINT) { if (row_ok) v = ldg16(row + j * Cc); }
-            else      { if (row_ok && coloff[j] >= 0) v = ldg16(row + coloff[j]); }
+            uint2 v = make_uint2(0, 0);
+            if (XINT) { if (row_ok) v = __ldg(reinterpret_cast<const uint2*>(row + j * Cc)); }
+            else      { if (row_ok && coloff[j] >= 0) v = __ldg(reinterpret_cast<const uint2*>(row + coloff[j])); }
             const float2 f0 = Half16<T>::unpack(v.x), f1 = Half16<T>::unpack(v.y);
-            const float2 f2 = Half16<T>::unpack(v.z), f3 = Half16<T>::unpack(v.w);
             x[j][0] = f2_pack(f0.x, f0.y); x[j][1] = f2_pack(f1.x, f1.y);
-            x[j][2] = f2_pack(f2.x, f2.y); x[j][3] = f2_pack(f3.x, f3.y);
         }
 #pragma unroll
         for (int kx = 0; kx < KS; ++kx) {
             const ulonglong2 w0 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * Cc));
-            const ulonglong2 w1 = __ldg(reinterpret_cast<const ulonglong2*>(wc + (ky * KS + kx) * Cc + 4));
 #pragma unroll
             for (int j = 0; j < TW; ++j) {
                 acc[j][0] = fma2(x[j * STRIDE + kx][0], w0.x, acc[j][0]);
                 acc[j][1] = fma2(x[j * STRIDE + kx][1], w0.y, acc[j][1]);
-                acc[j][2] = fma2(x[j * STRIDE + kx][2], w1.x, acc[j][2]);
-                acc[j][3] = fma2(x[j * STRIDE + kx][3], w1.y, acc[j][3]);
             }
         }
     }
@@ -85,21 +84,19 @@ __global__ void __launch_bounds__(kDwThreads, 2)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
               int H_, int W_, int C_, int OH_, int OW_, int strips, int items, int blocks_per_frame, int rpt, int slots) {
-    constexpr int TW = STRIDE == 1 ? kDwTW : 2;
+    constexpr int TW = STRIDE == 1 ? kDwTW : 4;
     constexpr int PAD = KS / 2;
     constexpr int NCOL = (TW - 1) * STRIDE + KS;
     // compile-time geometry for the specialised instantiations (square maps), run-time otherwise
     const int C = CC ? CC : C_, W = WW ? WW : W_, H = WW ? WW : H_;
     const int OW = WW ? (WW + 2 * PAD - KS) / STRIDE + 1 : OW_, OH = WW ? OW : OH_;
-    const int C8 = C >> 3;
+    const int C8 = C >> 2;                  // channel groups of 4
     const int64_t frame = blockIdx.x / blocks_per_frame;
     const int blk = blockIdx.x - (int)(frame * blocks_per_frame);
     const int item = blk * kDwThreads + threadIdx.x;
     if (item >= items) return;
 
-    uint64_t sums[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sums[c] = 0ull;
+    uint64_t sums[2] = {0ull, 0ull};
     {
         const int c8 = item % C8;
         const int t = item / C8;
@@ -107,45 +104,43 @@ dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float
         const int oyb = t / strips;
         const int ox0 = strip * TW;
         const int ix0 = ox0 * STRIDE - PAD;
-        const T* in_f = in + (size_t)frame * H * W * C + c8 * 8;
-        const float* wc = w + c8 * 8;
+        const T* in_f = in + (size_t)frame * H * W * C + c8 * kDwCH;
+        const float* wc = w + c8 * kDwCH;
         const int WCs = W * C;
         const bool x_interior = (ix0 >= 0) && (ix0 + NCOL <= W) && (ox0 + TW <= OW);
         int coloff[NCOL];                                   // element offset of each window column, -1 = padding
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) { const int ix = ix0 + j; coloff[j] = (ix >= 0 && ix < W) ? ix * C : -1; }
-        const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * 8));
-        const ulonglong2 b1 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * 8 + 4));
+        const ulonglong2 b0 = __ldg(reinterpret_cast<const ulonglong2*>(bias + c8 * kDwCH));
 
         for (int rr = 0; rr < rpt; ++rr) {
             const int oy = oyb * rpt + rr;
             if (oy >= OH) break;
-            uint64_t acc[TW][4];
-            if (x_interior) dw_row<T, KS, STRIDE, TW, true, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, b1, acc);
-            else            dw_row<T, KS, STRIDE, TW, false, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, b1, acc);
-            T* orow = out + (((size_t)frame * OH + oy) * OW) * C + c8 * 8;
+            uint64_t acc[TW][2];
+            if (x_interior) dw_row<T, KS, STRIDE, TW, true, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, acc);
+            else            dw_row<T, KS, STRIDE, TW, false, CC>(in_f, wc, C, WCs, H, oy, ix0, coloff, b0, acc);
+            T* orow = out + (((size_t)frame * OH + oy) * OW) * C + c8 * kDwCH;
 #pragma unroll
             for (int j = 0; j < TW; ++j) {
                 const int ox = ox0 + j;
                 if (ox < OW) {
-                    uint32_t o[4];
+                    uint32_t o[2];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < 2; ++c) {
                         const float2 a = f2_unpack(acc[j][c]);
                         const float y0 = silu_fast(a.x), y1 = silu_fast(a.y);
                         sums[c] = add2(sums[c], f2_pack(y0, y1));
                         o[c] = Half16<T>::pack(y0, y1);
                     }
-                    stg16(orow + (size_t)ox * C, make_uint4(o[0], o[1], o[2], o[3]));
+                    *reinterpret_cast<uint2*>(orow + (size_t)ox * C) = make_uint2(o[0], o[1]);
                 }
             }
         }
 
         // this thread is the only writer of its (frame, slot, channel group) slice
-        float* dst = partials + ((size_t)frame * slots + t) * C + c8 * 8;
-        const float2 s0 = f2_unpack(sums[0]), s1 = f2_unpack(sums[1]), s2 = f2_unpack(sums[2]), s3 = f2_unpack(sums[3]);
+        float* dst = partials + ((size_t)frame * slots + t) * C + c8 * kDwCH;
+        const float2 s0 = f2_unpack(sums[0]), s1 = f2_unpack(sums[1]);
         *reinterpret_cast<float4*>(dst) = make_float4(s0.x, s0.y, s1.x, s1.y);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(s2.x, s2.y, s3.x, s3.y);
     }
 }
 
@@ -156,10 +151,10 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
     const int strips = (OW + dw_tw(stride) - 1) / dw_tw(stride);
     const int rpt = dw_rpt(OH), slots = dw_slots(OH, OW, stride);
-    const int items = slots * (C / 8);
+    const int items = slots * (C / kDwCH);
     const int bpf = (items + kDwThreads - 1) / kDwThreads;
     if (frames <= 0) return cudaSuccess;
-    if ((C & 7) || C / 8 > kDwThreads || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if ((C & 7) || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(frames * bpf);
 #define DFD_DW(KS, ST, CC, WW) dwconv_kernel<T, KS, ST, CC, WW><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf, rpt, slots)
     // the twelve depthwise shapes of EfficientNet-B0 at 224x224 get compile-time geometry

@@ -24,12 +24,20 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
 
     for (int i = threadIdx.x; i < kSeFrames * C; i += kSeThreads) {
         const int f = i / C, c = i - f * C;
-        float acc = 0.f;
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = 0.f;
         if (f < nf) {
+            // 8 independent partial sums keep 8 loads in flight; they are combined in a fixed tree order
             const float* p = partials + ((size_t)(f0 + f) * nparts) * C + c;
-            for (int q = 0; q < nparts; ++q) acc += p[(size_t)q * C];
+            int q = 0;
+            for (; q + 8 <= nparts; q += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] += p[(size_t)(q + u) * C];
+            }
+            for (int u = 0; q < nparts; ++q, ++u) a[u] += p[(size_t)q * C];
         }
-        s_mean[i] = acc * inv_hw;
+        s_mean[i] = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) * inv_hw;
     }
     __syncthreads();
 
