@@ -43,6 +43,7 @@ struct GemmArgs {
     int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
     int64_t m_tiles;
     int stages;
+    int nacc, na;                   // TMEM accumulator buffers; epilogue group sets that take alternate tiles
     int nf_max, total_frames;       // gated: frames a tile can touch, frames in the tensor
     uint32_t g_stage_bytes;         // gated: bytes of the per-stage gate slice [nf_max][64] fp32
     int b_resident;                 // whole W lives in shared memory for the CTA's lifetime
@@ -68,14 +69,14 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
     float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += kColGroups * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], raw[S], tfull[2], tempty[2]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], raw[S], tfull[8], tempty[8]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 16);
 
     const uint32_t bres_base = smem_u32(smem_raw);
     const uint32_t smem_base = bres_base + p.b_res_bytes;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
     const uint32_t bar_raw = smem_u32(bars + 2 * kMaxStages);
-    const uint32_t bar_tfull = smem_u32(bars + 3 * kMaxStages), bar_tempty = smem_u32(bars + 3 * kMaxStages + 2);
+    const uint32_t bar_tfull = smem_u32(bars + 3 * kMaxStages), bar_tempty = smem_u32(bars + 3 * kMaxStages + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             mbar_init(bar_empty + 8 * s, 1);
             mbar_init(bar_raw + 8 * s, kProdThreads);
         }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, kEpiWarps * 32); }
+        for (int a = 0; a < p.nacc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kColGroups / p.na) * 128); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), p.tmem_cols);
@@ -243,16 +244,21 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // =================================== EPILOGUE ============================================
-        const int q = warp & 3, half = warp >> 2;      // half = column group of this warp
+        // Epilogue groups (4 warps = 128 TMEM lanes each) are split into `na` sets that take alternate tiles, so
+        // several tiles are drained concurrently; the kColGroups/na groups of one set split a tile's columns.
+        const int q = warp & 3, half = warp >> 2;      // half = epilogue group of this warp
+        const int gpt = kColGroups / p.na, set = half / gpt, sub = half - set * gpt;
         const int row = 32 * q + lane;
         T* D = reinterpret_cast<T*>(p.D);
         const T* R = reinterpret_cast<const T*>(p.R);
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        int64_t li = set;                               // index of the unit within this CTA's sequence
+        for (int64_t u = blockIdx.x + (int64_t)set * gridDim.x; u < units; u += (int64_t)p.na * gridDim.x, li += p.na) {
+            const int acc = (int)(li % p.nacc);
+            const uint32_t acc_phase = (uint32_t)(li / p.nacc) & 1u;
             const int64_t mt = u / p.n_chunks;
             const int nc = (int)(u - mt * p.n_chunks);
             const int64_t m0 = mt * p.rows_per_tile;
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             tc_fence_after_sync();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
             const int slots = POOL ? rows_valid / p.HW : 0;
-            for (int c16 = half; c16 * 16 < p.NBp; c16 += kColGroups) {
+            for (int c16 = sub; c16 * 16 < p.NBp; c16 += gpt) {
                 uint32_t r[16];
                 tmem_ld16(t_row + c16 * 16, r);
                 tmem_ld_wait();
@@ -338,7 +344,6 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             }
             tc_fence_before_sync();
             mbar_arrive(bar_tempty + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
@@ -368,9 +373,16 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.a_stage_bytes = (uint32_t)kcp_max * kLboA;
     a.b_stage_bytes = (uint32_t)kcp_max * a.lbo_b;
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
-    uint32_t cols = 32; while (cols < (uint32_t)(2 * a.NBp)) cols <<= 1;
+    {   // accumulator ring: as many buffers as fit in the 512 TMEM columns (<= 8); epilogue groups take alternate tiles
+        const int groups = epi_warps / 4, fit = 512 / a.NBp;
+        int na = groups; while (na > fit) na >>= 1;
+        a.na = na;
+        int nacc = (fit / na) * na; if (nacc > 8) nacc = 8 / na * na;
+        a.nacc = nacc;
+    }
+    uint32_t cols = 32; while (cols < (uint32_t)(a.nacc * a.NBp)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (3 * kMaxStages + 4) * 8 + 16;
+    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (3 * kMaxStages + 16) * 8 + 16;
     a.nf_max = a.gate ? (kBM - 1) / a.HW + 2 : 0;
     a.total_frames = (int)((a.M + a.HW - 1) / a.HW);
     a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
