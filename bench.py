@@ -240,10 +240,21 @@ def main():
         if e.launches:
             kernels[e.name.decode()] = {"launches": e.launches, "ms": round(e.ms, 4), "GBps": round(e.bytes / e.ms / 1e6, 1),
                                         "TFLOPs": round(e.flops / e.ms / 1e9, 2), "MB": round(e.bytes / 1e6, 1)}
+    # DRAM traffic per launch of each kernel class from the committed ncu capture of the same workload (profiles/)
+    traffic = {}
+    try:
+        import glob
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+        if files and (V, T) == (VIDEOS, FRAMES_PER_VIDEO):
+            tj = json.load(open(files[-1]))
+            traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["classes"].items()}
+            traffic["__file__"] = os.path.basename(files[-1])
+    except Exception:
+        traffic = {}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     d = kernels[dom]
     roofline = {"kernel": dom, "bound": "hbm", "achieved": d["GBps"], "peak": hbm_gbs, "unit": "GB/s",
-                "frac": round(d["GBps"] / hbm_gbs, 4), "traffic": None, "peak_kind": f"of {peak_kind}",
+                "frac": round(d["GBps"] / hbm_gbs, 4), "traffic": traffic.get(dom), "traffic_source": traffic.get("__file__"), "peak_kind": f"of {peak_kind}",
                 "avg_launch_ms": round(d["ms"] / d["launches"], 4), "algorithmic_bytes_per_launch": d["MB"] * 1e6 / d["launches"],
                 "share_of_step": round(d["ms"] / sum(k["ms"] for k in kernels.values()), 3)}
 
