@@ -3,13 +3,15 @@
 Public surface (mirrors the reference):
     PretrainedBackboneDetector, EnsembleDetector      src/pretrained_detector.py
     imagenet_normalize, decide                        app.py:1772-1780, 2090-2112
+    LogicRNNLSTM, LogicCell, create_model             src/RNNModel.py (temporal head of BASELINE config 3)
     FrameScorer, PackedWeights, make_offsets          high-throughput engine over the C ABI (include/dfd_b200.h)
 """
 from .decision import decide, imagenet_normalize
 from .engine import DEFAULT_PRECISION, FrameScorer, PackedWeights, make_offsets
 from .pretrained_detector import EnsembleDetector, PretrainedBackboneDetector
+from .rnn_model import LogicCell, LogicRNNLSTM, create_model
 from .sharding import gather_video_logits, score_videos_sharded, shard_bounds
 
 __all__ = ["PretrainedBackboneDetector", "EnsembleDetector", "imagenet_normalize", "decide", "FrameScorer",
            "PackedWeights", "make_offsets", "DEFAULT_PRECISION", "shard_bounds", "gather_video_logits",
-           "score_videos_sharded"]
+           "score_videos_sharded", "LogicCell", "LogicRNNLSTM", "create_model"]

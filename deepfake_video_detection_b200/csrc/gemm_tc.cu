@@ -52,7 +52,7 @@ struct GemmArgs {
     float inv_hw;
 };
 
-template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps>
+template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
     constexpr int kProdThreads = kProdWarps * 32;
@@ -310,6 +310,15 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                         if (part == 0 && col < ncol) p.feat[(size_t)(frame0 + s) * p.N + n0 + c16 * 16 + col] = tot * p.inv_hw;
                     }
                     asm volatile("bar.sync %0, 128;" :: "r"(1 + half) : "memory");
+                } else if (F32OUT) {
+                    if (valid) {                                      // fp32 output (recurrent head): 64 bytes per chunk
+                        float* dst = reinterpret_cast<float*>(p.D) + (size_t)m * p.N + n0 + c16 * 16;
+                        U32x8 o0, o1;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { o0.v[i] = __float_as_uint(v[i]); o1.v[i] = __float_as_uint(v[8 + i]); }
+                        stg32(dst, o0);
+                        if (ncol > 8) stg32(dst + 8, o1);
+                    }
                 } else if (valid) {
                     T* dst = D + (size_t)m * p.N + n0 + c16 * 16;
                     const bool wide = ((p.N & 15) == 0);              // every 16-column chunk is then 32-byte aligned
@@ -427,6 +436,18 @@ cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, cons
     a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
     if (dtype == kDtypeFP16) return launch_t<__half>(a, act, s);
     return launch_t<__nv_bfloat16>(a, act, s);
+}
+
+cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, float* D,
+                                  int64_t M, int K, int N, int dtype, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((K & 7) || (N & 7) || K < 8 || N < 8) return cudaErrorInvalidValue;
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = nullptr; a.D = D; a.feat = nullptr;
+    a.M = M; a.K = K; a.N = N; a.HW = 1;
+    a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
+    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, false, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+    return run(gemm_tc_kernel<__nv_bfloat16, false, false, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
 }
 
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,

@@ -9,7 +9,7 @@
 
 namespace dfd {
 
-constexpr int kPhThreads = 256;
+constexpr int kPhThreads = 512;
 constexpr int kFeat = 1280, kAttHidden = 64, kFc1 = 256;
 constexpr int kMaxT = 1024;
 
@@ -47,13 +47,22 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
 #pragma unroll
             for (int i = 0; i < kFeat / 32; ++i) x[i] = fv[(size_t)t * kFeat + lane + 32 * i];
             float score = 0.f;
-            for (int h = 0; h < kAttHidden; ++h) {
-                const float* wr = hw.att_w1 + (size_t)h * kFeat;
-                float acc = 0.f;
-#pragma unroll
-                for (int i = 0; i < kFeat / 32; ++i) acc = fmaf(x[i], __ldg(wr + lane + 32 * i), acc);
-                acc = warp_sum(acc) + __ldg(hw.att_b1 + h);
-                score = fmaf(fmaxf(acc, 0.f), __ldg(hw.att_w2 + h), score);
+            for (int h = 0; h < kAttHidden; h += 4) {          // 4 hidden units at a time: 4x the loads in flight
+                const float* wr = hw.att_w1 + (size_t)h * kFeat + lane;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < kFeat / 32; ++i) {
+                    a0 = fmaf(x[i], __ldg(wr + 32 * i), a0);
+                    a1 = fmaf(x[i], __ldg(wr + kFeat + 32 * i), a1);
+                    a2 = fmaf(x[i], __ldg(wr + 2 * kFeat + 32 * i), a2);
+                    a3 = fmaf(x[i], __ldg(wr + 3 * kFeat + 32 * i), a3);
+                }
+                a0 = warp_sum(a0) + __ldg(hw.att_b1 + h);     a1 = warp_sum(a1) + __ldg(hw.att_b1 + h + 1);
+                a2 = warp_sum(a2) + __ldg(hw.att_b1 + h + 2); a3 = warp_sum(a3) + __ldg(hw.att_b1 + h + 3);
+                score = fmaf(fmaxf(a0, 0.f), __ldg(hw.att_w2 + h), score);
+                score = fmaf(fmaxf(a1, 0.f), __ldg(hw.att_w2 + h + 1), score);
+                score = fmaf(fmaxf(a2, 0.f), __ldg(hw.att_w2 + h + 2), score);
+                score = fmaf(fmaxf(a3, 0.f), __ldg(hw.att_w2 + h + 3), score);
             }
             if (lane == 0) s_w[t] = 1.0f / (1.0f + expf(-(score + b2)));      // nn.Sigmoid, :70
         }
@@ -70,6 +79,7 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
         __syncthreads();
         for (int c = threadIdx.x; c < kFeat; c += kPhThreads) {               // (features * w).sum(dim=1), :131
             float acc = 0.f;
+#pragma unroll 4
             for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c] * s_w[t];
             s_pooled[c] = acc;
         }
@@ -84,13 +94,22 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
     __syncthreads();
     if (frame_scores) for (int t = threadIdx.x; t < T; t += kPhThreads) frame_scores[f0 + t] = s_w[t];
 
-    for (int j = warp; j < kFc1; j += kPhThreads / 32) {                      // relu(fc1(.)), :139
-        const float* wr = hw.fc1_w + (size_t)j * kFeat;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < kFeat / 32; ++i) acc = fmaf(s_pooled[lane + 32 * i], __ldg(wr + lane + 32 * i), acc);
-        acc = warp_sum(acc);
-        if (lane == 0) s_h1[j] = fmaxf(acc + __ldg(hw.fc1_b + j), 0.f);
+    for (int j = warp * 4; j < kFc1; j += (kPhThreads / 32) * 4) {           // relu(fc1(.)), :139 — 4 outputs per pass
+        const float* wr = hw.fc1_w + (size_t)j * kFeat + lane;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < kFeat / 32; ++i) {
+            const float xv = s_pooled[lane + 32 * i];
+            a0 = fmaf(xv, __ldg(wr + 32 * i), a0);
+            a1 = fmaf(xv, __ldg(wr + kFeat + 32 * i), a1);
+            a2 = fmaf(xv, __ldg(wr + 2 * kFeat + 32 * i), a2);
+            a3 = fmaf(xv, __ldg(wr + 3 * kFeat + 32 * i), a3);
+        }
+        a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+        if (lane == 0) {
+            s_h1[j] = fmaxf(a0 + __ldg(hw.fc1_b + j), 0.f);         s_h1[j + 1] = fmaxf(a1 + __ldg(hw.fc1_b + j + 1), 0.f);
+            s_h1[j + 2] = fmaxf(a2 + __ldg(hw.fc1_b + j + 2), 0.f); s_h1[j + 3] = fmaxf(a3 + __ldg(hw.fc1_b + j + 3), 0.f);
+        }
     }
     __syncthreads();
     if (warp < 2) {                                                           // fc2, :141

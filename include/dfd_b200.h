@@ -95,6 +95,21 @@ int dfd_score_videos(const dfd_weights_t* w, const void* d_in, int in_kind, cons
 /* number of kernel launches the last dfd_effnet_b0_features / dfd_score_videos call on this thread made */
 int dfd_last_launch_count(void);
 
+/* ---- temporal RNN head (BASELINE config 3): src/RNNModel.py:43-147 LogicRNNLSTM ------------------------
+ * Weights by reference state_dict key ("logic_cells.{l}.{and,or,not,forget,input,cell,output}_gate.{weight,bias}",
+ * "attention.{0,2}.*", "classifier.{0,3}.*"), HOST fp32.  The seven gate Linears of a LogicCell (:11-19) are
+ * stacked into one [7H, K] 16-bit GEMM operand per layer.
+ * dfd_rnn_forward: d_x fp32 (B,T,input_size) [already sorted by length when d_lengths is given, as the
+ * reference does at :92-95], d_lengths int32 (B,) or NULL -> d_prob fp32 (B,) = sigmoid(classifier(context)). */
+typedef struct dfd_rnn_weights dfd_rnn_weights_t;
+const char* dfd_rnn_last_error(void);
+int dfd_rnn_pack_weights(int n_tensors, const char* const* names, const float* const* data, const int64_t* numel,
+                         int input_size, int hidden, int layers, int dtype, dfd_rnn_weights_t** out);
+void dfd_rnn_free_weights(dfd_rnn_weights_t* w);
+int dfd_rnn_workspace_bytes(const dfd_rnn_weights_t* w, int64_t batch, int T, size_t* bytes);
+int dfd_rnn_forward(const dfd_rnn_weights_t* w, const float* d_x, const int32_t* d_lengths, int64_t batch, int T,
+                    float* d_prob, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement aid --------------------------------------------------------------------------------
  * dfd_profile_enable(1): from now on every kernel launched by this thread through this library is
  * bracketed by CUDA events recorded on the launch stream.  dfd_profile_collect synchronises on them and
