@@ -9,7 +9,7 @@ import os
 import threading
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libdfd_b200.so")
+LIB_PATH = os.environ.get("DFD_LIB_PATH") or os.path.join(PKG, "libdfd_b200.so")   # override: kernel-variant experiments only
 
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 IN_U8_HWC, IN_F32_NCHW, IN_H16_NCHW = 0, 1, 2
@@ -39,6 +39,7 @@ _SIGNATURES = {
     "dfd_profile_collect": (_int, [_vp, _int, C.POINTER(_int)]),
     # dfd_b200_kernels.h
     "dfd_k_stem": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
+    "dfd_k_stem_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "dfd_k_dw_num_partials": (_int, [_int, _int, _int, _int, _int]),
     "dfd_k_dwconv": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp]),
     "dfd_k_se": (_int, [_vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),

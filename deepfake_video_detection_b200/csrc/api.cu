@@ -76,6 +76,11 @@ struct BlockW {
     void* proj_w; float* proj_b;                       // [cout][mid] 16-bit, [cout]
 };
 
+bool use_simt_stem() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DFD_STEM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
+    return v == 1;
+}
 bool use_simt_gemm() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("DFD_GEMM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
@@ -92,6 +97,7 @@ int64_t chunk_frames() {
 struct dfd_weights {
     int dtype;
     float *stem_w, *stem_b;                            // [27][32], [32]
+    void* stem_w16;                                    // [32][96] 16-bit hi/lo split for the tcgen05 stem
     BlockW blocks[kNumBlocks];
     void* head_w; float* head_b;                       // [1280][320] 16-bit, [1280]
     dfd::HeadWeights hw;
@@ -167,6 +173,22 @@ bool pack_pw(Tensors& t, const std::string& conv, const std::string& bn, int N, 
     return true;
 }
 
+// stem weights [27][32] fp32 (tap-major) -> 16-bit [32][96] = [w_hi | w_hi | w_lo], taps padded 27 -> 32
+size_t pack_stem16(HostArena& a, const float* p27x32, int dtype) {
+    size_t off = a.alloc(32 * 96 * 2);
+    uint16_t* d = reinterpret_cast<uint16_t*>(a.bytes.data() + off);
+    for (int o = 0; o < 32; ++o)
+        for (int i = 0; i < 27; ++i) {
+            const float w = p27x32[i * 32 + o];
+            const uint16_t hi = to_h16(w, dtype);
+            float hf;
+            if (dtype == DFD_DTYPE_FP16) { __half h; memcpy(&h, &hi, 2); hf = __half2float(h); }
+            else { __nv_bfloat16 h; memcpy(&h, &hi, 2); hf = __bfloat162float(h); }
+            d[o * 96 + i] = hi; d[o * 96 + 32 + i] = hi; d[o * 96 + 64 + i] = to_h16(w - hf, dtype);
+        }
+    return off;
+}
+
 size_t pack_f32(HostArena& a, const float* src, size_t n) {
     size_t off = a.alloc(n * 4);
     memcpy(a.bytes.data() + off, src, n * 4);
@@ -197,7 +219,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
     W.dtype = dtype;
 
     // stem: [32][3][3][3] + BN -> fp32 [(ky*3+kx)*3+c][32]
-    size_t stem_w_off = 0, stem_b_off = 0;
+    size_t stem_w_off = 0, stem_b_off = 0, stem_w16_off = 0;
     {
         const float* w = t.get("backbone.0.weight", 32 * 27);
         std::vector<float> sc, sh;
@@ -209,6 +231,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
                         for (int kx = 0; kx < 3; ++kx)
                             p[((ky * 3 + kx) * 3 + c) * 32 + o] = w[((o * 3 + c) * 3 + ky) * 3 + kx] * sc[o];
             stem_w_off = pack_f32(a, p.data(), p.size());
+            stem_w16_off = pack_stem16(a, p.data(), dtype);
             stem_b_off = pack_f32(a, sh.data(), 32);
         }
     }
@@ -280,7 +303,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
     uint8_t* d = reinterpret_cast<uint8_t*>(dev);
     auto F = [&](size_t o) { return reinterpret_cast<float*>(d + o); };
     W.arena = dev; W.arena_bytes = a.bytes.size();
-    W.stem_w = F(stem_w_off); W.stem_b = F(stem_b_off);
+    W.stem_w = F(stem_w_off); W.stem_b = F(stem_b_off); W.stem_w16 = d + stem_w16_off;
     for (int i = 0; i < kNumBlocks; ++i) {
         BlockW& B = W.blocks[i]; const Off& o = off[i];
         B.exp_w = B.has_expand ? d + o.exp_w : nullptr; B.exp_b = B.has_expand ? F(o.exp_b) : nullptr;
@@ -376,7 +399,10 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
 
     int h = H / 2, wd = W / 2, cur = 0;
     prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
-    DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
+    if (in_kind == DFD_IN_U8_HWC && !use_simt_stem())
+        DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
+    else
+        DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
     for (int i = 0; i < kNumBlocks; ++i) {
         const BlockW& B = w->blocks[i];
         const void* x = io[cur];
@@ -512,6 +538,24 @@ int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_b
                int H, int W, int dtype, void* stream) {
     g_launches = 0;
     DFD_LAUNCH(dfd::launch_stem(d_in, in_kind, d_w, d_bias, d_out, frames, H, W, dtype, (cudaStream_t)stream), "stem kernel");
+    return DFD_OK;
+}
+int dfd_k_stem_tc(const uint8_t* d_in, const float* h_w27x32, const float* d_bias, void* d_out, int64_t frames,
+                  int H, int W, int dtype, void* stream) {
+    if (!d_in || !h_w27x32 || !d_bias || !d_out) return fail(DFD_EINVAL, "dfd_k_stem_tc: null pointer");
+    HostArena a;
+    const size_t off = pack_stem16(a, h_w27x32, dtype);
+    void* dw = nullptr;
+    DFD_CUDA(cudaMalloc(&dw, 32 * 96 * 2), "cudaMalloc(stem w16)");
+    cudaError_t e = cudaMemcpy(dw, a.bytes.data() + off, 32 * 96 * 2, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dw); return cuda_fail(e, "cudaMemcpy(stem w16)"); }
+    g_launches = 0;
+    { ProfScope ps; e = dfd::launch_stem_tc(d_in, dw, d_bias, d_out, frames, H, W, dtype, (cudaStream_t)stream); }
+    ++g_launches;
+    cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dw);
+    if (e != cudaSuccess) return cuda_fail(e, "stem kernel (tcgen05)");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "stem kernel (tcgen05) sync");
     return DFD_OK;
 }
 int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride) { return dfd::dw_num_partials(OH, OW, C, k, stride); }

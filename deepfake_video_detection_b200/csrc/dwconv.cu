@@ -23,16 +23,25 @@
 namespace dfd {
 
 constexpr int kDwThreads = 256;
-constexpr int kDwTW = 8;              // output columns per thread (stride 1); stride-2 layers use 4 to fit registers
 constexpr int kDwCH = 4;              // channels per thread
 
-static inline int dw_tw(int stride) { return stride == 1 ? kDwTW : 4; }
+// Strip width (output columns per thread) and CTAs/SM per layer shape, from a sweep on B200 (tools/sweep_dw.sh):
+// big maps want more resident warps (narrow strips, 3-4 CTAs/SM), the 14x14 / 7x7 maps want wide strips.
+struct DwCfg { int tw, minb; };
+static inline DwCfg dw_cfg(int C, int k, int stride, int W) {
+    if (stride == 1) {
+        if (W <= 14) return {8, 2};
+        return {4, 3};
+    }
+    if (k == 5 && W <= 56) return {4, 3};
+    return {2, 4};
+}
 static inline int dw_rpt(int OH) { return OH >= 56 ? 8 : 7; }          // output rows per thread
-static inline int dw_slots(int OH, int OW, int stride) {                 // (row group, column strip) pairs per frame
-    const int tw = dw_tw(stride), rpt = dw_rpt(OH);
+static inline int dw_slots(int OH, int OW, int tw) {                     // (row group, column strip) pairs per frame
+    const int rpt = dw_rpt(OH);
     return ((OH + rpt - 1) / rpt) * ((OW + tw - 1) / tw);
 }
-int dw_num_partials(int OH, int OW, int /*C*/, int /*k*/, int stride) { return dw_slots(OH, OW, stride); }
+int dw_num_partials(int OH, int OW, int C, int k, int stride) { return dw_slots(OH, OW, dw_cfg(C, k, stride, OW * stride).tw); }
 
 // x * sigmoid(x) with raw MUFU ex2 + rcp (no range fix-ups: e = inf -> rcp = 0 -> -0, which is the limit)
 __device__ __forceinline__ float silu_fast(float x) {
@@ -79,12 +88,11 @@ __device__ __forceinline__ void dw_row(const T* __restrict__ in_f, const float* 
     }
 }
 
-template <typename T, int KS, int STRIDE, int CC, int WW>
-__global__ void __launch_bounds__(kDwThreads, 2)
+template <typename T, int KS, int STRIDE, int CC, int WW, int TW, int MINB>
+__global__ void __launch_bounds__(kDwThreads, MINB)
 dwconv_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
               T* __restrict__ out, float* __restrict__ partials,
               int H_, int W_, int C_, int OH_, int OW_, int strips, int items, int blocks_per_frame, int rpt, int slots) {
-    constexpr int TW = STRIDE == 1 ? kDwTW : 4;
     constexpr int PAD = KS / 2;
     constexpr int NCOL = (TW - 1) * STRIDE + KS;
     // compile-time geometry for the specialised instantiations (square maps), run-time otherwise
@@ -149,23 +157,29 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
                                int64_t frames, int H, int W, int C, int k, int stride, cudaStream_t s) {
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
-    const int strips = (OW + dw_tw(stride) - 1) / dw_tw(stride);
-    const int rpt = dw_rpt(OH), slots = dw_slots(OH, OW, stride);
+    const DwCfg cfg = dw_cfg(C, k, stride, W);
+    const int strips = (OW + cfg.tw - 1) / cfg.tw;
+    const int rpt = dw_rpt(OH), slots = dw_slots(OH, OW, cfg.tw);
     const int items = slots * (C / kDwCH);
     const int bpf = (items + kDwThreads - 1) / kDwThreads;
     if (frames <= 0) return cudaSuccess;
     if ((C & 7) || frames * (int64_t)bpf > 0x7fffffffLL) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)(frames * bpf);
-#define DFD_DW(KS, ST, CC, WW) dwconv_kernel<T, KS, ST, CC, WW><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf, rpt, slots)
-    // the twelve depthwise shapes of EfficientNet-B0 at 224x224 get compile-time geometry
-#define DFD_DW_CASE(KS, ST, CC, WW) if (k == KS && stride == ST && C == CC && W == WW && H == WW) { DFD_DW(KS, ST, CC, WW); return cudaGetLastError(); }
-    DFD_DW_CASE(3, 1, 32, 112) DFD_DW_CASE(3, 2, 96, 112) DFD_DW_CASE(3, 1, 144, 56) DFD_DW_CASE(5, 2, 144, 56)
-    DFD_DW_CASE(5, 1, 240, 28) DFD_DW_CASE(3, 2, 240, 28) DFD_DW_CASE(3, 1, 480, 14) DFD_DW_CASE(5, 1, 480, 14)
-    DFD_DW_CASE(5, 1, 672, 14) DFD_DW_CASE(5, 2, 672, 14) DFD_DW_CASE(5, 1, 1152, 7) DFD_DW_CASE(3, 1, 1152, 7)
-    if (k == 3 && stride == 1) DFD_DW(3, 1, 0, 0);
-    else if (k == 3 && stride == 2) DFD_DW(3, 2, 0, 0);
-    else if (k == 5 && stride == 1) DFD_DW(5, 1, 0, 0);
-    else if (k == 5 && stride == 2) DFD_DW(5, 2, 0, 0);
+#define DFD_DW(KS, ST, CC, WW, TW, MB) dwconv_kernel<T, KS, ST, CC, WW, TW, MB><<<grid, kDwThreads, 0, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, strips, items, bpf, rpt, slots)
+    // the twelve depthwise shapes of EfficientNet-B0 at 224x224 get compile-time geometry;
+    // TW / MB must agree with dw_cfg()
+#define DFD_DW_CASE(KS, ST, CC, WW, TW, MB) if (k == KS && stride == ST && C == CC && W == WW && H == WW && cfg.tw == TW) { DFD_DW(KS, ST, CC, WW, TW, MB); return cudaGetLastError(); }
+    DFD_DW_CASE(3, 1, 32, 112, 4, 3) DFD_DW_CASE(3, 2, 96, 112, 2, 4) DFD_DW_CASE(3, 1, 144, 56, 4, 3) DFD_DW_CASE(5, 2, 144, 56, 4, 3)
+    DFD_DW_CASE(5, 1, 240, 28, 4, 3) DFD_DW_CASE(3, 2, 240, 28, 2, 4) DFD_DW_CASE(3, 1, 480, 14, 8, 2) DFD_DW_CASE(5, 1, 480, 14, 8, 2)
+    DFD_DW_CASE(5, 1, 672, 14, 8, 2) DFD_DW_CASE(5, 2, 672, 14, 4, 3) DFD_DW_CASE(5, 1, 1152, 7, 8, 2) DFD_DW_CASE(3, 1, 1152, 7, 8, 2)
+    // generic geometry (other crop sizes)
+    if (k == 3 && stride == 1 && cfg.tw == 4) DFD_DW(3, 1, 0, 0, 4, 3);
+    else if (k == 3 && stride == 1) DFD_DW(3, 1, 0, 0, 8, 2);
+    else if (k == 5 && stride == 1 && cfg.tw == 4) DFD_DW(5, 1, 0, 0, 4, 3);
+    else if (k == 5 && stride == 1) DFD_DW(5, 1, 0, 0, 8, 2);
+    else if (k == 3 && stride == 2) DFD_DW(3, 2, 0, 0, 2, 4);
+    else if (k == 5 && stride == 2 && cfg.tw == 4) DFD_DW(5, 2, 0, 0, 4, 3);
+    else if (k == 5 && stride == 2) DFD_DW(5, 2, 0, 0, 2, 4);
     else return cudaErrorInvalidValue;
 #undef DFD_DW_CASE
 #undef DFD_DW

@@ -191,11 +191,15 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                     const uint32_t a_base = smem_base + stage * stage_bytes;
                     uint32_t fl = 0, rem = rem0;
                     while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
+                    uint32_t fl_loaded = 0xffffffffu;               // the gate slice is re-read only when the frame changes
+                    uint4 gA = make_uint4(0, 0, 0, 0), gB = gA;
 #pragma unroll
                     for (int j = 0; j < kBM / kXRowStep; ++j) {
                         if (rb + kXRowStep * j < rows_valid) {
-                            const uint32_t gaddr = a_base + g_off + fl * 256 + q * 32;
-                            const uint4 gA = lds16(gaddr), gB = lds16(gaddr + 16);
+                            if (fl != fl_loaded) {
+                                const uint32_t gaddr = a_base + g_off + fl * 256 + q * 32;
+                                gA = lds16(gaddr); gB = lds16(gaddr + 16); fl_loaded = fl;
+                            }
                             const uint32_t addr = a_base + a_off + j * (kXRowStep * 16);
                             uint4 v = lds16(addr);
                             const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);

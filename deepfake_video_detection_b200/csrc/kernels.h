@@ -13,6 +13,11 @@ cudaError_t launch_preprocess(const uint8_t* in, void* out, int64_t frames, int 
 cudaError_t launch_stem(const void* in, int in_kind, const float* w, const float* bias, void* out,
                         int64_t frames, int H, int W, int dtype, cudaStream_t s);
 
+// stem as tcgen05 implicit GEMM for uint8 crops (stem_tc.cu).  w16: 16-bit [32][96] = [w_hi | w_hi | w_lo] per output
+// channel, each block 27 taps ((ky*3+kx)*3+c) zero-padded to 32.
+cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, void* out,
+                           int64_t frames, int H, int W, int dtype, cudaStream_t s);
+
 // K2 (dwconv.cu): depthwise kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU, NHWC, plus the
 // squeeze-excite spatial sums as per-block partials.  w: fp32 [k*k][C], bias fp32 [C].
 // partials: fp32 [frames][dw_num_partials][C] (sums of SiLU outputs over groups of output tiles).

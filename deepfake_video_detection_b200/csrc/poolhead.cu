@@ -24,16 +24,21 @@ __device__ __forceinline__ float warp_max(float x) {
     return x;
 }
 
+constexpr int kPhChunk = 32;          // frames staged in shared memory at a time (32 x 1280 fp32 = 160 KB)
+
 __global__ void __launch_bounds__(kPhThreads)
 pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int32_t* __restrict__ offsets,
                  int use_attention, float* __restrict__ logits, float* __restrict__ frame_scores) {
+    extern __shared__ float s_f[];                 // [kPhChunk][kFeat] features of the current frame chunk
     __shared__ float s_w[kMaxT];
+    __shared__ float s_hid[kPhChunk][kAttHidden + 1];
     __shared__ float s_pooled[kFeat];
     __shared__ float s_h1[kFc1];
     const int v = blockIdx.x;
     const int f0 = offsets[v];
     const int T = offsets[v + 1] - f0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = kPhThreads / 32;
     if (T <= 0 || T > kMaxT) {      // empty / over-long video: poison the outputs instead of guessing
         if (threadIdx.x < 2) logits[(size_t)v * 2 + threadIdx.x] = __int_as_float(0x7fc00000);
         return;
@@ -41,30 +46,32 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
     const float* fv = feat + (size_t)f0 * kFeat;
 
     if (use_attention) {
+        // scores: every W1 row is read ONCE per chunk of frames and applied to all frames staged in shared memory
         const float b2 = __ldg(hw.att_b2);
-        for (int t = warp; t < T; t += kPhThreads / 32) {
-            float x[kFeat / 32];
+        for (int c0 = 0; c0 < T; c0 += kPhChunk) {
+            const int tc = min(kPhChunk, T - c0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < tc * kFeat; i += kPhThreads) s_f[i] = fv[(size_t)c0 * kFeat + i];
+            __syncthreads();
+            for (int h = warp; h < kAttHidden; h += NW) {
+                float wr[kFeat / 32];
 #pragma unroll
-            for (int i = 0; i < kFeat / 32; ++i) x[i] = fv[(size_t)t * kFeat + lane + 32 * i];
-            float score = 0.f;
-            for (int h = 0; h < kAttHidden; h += 4) {          // 4 hidden units at a time: 4x the loads in flight
-                const float* wr = hw.att_w1 + (size_t)h * kFeat + lane;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-                for (int i = 0; i < kFeat / 32; ++i) {
-                    a0 = fmaf(x[i], __ldg(wr + 32 * i), a0);
-                    a1 = fmaf(x[i], __ldg(wr + kFeat + 32 * i), a1);
-                    a2 = fmaf(x[i], __ldg(wr + 2 * kFeat + 32 * i), a2);
-                    a3 = fmaf(x[i], __ldg(wr + 3 * kFeat + 32 * i), a3);
+                for (int i = 0; i < kFeat / 32; ++i) wr[i] = __ldg(hw.att_w1 + (size_t)h * kFeat + lane + 32 * i);
+                const float b1 = __ldg(hw.att_b1 + h), w2 = __ldg(hw.att_w2 + h);
+                for (int t = 0; t < tc; ++t) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kFeat / 32; ++i) acc = fmaf(s_f[t * kFeat + lane + 32 * i], wr[i], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) s_hid[t][h] = fmaxf(acc + b1, 0.f) * w2;          // ReLU then Linear(64,1) term
                 }
-                a0 = warp_sum(a0) + __ldg(hw.att_b1 + h);     a1 = warp_sum(a1) + __ldg(hw.att_b1 + h + 1);
-                a2 = warp_sum(a2) + __ldg(hw.att_b1 + h + 2); a3 = warp_sum(a3) + __ldg(hw.att_b1 + h + 3);
-                score = fmaf(fmaxf(a0, 0.f), __ldg(hw.att_w2 + h), score);
-                score = fmaf(fmaxf(a1, 0.f), __ldg(hw.att_w2 + h + 1), score);
-                score = fmaf(fmaxf(a2, 0.f), __ldg(hw.att_w2 + h + 2), score);
-                score = fmaf(fmaxf(a3, 0.f), __ldg(hw.att_w2 + h + 3), score);
             }
-            if (lane == 0) s_w[t] = 1.0f / (1.0f + expf(-(score + b2)));      // nn.Sigmoid, :70
+            __syncthreads();
+            for (int t = threadIdx.x; t < tc; t += kPhThreads) {
+                float score = 0.f;
+                for (int h = 0; h < kAttHidden; ++h) score += s_hid[t][h];           // fixed order
+                s_w[c0 + t] = 1.0f / (1.0f + expf(-(score + b2)));                   // nn.Sigmoid, :70
+            }
         }
         __syncthreads();
         if (warp == 0) {                                                      // F.softmax(dim=1), :127
@@ -79,8 +86,8 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
         __syncthreads();
         for (int c = threadIdx.x; c < kFeat; c += kPhThreads) {               // (features * w).sum(dim=1), :131
             float acc = 0.f;
-#pragma unroll 4
-            for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c] * s_w[t];
+            if (T <= kPhChunk) { for (int t = 0; t < T; ++t) acc += s_f[t * kFeat + c] * s_w[t]; }   // chunk still staged
+            else { for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c] * s_w[t]; }
             s_pooled[c] = acc;
         }
     } else {
@@ -94,7 +101,7 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
     __syncthreads();
     if (frame_scores) for (int t = threadIdx.x; t < T; t += kPhThreads) frame_scores[f0 + t] = s_w[t];
 
-    for (int j = warp * 4; j < kFc1; j += (kPhThreads / 32) * 4) {           // relu(fc1(.)), :139 — 4 outputs per pass
+    for (int j = warp * 4; j < kFc1; j += NW * 4) {                           // relu(fc1(.)), :139 — 4 outputs per pass
         const float* wr = hw.fc1_w + (size_t)j * kFeat + lane;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
@@ -123,7 +130,10 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
 cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos,
                              int use_attention, float* logits, float* frame_scores, cudaStream_t s) {
     if (videos <= 0) return cudaSuccess;
-    pool_head_kernel<<<(unsigned)videos, kPhThreads, 0, s>>>(hw, feat, offsets, use_attention, logits, frame_scores);
+    const size_t smem = (size_t)kPhChunk * kFeat * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pool_head_kernel<<<(unsigned)videos, kPhThreads, smem, s>>>(hw, feat, offsets, use_attention, logits, frame_scores);
     return cudaGetLastError();
 }
 

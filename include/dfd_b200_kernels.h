@@ -18,6 +18,11 @@ extern "C" {
 int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_bias, void* d_out,
                int64_t frames, int H, int W, int dtype, void* stream);
 
+/* the same stem as a tcgen05/TMEM implicit GEMM for uint8 crops (hi/lo split operands, ~fp32 accuracy).
+ * h_w27x32: HOST fp32 weights in the layout above (split + uploaded inside; synchronous; test/profiling aid). */
+int dfd_k_stem_tc(const uint8_t* d_in, const float* h_w27x32, const float* d_bias, void* d_out,
+                  int64_t frames, int H, int W, int dtype, void* stream);
+
 /* timm conv_dw + bn: depthwise kxk (k 3|5, stride 1|2, pad k/2) + bias + SiLU, plus the squeeze-excite
  * spatial sums as d_partials fp32 [frames][dfd_k_dw_num_partials(OH,OW,C,k,stride)][C].  d_w fp32 [k*k][C]. */
 int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride);

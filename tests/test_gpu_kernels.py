@@ -74,6 +74,26 @@ def test_stem(lib, prec, kind):
     close(out.cpu(), ref, rel)
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("frames,H,W", [(3, 64, 96), (2, 224, 224), (1, 32, 32)])
+def test_stem_tcgen05(lib, prec, frames, H, W):
+    """uint8 stem as tcgen05 implicit GEMM with hi/lo split operands: must agree with the fp32 conv to ~1 output rounding."""
+    from oracle import effnet_b0_oracle as O
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(7)
+    u8 = torch.randint(0, 256, (frames, H, W, 3), dtype=torch.uint8, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(32, generator=g) * 0.2
+    wp = w.permute(2, 3, 1, 0).reshape(27, 32).contiguous()               # host fp32 [(ky*3+kx)*3+c][oc]
+    out = torch.full((frames, H // 2, W // 2, 32), float("nan"), dtype=tdt, device="cuda")
+    u8d, bd = u8.cuda(), b.cuda()
+    chk(lib, lib.dfd_k_stem_tc(u8d.data_ptr(), wp.data_ptr(), bd.data_ptr(), out.data_ptr(), frames, H, W, code, stream()))
+    ref = F.silu(F.conv2d(O.prep_u8_hwc(u8), w, b, 2, 1)).permute(0, 2, 3, 1)
+    close(out.cpu(), ref, rel)
+    if prec == "fp16":      # the split keeps ~fp32 accuracy: error is one fp16 output rounding, not an input/weight rounding
+        assert (out.cpu().float() - ref.to(tdt).float()).abs().max().item() <= 2 * 2.0 ** -10 * ref.abs().max().item() * 0.51
+
+
 DW_SHAPES = [(32, 3, 1, 112), (96, 3, 2, 112), (144, 3, 1, 56), (144, 5, 2, 56), (240, 5, 1, 28), (240, 3, 2, 28),
              (480, 3, 1, 14), (480, 5, 1, 14), (672, 5, 1, 14), (672, 5, 2, 14), (1152, 5, 1, 7), (1152, 3, 1, 7)]
 
