@@ -9,9 +9,9 @@
 // with fp32 accumulation in TMEM: ~22 significant bits, i.e. the fp32 result up to the dropped x_lo*w_lo term.
 //
 // Builder warps do the im2col: one thread = one output pixel; the 27 bytes of its window go through the
-// per-CTA 3x256 fp32 table (the reference's exact prep arithmetic; zero padding is applied AFTER normalisation,
-// as F.conv2d does), are split into hi/lo halves and stored straight into the UMMA canonical K-major
-// no-swizzle layout.  One elected thread issues 6 tcgen05.mma (M=128, N=32, K=16) per tile; epilogue warps
+// per-CTA 3x256 table (the reference's exact fp32 prep arithmetic, already split into a packed hi|lo 16-bit
+// pair; zero padding is applied AFTER normalisation, as F.conv2d does) and are stored straight into the UMMA
+// canonical K-major no-swizzle layout.  One elected thread issues 6 tcgen05.mma (M=128, N=32, K=16) per tile; epilogue warps
 // read TMEM, add the bias, apply SiLU and store 64 contiguous bytes per pixel (NHWC).
 #include "common.cuh"
 #include "kernels.h"
@@ -22,8 +22,9 @@ constexpr int kStBM = 128, kStK = 96, kStN = 32;
 constexpr int kStChunks = kStK / 8;                       // 12 chunks of 8 halves
 constexpr uint32_t kStLboA = kStBM * 16 + 16, kStLboB = kStN * 16 + 16;
 constexpr uint32_t kStAStage = kStChunks * kStLboA;       // 24768 B
-constexpr int kStStages = 4, kStAcc = 8;
-constexpr int kStEpiWarps = 4, kStBuildWarps = 8;         // two builder sets of 128 threads take alternate tiles
+constexpr int kStStages = 6, kStAcc = 8;
+constexpr int kStSets = 4;                                // builder sets of 128 threads taking alternate tiles
+constexpr int kStEpiWarps = 4, kStBuildWarps = 4 * kStSets;
 constexpr int kStThreads = (kStEpiWarps + 1 + kStBuildWarps) * 32;
 
 template <typename T>
@@ -33,7 +34,7 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sp = smem_raw + kStStages * kStAStage;
     uint8_t* s_b = sp;                              sp += kStChunks * kStLboB;
-    float* s_lut = reinterpret_cast<float*>(sp);    sp += 768 * 4;
+    uint32_t* s_lut = reinterpret_cast<uint32_t*>(sp);  sp += 768 * 4;       // [c][u8] -> (hi | lo << 16)
     float* s_bias = reinterpret_cast<float*>(sp);   sp += kStN * 4;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sp);      // full[S], empty[S], tfull[ACC], tempty[ACC]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStStages + 2 * kStAcc);
@@ -43,7 +44,12 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
     const uint32_t bar_tfull = smem_u32(bars + 2 * kStStages), bar_tempty = smem_u32(bars + 2 * kStStages + kStAcc);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (int i = threadIdx.x; i < 768; i += kStThreads) s_lut[i] = prep_value(i >> 8, i & 255);
+    for (int i = threadIdx.x; i < 768; i += kStThreads) {
+        const float v = prep_value(i >> 8, i & 255);
+        const T h = Half16<T>::from_float(v);
+        const T l = Half16<T>::from_float(v - Half16<T>::to_float(h));
+        s_lut[i] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&h)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&l)) << 16);
+    }
     if (threadIdx.x < kStN) s_bias[threadIdx.x] = bias[threadIdx.x];
     for (int i = threadIdx.x; i < kStN * kStChunks; i += kStThreads) {          // W[32][96] -> canonical layout
         const int r = i / kStChunks, q = i - r * kStChunks;
@@ -68,13 +74,13 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
         const int bt = threadIdx.x - (kStEpiWarps + 1) * 32;
         const int set = bt >> 7, row = bt & 127;
         int64_t li = set;
-        for (int64_t tile = blockIdx.x + (int64_t)set * gridDim.x; tile < tiles; tile += 2 * (int64_t)gridDim.x, li += 2) {
+        for (int64_t tile = blockIdx.x + (int64_t)set * gridDim.x; tile < tiles; tile += kStSets * (int64_t)gridDim.x, li += kStSets) {
             const int stage = (int)(li % kStStages);
             const uint32_t phase = (uint32_t)(li / kStStages) & 1u;
             const int64_t pix = tile * kStBM + row;
-            float x[27];
+            uint32_t xw[28];                               // packed (hi | lo << 16) per tap; 0 = zero padding
 #pragma unroll
-            for (int i = 0; i < 27; ++i) x[i] = 0.f;
+            for (int i = 0; i < 28; ++i) xw[i] = 0u;
             if (pix < total) {
                 const int64_t frame = pix / ohw;
                 const int rem = (int)(pix - frame * ohw);
@@ -90,19 +96,18 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
                         const int ix = 2 * ox - 1 + kx;
                         if (ix < 0 || ix >= W) continue;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = s_lut[c * 256 + __ldg(rowp + kx * 3 + c)];
+                        for (int c = 0; c < 3; ++c) xw[(ky * 3 + kx) * 3 + c] = s_lut[c * 256 + __ldg(rowp + kx * 3 + c)];
                     }
                 }
             }
-            // hi/lo split, K layout [hi(27) 0(5) | lo(27) 0(5) | hi(27) 0(5)]
+            // K layout [hi(27) 0(5) | lo(27) 0(5) | hi(27) 0(5)]: pick the hi / lo halves of consecutive taps
             uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float a = (2 * i < 27) ? x[2 * i] : 0.f, b = (2 * i + 1 < 27) ? x[2 * i + 1] : 0.f;
-                const T ah = Half16<T>::from_float(a), bh = Half16<T>::from_float(b);
-                hi[i] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&ah)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&bh)) << 16);
-                lo[i] = Half16<T>::pack(a - Half16<T>::to_float(ah), b - Half16<T>::to_float(bh));
+            for (int i = 0; i < 14; ++i) {
+                hi[i] = __byte_perm(xw[2 * i], xw[2 * i + 1], 0x5410);
+                lo[i] = __byte_perm(xw[2 * i], xw[2 * i + 1], 0x7632);
             }
+            hi[14] = hi[15] = lo[14] = lo[15] = 0u;
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             const uint32_t dst = a_base0 + stage * kStAStage + row * 16;
 #pragma unroll
