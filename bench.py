@@ -203,9 +203,10 @@ def main():
     host.copy_(crops)
     host_logits = torch.empty((V, 2), dtype=torch.float32, pin_memory=True)
 
+    lens = [T] * V
+
     def e2e_step():
-        d = host.to(dev, non_blocking=True)
-        lg, _ = scorer.score(d, offsets)
+        lg, _ = scorer.score_host(host, lens)          # public API: chunked H2D overlapped with scoring
         if world > 1:
             lg = gather_video_logits(lg, total_videos)[rank * V:(rank + 1) * V]
         host_logits.copy_(lg, non_blocking=True)

@@ -90,8 +90,19 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#ifndef DFD_SILU_NR
+#define DFD_SILU_NR 0
+#endif
 __device__ __forceinline__ uint64_t neg_silu2(uint64_t x) {
     const float2 t = f2_unpack(mul2(x, f2_pack(-1.4426950408889634f, -1.4426950408889634f)));
+#if !DFD_SILU_NR
+    {   // two-MUFU form: ex2 + rcp.approx (fewer issue slots, twice the XU work)
+        float r0, r1;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(1.0f + ex2_approx(fminf(t.x, 126.f))));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.0f + ex2_approx(fminf(t.y, 126.f))));
+        return mul2(x, f2_pack(-r0, -r1));
+    }
+#endif
     const uint64_t e = f2_pack(ex2_approx(fminf(t.x, 126.f)), ex2_approx(fminf(t.y, 126.f)));
     const uint64_t d = add2(e, f2_pack(1.f, 1.f));                       // 1 + e^-x  in [1, 2^126]
     const float2 df = f2_unpack(d);

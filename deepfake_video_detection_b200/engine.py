@@ -186,6 +186,54 @@ class FrameScorer:
         return (logits, scores, feat) if return_features else (logits, scores)
 
 
+    def score_host(self, host_crops: torch.Tensor, frames_per_video: Sequence[int], chunk_videos: int = 8,
+                   use_temporal_attention: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """End-to-end scoring of HOST crops: uint8 (F,H,W,3) in (ideally pinned) host memory -> logits (V,2) and
+        frame_scores (F,) on the device.  Videos are processed in chunks; the H2D copy of chunk i+1 runs on a side
+        stream while chunk i is being scored (two device staging buffers), so the PCIe transfer hides behind the
+        kernels.  Per-video results do not depend on the chunking (every reduction is per video, fixed order)."""
+        if host_crops.device.type != "cpu" or host_crops.dtype != torch.uint8 or host_crops.dim() != 4:
+            raise ValueError("score_host expects uint8 (F,H,W,3) crops in host memory")
+        lens = [int(t) for t in frames_per_video]
+        if sum(lens) != host_crops.shape[0]:
+            raise ValueError("frames_per_video does not add up to the number of crops")
+        V = len(lens)
+        logits = torch.empty((V, 2), dtype=torch.float32, device=self.device)
+        scores = torch.empty((host_crops.shape[0],), dtype=torch.float32, device=self.device)
+        if V == 0:
+            return logits, scores
+        main = torch.cuda.current_stream(self.device)
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        chunks, v0, f0 = [], 0, 0
+        while v0 < V:
+            v1 = min(V, v0 + chunk_videos)
+            nf = sum(lens[v0:v1])
+            chunks.append((v0, v1, f0, f0 + nf))
+            v0, f0 = v1, f0 + nf
+        max_f = max(b - a for _, _, a, b in chunks)
+        stage = [torch.empty((max_f,) + tuple(host_crops.shape[1:]), dtype=torch.uint8, device=self.device) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        for i, (va, vb, fa, fb) in enumerate(chunks):
+            slot = i & 1
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(freed[slot])          # the chunk that used this buffer has been scored
+                else:
+                    self._copy_stream.wait_stream(main)
+                stage[slot][: fb - fa].copy_(host_crops[fa:fb], non_blocking=True)
+                ready[slot].record(self._copy_stream)
+            main.wait_event(ready[slot])
+            lg, sc = self.score(stage[slot][: fb - fa], make_offsets(lens[va:vb], self.device), use_temporal_attention)
+            logits[va:vb].copy_(lg)
+            scores[fa:fb].copy_(sc)
+            freed[slot].record(main)
+        for t in stage:
+            t.record_stream(main)
+        return logits, scores
+
+
 def make_offsets(frames_per_video: Sequence[int], device) -> torch.Tensor:
     """Host-side validation + upload of ragged video lengths (each video needs 1..1024 frames)."""
     lens = [int(t) for t in frames_per_video]
