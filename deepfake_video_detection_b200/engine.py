@@ -186,12 +186,16 @@ class FrameScorer:
         return (logits, scores, feat) if return_features else (logits, scores)
 
 
-    def score_host(self, host_crops: torch.Tensor, frames_per_video: Sequence[int], chunk_videos: int = 8,
+    def score_host(self, host_crops: torch.Tensor, frames_per_video: Sequence[int], chunk_videos: Optional[int] = None,
                    use_temporal_attention: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """End-to-end scoring of HOST crops: uint8 (F,H,W,3) in (ideally pinned) host memory -> logits (V,2) and
-        frame_scores (F,) on the device.  Videos are processed in chunks; the H2D copy of chunk i+1 runs on a side
-        stream while chunk i is being scored (two device staging buffers), so the PCIe transfer hides behind the
-        kernels.  Per-video results do not depend on the chunking (every reduction is per video, fixed order)."""
+        frame_scores (F,) on the device, asynchronously (nothing here waits for the GPU).
+
+        The H2D copy runs on a side stream into one of two persistent device staging buffers, so the transfer of
+        one call (or chunk) overlaps the scoring of the previous one; back-to-back calls therefore run at
+        max(copy, compute) per batch instead of copy + compute.  `host_crops` must stay unmodified until the
+        returned tensors are consumed (usual async-copy contract).  `chunk_videos` splits a call into chunks
+        (smaller staging buffers; per-video results do not depend on the chunking)."""
         if host_crops.device.type != "cpu" or host_crops.dtype != torch.uint8 or host_crops.dim() != 4:
             raise ValueError("score_host expects uint8 (F,H,W,3) crops in host memory")
         lens = [int(t) for t in frames_per_video]
@@ -203,34 +207,45 @@ class FrameScorer:
         if V == 0:
             return logits, scores
         main = torch.cuda.current_stream(self.device)
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(self.device)
+        chunk_videos = V if not chunk_videos else int(chunk_videos)
         chunks, v0, f0 = [], 0, 0
         while v0 < V:
             v1 = min(V, v0 + chunk_videos)
             nf = sum(lens[v0:v1])
             chunks.append((v0, v1, f0, f0 + nf))
             v0, f0 = v1, f0 + nf
-        max_f = max(b - a for _, _, a, b in chunks)
-        stage = [torch.empty((max_f,) + tuple(host_crops.shape[1:]), dtype=torch.uint8, device=self.device) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        freed = [torch.cuda.Event() for _ in range(2)]
-        for i, (va, vb, fa, fb) in enumerate(chunks):
-            slot = i & 1
-            with torch.cuda.stream(self._copy_stream):
-                if i >= 2:
-                    self._copy_stream.wait_event(freed[slot])          # the chunk that used this buffer has been scored
-                else:
-                    self._copy_stream.wait_stream(main)
-                stage[slot][: fb - fa].copy_(host_crops[fa:fb], non_blocking=True)
-                ready[slot].record(self._copy_stream)
-            main.wait_event(ready[slot])
-            lg, sc = self.score(stage[slot][: fb - fa], make_offsets(lens[va:vb], self.device), use_temporal_attention)
+        need = max(b - a for _, _, a, b in chunks) * host_crops[0].numel()
+        st = getattr(self, "_staging", None)
+        if st is None or st["bytes"] < need:
+            st = {"bytes": need, "copy_stream": torch.cuda.Stream(self.device), "turn": 0,
+                  "buf": [torch.empty(need, dtype=torch.uint8, device=self.device) for _ in range(2)],
+                  "freed": [None, None]}
+            self._staging = st
+        cs = st["copy_stream"]
+        frame_shape = tuple(host_crops.shape[1:])
+        for (va, vb, fa, fb) in chunks:
+            slot = st["turn"] & 1
+            st["turn"] += 1
+            dst = st["buf"][slot][: (fb - fa) * host_crops[0].numel()].view((fb - fa,) + frame_shape)
+            with torch.cuda.stream(cs):
+                if st["freed"][slot] is not None:
+                    cs.wait_event(st["freed"][slot])               # the batch that last used this buffer has been scored
+                dst.copy_(host_crops[fa:fb], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cs)
+            main.wait_event(ready)
+            key = tuple(lens[va:vb])
+            cache = self.__dict__.setdefault("_offsets_cache", {})
+            if key not in cache:                                   # small H2D upload, once per distinct length pattern
+                if len(cache) > 64:
+                    cache.clear()
+                cache[key] = make_offsets(key, self.device)
+            lg, sc = self.score(dst, cache[key], use_temporal_attention)
             logits[va:vb].copy_(lg)
             scores[fa:fb].copy_(sc)
-            freed[slot].record(main)
-        for t in stage:
-            t.record_stream(main)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            st["freed"][slot] = ev
         return logits, scores
 
 
