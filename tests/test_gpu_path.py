@@ -113,3 +113,57 @@ def test_errors_are_loud(scorer):
         scorer.features(torch.zeros((1, 224, 224, 3), dtype=torch.uint8))          # CPU tensor
     with pytest.raises(RuntimeError):
         scorer.features(torch.zeros((1, 100, 100, 3), dtype=torch.uint8, device="cuda"))   # unsupported size
+
+
+def test_score_host_matches_device_path(scorer, golden_crops):
+    """Public end-to-end entry (pinned host crops, overlapped H2D): same bits as scoring device-resident crops."""
+    from deepfake_video_detection_b200 import make_offsets
+    crops, offsets = golden_crops
+    lens = np.diff(offsets).tolist()
+    host = torch.from_numpy(crops).pin_memory()
+    ref_l, ref_s = scorer.score(torch.from_numpy(crops).cuda(), make_offsets(lens, "cuda"))
+    for chunk in (None, 3, 1):
+        for _ in range(2):                                  # second call reuses the staging buffers
+            lg, sc = scorer.score_host(host, lens, chunk_videos=chunk)
+            assert torch.equal(lg, ref_l) and torch.equal(sc, ref_s)
+
+
+def test_full_c2_batch_properties(scorer, synth_sd):
+    """BASELINE configs[1] size (64 videos x 32 crops): size-independent properties + spot parity against the oracle."""
+    from deepfake_video_detection_b200 import decide, make_offsets
+    from oracle import effnet_b0_oracle as O
+    V, T = 64, 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    crops = torch.randint(0, 256, (V * T, 224, 224, 3), dtype=torch.uint8, device="cuda", generator=g)
+    off = make_offsets([T] * V, "cuda")
+    logits, scores = scorer.score(crops, off)
+    assert torch.isfinite(logits).all() and torch.isfinite(scores).all()
+    assert torch.allclose(scores.view(V, T).sum(1), torch.ones(V, device="cuda"), atol=1e-5)       # softmax over T per video
+    # batch invariance: a video scored alone, or in a permuted batch, gives the same bits as inside the big batch
+    for v in (0, 17, 63):
+        lg1, sc1 = scorer.score(crops[v * T:(v + 1) * T], make_offsets([T], "cuda"))
+        assert torch.equal(lg1[0], logits[v]) and torch.equal(sc1, scores[v * T:(v + 1) * T])
+    perm = torch.randperm(V, generator=torch.Generator().manual_seed(1))
+    crops_p = crops.view(V, T, 224, 224, 3)[perm.cuda()].reshape(V * T, 224, 224, 3).contiguous()
+    lg_p, _ = scorer.score(crops_p, off)
+    assert torch.equal(lg_p, logits[perm.cuda()])
+    # spot parity against the fp32 oracle on two videos (uniform-noise crops are a harsh input: loose but meaningful)
+    for v in (3, 40):
+        ref, _ = O.score_ragged(synth_sd, crops[v * T:(v + 1) * T].cpu().numpy(), np.array([0, T]))
+        assert (logits[v].cpu() - ref[0]).abs().max().item() <= 2e-2
+        assert decide(logits[v:v + 1])[0]["is_fake"] == O.decide(ref)[0]["is_fake"] or abs(O.decide(ref)[0]["prob_fake"] - 0.5) < 1e-2
+
+
+def test_ragged_extremes(scorer):
+    """T = 1 and T = 64 (the reference clamps MAX_FRAMES to 1..64, app.py:2053) in one call; empty batch."""
+    from deepfake_video_detection_b200 import make_offsets
+    g = torch.Generator(device="cuda").manual_seed(9)
+    crops = torch.randint(0, 256, (65, 224, 224, 3), dtype=torch.uint8, device="cuda", generator=g)
+    logits, scores = scorer.score(crops, make_offsets([1, 64], "cuda"))
+    assert scores[0].item() == 1.0 and abs(scores[1:].sum().item() - 1.0) < 1e-5
+    l0, _ = scorer.score(crops[:1], make_offsets([1], "cuda"))
+    assert torch.equal(l0[0], logits[0])
+    e_l, e_s = scorer.score(crops[:0], make_offsets([], "cuda"))
+    assert e_l.shape == (0, 2) and e_s.shape == (0,)
+    with pytest.raises(ValueError):
+        make_offsets([0, 3], "cuda")
