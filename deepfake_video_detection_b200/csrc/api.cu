@@ -342,11 +342,14 @@ int dfd_preprocess_u8hwc_to_nchw(const uint8_t* d_in, void* d_out, int64_t frame
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
+// project layers on maps with at least this many pixels fold the SE gate into per-frame weights (gemm_tc.cu)
+constexpr int kFrameWeightsMinHW = 784;
+
 struct Plan {
-    size_t io_elems, e_elems, d_elems, part_floats, gate_floats;     // per frame
+    size_t io_elems, e_elems, d_elems, part_floats, gate_floats, wf_elems;     // per frame
     size_t per_frame_bytes() const {
         auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
-        return 2 * up(io_elems * 2) + up(e_elems * 2) + up(d_elems * 2) + up(part_floats * 4) + up(gate_floats * 4);
+        return 2 * up(io_elems * 2) + up(e_elems * 2) + up(d_elems * 2) + up(part_floats * 4) + up(gate_floats * 4) + up(wf_elems * 2);
     }
 };
 
@@ -366,6 +369,7 @@ Plan make_plan(int H, int W) {
             p.d_elems = std::max(p.d_elems, (size_t)oh * ow * mid);
             p.part_floats = std::max(p.part_floats, (size_t)dfd::dw_num_partials(oh, ow, mid, k, st) * mid);
             p.gate_floats = std::max(p.gate_floats, (size_t)mid);
+            if (oh * ow >= kFrameWeightsMinHW) p.wf_elems = std::max(p.wf_elems, (size_t)mid * cout);
             p.io_elems = std::max(p.io_elems, (size_t)oh * ow * cout);
             h = oh; w = ow; cin = cout;
         }
@@ -394,7 +398,8 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
     uint8_t* bufE = ws;                          ws += up(plan.e_elems * 2) * frames;
     uint8_t* bufD = ws;                          ws += up(plan.d_elems * 2) * frames;
     float* part = reinterpret_cast<float*>(ws);  ws += up(plan.part_floats * 4) * frames;
-    float* gate = reinterpret_cast<float*>(ws);
+    float* gate = reinterpret_cast<float*>(ws);  ws += up(plan.gate_floats * 4) * frames;
+    uint8_t* bufWf = ws;
     const int dt = w->dtype;
 
     int h = H / 2, wd = W / 2, cur = 0;
@@ -420,9 +425,18 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         prof_next(KC_SE, (double)frames * B.mid * (nparts + 1) * 4, 4.0 * frames * B.mid * B.rd, s);
         DFD_LAUNCH(dfd::launch_se(part, nparts, 1.0f / (float)(oh * ow), B.se_w1, B.se_b1, B.se_w2t, B.se_b2, gate,
                                   frames, B.mid, B.rd, s), "squeeze-excite kernel");
-        int rc = run_gemm(bufD, B.proj_w, B.proj_b, gate, B.has_skip ? x : nullptr, io[cur ^ 1],
-                          frames * oh * ow, B.mid, B.cout, oh * ow, 0, dt, s);
-        if (rc) return rc;
+        if (oh * ow >= kFrameWeightsMinHW && !use_simt_gemm()) {
+            // big maps: SE gate folded into per-frame weights, ungated GEMM on frame-aligned tiles
+            prof_next(KC_GEMM_PROJECT, (double)frames * B.cout * B.mid * 2 * 2, 0, s);
+            DFD_LAUNCH(dfd::launch_scale_weights(B.proj_w, gate, bufWf, frames, B.cout, B.mid, dt, s), "per-frame weight scaling");
+            prof_next(KC_GEMM_PROJECT, (double)frames * oh * ow * (B.mid + B.cout + (B.has_skip ? B.cout : 0)) * 2, 2.0 * frames * oh * ow * B.mid * B.cout, s);
+            DFD_LAUNCH(dfd::launch_gemm_tc_framew(bufD, bufWf, B.proj_b, B.has_skip ? x : nullptr, io[cur ^ 1],
+                                                  frames * oh * ow, B.mid, B.cout, oh * ow, dt, s), "gemm (tcgen05, per-frame weights)");
+        } else {
+            int rc = run_gemm(bufD, B.proj_w, B.proj_b, gate, B.has_skip ? x : nullptr, io[cur ^ 1],
+                              frames * oh * ow, B.mid, B.cout, oh * ow, 0, dt, s);
+            if (rc) return rc;
+        }
         cur ^= 1; h = oh; wd = ow;
     }
     prof_next(KC_GEMM_HEAD_POOL, (double)frames * h * wd * 320 * 2 + (double)frames * 1280 * 4, 2.0 * frames * h * wd * 320 * 1280, s);
@@ -574,6 +588,19 @@ int dfd_k_se(const float* d_partials, int nparts, float inv_hw, const float* d_w
 int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const float* d_gate, const void* d_R, void* d_D,
                int64_t M, int K, int N, int HW, int act, int dtype, int impl, void* stream) {
     g_launches = 0;
+    if (impl == 2) {                 // gated project conv via per-frame weights (needs gate, act == 0, M % HW == 0)
+        if (!d_gate || act || HW <= 0 || (M % HW)) return fail(DFD_EINVAL, "dfd_k_gemm impl 2: needs a gate, act == 0 and M % HW == 0");
+        void* wf = nullptr;
+        DFD_CUDA(cudaMalloc(&wf, (size_t)(M / HW) * N * K * 2), "cudaMalloc(per-frame weights)");
+        cudaError_t e = dfd::launch_scale_weights(d_W, d_gate, wf, M / HW, N, K, dtype, (cudaStream_t)stream);
+        if (e == cudaSuccess) e = dfd::launch_gemm_tc_framew(d_A, wf, d_bias, d_R, d_D, M, K, N, HW, dtype, (cudaStream_t)stream);
+        g_launches = 2;
+        cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(wf);
+        if (e != cudaSuccess) return cuda_fail(e, "gemm (tcgen05, per-frame weights)");
+        if (e2 != cudaSuccess) return cuda_fail(e2, "gemm (tcgen05, per-frame weights) sync");
+        return DFD_OK;
+    }
     if (impl == 1) DFD_LAUNCH(dfd::launch_gemm_simt(d_A, d_W, d_bias, d_gate, d_R, d_D, nullptr, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (simt)");
     else DFD_LAUNCH(dfd::launch_gemm_tc(d_A, d_W, d_bias, d_gate, d_R, d_D, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (tcgen05)");
     return DFD_OK;

@@ -42,6 +42,8 @@ struct GemmArgs {
     int NB, NBp, n_chunks;          // columns per work unit, padded to 16, units along N
     int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
     int64_t m_tiles;
+    int tpf;                        // > 0: frame-aligned tiling (tpf tiles per frame, the last one partial) with per-frame weights
+    int64_t w_frame_stride;         // elements between the weight matrices of consecutive frames (frame-aligned mode)
     int stages;
     int nacc, na;                   // TMEM accumulator buffers; epilogue group sets that take alternate tiles
     int nf_max, total_frames;       // gated: frames a tile can touch, frames in the tensor
@@ -51,6 +53,20 @@ struct GemmArgs {
     uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
 };
+
+// first row, valid rows and frame of M-tile `mt` (linear tiling, or frame-aligned tiling for per-frame weights)
+__device__ __forceinline__ void tile_origin(const GemmArgs& p, int64_t mt, int64_t& m0, int& rows_valid, int64_t& frame) {
+    if (p.tpf > 0) {
+        frame = mt / p.tpf;
+        const int t = (int)(mt - frame * p.tpf);
+        m0 = frame * p.HW + (int64_t)t * kBM;
+        rows_valid = min(kBM, p.HW - t * kBM);
+    } else {
+        frame = 0;
+        m0 = mt * p.rows_per_tile;
+        rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+    }
+}
 
 template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
@@ -130,8 +146,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
             const int64_t mt = u / p.n_chunks;
             const int nc = (int)(u - mt * p.n_chunks);
-            const int64_t m0 = mt * p.rows_per_tile;
-            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            int64_t m0, wframe; int rows_valid;
+            tile_origin(p, mt, m0, rows_valid, wframe);
             const int n0 = nc * p.NB;
             const int nb_valid = min(p.NB, p.N - n0);
             const uint32_t f0 = GATE ? (uint32_t)m0 / (uint32_t)p.HW : 0u;
@@ -150,10 +166,10 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                     }
                     if (!p.b_resident) {
                         const uint32_t b_base = a_base + p.a_stage_bytes;
-                        const T* wsrc = Wt + (size_t)(n0 + rb) * p.K + k0 + q * 8;
+                        const T* wsrc = Wt + (size_t)wframe * p.w_frame_stride + (size_t)(n0 + rb) * p.K + k0 + q * 8;
                         for (int r = rb; r < p.NBp; r += kRowStep) {
                             const bool ok = (r < nb_valid) && (q < kc);
-                            cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * p.K : Wt, ok);
+                            cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * p.K : Wt, ok);   // per-frame weights when tpf > 0
                         }
                     }
                 }
@@ -180,8 +196,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         int stage = 0; uint32_t phase = 0;
         for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
             const int64_t mt = u / p.n_chunks;
-            const int64_t m0 = mt * p.rows_per_tile;
-            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            int64_t m0, wframe; int rows_valid;
+            tile_origin(p, mt, m0, rows_valid, wframe);
             const uint32_t f0 = (uint32_t)m0 / (uint32_t)p.HW;
             const uint32_t rem0 = (uint32_t)m0 - f0 * (uint32_t)p.HW + rb;      // row rb relative to frame f0
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -265,8 +281,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             const uint32_t acc_phase = (uint32_t)(li / p.nacc) & 1u;
             const int64_t mt = u / p.n_chunks;
             const int nc = (int)(u - mt * p.n_chunks);
-            const int64_t m0 = mt * p.rows_per_tile;
-            const int rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+            int64_t m0, wframe; int rows_valid;
+            tile_origin(p, mt, m0, rows_valid, wframe);
             const int n0 = nc * p.NB;
             const int nb_valid = min(p.NB, p.N - n0);
             const bool valid = row < rows_valid;
@@ -401,7 +417,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
     const size_t budget = 227 * 1024;
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
-    a.b_resident = (bres <= 120 * 1024) ? 1 : 0;
+    a.b_resident = (bres <= 120 * 1024 && a.tpf == 0) ? 1 : 0;
     a.b_res_bytes = a.b_resident ? (uint32_t)bres : 0u;
     const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes;
     int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
@@ -440,6 +456,44 @@ cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, cons
     a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
     if (dtype == kDtypeFP16) return launch_t<__half>(a, act, s);
     return launch_t<__nv_bfloat16>(a, act, s);
+}
+
+// Project conv with the SE gate folded into per-frame weights Wf[frame][N][K] (scale_weights kernel): tiles are
+// frame-aligned so every tile uses one weight matrix and the A operand needs no transformation.
+cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bias, const void* R, void* D,
+                                  int64_t M, int K, int N, int HW, int dtype, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((K & 7) || (N & 7) || K < 8 || N < 8 || HW <= 0 || (M % HW) != 0) return cudaErrorInvalidValue;
+    GemmArgs a{};
+    a.A = A; a.W = Wf; a.bias = bias; a.gate = nullptr; a.R = R; a.D = D; a.feat = nullptr;
+    a.M = M; a.K = K; a.N = N; a.HW = HW;
+    a.tpf = (HW + kBM - 1) / kBM; a.w_frame_stride = (int64_t)N * K;
+    a.rows_per_tile = kBM; a.m_tiles = (M / HW) * a.tpf; a.inv_hw = 0.f;
+    if (dtype == kDtypeFP16) return launch_t<__half>(a, 0, s);
+    return launch_t<__nv_bfloat16>(a, 0, s);
+}
+
+template <typename T>
+__global__ void scale_weights_kernel(const T* __restrict__ W, const float* __restrict__ gate, T* __restrict__ Wf, int N, int K, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 2 consecutive k
+    if (i >= total) return;
+    const int k2 = (int)(i % (K / 2));
+    const int64_t fn = i / (K / 2);
+    const int n = (int)(fn % N);
+    const int64_t f = fn / N;
+    const uint32_t w = reinterpret_cast<const uint32_t*>(W)[(size_t)n * (K / 2) + k2];
+    const float2 g = *reinterpret_cast<const float2*>(gate + (size_t)f * K + 2 * k2);
+    const float2 x = Half16<T>::unpack(w);
+    reinterpret_cast<uint32_t*>(Wf)[i] = Half16<T>::pack(x.x * g.x, x.y * g.y);
+}
+// Wf[f][n][k] = W[n][k] * gate[f][k]
+cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int dtype, cudaStream_t s) {
+    const int64_t total = frames * N * (K / 2);
+    if (total <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (dtype == kDtypeFP16) scale_weights_kernel<__half><<<grid, 256, 0, s>>>((const __half*)W, gate, (__half*)Wf, N, K, total);
+    else scale_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, gate, (__nv_bfloat16*)Wf, N, K, total);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, float* D,

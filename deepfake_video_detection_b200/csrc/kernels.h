@@ -34,6 +34,11 @@ cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const flo
 // A, W, R, D 16-bit; bias fp32 [N]; gate fp32 [M/HW][K] or null; R [M,N] or null; act: 0 none, 1 SiLU.
 cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, const float* gate, const void* R,
                            void* D, int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s);
+// gated project conv for big maps (HW >= 784): fold the SE gate into per-frame weights, then an ungated GEMM on
+// frame-aligned tiles.  Wf: 16-bit [frames][N][K] scratch.
+cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int dtype, cudaStream_t s);
+cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bias, const void* R, void* D,
+                                  int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
 // plain D[M,N] (fp32) = A[M,K] * W[N,K]^T + bias — gate pre-activations of the recurrent head (rnn.cu)
 cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, float* D,
                                   int64_t M, int K, int N, int dtype, cudaStream_t s);

@@ -35,8 +35,9 @@ int dfd_k_se(const float* d_partials, int nparts, float inv_hw, const float* d_w
              const float* d_w2t, const float* d_b2, float* d_gate, int64_t frames, int C, int rd, void* stream);
 
 /* pointwise conv: D[M,N] = act((A .* gate)[M,K] * W[N,K]^T + bias) (+ R).  gate fp32 [M/HW][K] or NULL,
- * R [M,N] or NULL, act 0|1 (SiLU).  impl 0 = tcgen05/TMEM kernel (the product path), 1 = CUDA-core
- * bring-up kernel with identical rounding points. */
+ * R [M,N] or NULL, act 0|1 (SiLU).  impl 0 = tcgen05/TMEM kernel (the product path; gate applied to the A operand),
+ * 1 = CUDA-core bring-up kernel with identical rounding points, 2 = tcgen05 kernel with the gate folded into per-frame
+ * weights on frame-aligned tiles (what the engine uses for maps of >= 784 pixels; synchronous in this test entry). */
 int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const float* d_gate, const void* d_R,
                void* d_D, int64_t M, int K, int N, int HW, int act, int dtype, int impl, void* stream);
 

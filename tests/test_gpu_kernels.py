@@ -184,6 +184,27 @@ def test_gemm_tcgen05_gate_residual(lib, K, N, HW):
     _gemm_case(lib, "fp16", K, N, HW, 3, gate=True, res=True, act=False, impl=0)
 
 
+@pytest.mark.parametrize("K,N,HW,res", [(32, 16, 12544, False), (96, 24, 3136, False), (144, 24, 3136, True), (144, 40, 784, False), (240, 40, 784, True)])
+def test_gemm_tcgen05_per_frame_weights(lib, K, N, HW, res):
+    """Project convs of the big maps: SE gate folded into per-frame weights, frame-aligned tiles (partial last tile)."""
+    code, tdt, rel = DT["fp16"]
+    g = torch.Generator().manual_seed(K + N)
+    frames = 3
+    M = frames * HW
+    A = torch.randn(M, K, generator=g).to(tdt); Wt = (torch.randn(N, K, generator=g) / K ** 0.5).to(tdt)
+    bias = torch.randn(N, generator=g) * 0.3; G = torch.rand(frames, K, generator=g)
+    R = torch.randn(M, N, generator=g).to(tdt) if res else None
+    D = torch.full((M, N), float("nan"), dtype=tdt, device="cuda")
+    dev = [t.cuda() for t in (A, Wt, bias, G)] + ([R.cuda()] if res else [])
+    chk(lib, lib.dfd_k_gemm(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr() if res else None,
+                            D.data_ptr(), M, K, N, HW, 0, code, 2, stream()))
+    wf = (Wt.float().view(1, N, K) * G.view(frames, 1, K)).to(tdt).double()                  # weights are re-rounded, not activations
+    ref = torch.einsum("fmk,fnk->fmn", A.double().view(frames, HW, K), wf).reshape(M, N) + bias.double()
+    if res:
+        ref = ref + R.double()
+    close(D.cpu(), ref.float(), rel)
+
+
 @pytest.mark.parametrize("M_frames,HW", [(1, 49), (1, 1), (3, 127), (2, 129)])
 def test_gemm_tcgen05_ragged_m(lib, M_frames, HW):
     _gemm_case(lib, "fp16", 96, 24, HW, M_frames, gate=True, res=False, act=False, impl=0)
