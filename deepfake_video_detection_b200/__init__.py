@@ -7,11 +7,11 @@ Public surface (mirrors the reference):
     FrameScorer, PackedWeights, make_offsets          high-throughput engine over the C ABI (include/dfd_b200.h)
 """
 from .decision import decide, imagenet_normalize
-from .engine import DEFAULT_PRECISION, FrameScorer, PackedWeights, make_offsets
+from .engine import DEFAULT_PRECISION, FrameScorer, GraphedScorer, PackedWeights, make_offsets
 from .pretrained_detector import EnsembleDetector, PretrainedBackboneDetector
 from .rnn_model import LogicCell, LogicRNNLSTM, create_model
 from .sharding import gather_video_logits, score_videos_sharded, shard_bounds
 
 __all__ = ["PretrainedBackboneDetector", "EnsembleDetector", "imagenet_normalize", "decide", "FrameScorer",
-           "PackedWeights", "make_offsets", "DEFAULT_PRECISION", "shard_bounds", "gather_video_logits",
+           "PackedWeights", "GraphedScorer", "make_offsets", "DEFAULT_PRECISION", "shard_bounds", "gather_video_logits",
            "score_videos_sharded", "LogicCell", "LogicRNNLSTM", "create_model"]

@@ -8,9 +8,9 @@
 
 namespace dfd {
 
-constexpr int kSeFrames = 8;
 constexpr int kSeThreads = 256;
 
+template <int kSeFrames>
 __global__ void __launch_bounds__(kSeThreads)
 se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
           const float* __restrict__ w1, const float* __restrict__ b1,
@@ -81,20 +81,24 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
     }
 }
 
+template <int FPB>
+static cudaError_t launch_se_t(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,
+                               const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s) {
+    const size_t smem = (size_t)FPB * (C + rd) * sizeof(float);
+    if (smem > 64 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(se_kernel<FPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((frames + FPB - 1) / FPB);
+    se_kernel<FPB><<<grid, kSeThreads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,
                       const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s) {
     if (frames <= 0) return cudaSuccess;
-    const size_t smem = (size_t)kSeFrames * (C + rd) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
-    if (smem > 64 * 1024) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)((frames + kSeFrames - 1) / kSeFrames);
-    se_kernel<<<grid, kSeThreads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
-    return cudaGetLastError();
+    // wide layers do more FC work per frame: fewer frames per CTA keeps enough CTAs in flight
+    if (C >= 480) return launch_se_t<2>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, s);
+    return launch_se_t<8>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, s);
 }
 
 }  // namespace dfd

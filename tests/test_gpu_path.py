@@ -174,3 +174,16 @@ def test_ragged_extremes(scorer):
     assert e_l.shape == (0, 2) and e_s.shape == (0,)
     with pytest.raises(ValueError):
         make_offsets([0, 3], "cuda")
+
+
+def test_cuda_graph_capture_matches_eager(scorer, golden_crops):
+    """The whole step captured into one CUDA graph (small-batch latency path) gives the same bits as eager launches."""
+    from deepfake_video_detection_b200 import make_offsets
+    crops, offsets = golden_crops
+    lens = np.diff(offsets).tolist()
+    x = torch.from_numpy(crops).cuda()
+    ref_l, ref_s = scorer.score(x, make_offsets(lens, "cuda"))
+    g = scorer.capture(lens)
+    for _ in range(2):
+        lg, sc = g.run(x)
+        assert torch.equal(lg, ref_l) and torch.equal(sc, ref_s)
