@@ -93,7 +93,23 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 #ifndef DFD_SILU_NR
 #define DFD_SILU_NR 0
 #endif
+#ifndef DFD_SILU_TANH
+#define DFD_SILU_TANH 1
+#endif
+// x*sigmoid(x) = h + h*tanh(h), h = x/2: ONE MUFU (tanh.approx.f32, rel. error 2^-11) and two FMA-pipe ops.
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 __device__ __forceinline__ uint64_t neg_silu2(uint64_t x) {
+#if DFD_SILU_TANH
+    {
+        const float2 xf = f2_unpack(x);
+        return f2_pack(-silu_tanh(xf.x), -silu_tanh(xf.y));
+    }
+#endif
     const float2 t = f2_unpack(mul2(x, f2_pack(-1.4426950408889634f, -1.4426950408889634f)));
 #if !DFD_SILU_NR
     {   // two-MUFU form: ex2 + rcp.approx (fewer issue slots, twice the XU work)

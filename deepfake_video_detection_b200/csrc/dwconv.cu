@@ -45,6 +45,9 @@ int dw_num_partials(int OH, int OW, int C, int k, int stride) { return dw_slots(
 
 // x * sigmoid(x) with raw MUFU ex2 + rcp (no range fix-ups: e = inf -> rcp = 0 -> -0, which is the limit)
 __device__ __forceinline__ float silu_fast(float x) {
+#if DFD_SILU_TANH
+    return silu_tanh(x);
+#endif
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(-1.4426950408889634f * x)));
     return x * r;
