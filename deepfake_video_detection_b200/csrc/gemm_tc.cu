@@ -48,7 +48,8 @@ struct GemmArgs {
     int nacc, na;                   // TMEM accumulator buffers; epilogue group sets that take alternate tiles
     int nf_max, total_frames;       // gated: frames a tile can touch, frames in the tensor
     uint32_t g_stage_bytes;         // gated: bytes of the per-stage gate slice [nf_max][64] fp32
-    int b_resident;                 // whole W lives in shared memory for the CTA's lifetime
+    int b_resident;                 // 1: whole W lives in shared memory for the CTA's lifetime; 2: only the CTA's own
+                                    //    column chunk (grid is a multiple of n_chunks, so a CTA always works on the same chunk)
     int kchunks_pad;                // K/8 rounded up to even
     uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
@@ -111,13 +112,15 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
         const T* Wt = reinterpret_cast<const T*>(p.W);
         const int kch = p.K >> 3, per = p.NBp * p.kchunks_pad;
-        for (int c = 0; c < p.n_chunks; ++c) {
+        const int c_lo = p.b_resident == 2 ? (int)(blockIdx.x % p.n_chunks) : 0;
+        const int c_hi = p.b_resident == 2 ? c_lo + 1 : p.n_chunks;
+        for (int c = c_lo; c < c_hi; ++c) {
             const int nbv = min(p.NB, p.N - c * p.NB);
+            const uint32_t dst = bres_base + (p.b_resident == 2 ? 0 : c * p.b_chunk_bytes);
             for (int i = tp; i < per; i += kProdThreads) {
                 const int r = i / p.kchunks_pad, q = i - r * p.kchunks_pad;
                 const bool ok = r < nbv && q < kch;
-                cp_async16(bres_base + c * p.b_chunk_bytes + q * p.lbo_b + r * 16,
-                           ok ? Wt + (size_t)(c * p.NB + r) * p.K + q * 8 : Wt, ok);
+                cp_async16(dst + q * p.lbo_b + r * 16, ok ? Wt + (size_t)(c * p.NB + r) * p.K + q * 8 : Wt, ok);
             }
         }
         cp_async_commit();
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_base = smem_base + stage * stage_bytes;
-                    const uint32_t b_base = p.b_resident ? bres_base + nc * p.b_chunk_bytes + kb * 8 * p.lbo_b
+                    const uint32_t b_base = p.b_resident ? bres_base + (p.b_resident == 2 ? 0 : nc * p.b_chunk_bytes) + kb * 8 * p.lbo_b
                                                          : a_base + p.a_stage_bytes;
                     for (int j = 0; j < steps; ++j) {
                         const uint64_t adesc = umma_smem_desc(a_base + 2 * j * kLboA, kLboA, 128);
@@ -417,8 +420,13 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
     const size_t budget = 227 * 1024;
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
-    a.b_resident = (bres <= 120 * 1024 && a.tpf == 0) ? 1 : 0;
-    a.b_res_bytes = a.b_resident ? (uint32_t)bres : 0u;
+    const size_t res_limit = 152 * 1024;                              // leaves >= 3 A stages
+    a.b_resident = 0;
+    if (a.tpf == 0) {
+        if (bres <= res_limit) a.b_resident = 1;
+        else if (a.n_chunks > 1 && a.n_chunks <= g_num_sms && a.b_chunk_bytes <= res_limit) a.b_resident = 2;
+    }
+    a.b_res_bytes = a.b_resident == 1 ? (uint32_t)bres : (a.b_resident == 2 ? a.b_chunk_bytes : 0u);
     const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes;
     int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -428,7 +436,9 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t units = a.m_tiles * a.n_chunks;
-    const unsigned grid = (unsigned)(units < g_num_sms ? units : g_num_sms);
+    unsigned grid = (unsigned)(units < g_num_sms ? units : g_num_sms);
+    if (a.b_resident == 2) grid = (unsigned)((g_num_sms / a.n_chunks) * a.n_chunks);     // every CTA keeps one column chunk
+    if ((int64_t)grid > units) grid = (unsigned)units;
     kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
