@@ -187,3 +187,24 @@ def test_cuda_graph_capture_matches_eager(scorer, golden_crops):
     for _ in range(2):
         lg, sc = g.run(x)
         assert torch.equal(lg, ref_l) and torch.equal(sc, ref_s)
+
+
+def test_npz_batch_scorer_cli(tmp_path, synth_sd, golden, golden_crops):
+    """The reference's on-disk crop format (`data_prepare.py:279-281`) -> prediction CSV (`evaluate.py:469-475`)."""
+    import csv
+    from deepfake_video_detection_b200 import score_npz
+    crops, offsets = golden_crops
+    for v in range(4):
+        name = f"{'fake' if v % 2 else 'real'}_{v}.npz"
+        kw = {"label": np.int64(v % 2)} if v < 2 else {}
+        np.savez_compressed(tmp_path / name, faces=crops[offsets[v]:offsets[v + 1]], **kw)
+    torch.save(synth_sd, tmp_path / "ckpt.pt")
+    out = tmp_path / "preds.csv"
+    assert score_npz.main(["--data_dir", str(tmp_path), "--checkpoint", str(tmp_path / "ckpt.pt"), "--out_csv", str(out), "--batch_videos", "3"]) == 0
+    rows = list(csv.DictReader(open(out)))
+    assert [r["file"] for r in rows] == sorted(f"{'fake' if v % 2 else 'real'}_{v}.npz" for v in range(4))
+    probs = torch.softmax(torch.from_numpy(golden["logits"][:4]), 1)[:, 1]
+    for r in rows:
+        v = int(r["file"].split("_")[1].split(".")[0])
+        assert int(r["label"]) == v % 2 and abs(float(r["prob"]) - probs[v].item()) < 1e-2
+        assert int(r["pred"]) == int(probs[v].item() >= 0.5)

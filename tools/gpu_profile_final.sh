@@ -9,10 +9,10 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>/dev/null; cat gpurun_out/bench_ref_$tag.json
 CMD="python tools/prof_step.py --videos 64 --frames 32 --iters 2"
 $CMD > gpurun_out/prof_plain_$tag.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 66 -c 66 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 71 -c 71 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
 echo "launch list rc=$?"
 CMD2="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
-$CMD2 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"dwconv|gemm_tc|stem|se_kernel|pool_head" -s 66 -c 66 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
+$CMD2 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"dwconv|gemm_tc|stem|se_kernel|pool_head" -s 71 -c 71 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full rc=$?"
 ncu -i /tmp/full_$tag.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.csv 2>/dev/null
 du -sh gpurun_out
