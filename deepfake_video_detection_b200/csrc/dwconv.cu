@@ -19,6 +19,7 @@
 // partial rows up in a fixed order.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace dfd {
 
@@ -41,7 +42,20 @@ static inline int dw_slots(int OH, int OW, int tw) {                     // (row
     const int rpt = dw_rpt(OH);
     return ((OH + rpt - 1) / rpt) * ((OW + tw - 1) / tw);
 }
-int dw_num_partials(int OH, int OW, int C, int k, int stride) { return dw_slots(OH, OW, dw_cfg(C, k, stride, OW * stride).tw); }
+
+// Kernel choice per layer shape: the row-marching kernel (dwconv_march.cu) or the window-per-row kernel below.
+// A function of the shape only, so the partial-sum layout never depends on the batch.  DFD_DW_MARCH=0|1 overrides
+// it for sweeps (tools/sweep_dw.sh).
+static bool dw_use_march(int H, int W, int C, int k, int stride) {
+    static const char* e_march = getenv("DFD_DW_MARCH");
+    if (!dw_march_supported(H, W, C, k, stride)) return false;
+    if (e_march) return atoi(e_march) != 0;
+    return true;
+}
+int dw_num_partials(int OH, int OW, int C, int k, int stride) {
+    if (dw_use_march(OH * stride, OW * stride, C, k, stride)) return dw_march_slots(OH, OW);
+    return dw_slots(OH, OW, dw_cfg(C, k, stride, OW * stride).tw);
+}
 
 // x * sigmoid(x) with raw MUFU ex2 + rcp (no range fix-ups: e = inf -> rcp = 0 -> -0, which is the limit)
 __device__ __forceinline__ float silu_fast(float x) {
@@ -191,6 +205,8 @@ static cudaError_t launch_dw_t(const void* in, const float* w, const float* bias
 
 cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, void* out, float* partials,
                           int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s) {
+    if (k != 3 && k != 5) return cudaErrorInvalidValue;
+    if (dw_use_march(H, W, C, k, stride)) return launch_dwconv_march(in, w, bias, out, partials, frames, H, W, C, k, stride, dtype, s);
     if (dtype == kDtypeFP16) return launch_dw_t<__half>(in, w, bias, out, partials, frames, H, W, C, k, stride, s);
     return launch_dw_t<__nv_bfloat16>(in, w, bias, out, partials, frames, H, W, C, k, stride, s);
 }

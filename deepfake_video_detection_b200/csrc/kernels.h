@@ -25,6 +25,12 @@ int dw_num_partials(int OH, int OW, int C, int k, int stride);
 cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, void* out, float* partials,
                           int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
 
+// row-marching variant (dwconv_march.cu): same contract, partial rows = dw_march_slots
+bool dw_march_supported(int H, int W, int C, int k, int stride);
+int dw_march_slots(int OH, int OW);
+cudaError_t launch_dwconv_march(const void* in, const float* w, const float* bias, void* out, float* partials,
+                                int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
+
 // K2 tail (se.cu): mean -> FC(C->rd)+bias -> SiLU -> FC(rd->C)+bias -> sigmoid.  gate fp32 [frames][C].
 // w1 fp32 [rd][C], w2t fp32 [rd][C] (conv_expand transposed), b1 [rd], b2 [C].
 cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,

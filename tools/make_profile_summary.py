@@ -21,7 +21,7 @@ def klass(name):
     if "gemm_tc" in name:
         m = re.search(r"<[^,]+, *(\w+), *(\w+), *(\w+), *(\w+)", name)
         g, a, r, p = [x in ("1", "true") for x in m.groups()]
-        return "gemm_head_pool" if p else ("gemm_project" if g else "gemm_expand")
+        return "gemm_head_pool" if p else ("gemm_expand" if a else "gemm_project")
     return "other"
 
 rows = list(csv.reader(open(os.path.join(G, f"launches_{tag}.csv"))))
