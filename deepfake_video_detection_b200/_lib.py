@@ -40,6 +40,7 @@ _SIGNATURES = {
     # dfd_b200_kernels.h
     "dfd_k_stem": (_int, [_vp, _int, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "dfd_k_stem_tc": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
+    "dfd_k_set_dw_channel_block": (None, [_int]),
     "dfd_k_dw_num_partials": (_int, [_int, _int, _int, _int, _int]),
     "dfd_k_dwconv": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp]),
     "dfd_k_se": (_int, [_vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),

@@ -572,6 +572,7 @@ int dfd_k_stem_tc(const uint8_t* d_in, const float* h_w27x32, const float* d_bia
     if (e2 != cudaSuccess) return cuda_fail(e2, "stem kernel (tcgen05) sync");
     return DFD_OK;
 }
+void dfd_k_set_dw_channel_block(int cb) { dfd::dw_march_set_cb(cb); }
 int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride) { return dfd::dw_num_partials(OH, OW, C, k, stride); }
 int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,
                  int64_t frames, int H, int W, int C, int k, int stride, int dtype, void* stream) {

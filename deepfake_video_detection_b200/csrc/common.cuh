@@ -97,6 +97,7 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 #define DFD_SILU_TANH 1
 #endif
 // x*sigmoid(x) = h + h*tanh(h), h = x/2: ONE MUFU (tanh.approx.f32, rel. error 2^-11) and two FMA-pipe ops.
+__device__ __forceinline__ float tanh_approx(float x) { float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t; }
 __device__ __forceinline__ float silu_tanh(float x) {
     const float h = 0.5f * x;
     float t;

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
+#include <type_traits>
 
 namespace dfd {
 
@@ -32,13 +33,20 @@ constexpr int kMarchTW = 7;          // output columns per thread (odd: strips i
 constexpr int kMarchMaxThreads = 256;
 constexpr int kMarchMaxK = 4;        // 16-byte chunks a thread copies per input row (upper limit)
 
-template <typename T, int KS, int S, int NR, int MAXREG, bool FULL, int MAXK>
+// CC / WC / CBC: channels, (square) map size and channel block as compile-time constants for the network's own
+// layer shapes (every address offset becomes an immediate), 0 = run-time geometry.
+template <typename T, int KS, int S, int NR, int MAXREG, bool FULL, int MAXK, int CC = 0, int WC = 0, int CBC = 0>
 __global__ void __launch_bounds__(kMarchMaxThreads, 1) __maxnreg__(MAXREG)
 dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                     T* __restrict__ out, float* __restrict__ partials,
-                    int H, int W, int C, int OH, int OW, int CB, int strips, int rps, int segs, int pixw) {
+                    int H_, int W_, int C_, int OH_, int OW_, int CB_, int strips_, int rps, int segs, int pixw_) {
     constexpr int TW = kMarchTW;
     constexpr int PAD = KS / 2;
+    const int C = CC ? CC : C_, CB = CBC ? CBC : CB_;
+    const int W = WC ? WC : W_, H = WC ? WC : H_;
+    const int OW = WC ? (WC + 2 * PAD - KS) / S + 1 : OW_, OH = WC ? OW : OH_;
+    const int strips = WC ? (OW + TW - 1) / TW : strips_;
+    const int pixw = WC ? (((strips * TW - 1) * S + KS) > WC + 2 * PAD ? ((strips * TW - 1) * S + KS) : WC + 2 * PAD) : pixw_;
     constexpr int NCOL = (TW - 1) * S + KS;
     constexpr int RING = (KS + S - 1) / S;
     constexpr int PERIOD = S * RING;
@@ -64,9 +72,12 @@ dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const
     for (uint32_t i = threadIdx.x * 16; i < NR * rsb; i += blockDim.x * 16) sts16(sm0 + i, make_uint4(0, 0, 0, 0));
 
     uint64_t wr[KS * KS];
+    // weights and bias are halved on load (exact), so the accumulators hold h = x/2 and SiLU(x) = h + h*tanh(h)
+    // needs no extra multiply; the bits are those of the unscaled sum
+    const uint64_t half2 = f2_pack(0.5f, 0.5f);
 #pragma unroll
-    for (int i = 0; i < KS * KS; ++i) wr[i] = __ldg(reinterpret_cast<const unsigned long long*>(w + (size_t)i * C + c0));
-    const uint64_t b2 = __ldg(reinterpret_cast<const unsigned long long*>(bias + c0));
+    for (int i = 0; i < KS * KS; ++i) wr[i] = mul2(__ldg(reinterpret_cast<const unsigned long long*>(w + (size_t)i * C + c0)), half2);
+    const uint64_t b2 = mul2(__ldg(reinterpret_cast<const unsigned long long*>(bias + c0)), half2);
 
     // this thread's 16-byte chunks of a row: chunk i -> pixel i / (CB/8), 8-channel group i % (CB/8)
     const int cpp = CB >> 3, chunks = W * cpp;
@@ -156,7 +167,7 @@ dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const
                         for (int j = 0; j < TW; ++j) {
                             if (FULL || ox0 + j < OW) {
                                 const float2 a = f2_unpack(acc[slot][j]);
-                                const float y0 = silu_tanh(a.x), y1 = silu_tanh(a.y);
+                                const float y0 = fmaf(a.x, tanh_approx(a.x), a.x), y1 = fmaf(a.y, tanh_approx(a.y), a.y);
                                 sums = add2(sums, f2_pack(y0, y1));
                                 *reinterpret_cast<uint32_t*>(obase + (ro + (uint32_t)(j * C))) = Half16<T>::pack(y0, y1);
                             }
@@ -180,8 +191,36 @@ int dw_march_slots(int OH, int OW) {
     return ((OH + rps - 1) / rps) * ((OW + kMarchTW - 1) / kMarchTW);
 }
 
-// channel block: the largest divisor of C (multiple of 8) whose CTA (strips * CB/2 threads) fits the thread limit
-static int march_cb(int C, int strips, int max_threads) {
+// (k, stride, max regs, C, W, CB) instantiations with compile-time geometry: the twelve depthwise shapes of the
+// 224x224 network with their candidate channel blocks (tools/sweep_dw.py picks; march_cb() holds the choice)
+#define DFD_MARCH_SPEC_LIST \
+    DFD_MARCH_SPEC(3, 1, 128, 32, 112, 16) DFD_MARCH_SPEC(3, 1, 128, 32, 112, 32) \
+    DFD_MARCH_SPEC(3, 2, 128, 96, 112, 16) DFD_MARCH_SPEC(3, 2, 128, 96, 112, 32) DFD_MARCH_SPEC(3, 2, 128, 96, 112, 48) \
+    DFD_MARCH_SPEC(3, 1, 128, 144, 56, 16) DFD_MARCH_SPEC(3, 1, 128, 144, 56, 48) \
+    DFD_MARCH_SPEC(5, 2, 168, 144, 56, 16) DFD_MARCH_SPEC(5, 2, 168, 144, 56, 48) DFD_MARCH_SPEC(5, 2, 168, 144, 56, 72) \
+    DFD_MARCH_SPEC(5, 1, 168, 240, 28, 16) DFD_MARCH_SPEC(5, 1, 168, 240, 28, 48) DFD_MARCH_SPEC(5, 1, 168, 240, 28, 80) DFD_MARCH_SPEC(5, 1, 168, 240, 28, 120) \
+    DFD_MARCH_SPEC(3, 2, 128, 240, 28, 48) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 80) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 120) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 240) \
+    DFD_MARCH_SPEC(3, 1, 128, 480, 14, 32) DFD_MARCH_SPEC(3, 1, 128, 480, 14, 96) DFD_MARCH_SPEC(3, 1, 128, 480, 14, 160) DFD_MARCH_SPEC(3, 1, 128, 480, 14, 240) \
+    DFD_MARCH_SPEC(5, 1, 168, 480, 14, 32) DFD_MARCH_SPEC(5, 1, 168, 480, 14, 96) DFD_MARCH_SPEC(5, 1, 168, 480, 14, 160) DFD_MARCH_SPEC(5, 1, 168, 480, 14, 240) \
+    DFD_MARCH_SPEC(5, 1, 168, 672, 14, 32) DFD_MARCH_SPEC(5, 1, 168, 672, 14, 96) DFD_MARCH_SPEC(5, 1, 168, 672, 14, 112) DFD_MARCH_SPEC(5, 1, 168, 672, 14, 224) \
+    DFD_MARCH_SPEC(5, 2, 168, 672, 14, 96) DFD_MARCH_SPEC(5, 2, 168, 672, 14, 224) DFD_MARCH_SPEC(5, 2, 168, 672, 14, 336) \
+    DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 64) DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 128) DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 192) DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 384) \
+    DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 64) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 128) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 192) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 384)
+
+static int g_march_cb_override = 0;      // tuning aid (dfd_k_set_dw_channel_block): 0 = the table in march_cb()
+void dw_march_set_cb(int cb) { g_march_cb_override = cb; }
+
+// channel block.  The network's own shapes use the block tools/sweep_dw.py measured fastest on B200 (small blocks:
+// more resident CTAs per SM, i.e. more independent cp.async rings in flight); any other shape takes the largest
+// divisor of C (multiple of 8) whose CTA (strips * CB/2 threads) fits the thread limit.
+static int march_cb(int C, int k, int stride, int W, int strips, int max_threads) {
+    static const struct { int C, k, s, W, cb; } tuned[] = {
+        {32, 3, 1, 112, 16},  {96, 3, 2, 112, 48},  {144, 3, 1, 56, 16},  {144, 5, 2, 56, 16},
+        {240, 5, 1, 28, 16},  {240, 3, 2, 28, 48},  {480, 3, 1, 14, 32},  {480, 5, 1, 14, 32},
+        {672, 5, 1, 14, 32},  {1152, 5, 1, 7, 64},  {1152, 3, 1, 7, 64},
+    };
+    for (const auto& t : tuned)
+        if (t.C == C && t.k == k && t.s == stride && t.W == W && strips * (t.cb / 2) <= kMarchMaxThreads) return t.cb;
     int best = 0;
     for (int cb = 8; cb <= C; cb += 8)
         if (C % cb == 0 && strips * (cb / 2) <= max_threads) best = cb;
@@ -199,6 +238,8 @@ template <typename T>
 static cudaError_t launch_march_t(const void* in, const float* w, const float* bias, void* out, float* partials,
                                   int64_t frames, int H, int W, int C, int k, int stride, cudaStream_t s) {
     static const int max_threads = getenv("DFD_DW_MAXT") ? atoi(getenv("DFD_DW_MAXT")) : 128;
+    const int env_cb = g_march_cb_override;                                              // sweeps only
+    static const bool no_spec = getenv("DFD_DW_NOSPEC") != nullptr;
     constexpr int NR = 6;
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
@@ -208,7 +249,8 @@ static cudaError_t launch_march_t(const void* in, const float* w, const float* b
     if (!dw_march_supported(H, W, C, k, stride)) return cudaErrorInvalidValue;
     int mt = max_threads < strips * 4 ? strips * 4 : max_threads;
     if (mt > kMarchMaxThreads) mt = kMarchMaxThreads;
-    const int CB = march_cb(C, strips, mt);
+    int CB = march_cb(C, k, stride, W, strips, mt);
+    if (env_cb > 0 && (env_cb & 7) == 0 && C % env_cb == 0 && strips * (env_cb / 2) <= kMarchMaxThreads) CB = env_cb;
     const int threads = strips * (CB / 2);
     const int need = (strips * kMarchTW - 1) * stride + k;          // columns the last strip's window reaches
     const int pixw = need > W + 2 * pad ? need : W + 2 * pad;
@@ -216,14 +258,27 @@ static cudaError_t launch_march_t(const void* in, const float* w, const float* b
     const size_t smem = (size_t)NR * pixw * CB * 2;
     const int64_t grid = frames * segs * (C / CB);
     if (chunks > kMarchMaxK * threads || smem > 200 * 1024 || grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-#define DFD_MARCH(KS, ST, MR) if (k == KS && stride == ST) { \
-        auto kern = dwconv_march_kernel<T, KS, ST, NR, MR, false, 4>; \
-        if ((OW % kMarchTW) == 0) kern = chunks <= 2 * threads ? dwconv_march_kernel<T, KS, ST, NR, MR, true, 2> : dwconv_march_kernel<T, KS, ST, NR, MR, true, 4>; \
+#define DFD_MARCH_GO(kern) { \
         if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; } \
         kern<<<(unsigned)grid, threads, smem, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, CB, strips, rps, segs, pixw); \
         return cudaGetLastError(); }
+    // the network's own layer shapes at 224x224, fp16: compile-time geometry
+#define DFD_MARCH_SPEC(KS, ST, MR, CC_, WW_, CB_) \
+    if constexpr (std::is_same<T, __half>::value) if (!no_spec && k == KS && stride == ST && C == CC_ && W == WW_ && H == WW_ && CB == CB_) { \
+        constexpr int kOW = (WW_ + 2 * (KS / 2) - KS) / ST + 1; \
+        static_assert(kOW % kMarchTW == 0, "specialised shapes have whole strips"); \
+        constexpr int kMK = (WW_ * (CB_ / 8) <= 2 * (kOW / kMarchTW) * (CB_ / 2)) ? 2 : 4; \
+        auto kern = dwconv_march_kernel<__half, KS, ST, NR, MR, true, kMK, CC_, WW_, CB_>; \
+        DFD_MARCH_GO(kern) }
+    DFD_MARCH_SPEC_LIST
+#undef DFD_MARCH_SPEC
+#define DFD_MARCH(KS, ST, MR) if (k == KS && stride == ST) { \
+        auto kern = dwconv_march_kernel<T, KS, ST, NR, MR, false, 4>; \
+        if ((OW % kMarchTW) == 0) kern = chunks <= 2 * threads ? dwconv_march_kernel<T, KS, ST, NR, MR, true, 2> : dwconv_march_kernel<T, KS, ST, NR, MR, true, 4>; \
+        DFD_MARCH_GO(kern) }
     DFD_MARCH(3, 1, 128) DFD_MARCH(5, 1, 168) DFD_MARCH(3, 2, 128) DFD_MARCH(5, 2, 168)
 #undef DFD_MARCH
+#undef DFD_MARCH_GO
     return cudaErrorInvalidValue;
 }
 

@@ -25,6 +25,7 @@
 // enough bytes in flight", not tensor-pipe occupancy.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace dfd {
 
@@ -51,23 +52,45 @@ struct GemmArgs {
     int b_resident;                 // 1: whole W lives in shared memory for the CTA's lifetime; 2: only the CTA's own
                                     //    column chunk (grid is a multiple of n_chunks, so a CTA always works on the same chunk)
     int kchunks_pad;                // K/8 rounded up to even
+    int dbg;                        // timing experiments (DFD_GEMM_DBG): 1 skip loads, 2 skip MMAs, 4 skip stores
+    int cshift;                     // log2 of the 16-byte chunk columns a loader thread group spans (K < 64: fewer than 8)
     uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
+    // unit strides of the persistent loops, decomposed on the host so that no role divides per tile
+    int64_t stride1, strideE;       // grid, na * grid
+    int64_t d1_mt, dE_mt, d1_frame, dE_frame;
+    int d1_nc, dE_nc, d1_t, dE_t;
 };
 
-// first row, valid rows and frame of M-tile `mt` (linear tiling, or frame-aligned tiling for per-frame weights)
-__device__ __forceinline__ void tile_origin(const GemmArgs& p, int64_t mt, int64_t& m0, int& rows_valid, int64_t& frame) {
-    if (p.tpf > 0) {
-        frame = mt / p.tpf;
-        const int t = (int)(mt - frame * p.tpf);
-        m0 = frame * p.HW + (int64_t)t * kBM;
-        rows_valid = min(kBM, p.HW - t * kBM);
-    } else {
-        frame = 0;
-        m0 = mt * p.rows_per_tile;
-        rows_valid = (int)min((int64_t)p.rows_per_tile, p.M - m0);
+// Walks the work units u = u0, u0 + stride, ... of one warp role: (M tile, N chunk) and, for frame-aligned tiling
+// (per-frame weights), (frame, tile inside the frame).  Divisions happen once in init(); advance() only adds.
+struct TileIter {
+    int64_t u, mt, frame;
+    int nc, t;
+    __device__ __forceinline__ void init(const GemmArgs& p, int64_t u0) {
+        u = u0; mt = u0 / p.n_chunks; nc = (int)(u0 - mt * p.n_chunks);
+        frame = 0; t = 0;
+        if (p.tpf > 0) { frame = mt / p.tpf; t = (int)(mt - frame * p.tpf); }
     }
-}
+    __device__ __forceinline__ void advance(const GemmArgs& p, int64_t stride, int64_t d_mt, int d_nc, int64_t d_frame, int d_t) {
+        u += stride; mt += d_mt; nc += d_nc;
+        int carry = 0;
+        if (nc >= p.n_chunks) { nc -= p.n_chunks; ++mt; carry = 1; }
+        if (p.tpf > 0) {
+            t += d_t + carry; frame += d_frame;
+            if (t >= p.tpf) { t -= p.tpf; ++frame; }
+        }
+    }
+    __device__ __forceinline__ void next1(const GemmArgs& p) { advance(p, p.stride1, p.d1_mt, p.d1_nc, p.d1_frame, p.d1_t); }
+    __device__ __forceinline__ void nextE(const GemmArgs& p) { advance(p, p.strideE, p.dE_mt, p.dE_nc, p.dE_frame, p.dE_t); }
+    // first row and number of valid rows of the tile
+    __device__ __forceinline__ int64_t m0(const GemmArgs& p) const {
+        return p.tpf > 0 ? frame * p.HW + (int64_t)t * kBM : mt * p.rows_per_tile;
+    }
+    __device__ __forceinline__ int rows_valid(const GemmArgs& p, int64_t m0v) const {
+        return p.tpf > 0 ? min(kBM, p.HW - t * kBM) : (int)min((int64_t)p.rows_per_tile, p.M - m0v);
+    }
+};
 
 template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
@@ -77,7 +100,6 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps + kXformWarps) * 32;
     constexpr int kMmaWarp = kEpiWarps;
     constexpr int kColGroups = kEpiWarps / 4;       // epilogue warps sharing a TMEM lane quarter split the columns
-    constexpr int kRowStep = kProdWarps * 4;        // producer thread tp copies rows (tp >> 3) + kRowStep * j
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- shared memory carve-up ----------------------------------------------------------------
     const uint32_t stage_bytes = p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes) + p.g_stage_bytes;
@@ -141,38 +163,49 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         // quarter-warp copies 128 contiguous bytes of one row, and its 8 shared-memory writes land in 8
         // different bank groups (LBO is padded by 16 bytes).
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
-        const int q = tp & 7, rb = tp >> 3;
+        const int q = tp & ((1 << p.cshift) - 1), rb = tp >> p.cshift;
+        const int row_step = kProdThreads >> p.cshift, passes = kBM / row_step;
         const T* A = reinterpret_cast<const T*>(p.A);
         const T* Wt = reinterpret_cast<const T*>(p.W);
         const uint32_t a_off = q * kLboA + rb * 16, b_off = q * p.lbo_b + rb * 16;
+        const int K = p.K;
         int stage = 0; uint32_t phase = 0;
-        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const int64_t mt = u / p.n_chunks;
-            const int nc = (int)(u - mt * p.n_chunks);
-            int64_t m0, wframe; int rows_valid;
-            tile_origin(p, mt, m0, rows_valid, wframe);
-            const int n0 = nc * p.NB;
+        TileIter it; it.init(p, blockIdx.x);
+        for (; it.u < units; it.next1(p)) {
+            const int64_t m0 = it.m0(p);
+            const int rows_valid = it.rows_valid(p, m0);
+            const int n0 = it.nc * p.NB;
             const int nb_valid = min(p.NB, p.N - n0);
             const uint32_t f0 = GATE ? (uint32_t)m0 / (uint32_t)p.HW : 0u;
+            const T* arow = A + (size_t)(m0 + rb) * K + q * 8;
+            const T* wrow = Wt + (size_t)it.frame * p.w_frame_stride + (size_t)(n0 + rb) * K + q * 8;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int k0 = kb * kKB;
-                const int kc = min(8, (p.K - k0) >> 3);        // 16-byte chunks present in this k-block
+                const int kc = min(8, (K - k0) >> 3);          // 16-byte chunks present in this k-block
                 const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t a_base = smem_base + stage * stage_bytes;
-                if (q < kcp) {
-                    const T* src = A + (size_t)(m0 + rb) * p.K + k0 + q * 8;
+                if (q < kcp && !(p.dbg & 1)) {
+                    const T* src = arow + k0;
+                    if (rows_valid == kBM && q < kc) {          // full tile: no per-row predicates
 #pragma unroll
-                    for (int j = 0; j < kBM / kRowStep; ++j) {
-                        const bool ok = (rb + kRowStep * j < rows_valid) && (q < kc);
-                        cp_async16(a_base + a_off + j * (kRowStep * 16), ok ? src + (size_t)(kRowStep * j) * p.K : A, ok);
+                        for (int j = 0; j < 8; ++j)
+                            if (j < passes) cp_async16(a_base + a_off + j * (row_step * 16), src + (size_t)(row_step * j) * K, true);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j < passes) {
+                                const bool ok = (rb + row_step * j < rows_valid) && (q < kc);
+                                cp_async16(a_base + a_off + j * (row_step * 16), ok ? src + (size_t)(row_step * j) * K : A, ok);
+                            }
+                        }
                     }
                     if (!p.b_resident) {
                         const uint32_t b_base = a_base + p.a_stage_bytes;
-                        const T* wsrc = Wt + (size_t)wframe * p.w_frame_stride + (size_t)(n0 + rb) * p.K + k0 + q * 8;
-                        for (int r = rb; r < p.NBp; r += kRowStep) {
+                        const T* wsrc = wrow + k0;
+                        for (int r = rb; r < p.NBp; r += row_step) {
                             const bool ok = (r < nb_valid) && (q < kc);
-                            cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * p.K : Wt, ok);   // per-frame weights when tpf > 0
+                            cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * K : Wt, ok);   // per-frame weights when tpf > 0
                         }
                     }
                 }
@@ -197,10 +230,10 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         const int q = tx & 7, rb = tx >> 3;
         const uint32_t a_off = q * kLboA + rb * 16;
         int stage = 0; uint32_t phase = 0;
-        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const int64_t mt = u / p.n_chunks;
-            int64_t m0, wframe; int rows_valid;
-            tile_origin(p, mt, m0, rows_valid, wframe);
+        TileIter it; it.init(p, blockIdx.x);
+        for (; it.u < units; it.next1(p)) {
+            const int64_t m0 = it.m0(p);
+            const int rows_valid = it.rows_valid(p, m0);
             const uint32_t f0 = (uint32_t)m0 / (uint32_t)p.HW;
             const uint32_t rem0 = (uint32_t)m0 - f0 * (uint32_t)p.HW + rb;      // row rb relative to frame f0
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -242,8 +275,9 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         // =================================== MMA ISSUER ==========================================
         const uint32_t idesc = umma_idesc(Half16<T>::kUmmaFormat, kBM, (uint32_t)p.NBp);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const int nc = (int)(u % p.n_chunks);
+        TileIter it; it.init(p, blockIdx.x);
+        for (; it.u < units; it.next1(p)) {
+            const int nc = it.nc;
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NBp);
@@ -259,7 +293,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                     for (int j = 0; j < steps; ++j) {
                         const uint64_t adesc = umma_smem_desc(a_base + 2 * j * kLboA, kLboA, 128);
                         const uint64_t bdesc = umma_smem_desc(b_base + 2 * j * p.lbo_b, p.lbo_b, 128);
-                        umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        if (!(p.dbg & 2)) umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_empty + 8 * stage);                 // smem stage reusable once the MMAs retire
                     if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);
@@ -278,14 +312,12 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         const int row = 32 * q + lane;
         T* D = reinterpret_cast<T*>(p.D);
         const T* R = reinterpret_cast<const T*>(p.R);
-        int64_t li = set;                               // index of the unit within this CTA's sequence
-        for (int64_t u = blockIdx.x + (int64_t)set * gridDim.x; u < units; u += (int64_t)p.na * gridDim.x, li += p.na) {
-            const int acc = (int)(li % p.nacc);
-            const uint32_t acc_phase = (uint32_t)(li / p.nacc) & 1u;
-            const int64_t mt = u / p.n_chunks;
-            const int nc = (int)(u - mt * p.n_chunks);
-            int64_t m0, wframe; int rows_valid;
-            tile_origin(p, mt, m0, rows_valid, wframe);
+        int acc = set; uint32_t acc_phase = 0;         // set < na <= nacc, nacc is a multiple of na
+        TileIter it; it.init(p, blockIdx.x + (int64_t)set * gridDim.x);
+        for (; it.u < units; it.nextE(p)) {
+            const int nc = it.nc;
+            const int64_t m0 = it.m0(p);
+            const int rows_valid = it.rows_valid(p, m0);
             const int n0 = nc * p.NB;
             const int nb_valid = min(p.NB, p.N - n0);
             const bool valid = row < rows_valid;
@@ -342,7 +374,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                         stg32(dst, o0);
                         if (ncol > 8) stg32(dst + 8, o1);
                     }
-                } else if (valid) {
+                } else if (valid && !(p.dbg & 4)) {
                     T* dst = D + (size_t)m * p.N + n0 + c16 * 16;
                     const bool wide = ((p.N & 15) == 0);              // every 16-column chunk is then 32-byte aligned
                     if (RES) {
@@ -376,6 +408,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             }
             tc_fence_before_sync();
             mbar_arrive(bar_tempty + 8 * acc);
+            acc += p.na; if (acc >= p.nacc) { acc -= p.nacc; acc_phase ^= 1; }
         }
     }
 
@@ -402,6 +435,8 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.lbo_b = (uint32_t)a.NBp * 16 + 16;
     a.kchunks_pad = ((a.K >> 3) + 1) & ~1;
     const int kcp_max = a.kchunks_pad < 8 ? a.kchunks_pad : 8;       // 16-byte chunk columns a stage can hold
+    { static const int env_dbg = getenv("DFD_GEMM_DBG") ? atoi(getenv("DFD_GEMM_DBG")) : 0; a.dbg = env_dbg; }
+    a.cshift = kcp_max <= 2 ? 1 : (kcp_max <= 4 ? 2 : 3);
     a.a_stage_bytes = (uint32_t)kcp_max * kLboA;
     a.b_stage_bytes = (uint32_t)kcp_max * a.lbo_b;
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
@@ -410,6 +445,8 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
         int na = groups; while (na > fit) na >>= 1;
         a.na = na;
         int nacc = (fit / na) * na; if (nacc > 8) nacc = 8 / na * na;
+        static const int env_nacc = getenv("DFD_GEMM_NACC") ? atoi(getenv("DFD_GEMM_NACC")) : 0;         // experiments only
+        if (env_nacc >= na && nacc > env_nacc) nacc = env_nacc / na * na;
         a.nacc = nacc;
     }
     uint32_t cols = 32; while (cols < (uint32_t)(a.nacc * a.NBp)) cols <<= 1;
@@ -430,6 +467,8 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes;
     int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
+    static const int env_stages = getenv("DFD_GEMM_STAGES") ? atoi(getenv("DFD_GEMM_STAGES")) : 0;     // experiments only
+    if (env_stages >= 3 && stages > env_stages) stages = env_stages;
     if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
     const size_t smem = a.b_res_bytes + (size_t)stages * stage_bytes + fixed;
@@ -439,6 +478,15 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     unsigned grid = (unsigned)(units < g_num_sms ? units : g_num_sms);
     if (a.b_resident == 2) grid = (unsigned)((g_num_sms / a.n_chunks) * a.n_chunks);     // every CTA keeps one column chunk
     if ((int64_t)grid > units) grid = (unsigned)units;
+    {
+        auto split = [&](int64_t stride, int64_t& d_mt, int& d_nc, int64_t& d_frame, int& d_t) {
+            d_mt = stride / a.n_chunks; d_nc = (int)(stride % a.n_chunks);
+            d_frame = a.tpf > 0 ? d_mt / a.tpf : 0; d_t = a.tpf > 0 ? (int)(d_mt % a.tpf) : 0;
+        };
+        a.stride1 = grid; a.strideE = (int64_t)a.na * grid;
+        split(a.stride1, a.d1_mt, a.d1_nc, a.d1_frame, a.d1_t);
+        split(a.strideE, a.dE_mt, a.dE_nc, a.dE_frame, a.dE_t);
+    }
     kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
@@ -450,6 +498,15 @@ static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true, 16, 4, 0>, a, 16, 4, 0, s);
     if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false, 8, 4, 8>, a, 8, 4, 8, s);
     if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false, 8, 4, 8>, a, 8, 4, 8, s);
+    static const int env_prod = getenv("DFD_GEMM_PROD") ? atoi(getenv("DFD_GEMM_PROD")) : 0;          // experiments only
+    if (env_prod == 8 || env_prod == 16) {
+        if (!gate && !res && act) return env_prod == 8 ? run(gemm_tc_kernel<T, false, true, false, false, 16, 8, 0>, a, 16, 8, 0, s)
+                                                        : run(gemm_tc_kernel<T, false, true, false, false, 12, 16, 0>, a, 12, 16, 0, s);
+        if (!gate && !res && !act) return env_prod == 8 ? run(gemm_tc_kernel<T, false, false, false, false, 8, 8, 0>, a, 8, 8, 0, s)
+                                                         : run(gemm_tc_kernel<T, false, false, false, false, 8, 16, 0>, a, 8, 16, 0, s);
+        if (!gate && res && !act) return env_prod == 8 ? run(gemm_tc_kernel<T, false, false, true, false, 8, 8, 0>, a, 8, 8, 0, s)
+                                                        : run(gemm_tc_kernel<T, false, false, true, false, 8, 16, 0>, a, 8, 16, 0, s);
+    }
     if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false, 16, 4, 0>, a, 16, 4, 0, s);
     if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false, 8, 4, 0>, a, 8, 4, 0, s);
     if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false, 8, 4, 0>, a, 8, 4, 0, s);

@@ -28,6 +28,7 @@ cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, voi
 // row-marching variant (dwconv_march.cu): same contract, partial rows = dw_march_slots
 bool dw_march_supported(int H, int W, int C, int k, int stride);
 int dw_march_slots(int OH, int OW);
+void dw_march_set_cb(int cb);      // tuning aid: force the channel block of the next launches (0 = default)
 cudaError_t launch_dwconv_march(const void* in, const float* w, const float* bias, void* out, float* partials,
                                 int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
 

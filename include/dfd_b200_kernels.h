@@ -26,6 +26,8 @@ int dfd_k_stem_tc(const uint8_t* d_in, const float* h_w27x32, const float* d_bia
 /* timm conv_dw + bn: depthwise kxk (k 3|5, stride 1|2, pad k/2) + bias + SiLU, plus the squeeze-excite
  * spatial sums as d_partials fp32 [frames][dfd_k_dw_num_partials(OH,OW,C,k,stride)][C].  d_w fp32 [k*k][C]. */
 int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride);
+/* tuning aid for tools/sweep_dw.py: force the channel block (channels per CTA) of the following depthwise launches; 0 = built-in choice */
+void dfd_k_set_dw_channel_block(int cb);
 int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,
                  int64_t frames, int H, int W, int C, int k, int stride, int dtype, void* stream);
 
