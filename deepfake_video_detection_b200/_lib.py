@@ -35,6 +35,11 @@ _SIGNATURES = {
     "dfd_rnn_free_weights": (None, [_vp]),
     "dfd_rnn_workspace_bytes": (_int, [_vp, _i64, _int, C.POINTER(C.c_size_t)]),
     "dfd_rnn_forward": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp, C.c_size_t, _vp]),
+    "dfd_vit_last_error": (C.c_char_p, []),
+    "dfd_vit_pack_weights": (_int, [_int, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _int, C.POINTER(_vp)]),
+    "dfd_vit_free_weights": (None, [_vp]),
+    "dfd_vit_workspace_bytes": (_int, [_i64, C.POINTER(C.c_size_t)]),
+    "dfd_vit_features": (_int, [_vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     "dfd_profile_enable": (_int, [_int]),
     "dfd_profile_collect": (_int, [_vp, _int, C.POINTER(_int)]),
     # dfd_b200_kernels.h

@@ -162,6 +162,14 @@ __device__ __forceinline__ U32x8 ldg32(const void* p) {            // 256-bit re
     return r;
 }
 
+__device__ __forceinline__ U32x8 ldg32_coherent(const void* p) {   // 256-bit load of data this kernel also writes (in-place residual)
+    U32x8 r;
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]),
+                   "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p) : "memory");
+    return r;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -185,6 +193,11 @@ __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, boo
 __device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
 }
+// Same, but the completion counts as one of the barrier's EXPECTED arrivals (no pending-count increment): one
+// mbarrier operation per thread and stage instead of three (increment, completion, plain arrive).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -207,7 +220,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         if (mbar_try_wait(bar, parity)) return;
     }
     printf("dfd: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);

@@ -52,7 +52,9 @@ struct GemmArgs {
     int b_resident;                 // 1: whole W lives in shared memory for the CTA's lifetime; 2: only the CTA's own
                                     //    column chunk (grid is a multiple of n_chunks, so a CTA always works on the same chunk)
     int kchunks_pad;                // K/8 rounded up to even
-    int dbg;                        // timing experiments (DFD_GEMM_DBG): 1 skip loads, 2 skip MMAs, 4 skip stores
+    int dbg;                        // timing experiments (DFD_GEMM_DBG): 1 skip loads, 2 skip MMAs, 4 skip stores,
+                                    //    8 skip the transformers' proxy fence, 16 per-thread (not per-warp) arrivals
+    int xg;                         // gated: transformer warp groups taking alternate stages
     int cshift;                     // log2 of the 16-byte chunk columns a loader thread group spans (K < 64: fewer than 8)
     uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
@@ -92,7 +94,8 @@ struct TileIter {
     }
 };
 
-template <typename T, bool GATE, bool ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
+// ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
+template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
     constexpr int kProdThreads = kProdWarps * 32;
@@ -122,11 +125,11 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(bar_full + 8 * s, GATE ? kXformThreads : kProdThreads);
+            mbar_init(bar_full + 8 * s, GATE ? (p.dbg & 16 ? kXformThreads : kXformWarps) / p.xg : kProdThreads);
             mbar_init(bar_empty + 8 * s, 1);
             mbar_init(bar_raw + 8 * s, kProdThreads);
         }
-        for (int a = 0; a < p.nacc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kColGroups / p.na) * 128); }
+        for (int a = 0; a < p.nacc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kColGroups / p.na) * (p.dbg & 16 ? 128 : 4)); }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(s_tmem), p.tmem_cols);
@@ -156,6 +159,10 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
 
     const int num_kb = (p.K + kKB - 1) / kKB;
     const int64_t units = p.m_tiles * p.n_chunks;
+    // DFD_GEMM_DBG & 32: per-role wait accounting (block 0 prints cycles spent in each barrier wait)
+    const bool prof = (p.dbg & 32) != 0;
+    long long w0 = 0, w1 = 0, t_begin = prof ? clock64() : 0;
+#define DFD_TWAIT(acc, bar, par) { if (prof) { const long long c0_ = clock64(); mbar_wait(bar, par); acc += clock64() - c0_; } else mbar_wait(bar, par); }
 
     if (warp > kMmaWarp && warp <= kMmaWarp + kProdWarps) {
         // =================================== LOADERS =============================================
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 const int k0 = kb * kKB;
                 const int kc = min(8, (K - k0) >> 3);          // 16-byte chunks present in this k-block
                 const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
-                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
                 const uint32_t a_base = smem_base + stage * stage_bytes;
                 if (q < kcp && !(p.dbg & 1)) {
                     const T* src = arow + k0;
@@ -218,18 +225,20 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                     }
                 }
                 const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
-                cp_async_mbar_arrive(bar);                     // completes when this thread's copies have landed
-                mbar_arrive(bar);
+                cp_async_mbar_arrive_noinc(bar);               // arrives when this thread's copies have landed
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (GATE && warp > kMmaWarp + kProdWarps) {
         // =================================== TRANSFORMERS ========================================
+        // The warps form p.xg groups that take alternate stages: a stage's lds -> multiply -> sts -> proxy fence
+        // chain is latency-bound, so several stages are transformed concurrently.  One arrival per warp.
         const int tx = threadIdx.x - (kMmaWarp + 1 + kProdWarps) * 32;
-        constexpr int kXRowStep = kXformWarps > 0 ? kXformWarps * 4 : 1;
-        const int q = tx & 7, rb = tx >> 3;
+        const int gthreads = kXformThreads / p.xg;
+        const int grp = tx / gthreads, tg = tx - grp * gthreads;
+        const int q = tg & 7, rb = tg >> 3, xstep = gthreads >> 3, xpasses = kBM / xstep;
         const uint32_t a_off = q * kLboA + rb * 16;
-        int stage = 0; uint32_t phase = 0;
+        int stage = 0; uint32_t phase = 0; int turn = 0;
         TileIter it; it.init(p, blockIdx.x);
         for (; it.u < units; it.next1(p)) {
             const int64_t m0 = it.m0(p);
@@ -237,37 +246,41 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             const uint32_t f0 = (uint32_t)m0 / (uint32_t)p.HW;
             const uint32_t rem0 = (uint32_t)m0 - f0 * (uint32_t)p.HW + rb;      // row rb relative to frame f0
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int kc = min(8, (p.K - kb * kKB) >> 3);
-                mbar_wait(bar_raw + 8 * stage, phase);
-                if (q < kc) {
-                    const uint32_t a_base = smem_base + stage * stage_bytes;
-                    uint32_t fl = 0, rem = rem0;
-                    while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
-                    uint32_t fl_loaded = 0xffffffffu;               // the gate slice is re-read only when the frame changes
-                    uint4 gA = make_uint4(0, 0, 0, 0), gB = gA;
-#pragma unroll
-                    for (int j = 0; j < kBM / kXRowStep; ++j) {
-                        if (rb + kXRowStep * j < rows_valid) {
-                            if (fl != fl_loaded) {
-                                const uint32_t gaddr = a_base + g_off + fl * 256 + q * 32;
-                                gA = lds16(gaddr); gB = lds16(gaddr + 16); fl_loaded = fl;
-                            }
-                            const uint32_t addr = a_base + a_off + j * (kXRowStep * 16);
-                            uint4 v = lds16(addr);
-                            const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
-                            const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
-                            v.x = Half16<T>::pack(x0.x * __uint_as_float(gA.x), x0.y * __uint_as_float(gA.y));
-                            v.y = Half16<T>::pack(x1.x * __uint_as_float(gA.z), x1.y * __uint_as_float(gA.w));
-                            v.z = Half16<T>::pack(x2.x * __uint_as_float(gB.x), x2.y * __uint_as_float(gB.y));
-                            v.w = Half16<T>::pack(x3.x * __uint_as_float(gB.z), x3.y * __uint_as_float(gB.w));
-                            sts16(addr, v);
-                        }
-                        rem += kXRowStep;
+                if (turn == grp) {
+                    const int kc = min(8, (p.K - kb * kKB) >> 3);
+                    DFD_TWAIT(w0, bar_raw + 8 * stage, phase)
+                    if (q < kc) {
+                        const uint32_t a_base = smem_base + stage * stage_bytes;
+                        uint32_t fl = 0, rem = rem0;
                         while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
+                        uint32_t fl_loaded = 0xffffffffu;               // the gate slice is re-read only when the frame changes
+                        uint4 gA = make_uint4(0, 0, 0, 0), gB = gA;
+#pragma unroll 4
+                        for (int j = 0; j < xpasses; ++j) {
+                            if (rb + xstep * j < rows_valid) {
+                                if (fl != fl_loaded) {
+                                    const uint32_t gaddr = a_base + g_off + fl * 256 + q * 32;
+                                    gA = lds16(gaddr); gB = lds16(gaddr + 16); fl_loaded = fl;
+                                }
+                                const uint32_t addr = a_base + a_off + j * (xstep * 16);
+                                uint4 v = lds16(addr);
+                                const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
+                                const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
+                                v.x = Half16<T>::pack(x0.x * __uint_as_float(gA.x), x0.y * __uint_as_float(gA.y));
+                                v.y = Half16<T>::pack(x1.x * __uint_as_float(gA.z), x1.y * __uint_as_float(gA.w));
+                                v.z = Half16<T>::pack(x2.x * __uint_as_float(gB.x), x2.y * __uint_as_float(gB.y));
+                                v.w = Half16<T>::pack(x3.x * __uint_as_float(gB.z), x3.y * __uint_as_float(gB.w));
+                                sts16(addr, v);
+                            }
+                            rem += xstep;
+                            while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
+                        }
                     }
+                    if (!(p.dbg & 8)) fence_proxy_async_smem();
+                    if (p.dbg & 16) mbar_arrive(bar_full + 8 * stage);
+                    else { __syncwarp(); if (lane == 0) mbar_arrive(bar_full + 8 * stage); }
                 }
-                fence_proxy_async_smem();
-                mbar_arrive(bar_full + 8 * stage);
+                if (++turn == p.xg) turn = 0;
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -278,13 +291,13 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         TileIter it; it.init(p, blockIdx.x);
         for (; it.u < units; it.next1(p)) {
             const int nc = it.nc;
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            DFD_TWAIT(w0, bar_tempty + 8 * acc, acc_phase ^ 1)
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NBp);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int kc = min(8, (p.K - kb * kKB) >> 3);
                 const int steps = (kc + 1) >> 1;
-                mbar_wait(bar_full + 8 * stage, phase);
+                DFD_TWAIT(w1, bar_full + 8 * stage, phase)
                 tc_fence_after_sync();
                 if (lane == 0) {
                     const uint32_t a_base = smem_base + stage * stage_bytes;
@@ -322,7 +335,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             const int nb_valid = min(p.NB, p.N - n0);
             const bool valid = row < rows_valid;
             const int64_t m = m0 + row;
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            DFD_TWAIT(w0, bar_tfull + 8 * acc, acc_phase)
             tc_fence_after_sync();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
             const int slots = POOL ? rows_valid / p.HW : 0;
@@ -338,9 +351,14 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                     const int col = min(n0 + c16 * 16 + i, p.N - 2);
                     uint64_t x = add2(f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
                                       *reinterpret_cast<const uint64_t*>(&s_bias[col]));
-                    if (ACT) x = neg_silu2(x);                        // -silu(x); sign restored below
+                    if (ACT == 1) x = neg_silu2(x);                   // -silu(x); sign restored below
                     const float2 xf = f2_unpack(x);
-                    v[i] = ACT ? -xf.x : xf.x; v[i + 1] = ACT ? -xf.y : xf.y;
+                    if (ACT == 2) {
+                        v[i] = 0.5f * xf.x * (1.0f + erff(xf.x * 0.70710678118654752f));
+                        v[i + 1] = 0.5f * xf.y * (1.0f + erff(xf.y * 0.70710678118654752f));
+                    } else {
+                        v[i] = ACT == 1 ? -xf.x : xf.x; v[i + 1] = ACT == 1 ? -xf.y : xf.y;
+                    }
                 }
                 if (POOL) {
                     // Batch-invariant average pool: stage the SiLU'd tile in shared memory, then add each frame's
@@ -368,6 +386,14 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 } else if (F32OUT) {
                     if (valid) {                                      // fp32 output (recurrent head): 64 bytes per chunk
                         float* dst = reinterpret_cast<float*>(p.D) + (size_t)m * p.N + n0 + c16 * 16;
+                        if (RES) {                                    // fp32 residual (may alias D: same thread reads then writes)
+                            const float* rs = reinterpret_cast<const float*>(p.R) + (size_t)m * p.N + n0 + c16 * 16;
+                            const U32x8 r0 = ldg32_coherent(rs);
+                            U32x8 r1 = r0;
+                            if (ncol > 8) r1 = ldg32_coherent(rs + 8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { v[i] += __uint_as_float(r0.v[i]); if (ncol > 8) v[8 + i] += __uint_as_float(r1.v[i]); }
+                        }
                         U32x8 o0, o1;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { o0.v[i] = __float_as_uint(v[i]); o1.v[i] = __float_as_uint(v[8 + i]); }
@@ -407,11 +433,17 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(bar_tempty + 8 * acc);
+            if (p.dbg & 16) mbar_arrive(bar_tempty + 8 * acc);
+            else { __syncwarp(); if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); }     // one arrival per warp
             acc += p.na; if (acc >= p.nacc) { acc -= p.nacc; acc_phase ^= 1; }
         }
     }
 
+    if (prof && blockIdx.x == 0 && lane == 0)
+        printf("warp %2d (%s): total %lld cycles, wait0 %lld, wait1 %lld\n", warp,
+               warp < kMmaWarp ? "epilogue" : warp == kMmaWarp ? "mma" : warp <= kMmaWarp + kProdWarps ? "loader" : "xform",
+               clock64() - t_begin, w0, w1);
+#undef DFD_TWAIT
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kMmaWarp) { tc_fence_after_sync(); tmem_dealloc(tmem_base, p.tmem_cols); }
@@ -437,6 +469,9 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     const int kcp_max = a.kchunks_pad < 8 ? a.kchunks_pad : 8;       // 16-byte chunk columns a stage can hold
     { static const int env_dbg = getenv("DFD_GEMM_DBG") ? atoi(getenv("DFD_GEMM_DBG")) : 0; a.dbg = env_dbg; }
     a.cshift = kcp_max <= 2 ? 1 : (kcp_max <= 4 ? 2 : 3);
+    {   static const int env_xg = getenv("DFD_GEMM_XG") ? atoi(getenv("DFD_GEMM_XG")) : 4;
+        a.xg = xform_warps > 0 ? env_xg : 1;
+        if (a.xg < 1 || a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1; }
     a.a_stage_bytes = (uint32_t)kcp_max * kLboA;
     a.b_stage_bytes = (uint32_t)kcp_max * a.lbo_b;
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
@@ -471,6 +506,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     if (env_stages >= 3 && stages > env_stages) stages = env_stages;
     if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
+    while (a.xg > 1 && (a.xg > stages || a.xg > 4)) a.xg >>= 1;      // groups take alternate stages: never more groups than stages
     const size_t smem = a.b_res_bytes + (size_t)stages * stage_bytes + fixed;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -495,21 +531,13 @@ template <typename T>
 static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     const bool gate = a.gate != nullptr, res = a.R != nullptr;
     // <T, GATE, ACT, RES, POOL, epilogue warps, loader warps, transformer warps>
-    if (a.feat) return run(gemm_tc_kernel<T, false, true, false, true, 16, 4, 0>, a, 16, 4, 0, s);
-    if (gate && res && !act) return run(gemm_tc_kernel<T, true, false, true, false, 8, 4, 8>, a, 8, 4, 8, s);
-    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, false, false, false, 8, 4, 8>, a, 8, 4, 8, s);
-    static const int env_prod = getenv("DFD_GEMM_PROD") ? atoi(getenv("DFD_GEMM_PROD")) : 0;          // experiments only
-    if (env_prod == 8 || env_prod == 16) {
-        if (!gate && !res && act) return env_prod == 8 ? run(gemm_tc_kernel<T, false, true, false, false, 16, 8, 0>, a, 16, 8, 0, s)
-                                                        : run(gemm_tc_kernel<T, false, true, false, false, 12, 16, 0>, a, 12, 16, 0, s);
-        if (!gate && !res && !act) return env_prod == 8 ? run(gemm_tc_kernel<T, false, false, false, false, 8, 8, 0>, a, 8, 8, 0, s)
-                                                         : run(gemm_tc_kernel<T, false, false, false, false, 8, 16, 0>, a, 8, 16, 0, s);
-        if (!gate && res && !act) return env_prod == 8 ? run(gemm_tc_kernel<T, false, false, true, false, 8, 8, 0>, a, 8, 8, 0, s)
-                                                        : run(gemm_tc_kernel<T, false, false, true, false, 8, 16, 0>, a, 8, 16, 0, s);
-    }
-    if (!gate && !res && act) return run(gemm_tc_kernel<T, false, true, false, false, 16, 4, 0>, a, 16, 4, 0, s);
-    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, false, false, false, 8, 4, 0>, a, 8, 4, 0, s);
-    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, false, true, false, 8, 4, 0>, a, 8, 4, 0, s);
+    if (a.feat) return run(gemm_tc_kernel<T, false, 1, false, true, 16, 4, 0>, a, 16, 4, 0, s);
+    if (gate && res && !act) return run(gemm_tc_kernel<T, true, 0, true, false, 8, 4, 8>, a, 8, 4, 8, s);
+    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, 0, false, false, 8, 4, 8>, a, 8, 4, 8, s);
+    if (!gate && !res && act == 1) return run(gemm_tc_kernel<T, false, 1, false, false, 16, 4, 0>, a, 16, 4, 0, s);
+    if (!gate && !res && act == 2) return run(gemm_tc_kernel<T, false, 2, false, false, 16, 4, 0>, a, 16, 4, 0, s);
+    if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, 0, false, false, 8, 4, 0>, a, 8, 4, 0, s);
+    if (!gate && res && !act) return run(gemm_tc_kernel<T, false, 0, true, false, 8, 4, 0>, a, 8, 4, 0, s);
     return cudaErrorInvalidValue;
 }
 
@@ -563,16 +591,20 @@ cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, float* D,
+cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, const float* R, float* D,
                                   int64_t M, int K, int N, int dtype, cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
     if ((K & 7) || (N & 7) || K < 8 || N < 8) return cudaErrorInvalidValue;
     GemmArgs a{};
-    a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = nullptr; a.D = D; a.feat = nullptr;
+    a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = R; a.D = D; a.feat = nullptr;
     a.M = M; a.K = K; a.N = N; a.HW = 1;
     a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
-    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, false, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
-    return run(gemm_tc_kernel<__nv_bfloat16, false, false, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+    if (R) {
+        if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, true, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+        return run(gemm_tc_kernel<__nv_bfloat16, false, 0, true, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+    }
+    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+    return run(gemm_tc_kernel<__nv_bfloat16, false, 0, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
 }
 
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,

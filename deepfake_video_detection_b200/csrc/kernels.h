@@ -38,7 +38,7 @@ cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const flo
                       const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s);
 
 // K3 (gemm_tc.cu): pointwise conv as tcgen05/TMEM GEMM.  D[M,N] = act((A .* gate)[M,K] * W[N,K]^T + bias) (+ R)
-// A, W, R, D 16-bit; bias fp32 [N]; gate fp32 [M/HW][K] or null; R [M,N] or null; act: 0 none, 1 SiLU.
+// A, W, R, D 16-bit; bias fp32 [N]; gate fp32 [M/HW][K] or null; R [M,N] or null; act: 0 none, 1 SiLU, 2 exact GELU.
 cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, const float* gate, const void* R,
                            void* D, int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s);
 // gated project conv for big maps (HW >= 784): fold the SE gate into per-frame weights, then an ungated GEMM on
@@ -46,8 +46,9 @@ cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, cons
 cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int dtype, cudaStream_t s);
 cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bias, const void* R, void* D,
                                   int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
-// plain D[M,N] (fp32) = A[M,K] * W[N,K]^T + bias — gate pre-activations of the recurrent head (rnn.cu)
-cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, float* D,
+// D[M,N] (fp32) = A[M,K] * W[N,K]^T + bias (+ R fp32, may alias D) — gate pre-activations of the recurrent head
+// (rnn.cu) and the fp32 residual stream of the ViT encoder (vit.cu)
+cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, const float* R, float* D,
                                   int64_t M, int K, int N, int dtype, cudaStream_t s);
 // conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,

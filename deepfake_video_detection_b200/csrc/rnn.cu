@@ -261,7 +261,7 @@ int dfd_rnn_forward(const dfd_rnn_weights_t* w, const float* d_x, const int32_t*
         uint8_t* a0_next = a0 + (size_t)(t + 1) * B * K0 * 2 + (size_t)IN * 2;       // h slot of step t+1
         for (int l = 0; l < w->layers; ++l) {
             const bool last = l == w->layers - 1;
-            RNN_CK(dfd::launch_gemm_tc_f32out(l == 0 ? a0_t : a1, w->w[l], w->b[l], g, B, l == 0 ? K0 : H, 7 * H, w->dtype, s), "rnn gate gemm");
+            RNN_CK(dfd::launch_gemm_tc_f32out(l == 0 ? a0_t : a1, w->w[l], w->b[l], nullptr, g, B, l == 0 ? K0 : H, 7 * H, w->dtype, s), "rnn gate gemm");
             void* h16 = last ? (void*)a0_next : (void*)a1;
             const int stride = last ? K0 : H;
             float* o = last ? outs + (size_t)t * H : nullptr;

@@ -1,0 +1,400 @@
+// K6 — ViT-B/16 frame encoder (BASELINE config 5): reference src/models.py:88-107 `ViTFeatureExtractor`, i.e.
+// timm `vit_base_patch16_224(num_classes=0)` (un-vendored dependency, requirements.txt:12): x (B,3,224,224) fp32 ->
+// CLS feature (B,768) fp32.
+//
+// Every dense contraction (patch embedding, qkv, attention projection, the two MLP layers: 99 % of the 35 GFLOP per
+// image) runs on the tcgen05/TMEM GEMM of gemm_tc.cu with 16-bit operands and fp32 accumulation:
+//   patchify (fp32 NCHW -> 16-bit [B*196, 768], column = c*256 + ky*16 + kx, the Conv2d weight order)
+//   -> GEMM(+bias) -> assemble tokens: [cls | patches] + pos_embed -> residual stream X fp32 [B*197, 768]
+//   12 x { LN1(X) -> 16-bit ; qkv GEMM ; attention (softmax(QK^T/8)V per image and head, mma.sync m16n8k16, fp32
+//          softmax) ; proj GEMM with fp32 residual epilogue (X += ..., in place) ; LN2 ; fc1 GEMM + exact-erf GELU ;
+//          fc2 GEMM with fp32 residual epilogue }
+//   final LayerNorm on the CLS rows only -> fp32 features.
+// The residual stream stays fp32 end to end (only GEMM operands are rounded to 16 bits), LayerNorm statistics
+// and the softmax are fp32.  Every reduction has a fixed order: results do not depend on the batch.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/dfd_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+constexpr int kDim = 768, kDepth = 12, kHeads = 12, kHd = 64, kPatch = 16, kImg = 224, kGridP = 14;
+constexpr int kPatches = kGridP * kGridP, kTokens = kPatches + 1, kMlp = 3072, kPatchK = 3 * kPatch * kPatch;
+}
+
+struct dfd_vit_weights {
+    int dtype;
+    void* patch_w; float* patch_b;            // [768][768] 16-bit, [768]
+    float *cls, *pos;                          // [768], [197][768]
+    struct Block {
+        float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+        void *qkv_w, *proj_w, *fc1_w, *fc2_w;  // 16-bit [N][K] (K-major, as nn.Linear stores them)
+        float *qkv_b, *proj_b, *fc1_b, *fc2_b;
+    } blk[kDepth];
+    float *norm_w, *norm_b;
+    void* arena;
+};
+
+namespace dfd {
+
+// x fp32 (B,3,224,224) -> A [B*196][768] 16-bit: row = image*196 + py*14 + px, column = c*256 + ky*16 + kx
+template <typename T>
+__global__ void vit_patchify_kernel(const float* __restrict__ x, T* __restrict__ a, int64_t total8) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 8 consecutive kx
+    if (i >= total8) return;
+    const int kx0 = (int)(i & 1) * 8;
+    const int ky = (int)((i >> 1) & 15);
+    const int c = (int)((i >> 5) % 3);
+    const int64_t row = i / 96;
+    const int px = (int)(row % kGridP), py = (int)((row / kGridP) % kGridP);
+    const int64_t b = row / kPatches;
+    const float* src = x + (((size_t)b * 3 + c) * kImg + (py * kPatch + ky)) * kImg + px * kPatch + kx0;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    uint4 o;
+    o.x = Half16<T>::pack(v0.x, v0.y); o.y = Half16<T>::pack(v0.z, v0.w);
+    o.z = Half16<T>::pack(v1.x, v1.y); o.w = Half16<T>::pack(v1.z, v1.w);
+    *reinterpret_cast<uint4*>(a + (size_t)row * kPatchK + c * 256 + ky * 16 + kx0) = o;
+}
+
+// X[b][0] = cls + pos[0];  X[b][1+i] = P[b*196+i] + pos[1+i]   (P already carries the conv bias)
+template <typename T>
+__global__ void vit_assemble_kernel(const T* __restrict__ p, const float* __restrict__ cls, const float* __restrict__ pos,
+                                    float* __restrict__ x, int64_t total8) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 8 channels
+    if (i >= total8) return;
+    const int c8 = (int)(i % (kDim / 8)) * 8;
+    const int64_t row = i / (kDim / 8);
+    const int tok = (int)(row % kTokens);
+    const int64_t b = row / kTokens;
+    float v[8];
+    if (tok == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = cls[c8 + j];
+    } else {
+        const uint4 r = *reinterpret_cast<const uint4*>(p + ((size_t)b * kPatches + tok - 1) * kDim + c8);
+        const float2 a0 = Half16<T>::unpack(r.x), a1 = Half16<T>::unpack(r.y), a2 = Half16<T>::unpack(r.z), a3 = Half16<T>::unpack(r.w);
+        v[0] = a0.x; v[1] = a0.y; v[2] = a1.x; v[3] = a1.y; v[4] = a2.x; v[5] = a2.y; v[6] = a3.x; v[7] = a3.y;
+    }
+    const float* ps = pos + (size_t)tok * kDim + c8;
+    float* dst = x + (size_t)row * kDim + c8;
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0] + ps[0], v[1] + ps[1], v[2] + ps[2], v[3] + ps[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] + ps[4], v[5] + ps[5], v[6] + ps[6], v[7] + ps[7]);
+}
+
+// LayerNorm over 768 channels, eps 1e-6, one warp per row: fp32 statistics (mean, then centred variance).
+// Input row r lives at x + r * in_stride floats.  OUT = 16-bit GEMM operand or fp32 (final norm).
+template <typename OUT>
+__global__ void vit_layernorm_kernel(const float* __restrict__ x, int64_t in_stride, const float* __restrict__ w,
+                                     const float* __restrict__ b, OUT* __restrict__ y, int64_t rows) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)r * in_stride);
+    float4 v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { v[j] = src[lane + 32 * j]; s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / kDim);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const float a = v[j].x - mean, c = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+        q += (a * a + c * c) + (d * d + e * e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / kDim) + 1e-6f);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const int c0 = (lane + 32 * j) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(w + c0), be = *reinterpret_cast<const float4*>(b + c0);
+        const float o0 = (v[j].x - mean) * rstd * g.x + be.x, o1 = (v[j].y - mean) * rstd * g.y + be.y;
+        const float o2 = (v[j].z - mean) * rstd * g.z + be.z, o3 = (v[j].w - mean) * rstd * g.w + be.w;
+        if constexpr (sizeof(OUT) == 4) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + (size_t)r * kDim + c0) = make_float4(o0, o1, o2, o3);
+        } else {
+            uint2 o; o.x = Half16<OUT>::pack(o0, o1); o.y = Half16<OUT>::pack(o2, o3);
+            *reinterpret_cast<uint2*>(y + (size_t)r * kDim + c0) = o;
+        }
+    }
+}
+
+// ---- attention: one CTA per (image, head); softmax(Q K^T / 8) V over 197 tokens, head dim 64 -----------------------
+// qkv [B*197][2304] 16-bit with timm's column order (which*768 + head*64 + d).  Q, K (row-major, padded rows) and
+// V^T are staged in shared memory; each warp owns 16-query tiles: S = Q K^T with mma.sync m16n8k16 (fp32 accumulate,
+// the whole 16 x 208 score tile lives in registers, so the softmax is exact, not online), P rounded to 16 bits
+// feeds the second mma.sync against V^T.  Out: o [B*197][768] 16-bit (column = head*64 + d).
+constexpr int kTokPad = 208;                 // 197 padded to 13 tiles of 16
+constexpr int kQKStride = 72;                // halves per staged Q / K row: 64 + 8 (conflict-free fragment loads)
+constexpr int kVtStride = 216;               // halves per staged V^T row: 208 + 8
+
+template <typename T>
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    if constexpr (Half16<T>::kCode == kDtypeFP16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) vit_attention_kernel(const T* __restrict__ qkv, T* __restrict__ o) {
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    T* sQ = reinterpret_cast<T*>(att_smem);                       // [208][72]
+    T* sK = sQ + kTokPad * kQKStride;                             // [208][72]
+    T* sVt = sK + kTokPad * kQKStride;                            // [64][216]
+    const int head = blockIdx.x % kHeads;
+    const int64_t img = blockIdx.x / kHeads;
+    const T* base = qkv + (size_t)img * kTokens * (3 * kDim) + head * kHd;
+    const int tid = threadIdx.x;
+    // stage Q, K (16-byte chunks) and V^T (scattered 2-byte stores); padded rows / columns are zero
+    for (int i = tid; i < kTokPad * 8; i += 128) {
+        const int tok = i >> 3, ch = (i & 7) * 8;
+        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+        if (tok < kTokens) {
+            const T* row = base + (size_t)tok * (3 * kDim) + ch;
+            q = *reinterpret_cast<const uint4*>(row);
+            k = *reinterpret_cast<const uint4*>(row + kDim);
+            v = *reinterpret_cast<const uint4*>(row + 2 * kDim);
+        }
+        *reinterpret_cast<uint4*>(sQ + tok * kQKStride + ch) = q;
+        *reinterpret_cast<uint4*>(sK + tok * kQKStride + ch) = k;
+        const T* vh = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sVt[(ch + j) * kVtStride + tok] = vh[j];
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    for (int qt = warp; qt < kTokPad / 16; qt += 4) {
+        const int q0 = qt * 16;
+        uint32_t aq[4][4];                                          // Q fragments for the 4 k-steps of the head dim
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const T* r0 = sQ + (q0 + g) * kQKStride + ks * 16 + 2 * t;
+            const T* r1 = r0 + 8 * kQKStride;
+            aq[ks][0] = *reinterpret_cast<const uint32_t*>(r0);     aq[ks][1] = *reinterpret_cast<const uint32_t*>(r1);
+            aq[ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8); aq[ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+        }
+        float s[kTokPad / 8][4];
+#pragma unroll
+        for (int nt = 0; nt < kTokPad / 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+            const T* kr = sK + (nt * 8 + g) * kQKStride + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                mma16816<T>(s[nt], aq[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+        }
+        // softmax over the 197 valid keys of rows q0+g (c0,c1) and q0+g+8 (c2,c3): scale 1/8, mask the padding
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < kTokPad / 8; ++nt) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const bool ok = nt * 8 + 2 * t + j < kTokens;
+                s[nt][j] = ok ? s[nt][j] * 0.125f : -INFINITY;
+                s[nt][2 + j] = ok ? s[nt][2 + j] * 0.125f : -INFINITY;
+                m0 = fmaxf(m0, s[nt][j]); m1 = fmaxf(m1, s[nt][2 + j]);
+            }
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < kTokPad / 8; ++nt) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                s[nt][j] = __expf(s[nt][j] - m0); s[nt][2 + j] = __expf(s[nt][2 + j] - m1);
+                l0 += s[nt][j]; l1 += s[nt][2 + j];
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // O = P V: the score fragments of two adjacent 8-key tiles are exactly one 16-key A fragment
+        float acc[kHd / 8][4];
+#pragma unroll
+        for (int dt = 0; dt < kHd / 8; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kTokPad / 16; ++kk) {
+            uint32_t ap[4];
+            ap[0] = Half16<T>::pack(s[2 * kk][0], s[2 * kk][1]);         ap[1] = Half16<T>::pack(s[2 * kk][2], s[2 * kk][3]);
+            ap[2] = Half16<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]); ap[3] = Half16<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+            for (int dt = 0; dt < kHd / 8; ++dt) {
+                const T* vr = sVt + (dt * 8 + g) * kVtStride + kk * 16 + 2 * t;
+                mma16816<T>(acc[dt], ap, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+            }
+        }
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int r0 = q0 + g, r1 = r0 + 8;
+        T* ob = o + (size_t)img * kTokens * kDim + head * kHd + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < kHd / 8; ++dt) {
+            if (r0 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * kDim + dt * 8) = Half16<T>::pack(acc[dt][0] * i0, acc[dt][1] * i0);
+            if (r1 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * kDim + dt * 8) = Half16<T>::pack(acc[dt][2] * i1, acc[dt][3] * i1);
+        }
+    }
+}
+
+constexpr size_t kAttSmem = (size_t)(2 * kTokPad * kQKStride + kHd * kVtStride) * 2;
+
+}  // namespace dfd
+
+namespace {
+thread_local std::string g_vit_err;
+int vfail(int code, const std::string& m) { g_vit_err = m; return code; }
+uint16_t vh16(float v, int dtype) {
+    if (dtype == DFD_DTYPE_FP16) { __half h = __float2half_rn(v); uint16_t u; memcpy(&u, &h, 2); return u; }
+    __nv_bfloat16 h = __float2bfloat16_rn(v); uint16_t u; memcpy(&u, &h, 2); return u;
+}
+size_t vup(size_t b) { return (b + 255) & ~size_t(255); }
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* dfd_vit_last_error(void) { return g_vit_err.c_str(); }
+
+int dfd_vit_pack_weights(int n, const char* const* names, const float* const* data, const int64_t* numel,
+                         int dtype, dfd_vit_weights_t** out) {
+    if (!names || !data || !numel || !out || n <= 0) return vfail(DFD_EINVAL, "dfd_vit_pack_weights: null argument");
+    if (dtype != DFD_DTYPE_BF16 && dtype != DFD_DTYPE_FP16) return vfail(DFD_EINVAL, "dfd_vit_pack_weights: unknown dtype");
+    std::unordered_map<std::string, std::pair<const float*, int64_t>> t;
+    for (int i = 0; i < n; ++i) {
+        if (!names[i]) continue;
+        std::string k = names[i];
+        if (k.rfind("vit.", 0) == 0) k = k.substr(4);             // the reference keeps the timm model under `.vit` (models.py:93)
+        t[k] = {data[i], numel[i]};
+    }
+    std::string missing;
+    auto get = [&](const std::string& k, int64_t ne) -> const float* {
+        auto it = t.find(k);
+        if (it == t.end() || it->second.second != ne) { if (missing.empty()) missing = k; return nullptr; }
+        return it->second.first;
+    };
+    std::vector<uint8_t> host;
+    auto alloc = [&](size_t nb) { size_t o = (host.size() + 255) & ~size_t(255); host.resize(o + nb, 0); return o; };
+    auto put16 = [&](const std::string& k, int64_t ne) {
+        const size_t off = alloc((size_t)ne * 2);
+        const float* p = get(k, ne);
+        if (p) { uint16_t* d = reinterpret_cast<uint16_t*>(host.data() + off); for (int64_t i = 0; i < ne; ++i) d[i] = vh16(p[i], dtype); }
+        return off;
+    };
+    auto put32 = [&](const std::string& k, int64_t ne) {
+        const size_t off = alloc((size_t)ne * 4);
+        const float* p = get(k, ne);
+        if (p) memcpy(host.data() + off, p, (size_t)ne * 4);
+        return off;
+    };
+    size_t o_patch_w = put16("patch_embed.proj.weight", (int64_t)kDim * kPatchK), o_patch_b = put32("patch_embed.proj.bias", kDim);
+    size_t o_cls = put32("cls_token", kDim), o_pos = put32("pos_embed", (int64_t)kTokens * kDim);
+    size_t ob[kDepth][12];
+    for (int i = 0; i < kDepth; ++i) {
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        ob[i][0] = put32(p + "norm1.weight", kDim); ob[i][1] = put32(p + "norm1.bias", kDim);
+        ob[i][2] = put32(p + "norm2.weight", kDim); ob[i][3] = put32(p + "norm2.bias", kDim);
+        ob[i][4] = put16(p + "attn.qkv.weight", (int64_t)3 * kDim * kDim); ob[i][5] = put32(p + "attn.qkv.bias", 3 * kDim);
+        ob[i][6] = put16(p + "attn.proj.weight", (int64_t)kDim * kDim);    ob[i][7] = put32(p + "attn.proj.bias", kDim);
+        ob[i][8] = put16(p + "mlp.fc1.weight", (int64_t)kMlp * kDim);      ob[i][9] = put32(p + "mlp.fc1.bias", kMlp);
+        ob[i][10] = put16(p + "mlp.fc2.weight", (int64_t)kDim * kMlp);     ob[i][11] = put32(p + "mlp.fc2.bias", kDim);
+    }
+    size_t o_nw = put32("norm.weight", kDim), o_nb = put32("norm.bias", kDim);
+    if (!missing.empty()) return vfail(DFD_EKEY, "dfd_vit_pack_weights: state_dict tensor " + missing + " absent or wrong size");
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, host.size()) != cudaSuccess) return vfail(DFD_ECUDA, "cudaMalloc(vit weights) failed");
+    if (cudaMemcpy(dev, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return vfail(DFD_ECUDA, "cudaMemcpy(vit weights) failed"); }
+    auto* W = new dfd_vit_weights();
+    uint8_t* d = reinterpret_cast<uint8_t*>(dev);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(d + off); };
+    W->dtype = dtype; W->arena = dev;
+    W->patch_w = d + o_patch_w; W->patch_b = F(o_patch_b); W->cls = F(o_cls); W->pos = F(o_pos);
+    for (int i = 0; i < kDepth; ++i) {
+        auto& b = W->blk[i];
+        b.ln1_w = F(ob[i][0]); b.ln1_b = F(ob[i][1]); b.ln2_w = F(ob[i][2]); b.ln2_b = F(ob[i][3]);
+        b.qkv_w = d + ob[i][4]; b.qkv_b = F(ob[i][5]); b.proj_w = d + ob[i][6]; b.proj_b = F(ob[i][7]);
+        b.fc1_w = d + ob[i][8]; b.fc1_b = F(ob[i][9]); b.fc2_w = d + ob[i][10]; b.fc2_b = F(ob[i][11]);
+    }
+    W->norm_w = F(o_nw); W->norm_b = F(o_nb);
+    *out = W;
+    return DFD_OK;
+}
+
+void dfd_vit_free_weights(dfd_vit_weights_t* w) { if (w) { if (w->arena) cudaFree(w->arena); delete w; } }
+
+int dfd_vit_workspace_bytes(int64_t images, size_t* bytes) {
+    if (!bytes || images <= 0) return vfail(DFD_EINVAL, "dfd_vit_workspace_bytes: bad argument");
+    const size_t M = (size_t)images * kTokens;
+    *bytes = vup(M * kDim * 4) + vup(M * kDim * 2) + vup(M * kMlp * 2) + 1024;
+    return DFD_OK;
+}
+
+int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t images, float* d_features,
+                     void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!w || !d_in || !d_features || !d_workspace) return vfail(DFD_EINVAL, "dfd_vit_features: null pointer");
+    size_t need = 0;
+    int rc = dfd_vit_workspace_bytes(images, &need);
+    if (rc) return rc;
+    if (workspace_bytes < need) return vfail(DFD_ENOMEM, "dfd_vit_features: workspace too small");
+    if (images * kTokens * (int64_t)kMlp > 0x7fffffffffLL) return vfail(DFD_EINVAL, "dfd_vit_features: batch too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t M = images * kTokens, MP = images * kPatches;
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255));
+    float* X = reinterpret_cast<float*>(ws);   ws += vup((size_t)M * kDim * 4);     // fp32 residual stream
+    void* H16 = ws;                            ws += vup((size_t)M * kDim * 2);     // LN output / attention output / patch GEMM output
+    void* BIG = ws;                                                                  // patches / qkv / MLP hidden
+    const int dt = w->dtype;
+    const bool f16 = dt == DFD_DTYPE_FP16;
+    cudaError_t e;
+#define VIT_CK(call, what) do { e = (call); if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
+    auto ln = [&](const float* in, int64_t stride, const float* g, const float* b, void* out, bool out_f32, int64_t rows) {
+        const unsigned grid = (unsigned)((rows + 7) / 8);
+        if (out_f32) dfd::vit_layernorm_kernel<float><<<grid, 256, 0, s>>>(in, stride, g, b, (float*)out, rows);
+        else if (f16) dfd::vit_layernorm_kernel<__half><<<grid, 256, 0, s>>>(in, stride, g, b, (__half*)out, rows);
+        else dfd::vit_layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, stride, g, b, (__nv_bfloat16*)out, rows);
+        return cudaGetLastError();
+    };
+    {
+        const int64_t n8 = MP * (kPatchK / 8);
+        const unsigned grid = (unsigned)((n8 + 255) / 256);
+        if (f16) dfd::vit_patchify_kernel<__half><<<grid, 256, 0, s>>>(d_in, (__half*)BIG, n8);
+        else dfd::vit_patchify_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(d_in, (__nv_bfloat16*)BIG, n8);
+        VIT_CK(cudaGetLastError(), "vit patchify");
+        VIT_CK(dfd::launch_gemm_tc(BIG, w->patch_w, w->patch_b, nullptr, nullptr, H16, MP, kPatchK, kDim, 1, 0, dt, s), "vit patch-embed gemm");
+        const int64_t a8 = M * (kDim / 8);
+        const unsigned agrid = (unsigned)((a8 + 255) / 256);
+        if (f16) dfd::vit_assemble_kernel<__half><<<agrid, 256, 0, s>>>((const __half*)H16, w->cls, w->pos, X, a8);
+        else dfd::vit_assemble_kernel<__nv_bfloat16><<<agrid, 256, 0, s>>>((const __nv_bfloat16*)H16, w->cls, w->pos, X, a8);
+        VIT_CK(cudaGetLastError(), "vit assemble");
+    }
+    if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAttSmem), "vit attention smem");
+    else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAttSmem), "vit attention smem");
+    for (int i = 0; i < kDepth; ++i) {
+        const auto& b = w->blk[i];
+        VIT_CK(ln(X, kDim, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");
+        VIT_CK(dfd::launch_gemm_tc(H16, b.qkv_w, b.qkv_b, nullptr, nullptr, BIG, M, kDim, 3 * kDim, 1, 0, dt, s), "vit qkv gemm");
+        if (f16) dfd::vit_attention_kernel<__half><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __half*)BIG, (__half*)H16);
+        else dfd::vit_attention_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
+        VIT_CK(cudaGetLastError(), "vit attention");
+        VIT_CK(dfd::launch_gemm_tc_f32out(H16, b.proj_w, b.proj_b, X, X, M, kDim, kDim, dt, s), "vit proj gemm");
+        VIT_CK(ln(X, kDim, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");
+        VIT_CK(dfd::launch_gemm_tc(H16, b.fc1_w, b.fc1_b, nullptr, nullptr, BIG, M, kDim, kMlp, 1, 2, dt, s), "vit fc1 gemm");
+        VIT_CK(dfd::launch_gemm_tc_f32out(BIG, b.fc2_w, b.fc2_b, X, X, M, kMlp, kDim, dt, s), "vit fc2 gemm");
+    }
+    VIT_CK(ln(X, (int64_t)kTokens * kDim, w->norm_w, w->norm_b, d_features, true, images), "vit final norm");
+#undef VIT_CK
+    return DFD_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -110,6 +110,23 @@ int dfd_rnn_workspace_bytes(const dfd_rnn_weights_t* w, int64_t batch, int T, si
 int dfd_rnn_forward(const dfd_rnn_weights_t* w, const float* d_x, const int32_t* d_lengths, int64_t batch, int T,
                     float* d_prob, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- ViT-B/16 frame encoder (BASELINE config 5): src/models.py:88-107 ViTFeatureExtractor ------------------
+ * = timm `vit_base_patch16_224(num_classes=0)` (models.py:93): 224x224 images -> CLS feature after the final norm.
+ * Weights by reference state_dict key, with or without the `vit.` prefix ("vit.patch_embed.proj.weight",
+ * "vit.cls_token", "vit.pos_embed", "vit.blocks.{i}.{norm1,norm2}.{weight,bias}",
+ * "vit.blocks.{i}.attn.{qkv,proj}.{weight,bias}", "vit.blocks.{i}.mlp.{fc1,fc2}.{weight,bias}", "vit.norm.*"), HOST
+ * fp32; Linear / conv weights are cast to `dtype` (GEMM operands), everything else stays fp32.
+ * dfd_vit_features: d_in fp32 (B,3,224,224), already normalised (what forward() receives, models.py:105-107)
+ * -> d_features fp32 (B,768).  Workspace: dfd_vit_workspace_bytes(B) bytes, not shared between concurrent calls. */
+typedef struct dfd_vit_weights dfd_vit_weights_t;
+const char* dfd_vit_last_error(void);
+int dfd_vit_pack_weights(int n_tensors, const char* const* names, const float* const* data, const int64_t* numel,
+                         int dtype, dfd_vit_weights_t** out);
+void dfd_vit_free_weights(dfd_vit_weights_t* w);
+int dfd_vit_workspace_bytes(int64_t images, size_t* bytes);
+int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t images, float* d_features,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement aid --------------------------------------------------------------------------------
  * dfd_profile_enable(1): from now on every kernel launched by this thread through this library is
  * bracketed by CUDA events recorded on the launch stream.  dfd_profile_collect synchronises on them and

@@ -132,9 +132,85 @@ class EfficientNet(nn.Module):
         return self.classifier(self.global_pool(self.forward_features(x)))
 
 
+# ---------------------------------------------------------------------------------------------------------
+# `vit_base_patch16_224` (reference call site src/models.py:93, `num_classes=0`): timm's VisionTransformer with
+# timm's module / parameter names — patch_embed.proj (Conv2d 16x16 s16), cls_token, pos_embed (1,197,768),
+# blocks.{i}.{norm1, attn.qkv, attn.proj, norm2, mlp.fc1, mlp.fc2}, norm (LayerNorm eps 1e-6), fc_norm / head =
+# Identity for num_classes=0, global_pool='token' (the CLS row after the final norm), exact-erf GELU,
+# qkv_bias=True, pre-norm blocks without LayerScale.
+class PatchEmbed(nn.Module):
+    def __init__(self, img=224, patch=16, cin=3, dim=768):
+        super().__init__()
+        self.proj = nn.Conv2d(cin, dim, patch, patch)
+        self.num_patches = (img // patch) ** 2
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)          # (B, 196, dim), row-major patch order
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.num_heads, self.scale = heads, (dim // heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.unbind(0)
+        attn = ((q * self.scale) @ k.transpose(-2, -1)).softmax(dim=-1)
+        return self.proj((attn @ v).transpose(1, 2).reshape(B, N, C))
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.act, self.fc2 = nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Block(nn.Module):
+    def __init__(self, dim, heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img=224, patch=16, dim=768, depth=12, heads=12, num_classes=1000):
+        super().__init__()
+        self.num_features = self.embed_dim = dim
+        self.patch_embed = PatchEmbed(img, patch, 3, dim)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, self.patch_embed.num_patches + 1, dim) * 0.02)
+        self.blocks = nn.Sequential(*[Block(dim, heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.fc_norm = nn.Identity()
+        self.head = nn.Linear(dim, num_classes) if num_classes > 0 else nn.Identity()
+
+    def forward_features(self, x):
+        x = self.patch_embed(x)
+        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + self.pos_embed
+        return self.norm(self.blocks(x))
+
+    def forward(self, x):
+        return self.head(self.fc_norm(self.forward_features(x)[:, 0]))
+
+
 def create_model(model_name, pretrained=False, **kwargs):
     if pretrained:
         raise RuntimeError("timm stand-in: no pretrained weights offline (pass pretrained=False)")
     if model_name == "efficientnet_b0":
         return EfficientNet(num_classes=kwargs.get("num_classes", 1000))
+    if model_name == "vit_base_patch16_224":
+        return VisionTransformer(num_classes=kwargs.get("num_classes", 1000))
     raise ValueError(f"timm stand-in: unsupported model {model_name!r}")
