@@ -278,6 +278,29 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo,
     d |= (uint64_t)1 << 46;
     return d;   // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
+// Same for the 128-byte-swizzled K-major layout TMA produces (box = 64 elements x rows, CU_TENSOR_MAP_SWIZZLE_128B):
+// rows 128 B apart, 8-row groups 1024 B apart, 16-byte chunk index XORed with (row & 7).  A 16-element K step
+// advances the start address by 32 bytes inside the swizzle atom.  The tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)1 << 16;                        // LBO: unused for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;              // SBO
+    d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+// TMA: 2-D tiled bulk copy global -> shared, completion counted in bytes on an mbarrier (issued by ONE thread)
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
+}
 // Instruction descriptor for kind::f16: fp32 accumulate, K-major A and B, M x N tile.
 __device__ __host__ constexpr uint32_t umma_idesc(uint32_t ab_format, uint32_t m, uint32_t n) {
     return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

@@ -25,7 +25,10 @@
 // enough bytes in flight", not tensor-pipe occupancy.
 #include "common.cuh"
 #include "kernels.h"
+#include <cuda.h>
 #include <cstdlib>
+#include <cstring>
+#include <unordered_map>
 
 namespace dfd {
 
@@ -35,7 +38,7 @@ constexpr int kMaxStages = 16;
 // Warp roles are template parameters: D-heavy layers (expand, head: SiLU on every output) get 16 epilogue
 // and 4 loader warps; A-heavy gated project layers 8 epilogue, 4 loader and 8 transformer warps.  Epilogue
 // warps come first so that (warp index % 4) is the TMEM lane quarter a warp may access.
-constexpr uint32_t kLboA = kBM * 16 + 16;                            // +16: bank-conflict-free staging stores
+constexpr uint32_t kAStageBytes = kBM * 128;                         // A tile of a stage: 128 rows x 64 elements, 128-byte swizzle (TMA)
 
 struct GemmArgs {
     const void* A; const void* W; const float* bias; const float* gate; const void* R; void* D; float* feat;
@@ -56,7 +59,7 @@ struct GemmArgs {
                                     //    8 skip the transformers' proxy fence, 16 per-thread (not per-warp) arrivals
     int xg;                         // gated: transformer warp groups taking alternate stages
     int cshift;                     // log2 of the 16-byte chunk columns a loader thread group spans (K < 64: fewer than 8)
-    uint32_t lbo_b, a_stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
+    uint32_t lbo_b, stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
     // unit strides of the persistent loops, decomposed on the host so that no role divides per tile
     int64_t stride1, strideE;       // grid, na * grid
@@ -96,7 +99,7 @@ struct TileIter {
 
 // ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
 template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
-__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
     constexpr int kProdThreads = kProdWarps * 32;
     constexpr int kXformThreads = kXformWarps * 32;
@@ -105,17 +108,18 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     constexpr int kColGroups = kEpiWarps / 4;       // epilogue warps sharing a TMEM lane quarter split the columns
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- shared memory carve-up ----------------------------------------------------------------
-    const uint32_t stage_bytes = p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes) + p.g_stage_bytes;
-    const uint32_t g_off = stage_bytes - p.g_stage_bytes;          // gate slice sits at the end of a stage
-    uint8_t* sp = smem_raw + p.b_res_bytes + (size_t)p.stages * stage_bytes;
+    // [resident W][pad to 1024][stages x (A tile 16 KB | streamed W block | gate slice), 1024-aligned][bias, pool, barriers]
+    const uint32_t stage_bytes = p.stage_bytes;
+    const uint32_t g_off = kAStageBytes + (p.b_resident ? 0u : p.b_stage_bytes);
+    const uint32_t bres_base = smem_u32(smem_raw);
+    const uint32_t smem_base = (bres_base + p.b_res_bytes + 1023u) & ~1023u;
+    uint8_t* sp = smem_raw + (smem_base - bres_base) + (size_t)p.stages * stage_bytes;
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
     float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += kColGroups * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
     uint64_t* bars = reinterpret_cast<uint64_t*>(sp);             // full[S], empty[S], raw[S], tfull[8], tempty[8]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 16);
 
-    const uint32_t bres_base = smem_u32(smem_raw);
-    const uint32_t smem_base = bres_base + p.b_res_bytes;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kMaxStages);
     const uint32_t bar_raw = smem_u32(bars + 2 * kMaxStages);
     const uint32_t bar_tfull = smem_u32(bars + 3 * kMaxStages), bar_tempty = smem_u32(bars + 3 * kMaxStages + 8);
@@ -125,9 +129,11 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(bar_full + 8 * s, GATE ? (p.dbg & 16 ? kXformThreads : kXformWarps) / p.xg : kProdThreads);
+            // landed stage = 1 arrival of the TMA issuer (+ its transaction bytes) + the cp.async loaders, if any
+            const uint32_t landed = 1u + ((GATE || !p.b_resident) ? kProdThreads : 0u);
+            mbar_init(bar_full + 8 * s, GATE ? (p.dbg & 16 ? kXformThreads : kXformWarps) / p.xg : landed);
             mbar_init(bar_empty + 8 * s, 1);
-            mbar_init(bar_raw + 8 * s, kProdThreads);
+            mbar_init(bar_raw + 8 * s, landed);
         }
         for (int a = 0; a < p.nacc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kColGroups / p.na) * (p.dbg & 16 ? 128 : 4)); }
         fence_barrier_init();
@@ -166,67 +172,58 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
 
     if (warp > kMmaWarp && warp <= kMmaWarp + kProdWarps) {
         // =================================== LOADERS =============================================
-        // Thread tp owns 16-byte chunk column q = tp % 8 of rows rb + kRowStep*j: no divisions in the loop, a
-        // quarter-warp copies 128 contiguous bytes of one row, and its 8 shared-memory writes land in 8
-        // different bank groups (LBO is padded by 16 bytes).
+        // A tiles: ONE thread issues one TMA per stage (box 64 x 128, zero fill outside the tensor), completion
+        // counted in bytes on the stage barrier.  The other loader threads only copy what TMA does not: streamed
+        // weight blocks (cp.async straight into the no-swizzle UMMA layout) and the gate slice of gated layers.
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
-        const int q = tp & ((1 << p.cshift) - 1), rb = tp >> p.cshift;
-        const int row_step = kProdThreads >> p.cshift, passes = kBM / row_step;
-        const T* A = reinterpret_cast<const T*>(p.A);
-        const T* Wt = reinterpret_cast<const T*>(p.W);
-        const uint32_t a_off = q * kLboA + rb * 16, b_off = q * p.lbo_b + rb * 16;
-        const int K = p.K;
-        int stage = 0; uint32_t phase = 0;
-        TileIter it; it.init(p, blockIdx.x);
-        for (; it.u < units; it.next1(p)) {
-            const int64_t m0 = it.m0(p);
-            const int rows_valid = it.rows_valid(p, m0);
-            const int n0 = it.nc * p.NB;
-            const int nb_valid = min(p.NB, p.N - n0);
-            const uint32_t f0 = GATE ? (uint32_t)m0 / (uint32_t)p.HW : 0u;
-            const T* arow = A + (size_t)(m0 + rb) * K + q * 8;
-            const T* wrow = Wt + (size_t)it.frame * p.w_frame_stride + (size_t)(n0 + rb) * K + q * 8;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int k0 = kb * kKB;
-                const int kc = min(8, (K - k0) >> 3);          // 16-byte chunks present in this k-block
-                const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
-                DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
-                const uint32_t a_base = smem_base + stage * stage_bytes;
-                if (q < kcp && !(p.dbg & 1)) {
-                    const T* src = arow + k0;
-                    if (rows_valid == kBM && q < kc) {          // full tile: no per-row predicates
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j < passes) cp_async16(a_base + a_off + j * (row_step * 16), src + (size_t)(row_step * j) * K, true);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            if (j < passes) {
-                                const bool ok = (rb + row_step * j < rows_valid) && (q < kc);
-                                cp_async16(a_base + a_off + j * (row_step * 16), ok ? src + (size_t)(row_step * j) * K : A, ok);
+        const bool cp_work = GATE || !p.b_resident;
+        if (tp == 0) tma_prefetch_desc(&tmA);
+        if (tp == 0 || cp_work) {
+            const int q = tp & 7, rb = tp >> 3;
+            constexpr int row_step = kProdThreads >> 3;
+            const T* Wt = reinterpret_cast<const T*>(p.W);
+            const uint32_t b_off = q * p.lbo_b + rb * 16;
+            const int K = p.K;
+            int stage = 0; uint32_t phase = 0;
+            TileIter it; it.init(p, blockIdx.x);
+            for (; it.u < units; it.next1(p)) {
+                const int64_t m0 = it.m0(p);
+                const int n0 = it.nc * p.NB;
+                const int nb_valid = min(p.NB, p.N - n0);
+                const uint32_t f0 = GATE ? (uint32_t)m0 / (uint32_t)p.HW : 0u;
+                const T* wrow = Wt + (size_t)it.frame * p.w_frame_stride + (size_t)(n0 + rb) * K + q * 8;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int k0 = kb * kKB;
+                    const int kc = min(8, (K - k0) >> 3);          // 16-byte chunks present in this k-block
+                    const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
+                    DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
+                    const uint32_t a_base = smem_base + stage * stage_bytes;
+                    const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
+                    if (tp == 0) {
+                        mbar_arrive_expect_tx(bar, (p.dbg & 1) ? 0u : kAStageBytes);
+                        if (!(p.dbg & 1)) tma_load_2d(a_base, &tmA, k0, (int)m0, bar);
+                    }
+                    if (cp_work) {
+                        if (!p.b_resident && q < kcp) {
+                            const uint32_t b_base = a_base + kAStageBytes;
+                            const T* wsrc = wrow + k0;
+                            for (int r = rb; r < p.NBp; r += row_step) {
+                                const bool ok = (r < nb_valid) && (q < kc);
+                                cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * K : Wt, ok);   // per-frame weights when tpf > 0
                             }
                         }
-                    }
-                    if (!p.b_resident) {
-                        const uint32_t b_base = a_base + p.a_stage_bytes;
-                        const T* wsrc = wrow + k0;
-                        for (int r = rb; r < p.NBp; r += row_step) {
-                            const bool ok = (r < nb_valid) && (q < kc);
-                            cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * K : Wt, ok);   // per-frame weights when tpf > 0
+                        if (GATE) {                                // gate slice [nf_max][64] fp32 for this k-block
+                            for (int i = tp; i < p.nf_max * 16; i += kProdThreads) {
+                                const uint32_t fl = i >> 4, c = i & 15;
+                                const bool ok = (f0 + fl < (uint32_t)p.total_frames) && (k0 + (int)c * 4 < p.K);
+                                cp_async16(a_base + g_off + fl * 256 + c * 16,
+                                           ok ? p.gate + (size_t)(f0 + fl) * p.K + k0 + c * 4 : p.gate, ok);
+                            }
                         }
+                        cp_async_mbar_arrive_noinc(bar);           // arrives when this thread's copies have landed
                     }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (GATE) {                                    // gate slice [nf_max][64] fp32 for this k-block
-                    for (int i = tp; i < p.nf_max * 16; i += kProdThreads) {
-                        const uint32_t fl = i >> 4, c = i & 15;
-                        const bool ok = (f0 + fl < (uint32_t)p.total_frames) && (k0 + (int)c * 4 < p.K);
-                        cp_async16(a_base + g_off + fl * 256 + c * 16,
-                                   ok ? p.gate + (size_t)(f0 + fl) * p.K + k0 + c * 4 : p.gate, ok);
-                    }
-                }
-                const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
-                cp_async_mbar_arrive_noinc(bar);               // arrives when this thread's copies have landed
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (GATE && warp > kMmaWarp + kProdWarps) {
@@ -237,7 +234,6 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         const int gthreads = kXformThreads / p.xg;
         const int grp = tx / gthreads, tg = tx - grp * gthreads;
         const int q = tg & 7, rb = tg >> 3, xstep = gthreads >> 3, xpasses = kBM / xstep;
-        const uint32_t a_off = q * kLboA + rb * 16;
         int stage = 0; uint32_t phase = 0; int turn = 0;
         TileIter it; it.init(p, blockIdx.x);
         for (; it.u < units; it.next1(p)) {
@@ -262,7 +258,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                                     const uint32_t gaddr = a_base + g_off + fl * 256 + q * 32;
                                     gA = lds16(gaddr); gB = lds16(gaddr + 16); fl_loaded = fl;
                                 }
-                                const uint32_t addr = a_base + a_off + j * (xstep * 16);
+                                const int r = rb + xstep * j;                       // 128-byte swizzle: chunk q of row r
+                                const uint32_t addr = a_base + r * 128 + ((q ^ (r & 7)) << 4);
                                 uint4 v = lds16(addr);
                                 const float2 x0 = Half16<T>::unpack(v.x), x1 = Half16<T>::unpack(v.y);
                                 const float2 x2 = Half16<T>::unpack(v.z), x3 = Half16<T>::unpack(v.w);
@@ -302,9 +299,9 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 if (lane == 0) {
                     const uint32_t a_base = smem_base + stage * stage_bytes;
                     const uint32_t b_base = p.b_resident ? bres_base + (p.b_resident == 2 ? 0 : nc * p.b_chunk_bytes) + kb * 8 * p.lbo_b
-                                                         : a_base + p.a_stage_bytes;
+                                                         : a_base + kAStageBytes;
                     for (int j = 0; j < steps; ++j) {
-                        const uint64_t adesc = umma_smem_desc(a_base + 2 * j * kLboA, kLboA, 128);
+                        const uint64_t adesc = umma_smem_desc_sw128(a_base + 32 * j);
                         const uint64_t bdesc = umma_smem_desc(b_base + 2 * j * p.lbo_b, p.lbo_b, 128);
                         if (!(p.dbg & 2)) umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
                     }
@@ -452,6 +449,42 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
 // ---------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
+// Tensor map of the A operand: [M rows][K elements] 16-bit row-major, box = 64 elements x 128 rows, 128-byte swizzle,
+// zero fill outside the tensor (K tails, the last M tile).  cuTensorMapEncodeTiled comes from the driver through the
+// runtime's entry-point query (no link against libcuda); maps are cached per thread by (pointer, M, K).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static cudaError_t make_tmap_a(const void* A, int64_t M, int K, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    struct Key { const void* p; int64_t m; int k; bool operator==(const Key& o) const { return p == o.p && m == o.m && k == o.k; } };
+    struct Hash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) ^ (size_t)k.m * 1315423911u ^ (size_t)k.k * 2654435761u; } };
+    thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+    const Key key{A, M, K};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return cudaSuccess; }
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    // 16-bit payload: the element type only matters for the (unused) NaN fill, UINT16 serves fp16 and bf16 alike
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(A), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return cudaSuccess;
+}
+
 template <typename KernelT>
 static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, int xform_warps, cudaStream_t s) {
     if (g_num_sms == 0) {
@@ -472,7 +505,6 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     {   static const int env_xg = getenv("DFD_GEMM_XG") ? atoi(getenv("DFD_GEMM_XG")) : 4;
         a.xg = xform_warps > 0 ? env_xg : 1;
         if (a.xg < 1 || a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1; }
-    a.a_stage_bytes = (uint32_t)kcp_max * kLboA;
     a.b_stage_bytes = (uint32_t)kcp_max * a.lbo_b;
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
     {   // accumulator ring: as many buffers as fit in the 512 TMEM columns (<= 8); epilogue groups take alternate tiles
@@ -499,15 +531,17 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
         else if (a.n_chunks > 1 && a.n_chunks <= g_num_sms && a.b_chunk_bytes <= res_limit) a.b_resident = 2;
     }
     a.b_res_bytes = a.b_resident == 1 ? (uint32_t)bres : (a.b_resident == 2 ? a.b_chunk_bytes : 0u);
-    const size_t stage_bytes = a.a_stage_bytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes;
-    int stages = (int)((budget - fixed - a.b_res_bytes) / stage_bytes);
+    const size_t stage_bytes = ((size_t)kAStageBytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes + 1023) & ~size_t(1023);
+    a.stage_bytes = (uint32_t)stage_bytes;
+    const size_t bres_pad = ((size_t)a.b_res_bytes + 1023) & ~size_t(1023);      // + worst-case alignment of the stage ring
+    int stages = (int)((budget - fixed - bres_pad - 1024) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     static const int env_stages = getenv("DFD_GEMM_STAGES") ? atoi(getenv("DFD_GEMM_STAGES")) : 0;     // experiments only
     if (env_stages >= 3 && stages > env_stages) stages = env_stages;
     if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
     while (a.xg > 1 && (a.xg > stages || a.xg > 4)) a.xg >>= 1;      // groups take alternate stages: never more groups than stages
-    const size_t smem = a.b_res_bytes + (size_t)stages * stage_bytes + fixed;
+    const size_t smem = bres_pad + 1024 + (size_t)stages * stage_bytes + fixed;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t units = a.m_tiles * a.n_chunks;
@@ -523,7 +557,10 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
         split(a.stride1, a.d1_mt, a.d1_nc, a.d1_frame, a.d1_t);
         split(a.strideE, a.dE_mt, a.dE_nc, a.dE_frame, a.dE_t);
     }
-    kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a);
+    CUtensorMap tmA;
+    e = make_tmap_a(a.A, a.M, a.K, &tmA);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a, tmA);
     return cudaGetLastError();
 }
 
