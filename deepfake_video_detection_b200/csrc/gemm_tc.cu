@@ -56,7 +56,8 @@ struct GemmArgs {
                                     //    column chunk (grid is a multiple of n_chunks, so a CTA always works on the same chunk)
     int kchunks_pad;                // K/8 rounded up to even
     int dbg;                        // timing experiments (DFD_GEMM_DBG): 1 skip loads, 2 skip MMAs, 4 skip stores,
-                                    //    8 skip the transformers' proxy fence, 16 per-thread (not per-warp) arrivals
+                                    //    8 skip the transformers' proxy fence, 16 per-thread (not per-warp) arrivals,
+                                    //    32 per-role wait accounting, 64 transformers skip the tile, 128 transformers skip the stores
     int xg;                         // gated: transformer warp groups taking alternate stages
     int cshift;                     // log2 of the 16-byte chunk columns a loader thread group spans (K < 64: fewer than 8)
     uint32_t lbo_b, stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
@@ -99,7 +100,7 @@ struct TileIter {
 
 // ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
 template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
-__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA) {
+__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
     constexpr int kProdThreads = kProdWarps * 32;
     constexpr int kXformThreads = kXformWarps * 32;
@@ -129,11 +130,10 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
-            // landed stage = 1 arrival of the TMA issuer (+ its transaction bytes) + the cp.async loaders, if any
-            const uint32_t landed = 1u + ((GATE || !p.b_resident) ? kProdThreads : 0u);
-            mbar_init(bar_full + 8 * s, GATE ? (p.dbg & 16 ? kXformThreads : kXformWarps) / p.xg : landed);
+            // a landed stage = the TMA issuer's arrival + its transaction bytes
+            mbar_init(bar_full + 8 * s, GATE ? (p.dbg & 16 ? kXformThreads : kXformWarps) / p.xg : 1);
             mbar_init(bar_empty + 8 * s, 1);
-            mbar_init(bar_raw + 8 * s, landed);
+            mbar_init(bar_raw + 8 * s, 1 + 64);                 // TMA issuer + the 64 gate-slice copiers
         }
         for (int a = 0; a < p.nacc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, (kColGroups / p.na) * (p.dbg & 16 ? 128 : 4)); }
         fence_barrier_init();
@@ -172,56 +172,49 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
 
     if (warp > kMmaWarp && warp <= kMmaWarp + kProdWarps) {
         // =================================== LOADERS =============================================
-        // A tiles: ONE thread issues one TMA per stage (box 64 x 128, zero fill outside the tensor), completion
-        // counted in bytes on the stage barrier.  The other loader threads only copy what TMA does not: streamed
-        // weight blocks (cp.async straight into the no-swizzle UMMA layout) and the gate slice of gated layers.
+        // ONE thread issues the TMA copies of a stage — the A tile (box 64 x 128, zero fill outside the tensor) and,
+        // for weights too large to stay resident, the W block (box 64 x NBp) — both into the 128-byte-swizzled UMMA
+        // layout, completion counted in bytes on the stage barrier.  No other loader thread has work in the main loop.
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
-        const bool cp_work = GATE || !p.b_resident;
-        if (tp == 0) tma_prefetch_desc(&tmA);
-        if (tp == 0 || cp_work) {
-            const int q = tp & 7, rb = tp >> 3;
-            constexpr int row_step = kProdThreads >> 3;
-            const T* Wt = reinterpret_cast<const T*>(p.W);
-            const uint32_t b_off = q * p.lbo_b + rb * 16;
-            const int K = p.K;
+        if (tp == 0) {
+            tma_prefetch_desc(&tmA);
+            if (!p.b_resident) tma_prefetch_desc(&tmB);
+            const uint32_t tx_bytes = kAStageBytes + (p.b_resident ? 0u : p.b_stage_bytes);
             int stage = 0; uint32_t phase = 0;
             TileIter it; it.init(p, blockIdx.x);
             for (; it.u < units; it.next1(p)) {
-                const int64_t m0 = it.m0(p);
-                const int n0 = it.nc * p.NB;
-                const int nb_valid = min(p.NB, p.N - n0);
-                const uint32_t f0 = GATE ? (uint32_t)m0 / (uint32_t)p.HW : 0u;
-                const T* wrow = Wt + (size_t)it.frame * p.w_frame_stride + (size_t)(n0 + rb) * K + q * 8;
+                const int m0 = (int)it.m0(p);
+                const int wrow = (int)it.frame * p.N + it.nc * p.NB;       // per-frame weights when tpf > 0
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const int k0 = kb * kKB;
-                    const int kc = min(8, (K - k0) >> 3);          // 16-byte chunks present in this k-block
-                    const int kcp = (kc + 1) & ~1;                 // MMA consumes chunk pairs: pad with zeros
                     DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
                     const uint32_t a_base = smem_base + stage * stage_bytes;
                     const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
-                    if (tp == 0) {
-                        mbar_arrive_expect_tx(bar, (p.dbg & 1) ? 0u : kAStageBytes);
-                        if (!(p.dbg & 1)) tma_load_2d(a_base, &tmA, k0, (int)m0, bar);
+                    mbar_arrive_expect_tx(bar, (p.dbg & 1) ? 0u : tx_bytes);
+                    if (!(p.dbg & 1)) {
+                        tma_load_2d(a_base, &tmA, kb * kKB, m0, bar);
+                        if (!p.b_resident) tma_load_2d(a_base + kAStageBytes, &tmB, kb * kKB, wrow, bar);
                     }
-                    if (cp_work) {
-                        if (!p.b_resident && q < kcp) {
-                            const uint32_t b_base = a_base + kAStageBytes;
-                            const T* wsrc = wrow + k0;
-                            for (int r = rb; r < p.NBp; r += row_step) {
-                                const bool ok = (r < nb_valid) && (q < kc);
-                                cp_async16(b_base + b_off + (r - rb) * 16, ok ? wsrc + (size_t)(r - rb) * K : Wt, ok);   // per-frame weights when tpf > 0
-                            }
-                        }
-                        if (GATE) {                                // gate slice [nf_max][64] fp32 for this k-block
-                            for (int i = tp; i < p.nf_max * 16; i += kProdThreads) {
-                                const uint32_t fl = i >> 4, c = i & 15;
-                                const bool ok = (f0 + fl < (uint32_t)p.total_frames) && (k0 + (int)c * 4 < p.K);
-                                cp_async16(a_base + g_off + fl * 256 + c * 16,
-                                           ok ? p.gate + (size_t)(f0 + fl) * p.K + k0 + c * 4 : p.gate, ok);
-                            }
-                        }
-                        cp_async_mbar_arrive_noinc(bar);           // arrives when this thread's copies have landed
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (GATE && tp >= 32 && tp < 96) {
+            // gated layers: loader warps 1-2 stage the per-frame gate slice [nf_max][64] fp32 of every k-block next to
+            // the A tile (cp.async; the landed-barrier counts their 64 completion arrivals besides the TMA bytes)
+            const int i = tp - 32;
+            const uint32_t fl = i >> 4, c = i & 15;
+            int stage = 0; uint32_t phase = 0;
+            TileIter it; it.init(p, blockIdx.x);
+            for (; it.u < units; it.next1(p)) {
+                const uint32_t f0 = (uint32_t)it.m0(p) / (uint32_t)p.HW;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int k0 = kb * kKB;
+                    DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
+                    const uint32_t g_base = smem_base + stage * stage_bytes + g_off;
+                    for (uint32_t f = fl; f < (uint32_t)p.nf_max; f += 4) {
+                        const bool ok = (f0 + f < (uint32_t)p.total_frames) && (k0 + (int)c * 4 < p.K);
+                        cp_async16(g_base + f * 256 + c * 16, ok ? p.gate + (size_t)(f0 + f) * p.K + k0 + c * 4 : p.gate, ok);
                     }
+                    cp_async_mbar_arrive_noinc(bar_raw + 8 * stage);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -245,7 +238,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 if (turn == grp) {
                     const int kc = min(8, (p.K - kb * kKB) >> 3);
                     DFD_TWAIT(w0, bar_raw + 8 * stage, phase)
-                    if (q < kc) {
+                    if (q < kc && !(p.dbg & 64)) {
                         const uint32_t a_base = smem_base + stage * stage_bytes;
                         uint32_t fl = 0, rem = rem0;
                         while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
@@ -267,7 +260,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                                 v.y = Half16<T>::pack(x1.x * __uint_as_float(gA.z), x1.y * __uint_as_float(gA.w));
                                 v.z = Half16<T>::pack(x2.x * __uint_as_float(gB.x), x2.y * __uint_as_float(gB.y));
                                 v.w = Half16<T>::pack(x3.x * __uint_as_float(gB.z), x3.y * __uint_as_float(gB.w));
-                                sts16(addr, v);
+                                if (!(p.dbg & 128)) sts16(addr, v);
+                                else asm volatile("" :: "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
                             }
                             rem += xstep;
                             while (rem >= (uint32_t)p.HW) { rem -= p.HW; ++fl; }
@@ -284,6 +278,12 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     } else if (warp == kMmaWarp) {
         // =================================== MMA ISSUER ==========================================
         const uint32_t idesc = umma_idesc(Half16<T>::kUmmaFormat, kBM, (uint32_t)p.NBp);
+        const uint64_t a_d0 = umma_smem_desc_sw128(smem_base);
+        const uint64_t b_d0 = p.b_resident ? umma_smem_desc(bres_base, p.lbo_b, 128) : umma_smem_desc_sw128(smem_base + kAStageBytes);
+        const uint32_t a_hi = (uint32_t)(a_d0 >> 32), a_lo0 = (uint32_t)a_d0, b_hi = (uint32_t)(b_d0 >> 32);
+        const uint32_t b_lo_res = (uint32_t)b_d0, b_lo_str = (uint32_t)b_d0;
+        const uint32_t stage_step = stage_bytes >> 4, b_chunk_step = p.b_chunk_bytes >> 4, b_kb_step = (8 * p.lbo_b) >> 4;
+        const uint32_t b_jstep = p.b_resident ? (2 * p.lbo_b) >> 4 : 2u;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         TileIter it; it.init(p, blockIdx.x);
         for (; it.u < units; it.next1(p)) {
@@ -297,13 +297,15 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                 DFD_TWAIT(w1, bar_full + 8 * stage, phase)
                 tc_fence_after_sync();
                 if (lane == 0) {
-                    const uint32_t a_base = smem_base + stage * stage_bytes;
-                    const uint32_t b_base = p.b_resident ? bres_base + (p.b_resident == 2 ? 0 : nc * p.b_chunk_bytes) + kb * 8 * p.lbo_b
-                                                         : a_base + kAStageBytes;
-                    for (int j = 0; j < steps; ++j) {
-                        const uint64_t adesc = umma_smem_desc_sw128(a_base + 32 * j);
-                        const uint64_t bdesc = umma_smem_desc(b_base + 2 * j * p.lbo_b, p.lbo_b, 128);
-                        if (!(p.dbg & 2)) umma_f16(d_tmem, adesc, bdesc, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    // descriptors differ only in the 14-bit start-address field: add to the low word
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step;
+                    const uint32_t b_lo = p.b_resident ? b_lo_res + (uint32_t)(p.b_resident == 2 ? 0 : nc) * b_chunk_step + (uint32_t)kb * b_kb_step
+                                                       : b_lo_str + (uint32_t)stage * stage_step;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < steps && !(p.dbg & 2))
+                            umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2u * j), ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)j * b_jstep),
+                                     idesc, (kb > 0 || j > 0) ? 1u : 0u);
                     }
                     umma_commit(bar_empty + 8 * stage);                 // smem stage reusable once the MMAs retire
                     if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);
@@ -449,13 +451,14 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
 // ---------------------------------------------------------------------------------------------------
 static int g_num_sms = 0;
 
-// Tensor map of the A operand: [M rows][K elements] 16-bit row-major, box = 64 elements x 128 rows, 128-byte swizzle,
+// Tensor map of a K-major operand (A, or streamed W): [M rows][K elements] 16-bit row-major, box = 64 elements x box_rows,
+// 128-byte swizzle,
 // zero fill outside the tensor (K tails, the last M tile).  cuTensorMapEncodeTiled comes from the driver through the
 // runtime's entry-point query (no link against libcuda); maps are cached per thread by (pointer, M, K).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static cudaError_t make_tmap_a(const void* A, int64_t M, int K, CUtensorMap* out) {
+static cudaError_t make_tmap(const void* A, int64_t M, int K, int box_rows, CUtensorMap* out) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -465,15 +468,15 @@ static cudaError_t make_tmap_a(const void* A, int64_t M, int K, CUtensorMap* out
         if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
         encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    struct Key { const void* p; int64_t m; int k; bool operator==(const Key& o) const { return p == o.p && m == o.m && k == o.k; } };
-    struct Hash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) ^ (size_t)k.m * 1315423911u ^ (size_t)k.k * 2654435761u; } };
+    struct Key { const void* p; int64_t m; int k, b; bool operator==(const Key& o) const { return p == o.p && m == o.m && k == o.k && b == o.b; } };
+    struct Hash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) ^ (size_t)k.m * 1315423911u ^ (size_t)k.k * 2654435761u ^ (size_t)k.b * 40503u; } };
     thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
-    const Key key{A, M, K};
+    const Key key{A, M, K, box_rows};
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return cudaSuccess; }
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
     const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)kBM};
+    const cuuint32_t box[2] = {(cuuint32_t)kKB, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     // 16-bit payload: the element type only matters for the (unused) NaN fill, UINT16 serves fp16 and bf16 alike
     const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(A), dims, strides, box, estr,
@@ -505,7 +508,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     {   static const int env_xg = getenv("DFD_GEMM_XG") ? atoi(getenv("DFD_GEMM_XG")) : 4;
         a.xg = xform_warps > 0 ? env_xg : 1;
         if (a.xg < 1 || a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1; }
-    a.b_stage_bytes = (uint32_t)kcp_max * a.lbo_b;
+    a.b_stage_bytes = (uint32_t)a.NBp * 128u;                      // streamed W block: NBp rows x 64 elements, 128-byte swizzle
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
     {   // accumulator ring: as many buffers as fit in the 512 TMEM columns (<= 8); epilogue groups take alternate tiles
         const int groups = epi_warps / 4, fit = 512 / a.NBp;
@@ -557,10 +560,17 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
         split(a.stride1, a.d1_mt, a.d1_nc, a.d1_frame, a.d1_t);
         split(a.strideE, a.dE_mt, a.dE_nc, a.dE_frame, a.dE_t);
     }
-    CUtensorMap tmA;
-    e = make_tmap_a(a.A, a.M, a.K, &tmA);
+    CUtensorMap tmA, tmB;
+    e = make_tmap(a.A, a.M, a.K, kBM, &tmA);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a, tmA);
+    if (!a.b_resident) {
+        if (a.tpf > 0 && a.w_frame_stride != (int64_t)a.N * a.K) return cudaErrorInvalidValue;
+        e = make_tmap(a.W, a.tpf > 0 ? (a.M / a.HW) * a.N : (int64_t)a.N, a.K, a.NBp, &tmB);
+        if (e != cudaSuccess) return e;
+    } else {
+        tmB = tmA;
+    }
+    kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a, tmA, tmB);
     return cudaGetLastError();
 }
 
