@@ -74,7 +74,15 @@ struct BlockW {
     float* dw_w; float* dw_b;                          // [k*k][mid], [mid]
     float *se_w1, *se_b1, *se_w2t, *se_b2;             // [rd][mid], [rd], [rd][mid], [mid]
     void* proj_w; float* proj_b;                       // [cout][mid] 16-bit, [cout]
+    // Pixel packing for narrow layers (K < 64): r consecutive pixels of the NHWC map are ONE GEMM row of r*K channels
+    // against the block-diagonal weight diag(W, .., W) [r*N][r*K]; the output rows [M/r][r*N] are the same bytes as
+    // [M][N].  Full 128-byte TMA rows and r times fewer tiles for free (the tensor pipe has the headroom).
+    int exp_pack, proj_pack;                           // r (1 = not packed)
+    void* exp_wp; float* exp_bp; void* proj_wp; float* proj_bp;
 };
+
+// r = pixels per GEMM row for a pointwise layer with K input channels (r*K <= 64)
+int pack_factor(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 
 bool use_simt_stem() {
     static int v = -1;
@@ -173,6 +181,21 @@ bool pack_pw(Tensors& t, const std::string& conv, const std::string& bn, int N, 
     return true;
 }
 
+// block-diagonal copy of a packed pointwise layer: [r*N][r*K] 16-bit (+ bias repeated r times)
+void pack_pw_diag(HostArena& a, size_t w_off, size_t b_off, int N, int K, int r, size_t& wp_off, size_t& bp_off) {
+    wp_off = a.alloc((size_t)r * N * r * K * 2);
+    bp_off = a.alloc((size_t)r * N * 4);
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(a.bytes.data() + w_off);
+    const float* b = reinterpret_cast<const float*>(a.bytes.data() + b_off);
+    uint16_t* wd = reinterpret_cast<uint16_t*>(a.bytes.data() + wp_off);     // zero-initialised by alloc
+    float* bd = reinterpret_cast<float*>(a.bytes.data() + bp_off);
+    for (int i = 0; i < r; ++i)
+        for (int n = 0; n < N; ++n) {
+            bd[i * N + n] = b[n];
+            for (int k = 0; k < K; ++k) wd[((size_t)i * N + n) * (r * K) + i * K + k] = w[(size_t)n * K + k];
+        }
+}
+
 // stem weights [27][32] fp32 (tap-major) -> 16-bit [32][96] = [w_hi | w_hi | w_lo], taps padded 27 -> 32
 size_t pack_stem16(HostArena& a, const float* p27x32, int dtype) {
     size_t off = a.alloc(32 * 96 * 2);
@@ -214,7 +237,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
         if (names[i]) t.map[names[i]] = {data[i], numel[i]};
 
     HostArena a;
-    struct Off { size_t exp_w, exp_b, dw_w, dw_b, se_w1, se_b1, se_w2t, se_b2, proj_w, proj_b; } off[kNumBlocks];
+    struct Off { size_t exp_w, exp_b, dw_w, dw_b, se_w1, se_b1, se_w2t, se_b2, proj_w, proj_b, exp_wp, exp_bp, proj_wp, proj_bp; } off[kNumBlocks];
     dfd_weights W{};
     W.dtype = dtype;
 
@@ -250,7 +273,10 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
             const std::string conv_pr = p + (B.has_expand ? ".conv_pwl" : ".conv_pw");
             Off& o = off[bi];
             memset(&o, 0, sizeof(o));
-            if (B.has_expand) pack_pw(t, p + ".conv_pw", p + ".bn1", B.mid, B.cin, dtype, a, o.exp_w, o.exp_b);
+            B.exp_pack = B.has_expand ? pack_factor(B.cin) : 1;
+            B.proj_pack = pack_factor(B.mid);
+            if (B.has_expand && pack_pw(t, p + ".conv_pw", p + ".bn1", B.mid, B.cin, dtype, a, o.exp_w, o.exp_b) && B.exp_pack > 1)
+                pack_pw_diag(a, o.exp_w, o.exp_b, B.mid, B.cin, B.exp_pack, o.exp_wp, o.exp_bp);
             {   // depthwise [mid][1][k][k] + BN -> fp32 [k*k][mid]
                 const int kk = B.k * B.k;
                 const float* w = t.get(p + ".conv_dw.weight", (int64_t)B.mid * kk);
@@ -278,7 +304,8 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
                     o.se_b2 = pack_f32(a, b2, B.mid);
                 }
             }
-            pack_pw(t, conv_pr, bn_pr, B.cout, B.mid, dtype, a, o.proj_w, o.proj_b);
+            if (pack_pw(t, conv_pr, bn_pr, B.cout, B.mid, dtype, a, o.proj_w, o.proj_b) && B.proj_pack > 1)
+                pack_pw_diag(a, o.proj_w, o.proj_b, B.cout, B.mid, B.proj_pack, o.proj_wp, o.proj_bp);
             cin = B.cout;
         }
     }
@@ -310,6 +337,8 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
         B.dw_w = F(o.dw_w); B.dw_b = F(o.dw_b);
         B.se_w1 = F(o.se_w1); B.se_b1 = F(o.se_b1); B.se_w2t = F(o.se_w2t); B.se_b2 = F(o.se_b2);
         B.proj_w = d + o.proj_w; B.proj_b = F(o.proj_b);
+        B.exp_wp = B.exp_pack > 1 ? d + o.exp_wp : nullptr; B.exp_bp = B.exp_pack > 1 ? F(o.exp_bp) : nullptr;
+        B.proj_wp = B.proj_pack > 1 ? d + o.proj_wp : nullptr; B.proj_bp = B.proj_pack > 1 ? F(o.proj_bp) : nullptr;
     }
     W.head_w = d + head_w_off; W.head_b = F(head_b_off);
     W.hw.att_w1 = F(hoff[0]); W.hw.att_b1 = F(hoff[1]); W.hw.att_w2 = F(hoff[2]); W.hw.att_b2 = F(hoff[3]);
@@ -369,7 +398,7 @@ Plan make_plan(int H, int W) {
             p.d_elems = std::max(p.d_elems, (size_t)oh * ow * mid);
             p.part_floats = std::max(p.part_floats, (size_t)dfd::dw_num_partials(oh, ow, mid, k, st) * mid);
             p.gate_floats = std::max(p.gate_floats, (size_t)mid);
-            if (oh * ow >= kFrameWeightsMinHW) p.wf_elems = std::max(p.wf_elems, (size_t)mid * cout);
+            if (oh * ow >= kFrameWeightsMinHW) { const size_t r = pack_factor(mid); p.wf_elems = std::max(p.wf_elems, r * r * mid * cout); }
             p.io_elems = std::max(p.io_elems, (size_t)oh * ow * cout);
             h = oh; w = ow; cin = cout;
         }
@@ -381,9 +410,11 @@ size_t in_frame_bytes(int in_kind, int H, int W) {
     return in_kind == DFD_IN_U8_HWC ? px : (in_kind == DFD_IN_F32_NCHW ? px * 4 : px * 2);
 }
 
+// r > 1: pixel-packed call (Wt / bias are the block-diagonal copies): M/r rows of r*K channels -> r*N outputs
 int run_gemm(const void* A, const void* Wt, const float* bias, const float* gate, const void* R, void* D,
-             int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s) {
+             int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s, int r = 1) {
     prof_next(gate ? KC_GEMM_PROJECT : KC_GEMM_EXPAND, (double)M * (K + N + (R ? N : 0)) * 2, 2.0 * M * K * N, s);
+    M /= r; K *= r; N *= r; HW /= r;
     if (use_simt_gemm()) DFD_LAUNCH(dfd::launch_gemm_simt(A, Wt, bias, gate, R, D, nullptr, M, K, N, HW, act, dtype, s), "gemm (simt)");
     else DFD_LAUNCH(dfd::launch_gemm_tc(A, Wt, bias, gate, R, D, M, K, N, HW, act, dtype, s), "gemm (tcgen05)");
     return DFD_OK;
@@ -413,7 +444,9 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         const void* x = io[cur];
         const void* e = x;
         if (B.has_expand) {
-            int rc = run_gemm(x, B.exp_w, B.exp_b, nullptr, nullptr, bufE, frames * h * wd, B.cin, B.mid, h * wd, 1, dt, s);
+            const int r = (B.exp_pack > 1 && !use_simt_gemm() && (h * wd) % B.exp_pack == 0) ? B.exp_pack : 1;
+            int rc = run_gemm(x, r > 1 ? B.exp_wp : B.exp_w, r > 1 ? B.exp_bp : B.exp_b, nullptr, nullptr, bufE,
+                              frames * h * wd, B.cin, B.mid, h * wd, 1, dt, s, r);
             if (rc) return rc;
             e = bufE;
         }
@@ -428,10 +461,11 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         if (oh * ow >= kFrameWeightsMinHW && !use_simt_gemm()) {
             // big maps: SE gate folded into per-frame weights, ungated GEMM on frame-aligned tiles
             prof_next(KC_GEMM_PROJECT, (double)frames * B.cout * B.mid * 2 * 2, 0, s);
-            DFD_LAUNCH(dfd::launch_scale_weights(B.proj_w, gate, bufWf, frames, B.cout, B.mid, dt, s), "per-frame weight scaling");
+            const int r = (B.proj_pack > 1 && (oh * ow) % B.proj_pack == 0) ? B.proj_pack : 1;
+            DFD_LAUNCH(dfd::launch_scale_weights(r > 1 ? B.proj_wp : B.proj_w, gate, bufWf, frames, B.cout * r, B.mid * r, B.mid, dt, s), "per-frame weight scaling");
             prof_next(KC_GEMM_PROJECT, (double)frames * oh * ow * (B.mid + B.cout + (B.has_skip ? B.cout : 0)) * 2, 2.0 * frames * oh * ow * B.mid * B.cout, s);
-            DFD_LAUNCH(dfd::launch_gemm_tc_framew(bufD, bufWf, B.proj_b, B.has_skip ? x : nullptr, io[cur ^ 1],
-                                                  frames * oh * ow, B.mid, B.cout, oh * ow, dt, s), "gemm (tcgen05, per-frame weights)");
+            DFD_LAUNCH(dfd::launch_gemm_tc_framew(bufD, bufWf, r > 1 ? B.proj_bp : B.proj_b, B.has_skip ? x : nullptr, io[cur ^ 1],
+                                                  frames * oh * ow / r, B.mid * r, B.cout * r, oh * ow / r, dt, s), "gemm (tcgen05, per-frame weights)");
         } else {
             int rc = run_gemm(bufD, B.proj_w, B.proj_b, gate, B.has_skip ? x : nullptr, io[cur ^ 1],
                               frames * oh * ow, B.mid, B.cout, oh * ow, 0, dt, s);
@@ -593,7 +627,7 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
         if (!d_gate || act || HW <= 0 || (M % HW)) return fail(DFD_EINVAL, "dfd_k_gemm impl 2: needs a gate, act == 0 and M % HW == 0");
         void* wf = nullptr;
         DFD_CUDA(cudaMalloc(&wf, (size_t)(M / HW) * N * K * 2), "cudaMalloc(per-frame weights)");
-        cudaError_t e = dfd::launch_scale_weights(d_W, d_gate, wf, M / HW, N, K, dtype, (cudaStream_t)stream);
+        cudaError_t e = dfd::launch_scale_weights(d_W, d_gate, wf, M / HW, N, K, K, dtype, (cudaStream_t)stream);
         if (e == cudaSuccess) e = dfd::launch_gemm_tc_framew(d_A, wf, d_bias, d_R, d_D, M, K, N, HW, dtype, (cudaStream_t)stream);
         g_launches = 2;
         cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);

@@ -616,7 +616,7 @@ cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bi
 }
 
 template <typename T>
-__global__ void scale_weights_kernel(const T* __restrict__ W, const float* __restrict__ gate, T* __restrict__ Wf, int N, int K, int64_t total) {
+__global__ void scale_weights_kernel(const T* __restrict__ W, const float* __restrict__ gate, T* __restrict__ Wf, int N, int K, int Kg, int64_t total) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 2 consecutive k
     if (i >= total) return;
     const int k2 = (int)(i % (K / 2));
@@ -624,17 +624,18 @@ __global__ void scale_weights_kernel(const T* __restrict__ W, const float* __res
     const int n = (int)(fn % N);
     const int64_t f = fn / N;
     const uint32_t w = reinterpret_cast<const uint32_t*>(W)[(size_t)n * (K / 2) + k2];
-    const float2 g = *reinterpret_cast<const float2*>(gate + (size_t)f * K + 2 * k2);
+    const float2 g = *reinterpret_cast<const float2*>(gate + (size_t)f * Kg + (2 * k2) % Kg);
     const float2 x = Half16<T>::unpack(w);
     reinterpret_cast<uint32_t*>(Wf)[i] = Half16<T>::pack(x.x * g.x, x.y * g.y);
 }
-// Wf[f][n][k] = W[n][k] * gate[f][k]
-cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int dtype, cudaStream_t s) {
+// Wf[f][n][k] = W[n][k] * gate[f][k % Kg]   (Kg < K: pixel-packed block-diagonal weights, the gate repeats per pixel)
+cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int Kg, int dtype, cudaStream_t s) {
     const int64_t total = frames * N * (K / 2);
     if (total <= 0) return cudaSuccess;
+    if (Kg <= 0 || (Kg & 1) || K % Kg) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (dtype == kDtypeFP16) scale_weights_kernel<__half><<<grid, 256, 0, s>>>((const __half*)W, gate, (__half*)Wf, N, K, total);
-    else scale_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, gate, (__nv_bfloat16*)Wf, N, K, total);
+    if (dtype == kDtypeFP16) scale_weights_kernel<__half><<<grid, 256, 0, s>>>((const __half*)W, gate, (__half*)Wf, N, K, Kg, total);
+    else scale_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, gate, (__nv_bfloat16*)Wf, N, K, Kg, total);
     return cudaGetLastError();
 }
 

@@ -43,7 +43,8 @@ cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, cons
                            void* D, int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s);
 // gated project conv for big maps (HW >= 784): fold the SE gate into per-frame weights, then an ungated GEMM on
 // frame-aligned tiles.  Wf: 16-bit [frames][N][K] scratch.
-cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int dtype, cudaStream_t s);
+// Kg = gate row length (K, or K / r for pixel-packed block-diagonal weights: the gate repeats per packed pixel)
+cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int Kg, int dtype, cudaStream_t s);
 cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bias, const void* R, void* D,
                                   int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
 // D[M,N] (fp32) = A[M,K] * W[N,K]^T + bias (+ R fp32, may alias D) — gate pre-activations of the recurrent head
