@@ -106,6 +106,7 @@ struct dfd_weights {
     int dtype;
     float *stem_w, *stem_b;                            // [27][32], [32]
     void* stem_w16;                                    // [32][96] 16-bit hi/lo split for the tcgen05 stem
+    void* stem_wrow; float* stem_b4;                   // row-variant stem: fp16 [2][32][32], fp32 [4][32] (pack_stem_row)
     BlockW blocks[kNumBlocks];
     void* head_w; float* head_b;                       // [1280][320] 16-bit, [1280]
     dfd::HeadWeights hw;
@@ -212,6 +213,36 @@ size_t pack_stem16(HostArena& a, const float* p27x32, int dtype) {
     return off;
 }
 
+// Row-variant stem operands (stem_tc.cu): fp16 [hi|lo][32 oc][32 k], k = ky*10 + kx*3 + c, holding
+// w' = 256 * w / (255 * std_c) split in two fp16 terms, and the four bias vectors [top*2 + left][32] that absorb
+// -sum_inb w * mean_c / std_c over the taps that are inside the image (tensor prep of app.py:1772-1780 folded in).
+void pack_stem_row(HostArena& a, const float* p27x32, const float* bias32, size_t& w_off, size_t& b4_off) {
+    const double mean[3] = {(double)0.485f, (double)0.456f, (double)0.406f}, stdv[3] = {(double)0.229f, (double)0.224f, (double)0.225f};
+    w_off = a.alloc(2 * 32 * 32 * 2);
+    b4_off = a.alloc(4 * 32 * 4);
+    uint16_t* wd = reinterpret_cast<uint16_t*>(a.bytes.data() + w_off);
+    float* bd = reinterpret_cast<float*>(a.bytes.data() + b4_off);
+    for (int o = 0; o < 32; ++o) {
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                for (int c = 0; c < 3; ++c) {
+                    const double w = 256.0 * (double)p27x32[((ky * 3 + kx) * 3 + c) * 32 + o] / (255.0 * stdv[c]);
+                    const __half hi = __float2half_rn((float)w);
+                    const __half lo = __float2half_rn((float)(w - (double)__half2float(hi)));
+                    const int k = ky * 10 + kx * 3 + c;
+                    memcpy(&wd[(size_t)o * 32 + k], &hi, 2);
+                    memcpy(&wd[(size_t)(32 + o) * 32 + k], &lo, 2);
+                }
+        for (int cs = 0; cs < 4; ++cs) {
+            double b = (double)bias32[o];
+            for (int ky = (cs & 2) ? 1 : 0; ky < 3; ++ky)
+                for (int kx = (cs & 1) ? 1 : 0; kx < 3; ++kx)
+                    for (int c = 0; c < 3; ++c) b -= (double)p27x32[((ky * 3 + kx) * 3 + c) * 32 + o] * mean[c] / stdv[c];
+            bd[cs * 32 + o] = (float)b;
+        }
+    }
+}
+
 size_t pack_f32(HostArena& a, const float* src, size_t n) {
     size_t off = a.alloc(n * 4);
     memcpy(a.bytes.data() + off, src, n * 4);
@@ -242,7 +273,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
     W.dtype = dtype;
 
     // stem: [32][3][3][3] + BN -> fp32 [(ky*3+kx)*3+c][32]
-    size_t stem_w_off = 0, stem_b_off = 0, stem_w16_off = 0;
+    size_t stem_w_off = 0, stem_b_off = 0, stem_w16_off = 0, stem_wrow_off = 0, stem_b4_off = 0;
     {
         const float* w = t.get("backbone.0.weight", 32 * 27);
         std::vector<float> sc, sh;
@@ -256,6 +287,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
             stem_w_off = pack_f32(a, p.data(), p.size());
             stem_w16_off = pack_stem16(a, p.data(), dtype);
             stem_b_off = pack_f32(a, sh.data(), 32);
+            pack_stem_row(a, p.data(), sh.data(), stem_wrow_off, stem_b4_off);
         }
     }
     int bi = 0, cin = 32;
@@ -332,6 +364,7 @@ int dfd_pack_weights(int n_tensors, const char* const* names, const float* const
     auto F = [&](size_t o) { return reinterpret_cast<float*>(d + o); };
     W.arena = dev; W.arena_bytes = a.bytes.size();
     W.stem_w = F(stem_w_off); W.stem_b = F(stem_b_off); W.stem_w16 = d + stem_w16_off;
+    W.stem_wrow = d + stem_wrow_off; W.stem_b4 = F(stem_b4_off);
     for (int i = 0; i < kNumBlocks; ++i) {
         BlockW& B = W.blocks[i]; const Off& o = off[i];
         B.exp_w = B.has_expand ? d + o.exp_w : nullptr; B.exp_b = B.has_expand ? F(o.exp_b) : nullptr;
@@ -437,7 +470,7 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
     int h = H / 2, wd = W / 2, cur = 0;
     prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
     if (in_kind == DFD_IN_U8_HWC && !use_simt_stem())
-        DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
+        DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, w->stem_wrow, w->stem_b4, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
     else
         DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
     for (int i = 0; i < kNumBlocks; ++i) {
@@ -592,14 +625,19 @@ int dfd_k_stem(const void* d_in, int in_kind, const float* d_w, const float* d_b
 int dfd_k_stem_tc(const uint8_t* d_in, const float* h_w27x32, const float* d_bias, void* d_out, int64_t frames,
                   int H, int W, int dtype, void* stream) {
     if (!d_in || !h_w27x32 || !d_bias || !d_out) return fail(DFD_EINVAL, "dfd_k_stem_tc: null pointer");
+    float hb[32];
+    DFD_CUDA(cudaMemcpy(hb, d_bias, sizeof(hb), cudaMemcpyDeviceToHost), "cudaMemcpy(stem bias)");
     HostArena a;
     const size_t off = pack_stem16(a, h_w27x32, dtype);
-    void* dw = nullptr;
-    DFD_CUDA(cudaMalloc(&dw, 32 * 96 * 2), "cudaMalloc(stem w16)");
-    cudaError_t e = cudaMemcpy(dw, a.bytes.data() + off, 32 * 96 * 2, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(dw); return cuda_fail(e, "cudaMemcpy(stem w16)"); }
+    size_t wrow_off = 0, b4_off = 0;
+    pack_stem_row(a, h_w27x32, hb, wrow_off, b4_off);
+    uint8_t* dw = nullptr;
+    DFD_CUDA(cudaMalloc(&dw, a.bytes.size()), "cudaMalloc(stem operands)");
+    cudaError_t e = cudaMemcpy(dw, a.bytes.data(), a.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dw); return cuda_fail(e, "cudaMemcpy(stem operands)"); }
     g_launches = 0;
-    { ProfScope ps; e = dfd::launch_stem_tc(d_in, dw, d_bias, d_out, frames, H, W, dtype, (cudaStream_t)stream); }
+    { ProfScope ps; e = dfd::launch_stem_tc(d_in, dw + off, d_bias, dw + wrow_off, reinterpret_cast<const float*>(dw + b4_off), d_out,
+                                            frames, H, W, dtype, (cudaStream_t)stream); }
     ++g_launches;
     cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
     cudaFree(dw);

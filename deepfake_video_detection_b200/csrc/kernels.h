@@ -15,7 +15,9 @@ cudaError_t launch_stem(const void* in, int in_kind, const float* w, const float
 
 // stem as tcgen05 implicit GEMM for uint8 crops (stem_tc.cu).  w16: 16-bit [32][96] = [w_hi | w_hi | w_lo] per output
 // channel, each block 27 taps ((ky*3+kx)*3+c) zero-padded to 32.
-cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, void* out,
+// Row variant (output width <= 128, used when wrow / bias4 are given): raw uint8 bytes are the fp16 A operand, fetched
+// with one bulk copy per output row; wrow fp16 [2][32][32] + bias4 fp32 [4][32] fold the tensor prep (api.cu pack_stem_row).
+cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, const void* wrow, const float* bias4, void* out,
                            int64_t frames, int H, int W, int dtype, cudaStream_t s);
 
 // K2 (dwconv.cu): depthwise kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU, NHWC, plus the

@@ -5,6 +5,7 @@
 // applied to the A operand inside the project GEMM (gemm_tc.cu), so the dw output is never re-written.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace dfd {
 
@@ -22,6 +23,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
     const int64_t f0 = (int64_t)blockIdx.x * kSeFrames;
     const int nf = (int)min((int64_t)kSeFrames, frames - f0);
 
+#pragma unroll 4
     for (int i = threadIdx.x; i < kSeFrames * C; i += kSeThreads) {
         const int f = i / C, c = i - f * C;
         float a[8];
@@ -47,6 +49,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
 #pragma unroll
         for (int f = 0; f < kSeFrames; ++f) acc[f] = 0.f;
         const float* wr = w1 + (size_t)j * C;
+#pragma unroll 4
         for (int c = lane; c < C; c += 32) {
             const float wv = __ldg(wr + c);
 #pragma unroll
@@ -70,6 +73,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
         const float bc = __ldg(b2 + c);
 #pragma unroll
         for (int f = 0; f < kSeFrames; ++f) acc[f] = bc;
+#pragma unroll 8
         for (int j = 0; j < rd; ++j) {
             const float wv = __ldg(w2t + (size_t)j * C + c);
 #pragma unroll
@@ -96,8 +100,11 @@ static cudaError_t launch_se_t(const float* partials, int nparts, float inv_hw, 
 cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,
                       const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s) {
     if (frames <= 0) return cudaSuccess;
-    // wide layers do more FC work per frame: fewer frames per CTA keeps enough CTAs in flight
-    if (C >= 480) return launch_se_t<2>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, s);
+    // Every CTA streams both FC matrices (2*rd*C fp32, 442 KB at C = 1152) from L2, so frames per CTA sets the L2
+    // traffic: 2 frames per CTA made the wide layers L2-bound (453 MB per launch, 105 us); 8 frames per CTA = 4x less.
+    static const int env_fpb = getenv("DFD_SE_FPB") ? atoi(getenv("DFD_SE_FPB")) : 8;      // experiments only
+    if (env_fpb == 2) return launch_se_t<2>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, s);
+    if (env_fpb == 4) return launch_se_t<4>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, s);
     return launch_se_t<8>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, s);
 }
 

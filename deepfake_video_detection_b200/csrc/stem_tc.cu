@@ -15,6 +15,7 @@
 // read TMEM, add the bias, apply SiLU and store 64 contiguous bytes per pixel (NHWC).
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace dfd {
 
@@ -174,7 +175,197 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
     if (warp == kStEpiWarps) { tc_fence_after_sync(); tmem_dealloc(tmem_base, kStAcc * kStN); }
 }
 
-cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, void* out,
+// ---------------------------------------------------------------------------------------------------------------
+// Row variant (maps up to 128 output columns, i.e. the 224x224 crops): one tile = ONE OUTPUT ROW of one frame.
+//  * the three input rows a tile needs are 3*W*3 contiguous bytes: one thread fetches them with a single 1-D bulk
+//    copy (cp.async.bulk, completion in bytes on an mbarrier) into a ring of raw-byte stages — no per-byte global
+//    loads, every input byte crosses the SM boundary once per output row (1.5x in total);
+//  * the raw uint8 values ARE the A operand: an integer 0..255 is exact in fp16 (PRMT with the 0x64 magic byte gives
+//    1024 + u, one HSUB2 removes the 1024), so the tensor prep of app.py:2084-2085 moves into the weights:
+//        y = sum_inb w * ((u/255 - mean_c)/std_c) + b = sum_inb (w / (255 std_c)) * u + [b - sum_inb w * mean_c/std_c]
+//    with w' = 256 * w / (255 std_c) split into fp16 hi + lo (two MMAs against the same A tile, ~22 significant bits,
+//    the 2^-8 is applied with the bias in the epilogue) and FOUR bias vectors for the in-bounds tap sets of the
+//    interior / left column / top row / top-left corner (zero padding happens after normalisation, as F.conv2d does);
+//  * a builder thread (= one output pixel) reads its 3 x 9 window bytes as 9 aligned 32-bit shared-memory words.
+// K layout: k = ky*10 + kx*3 + c (9 taps + 1 zero per input row, 32 in all).
+constexpr int kSrK = 32, kSrChunks = kSrK / 8;
+constexpr uint32_t kSrAStage = kSrChunks * kStLboA;      // 8256 B
+constexpr int kSrN = 2 * kStN;                           // MMA N: W_hi and W_lo stacked (the epilogue adds the two halves)
+constexpr uint32_t kSrLboB = kSrN * 16 + 16;
+constexpr uint32_t kSrBBytes = kSrChunks * kSrLboB;
+constexpr int kSrStages = 8, kSrRaw = 8, kSrAcc = 8;
+// kSrEpiSets epilogue sets and kSrSets builder sets (4 warps each) take alternate tiles: both roles are latency-bound per tile
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <typename T, int kSrEpiSets, int kSrSets>
+__global__ void __launch_bounds__((4 * kSrEpiSets + 2 + 4 * kSrSets) * 32, 1)
+stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow, const float* __restrict__ bias4,
+                T* __restrict__ out, int H, int W, int OH, int OW, int64_t tiles, uint32_t raw_stride) {
+    constexpr int kSrEpiWarps = 4 * kSrEpiSets, kSrMmaWarp = kSrEpiWarps, kSrRawWarp = kSrEpiWarps + 1;
+    constexpr int kSrThreads = (kSrEpiWarps + 2 + 4 * kSrSets) * 32;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* sp = smem_raw + kSrStages * kSrAStage;
+    uint8_t* s_rawb = sp;                           sp += kSrRaw * raw_stride;
+    uint8_t* s_b = sp;                              sp += kSrBBytes;
+    float* s_bias = reinterpret_cast<float*>(sp);   sp += 4 * kStN * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);      // afull[S], aempty[S], rfull[R], rempty[R], tfull[ACC], tempty[ACC]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc);
+
+    const uint32_t a_base0 = smem_u32(smem_raw), raw_base0 = smem_u32(s_rawb), b_base = smem_u32(s_b);
+    const uint32_t bar_afull = smem_u32(bars), bar_aempty = smem_u32(bars + kSrStages);
+    const uint32_t bar_rfull = smem_u32(bars + 2 * kSrStages), bar_rempty = smem_u32(bars + 2 * kSrStages + kSrRaw);
+    const uint32_t bar_tfull = smem_u32(bars + 2 * kSrStages + 2 * kSrRaw), bar_tempty = bar_tfull + 8 * kSrAcc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t RB = (uint32_t)W * 3;
+
+    for (int i = threadIdx.x; i < 4 * kStN; i += kSrThreads) s_bias[i] = bias4[i];
+    for (int i = threadIdx.x; i < 2 * kStN * kSrChunks; i += kSrThreads) {        // [hi|lo][32 oc][32 k] -> canonical layout
+        const int h = i / (kStN * kSrChunks), r = (i / kSrChunks) % kStN, q = i % kSrChunks;
+        *reinterpret_cast<uint4*>(s_b + q * kSrLboB + (h * kStN + r) * 16) = __ldg(reinterpret_cast<const uint4*>(wrow + (h * kStN + r) * kSrK + q * 8));
+    }
+    for (int i = threadIdx.x; i < kSrRaw * 4; i += kSrThreads)                     // 16 zero bytes in front of every raw stage
+        *reinterpret_cast<uint32_t*>(s_rawb + (i >> 2) * raw_stride + (i & 3) * 4) = 0u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSrStages; ++s) { mbar_init(bar_afull + 8 * s, 128); mbar_init(bar_aempty + 8 * s, 1); }
+        for (int s = 0; s < kSrRaw; ++s) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, 128); }
+        for (int a = 0; a < kSrAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
+        fence_barrier_init();
+    }
+    if (warp == kSrMmaWarp) tmem_alloc(smem_u32(s_tmem), kSrAcc * kSrN);
+    fence_proxy_async_smem();                       // W tiles were written with st.shared
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == kSrRawWarp) {
+        // ================================ RAW LOADER ============================================
+        if (lane == 0) {
+            int64_t li = 0;
+            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++li) {
+                const int stage = (int)(li % kSrRaw);
+                mbar_wait(bar_rempty + 8 * stage, ((uint32_t)(li / kSrRaw) & 1u) ^ 1u);
+                const int64_t frame = tile / OH;
+                const int oy = (int)(tile - frame * OH);
+                const uint8_t* src = in + ((size_t)frame * H + (2 * oy - 1)) * RB;        // input rows 2oy-1 .. 2oy+1
+                uint32_t dst = raw_base0 + stage * raw_stride + 16, bytes = 3 * RB;
+                if (oy == 0) { src += RB; dst += RB; bytes = 2 * RB; }                     // row -1 is padding (masked by the builders)
+                mbar_arrive_expect_tx(bar_rfull + 8 * stage, bytes);
+                bulk_load_1d(dst, src, bytes, bar_rfull + 8 * stage);
+            }
+        }
+    } else if (warp > kSrRawWarp) {
+        // ================================ BUILDERS (im2col from shared memory) ==================
+        const int bt = threadIdx.x - (kSrRawWarp + 1) * 32;
+        const int set = bt >> 7, row = bt & 127;
+        const uint32_t magic = 0x00000064u;                       // byte 4 = 0x64, bytes 5..7 = 0
+        const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
+        int64_t li = set;
+        for (int64_t tile = blockIdx.x + (int64_t)set * gridDim.x; tile < tiles; tile += kSrSets * (int64_t)gridDim.x, li += kSrSets) {
+            const int rstage = (int)(li % kSrRaw), astage = (int)(li % kSrStages);
+            const bool top = (tile % OH) == 0;
+            uint32_t h2[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h2[i] = 0u;
+            mbar_wait(bar_rfull + 8 * rstage, (uint32_t)(li / kSrRaw) & 1u);
+            if (row < OW) {
+                const uint32_t rb = raw_base0 + rstage * raw_stride;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    if (r == 0 && top) continue;                                           // padding row: zeros
+                    const uint32_t s0 = 16u + r * RB + 6u * row - 3u;                      // first byte of the 9-byte window
+                    const uint32_t wa = rb + (s0 & ~3u), sh = (s0 & 3u) * 8u;
+                    uint32_t x0, x1, x2;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(wa));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(wa + 4));
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x2) : "r"(wa + 8));
+                    uint32_t a0 = __funnelshift_r(x0, x1, sh), a1 = __funnelshift_r(x1, x2, sh), a2 = x2 >> sh;
+                    if (row == 0) a0 &= 0xff000000u;                                       // left padding column: taps kx = 0
+                    uint32_t p[5];
+                    p[0] = __byte_perm(a0, magic, 0x4140); p[1] = __byte_perm(a0, magic, 0x4342);
+                    p[2] = __byte_perm(a1, magic, 0x4140); p[3] = __byte_perm(a1, magic, 0x4342);
+                    p[4] = __byte_perm(a2, magic, 0x4540);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) {
+                        __half2 v = __hsub2(*reinterpret_cast<__half2*>(&p[i]), k1024);      // exact: 1024 + u -> u
+                        h2[r * 5 + i] = *reinterpret_cast<uint32_t*>(&v);
+                    }
+                }
+            }
+            mbar_arrive(bar_rempty + 8 * rstage);
+            mbar_wait(bar_aempty + 8 * astage, ((uint32_t)(li / kSrStages) & 1u) ^ 1u);
+            if (row < OW) {
+                const uint32_t dst = a_base0 + astage * kSrAStage + row * 16;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sts16(dst + q * kStLboA, make_uint4(h2[4 * q], h2[4 * q + 1], h2[4 * q + 2], h2[4 * q + 3]));
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar_afull + 8 * astage);
+        }
+    } else if (warp == kSrMmaWarp) {
+        // ================================ MMA ISSUER ============================================
+        // two MMAs per tile (K = 32) against [W_hi ; W_lo] (N = 64); descriptors differ only in the start-address field
+        const uint32_t idesc = umma_idesc(0u /* fp16 operands whatever the output type */, kStBM, kSrN);
+        const uint64_t a_d0 = umma_smem_desc(a_base0, kStLboA, 128);
+        const uint64_t b_d0 = umma_smem_desc(b_base, kSrLboB, 128), b_d1 = umma_smem_desc(b_base + 2 * kSrLboB, kSrLboB, 128);
+        const uint32_t a_hi = (uint32_t)(a_d0 >> 32), a_lo0 = (uint32_t)a_d0;
+        int64_t li = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++li) {
+            const int stage = (int)(li % kSrStages), acc = (int)(li % kSrAcc);
+            mbar_wait(bar_tempty + 8 * acc, ((uint32_t)(li / kSrAcc) & 1u) ^ 1u);
+            mbar_wait(bar_afull + 8 * stage, (uint32_t)(li / kSrStages) & 1u);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kSrAStage >> 4);
+                umma_f16(tmem_base + acc * kSrN, ((uint64_t)a_hi << 32) | a_lo, b_d0, idesc, 0u);
+                umma_f16(tmem_base + acc * kSrN, ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4)), b_d1, idesc, 1u);
+                umma_commit(bar_aempty + 8 * stage);
+                umma_commit(bar_tfull + 8 * acc);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================ EPILOGUE ==============================================
+        const int q = warp & 3, eset = warp >> 2;          // TMEM lane quarter, epilogue set
+        const int row = 32 * q + lane;
+        int64_t li = eset;
+        for (int64_t tile = blockIdx.x + (int64_t)eset * gridDim.x; tile < tiles; tile += kSrEpiSets * (int64_t)gridDim.x, li += kSrEpiSets) {
+            const int acc = (int)(li % kSrAcc);
+            mbar_wait(bar_tfull + 8 * acc, (uint32_t)(li / kSrAcc) & 1u);
+            tc_fence_after_sync();
+            const float* bs = s_bias + (((tile % OH) == 0 ? 2 : 0) + (row == 0 ? 1 : 0)) * kStN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * kSrN;
+            uint32_t r[4][16];                                  // columns 0-31: A * W_hi, 32-63: A * W_lo
+            tmem_ld16(t_row, r[0]);
+            tmem_ld16(t_row + 16, r[1]);
+            tmem_ld16(t_row + 32, r[2]);
+            tmem_ld16(t_row + 48, r[3]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c16 = 0; c16 < 2; ++c16) {
+                U32x8 o;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a = fmaf(__uint_as_float(r[c16][2 * i]) + __uint_as_float(r[2 + c16][2 * i]), 0.00390625f, bs[c16 * 16 + 2 * i]);
+                    const float b = fmaf(__uint_as_float(r[c16][2 * i + 1]) + __uint_as_float(r[2 + c16][2 * i + 1]), 0.00390625f, bs[c16 * 16 + 2 * i + 1]);
+                    o.v[i] = Half16<T>::pack(silu_tanh(a), silu_tanh(b));
+                }
+                if (row < OW) stg32(out + ((size_t)tile * OW + row) * kStN + c16 * 16, o);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kSrMmaWarp) { tc_fence_after_sync(); tmem_dealloc(tmem_base, kSrAcc * kSrN); }
+}
+
+cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, const void* wrow, const float* bias4, void* out,
                            int64_t frames, int H, int W, int dtype, cudaStream_t s) {
     const int OH = H / 2, OW = W / 2;
     const int64_t total = frames * OH * OW;
@@ -182,6 +373,28 @@ cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias
     int dev = 0, sms = 0;
     cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
+    if (wrow && bias4 && OW <= kStBM && (W & 15) == 0 && (H & 1) == 0) {
+        // row variant: one tile per output row
+        const uint32_t raw_stride = (16u + 3u * (uint32_t)W * 3u + 127u) & ~127u;
+        const size_t smem = kSrStages * kSrAStage + kSrRaw * raw_stride + kSrBBytes + 4 * kStN * 4 + (2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc) * 8 + 16;
+        const int64_t tiles = frames * OH;
+        const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+        static const int env_cfg = getenv("DFD_STEM_CFG") ? atoi(getenv("DFD_STEM_CFG")) : 0;         // experiments only
+#define DFD_STEM_ROW(TT, E, B) { \
+            auto kern = stem_row_kernel<TT, E, B>; \
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; \
+            kern<<<grid, (4 * E + 2 + 4 * B) * 32, smem, s>>>(in, (const __half*)wrow, bias4, (TT*)out, H, W, OH, OW, tiles, raw_stride); }
+        if (dtype == kDtypeFP16) {
+            if (env_cfg == 1) DFD_STEM_ROW(__half, 3, 3)
+            else if (env_cfg == 2) DFD_STEM_ROW(__half, 4, 2)
+            else if (env_cfg == 3) DFD_STEM_ROW(__half, 3, 4)
+            else DFD_STEM_ROW(__half, 2, 4)
+        } else {
+            DFD_STEM_ROW(__nv_bfloat16, 2, 4)
+        }
+#undef DFD_STEM_ROW
+        return cudaGetLastError();
+    }
     const size_t smem = kStStages * kStAStage + kStChunks * kStLboB + 768 * 4 + kStN * 4 + (2 * kStStages + 2 * kStAcc) * 8 + 16;
     const int64_t tiles = (total + kStBM - 1) / kStBM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
