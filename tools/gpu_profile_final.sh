@@ -1,18 +1,25 @@
 #!/bin/bash
-# Evidence run for profiles/: full tests, smoke, bench, then ncu launch list at the bench size and a --set full
-# capture of the dominant kernels (CSV pages exported on the box).  Usage: bash tools/gpu_profile_final.sh <tag>
+# Evidence run for profiles/: full tests, smoke, bench (+ reference arm), config-3 / config-5 timings, then the ncu launch
+# list at the bench size and a --set full capture of every kernel class (CSV pages exported on the box).
+# Usage: bash tools/gpu_profile_final.sh <tag>
 tag=${1:-r01}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$tag.log
-python __graft_entry__.py smoke > gpurun_out/smoke_$tag.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_$tag.log
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; cat gpurun_out/bench_$tag.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>/dev/null; cat gpurun_out/bench_ref_$tag.json
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$tag.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$tag.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_$tag.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; cat gpurun_out/bench_$tag.json
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>/dev/null; cat gpurun_out/bench_ref_$tag.json
+timeout 300 python tools/bench_vit.py --batch 512 --iters 5 > gpurun_out/bench_vit_$tag.json 2>&1; cat gpurun_out/bench_vit_$tag.json
+timeout 300 python tools/bench_rnn.py > gpurun_out/bench_rnn_$tag.json 2>&1; cat gpurun_out/bench_rnn_$tag.json
 CMD="python tools/prof_step.py --videos 64 --frames 32 --iters 2"
-$CMD > gpurun_out/prof_plain_$tag.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 71 -c 71 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
+timeout 300 $CMD > gpurun_out/prof_plain_$tag.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 71 -c 71 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
 echo "launch list rc=$?"
+CMDV="python tools/bench_vit.py --batch 128 --iters 1"
+timeout 300 $CMDV > /dev/null 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_tensor.sum --clock-control none -s 176 -c 88 --csv --log-file gpurun_out/launches_vit_$tag.csv $CMDV > gpurun_out/ncu_list_vit_$tag.log 2>&1
+echo "vit launch list rc=$?"
 CMD2="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
-$CMD2 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"dwconv|gemm_tc|stem|se_kernel|pool_head" -s 71 -c 71 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
+timeout 300 $CMD2 > /dev/null 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"dwconv|gemm_tc|stem|se_kernel|pool_head" -s 66 -c 66 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full rc=$?"
 ncu -i /tmp/full_$tag.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.csv 2>/dev/null
 du -sh gpurun_out

@@ -18,6 +18,7 @@ def klass(name):
     if "stem" in name: return "stem"
     if "pool_head" in name: return "attn_pool_head"
     if "preprocess" in name: return "preprocess"
+    if "scale_weights" in name: return "gemm_project"      # per-frame weight scaling belongs to the project step (bench.py counts it there)
     if "gemm_tc" in name:
         m = re.search(r"<[^,]+, *(\w+), *(\w+), *(\w+), *(\w+)", name)
         g, a, r, p = [x in ("1", "true") for x in m.groups()]

@@ -3,7 +3,7 @@ import csv, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 h = rows[0]
 pat = sys.argv[2] if len(sys.argv) > 2 else "."
-cols = {"t_us": "gpu__time_duration.sum", "dramR_MB": "dram__bytes_read.sum", "dramW_MB": "dram__bytes_write.sum",
+cols = {"t_us": "gpu__time_duration.sum", "dramR": "dram__bytes_read.sum", "dramW": "dram__bytes_write.sum",
         "dram%": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts%": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1%": "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1hit": "l1tex__t_sector_hit_rate.pct",
         "fma%": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "alu%": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
@@ -17,7 +17,9 @@ cols = {"t_us": "gpu__time_duration.sum", "dramR_MB": "dram__bytes_read.sum", "d
         "ipc": "sm__inst_executed.avg.per_cycle_active", "tensor%": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"}
 idx = {k: h.index(v) for k, v in cols.items() if v in h}
 ki, gi = h.index("Kernel Name"), h.index("Grid Size")
-print("kernel".ljust(34), "grid".rjust(8), " ".join(k.rjust(9) for k in idx))
+units = rows[1]                      # ncu scales each column: take the unit of the byte columns from the unit row
+label = lambda k: (k + "_" + units[idx[k]].replace("byte", "B")) if k.startswith("dram") and "byte" in units[idx[k]] else k
+print("kernel".ljust(34), "grid".rjust(8), " ".join(label(k).rjust(9) for k in idx))
 for r in rows[2:]:
     name = re.sub(r"\(.*", "", r[ki]).replace("void dfd::", "").replace("void ", "")
     if not re.search(pat, name):
