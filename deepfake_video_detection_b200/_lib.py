@@ -40,6 +40,9 @@ _SIGNATURES = {
     "dfd_vit_free_weights": (None, [_vp]),
     "dfd_vit_workspace_bytes": (_int, [_i64, C.POINTER(C.c_size_t)]),
     "dfd_vit_features": (_int, [_vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
+    "dfd_resize_last_error": (C.c_char_p, []),
+    "dfd_crop_resize_workspace_bytes": (_int, [_vp, _i64, _int, C.POINTER(C.c_size_t)]),
+    "dfd_crop_resize_u8": (_int, [_vp, _vp, _i64, _int, _vp, _vp, C.c_size_t, _vp]),
     "dfd_profile_enable": (_int, [_int]),
     "dfd_profile_collect": (_int, [_vp, _int, C.POINTER(_int)]),
     # dfd_b200_kernels.h
@@ -53,6 +56,11 @@ _SIGNATURES = {
     "dfd_k_gemm_pool": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class CropBox(C.Structure):                      # dfd_crop_box
+    _fields_ = [("frame_offset", C.c_int64), ("frame_w", C.c_int32), ("frame_h", C.c_int32),
+                ("x1", C.c_int32), ("y1", C.c_int32), ("x2", C.c_int32), ("y2", C.c_int32)]
 
 
 class ProfileEntry(C.Structure):

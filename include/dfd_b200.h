@@ -127,6 +127,23 @@ int dfd_vit_workspace_bytes(int64_t images, size_t* bytes);
 int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t images, float* d_features,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K0: crop + resize in front of the path: app.py:1964-1978, src/data_prepare.py:54-56 ----------
+ * `pil.crop((x1, y1, x2, y2)).resize((S, S))` — Pillow's BICUBIC (antialiased, separable, 8-bit intermediate, 22-bit
+ * fixed-point coefficients) reproduced bit-exactly, straight from full uint8 HWC video frames resident on the device.
+ * `h_boxes` is a HOST array: frame_offset = byte offset of the frame inside d_frames, frame_w / frame_h its extent in
+ * pixels, (x1, y1, x2, y2) the box already clamped to the frame as the reference does at app.py:1968-1973 (an empty or
+ * out-of-frame box is DFD_EINVAL — the reference skips those).  d_out: uint8 (n, S, S, 3), ready for dfd_score_videos
+ * (DFD_IN_U8_HWC).  The coefficient tables are built on the host and uploaded on `stream` before the call returns. */
+typedef struct dfd_crop_box {
+    int64_t frame_offset;
+    int32_t frame_w, frame_h;
+    int32_t x1, y1, x2, y2;
+} dfd_crop_box;
+const char* dfd_resize_last_error(void);
+int dfd_crop_resize_workspace_bytes(const dfd_crop_box* h_boxes, int64_t n, int out_size, size_t* bytes);
+int dfd_crop_resize_u8(const uint8_t* d_frames, const dfd_crop_box* h_boxes, int64_t n, int out_size, uint8_t* d_out,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- measurement aid --------------------------------------------------------------------------------
  * dfd_profile_enable(1): from now on every kernel launched by this thread through this library is
  * bracketed by CUDA events recorded on the launch stream.  dfd_profile_collect synchronises on them and
