@@ -249,7 +249,82 @@ __global__ void __launch_bounds__(128) vit_attention_kernel(const T* __restrict_
 
 constexpr size_t kAttSmem = (size_t)(2 * kTokPad * kQKStride + kHd * kVtStride) * 2;
 
+// ---- DeepfakeModel head (src/models.py:199-291): SimpleGCN over the frame graph + mean pool + classifier ------------
+//   g = relu(fc2(relu(fc1(A_norm @ H))));  logits = Linear(64 -> C)(relu(Linear(128 -> 64)(mean_n g)))      (:186-197, :283-291)
+// One CTA per video, fp32.  fc1(A @ H) is evaluated as A @ (H W1^T) + b1 (same function, N x 256 intermediate instead
+// of N x 768).  Every sum runs in a fixed order.  Weights are packed transposed so that threads read consecutive words.
+constexpr int kGcnF = 768, kGcnHid = 256, kGcnOut = 128, kGcnC1 = 64, kGcnMaxNodes = 64, kGcnChunk = 8;
+struct GcnW { const float *w1t, *b1, *w2t, *b2, *c1t, *cb1, *c2, *cb2; int classes; };
+
+__global__ void __launch_bounds__(256) gcn_head_kernel(GcnW w, const float* __restrict__ feats, const float* __restrict__ adj,
+                                                       int N, float* __restrict__ logits) {
+    extern __shared__ float gs[];
+    float* sT = gs;                          // [N][256]  H W1^T, later g2 [N][128]
+    float* sG = sT + N * kGcnHid;            // [N][256]  relu(A T + b1)
+    float* sA = sG + N * kGcnHid;            // [N][N]
+    float* sH = sA + N * N;                  // [8][768] chunk of the node features; later pooled[128] + c1[64]
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float* H = feats + (size_t)b * N * kGcnF;
+    for (int i = t; i < N * N; i += 256) sA[i] = adj[(size_t)b * N * N + i];
+    for (int n0 = 0; n0 < N; n0 += kGcnChunk) {
+        const int nn = min(kGcnChunk, N - n0);
+        __syncthreads();
+        for (int i = t; i < nn * kGcnF; i += 256) sH[i] = H[(size_t)n0 * kGcnF + i];
+        __syncthreads();
+        float acc[kGcnChunk];
+#pragma unroll
+        for (int n = 0; n < kGcnChunk; ++n) acc[n] = 0.f;
+        for (int k = 0; k < kGcnF; ++k) {
+            const float wv = __ldg(w.w1t + (size_t)k * kGcnHid + t);
+#pragma unroll
+            for (int n = 0; n < kGcnChunk; ++n) acc[n] = fmaf(sH[n * kGcnF + k], wv, acc[n]);     // rows >= nn hold stale data: unused
+        }
+#pragma unroll
+        for (int n = 0; n < kGcnChunk; ++n) if (n < nn) sT[(n0 + n) * kGcnHid + t] = acc[n];
+    }
+    __syncthreads();
+    {
+        const float bj = __ldg(w.b1 + t);
+        for (int n = 0; n < N; ++n) {
+            float a = 0.f;
+            for (int m = 0; m < N; ++m) a = fmaf(sA[n * N + m], sT[m * kGcnHid + t], a);
+            sG[n * kGcnHid + t] = fmaxf(a + bj, 0.f);
+        }
+    }
+    __syncthreads();
+    {
+        const int o = t & (kGcnOut - 1), half = t >> 7;
+        const float bo = __ldg(w.b2 + o);
+        for (int n = half; n < N; n += 2) {
+            float a = 0.f;
+            for (int j = 0; j < kGcnHid; ++j) a = fmaf(sG[n * kGcnHid + j], __ldg(w.w2t + (size_t)j * kGcnOut + o), a);
+            sT[n * kGcnOut + o] = fmaxf(a + bo, 0.f);
+        }
+    }
+    __syncthreads();
+    float* pooled = sH; float* c1 = sH + kGcnOut;
+    if (t < kGcnOut) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a += sT[n * kGcnOut + t];
+        pooled[t] = a / (float)N;
+    }
+    __syncthreads();
+    if (t < kGcnC1) {
+        float a = __ldg(w.cb1 + t);
+        for (int o = 0; o < kGcnOut; ++o) a = fmaf(pooled[o], __ldg(w.c1t + (size_t)o * kGcnC1 + t), a);
+        c1[t] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    if (t < w.classes) {
+        float a = __ldg(w.cb2 + t);
+        for (int i = 0; i < kGcnC1; ++i) a = fmaf(c1[i], __ldg(w.c2 + (size_t)t * kGcnC1 + i), a);
+        logits[(size_t)b * w.classes + t] = a;
+    }
+}
+
 }  // namespace dfd
+
+struct dfd_gcn_weights { dfd::GcnW w; void* arena; };
 
 namespace {
 thread_local std::string g_vit_err;
@@ -393,6 +468,58 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
     }
     VIT_CK(ln(X, (int64_t)kTokens * kDim, w->norm_w, w->norm_b, d_features, true, images), "vit final norm");
 #undef VIT_CK
+    return DFD_OK;
+}
+
+int dfd_gcn_pack_weights(int n, const char* const* names, const float* const* data, const int64_t* numel,
+                         int num_classes, dfd_gcn_weights_t** out) {
+    using namespace dfd;
+    if (!names || !data || !numel || !out || n <= 0 || num_classes < 1 || num_classes > 64) return vfail(DFD_EINVAL, "dfd_gcn_pack_weights: bad argument");
+    std::unordered_map<std::string, std::pair<const float*, int64_t>> t;
+    for (int i = 0; i < n; ++i) if (names[i]) t[names[i]] = {data[i], numel[i]};
+    std::string missing;
+    auto get = [&](const std::string& k, int64_t ne) -> const float* {
+        auto it = t.find(k);
+        if (it == t.end() || it->second.second != ne) { if (missing.empty()) missing = k; return nullptr; }
+        return it->second.first;
+    };
+    std::vector<float> host;
+    auto put = [&](const float* p, int rows, int cols, bool transpose) {          // -> offset (floats), 64-float aligned
+        const size_t off = (host.size() + 63) & ~size_t(63);
+        host.resize(off + (size_t)rows * cols, 0.f);
+        if (p) for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c)
+            host[off + (transpose ? (size_t)c * rows + r : (size_t)r * cols + c)] = p[(size_t)r * cols + c];
+        return off;
+    };
+    const size_t o_w1 = put(get("gcn.fc1.weight", (int64_t)kGcnHid * kGcnF), kGcnHid, kGcnF, true), o_b1 = put(get("gcn.fc1.bias", kGcnHid), 1, kGcnHid, false);
+    const size_t o_w2 = put(get("gcn.fc2.weight", (int64_t)kGcnOut * kGcnHid), kGcnOut, kGcnHid, true), o_b2 = put(get("gcn.fc2.bias", kGcnOut), 1, kGcnOut, false);
+    const size_t o_c1 = put(get("classifier.0.weight", (int64_t)kGcnC1 * kGcnOut), kGcnC1, kGcnOut, true), o_cb1 = put(get("classifier.0.bias", kGcnC1), 1, kGcnC1, false);
+    const size_t o_c2 = put(get("classifier.3.weight", (int64_t)num_classes * kGcnC1), num_classes, kGcnC1, false), o_cb2 = put(get("classifier.3.bias", num_classes), 1, num_classes, false);
+    if (!missing.empty()) return vfail(DFD_EKEY, "dfd_gcn_pack_weights: state_dict tensor " + missing + " absent or wrong size (vit_out 768, gcn 256/128, classifier 64 are the built sizes)");
+    void* dev = nullptr;
+    if (cudaMalloc(&dev, host.size() * 4) != cudaSuccess) return vfail(DFD_ECUDA, "cudaMalloc(gcn weights) failed");
+    if (cudaMemcpy(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(dev); return vfail(DFD_ECUDA, "cudaMemcpy(gcn weights) failed"); }
+    const float* d = reinterpret_cast<const float*>(dev);
+    auto* W = new dfd_gcn_weights();
+    W->arena = dev;
+    W->w = GcnW{d + o_w1, d + o_b1, d + o_w2, d + o_b2, d + o_c1, d + o_cb1, d + o_c2, d + o_cb2, num_classes};
+    *out = W;
+    return DFD_OK;
+}
+
+void dfd_gcn_free_weights(dfd_gcn_weights_t* w) { if (w) { if (w->arena) cudaFree(w->arena); delete w; } }
+
+int dfd_gcn_head(const dfd_gcn_weights_t* w, const float* d_feats, const float* d_adj, int64_t videos, int nodes,
+                 float* d_logits, void* stream) {
+    using namespace dfd;
+    if (!w || !d_feats || !d_adj || !d_logits) return vfail(DFD_EINVAL, "dfd_gcn_head: null pointer");
+    if (videos <= 0 || nodes < 1 || nodes > kGcnMaxNodes) return vfail(DFD_EINVAL, "dfd_gcn_head: 1 <= nodes <= 64 and videos >= 1 required");
+    const size_t smem = ((size_t)nodes * 2 * kGcnHid + (size_t)nodes * nodes + (size_t)kGcnChunk * kGcnF) * 4;
+    cudaError_t e = cudaFuncSetAttribute(gcn_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string("gcn head smem: ") + cudaGetErrorString(e));
+    gcn_head_kernel<<<(unsigned)videos, 256, smem, (cudaStream_t)stream>>>(w->w, d_feats, d_adj, nodes, d_logits);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string("gcn head: ") + cudaGetErrorString(e));
     return DFD_OK;
 }
 

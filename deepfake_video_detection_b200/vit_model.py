@@ -127,3 +127,77 @@ class ViTFeatureExtractor(nn.Module):            # models.py:88-107
             if rc:
                 raise RuntimeError(f"dfd_vit_features failed ({rc}): {lib.dfd_vit_last_error().decode()}")
         return out
+
+
+class SimpleGCN(nn.Module):                      # models.py:177-197 (parameter container + eager forward)
+    def __init__(self, in_dim, hid_dim=256, out_dim=128, dropout=0.3):
+        super().__init__()
+        self.fc1, self.fc2, self.dropout = nn.Linear(in_dim, hid_dim), nn.Linear(hid_dim, out_dim), nn.Dropout(dropout)
+
+    def forward(self, H, A_norm):
+        H = self.dropout(F.relu(self.fc1(torch.bmm(A_norm, H))))
+        return F.relu(self.fc2(H))
+
+
+class DeepfakeModel(nn.Module):
+    """Drop-in for `src/models.DeepfakeModel` (models.py:199-291) with the `timm_vit` backbone: ViT-B/16 frame features ->
+    SimpleGCN over the frame graph -> mean pool -> classifier.  `forward(images[B,N,3,224,224], A_norm[B,N,N]) -> [B,C]`.
+    Same children / state_dict keys (`vit.vit.*`, `gcn.*`, `classifier.*`).  Eval mode runs in libdfd_b200.so (ViT encoder
+    + one fused head kernel per video); training mode keeps the eager graph.  CLIP / DINOv2 backbones are not built."""
+
+    def __init__(self, vit_out=768, gcn_hid=256, gcn_out=128, num_classes=2, pretrained_vit=False,
+                 vit_model_name="vit_base_patch16_224", vit_pretrained_path=None, backbone: str = "timm_vit",
+                 precision: str = DEFAULT_PRECISION, **_unused):
+        super().__init__()
+        if (backbone or "timm_vit").lower() not in {"timm_vit", "vit", "timm"}:
+            raise ValueError(f"DeepfakeModel (B200 build): only the timm_vit backbone is built, got {backbone!r}")
+        if (vit_out, gcn_hid, gcn_out) != (768, 256, 128):
+            raise ValueError("DeepfakeModel (B200 build): built for the reference's default sizes (768, 256, 128)")
+        self.vit = ViTFeatureExtractor(model_name=vit_model_name, pretrained=pretrained_vit, out_dim=vit_out, precision=precision)
+        self.vit_proj = nn.Identity()
+        if vit_pretrained_path is not None:
+            self.vit.load_state_dict(torch.load(vit_pretrained_path, map_location="cpu"))
+        self.gcn = SimpleGCN(in_dim=vit_out, hid_dim=gcn_hid, out_dim=gcn_out)
+        self.classifier = nn.Sequential(nn.Linear(gcn_out, 64), nn.ReLU(), nn.Dropout(0.3), nn.Linear(64, num_classes))
+        self.num_classes = num_classes
+        self._head, self._head_key = None, None
+
+    def _pack_head(self, device):
+        tensors = [(k, v) for k, v in self.state_dict(keep_vars=True).items() if not k.startswith("vit.")]
+        key = (str(device), tuple((t.data_ptr(), t._version) for _, t in tensors))
+        if self._head is not None and key == self._head_key:
+            return self._head
+        lib = _lib.load()
+        if self._head is not None:
+            lib.dfd_gcn_free_weights(self._head)
+        keep = [(k.encode(), v.detach().to("cpu", torch.float32).contiguous()) for k, v in tensors]
+        n = len(keep)
+        names = (C.c_char_p * n)(*[k for k, _ in keep])
+        data = (C.c_void_p * n)(*[v.data_ptr() for _, v in keep])
+        numel = (C.c_int64 * n)(*[v.numel() for _, v in keep])
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            rc = lib.dfd_gcn_pack_weights(n, names, data, numel, self.num_classes, C.byref(h))
+        if rc:
+            raise RuntimeError(f"dfd_gcn_pack_weights failed ({rc}): {lib.dfd_vit_last_error().decode()}")
+        self._head, self._head_key = h, key
+        return h
+
+    def forward(self, images, A_norm):
+        B, N, Cc, H, W = images.shape
+        x = images.reshape(B * N, Cc, H, W)
+        if self.training:
+            feats = self.vit_proj(self.vit(x)).view(B, N, -1)
+            return self.classifier(self.gcn(feats, A_norm).mean(dim=1))
+        feats = self.vit(x)                                        # (B*N, 768) fp32, raises on CPU tensors
+        lib = _lib.load()
+        h = self._pack_head(images.device)
+        adj = A_norm.to(device=images.device, dtype=torch.float32).contiguous()
+        if tuple(adj.shape) != (B, N, N):
+            raise ValueError(f"DeepfakeModel: A_norm must be ({B},{N},{N}), got {tuple(adj.shape)}")
+        out = torch.empty((B, self.num_classes), dtype=torch.float32, device=images.device)
+        with torch.cuda.device(images.device):
+            rc = lib.dfd_gcn_head(h, feats.data_ptr(), adj.data_ptr(), B, N, out.data_ptr(), _stream_ptr(images.device))
+        if rc:
+            raise RuntimeError(f"dfd_gcn_head failed ({rc}): {lib.dfd_vit_last_error().decode()}")
+        return out

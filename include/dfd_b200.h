@@ -127,6 +127,19 @@ int dfd_vit_workspace_bytes(int64_t images, size_t* bytes);
 int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t images, float* d_features,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- DeepfakeModel head: src/models.py:177-197 SimpleGCN + :283-291 mean pool + classifier ------
+ * logits = classifier(mean_n relu(fc2(relu(fc1(A_norm @ H))))) on the ViT frame features H of each video.
+ * Weights by reference state_dict key ("gcn.fc1.*", "gcn.fc2.*", "classifier.0.*", "classifier.3.*"), HOST fp32; built for
+ * the reference's default sizes (vit_out 768, gcn 256 / 128, classifier 64).  d_feats fp32 (videos*nodes, 768) = output
+ * of dfd_vit_features, d_adj fp32 (videos, nodes, nodes) = normalize_adjacency (src/utils.py:95-104), nodes <= 64
+ * (app.py:2230 uses 16) -> d_logits fp32 (videos, num_classes).  Errors: dfd_vit_last_error(). */
+typedef struct dfd_gcn_weights dfd_gcn_weights_t;
+int dfd_gcn_pack_weights(int n_tensors, const char* const* names, const float* const* data, const int64_t* numel,
+                         int num_classes, dfd_gcn_weights_t** out);
+void dfd_gcn_free_weights(dfd_gcn_weights_t* w);
+int dfd_gcn_head(const dfd_gcn_weights_t* w, const float* d_feats, const float* d_adj, int64_t videos, int nodes,
+                 float* d_logits, void* stream);
+
 /* ---- K0: crop + resize in front of the path: app.py:1964-1978, src/data_prepare.py:54-56 ----------
  * `pil.crop((x1, y1, x2, y2)).resize((S, S))` — Pillow's BICUBIC (antialiased, separable, 8-bit intermediate, 22-bit
  * fixed-point coefficients) reproduced bit-exactly, straight from full uint8 HWC video frames resident on the device.

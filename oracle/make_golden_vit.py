@@ -23,7 +23,21 @@ def main():
     x = V.synth_images(0, N_IMAGES)
     with torch.no_grad():
         f = m(x)
-    np.savez_compressed(GOLDEN, features=f.numpy())
+    # DeepfakeModel (ViT + SimpleGCN + classifier, models.py:199-291) on 2 videos x 4 nodes, chain graph as app.py:2245-2250
+    from src.models import DeepfakeModel
+    from src.utils import normalize_adjacency
+    dm = DeepfakeModel().eval()
+    print("DeepfakeModel strict load:", dm.load_state_dict(V.synth_deepfake_state_dict(0), strict=True))
+    A = np.zeros((4, 4), np.float32)
+    for i in range(3):
+        A[i, i + 1] = A[i + 1, i] = 1.0
+    A_norm = torch.from_numpy(normalize_adjacency(A)).float().unsqueeze(0).repeat(2, 1, 1)
+    assert torch.equal(A_norm[0], V.chain_adjacency(4))
+    imgs = V.synth_images(2, 8).view(2, 4, 3, 224, 224)
+    with torch.no_grad():
+        dl = dm(imgs, A_norm)
+    print("DeepfakeModel logits", dl)
+    np.savez_compressed(GOLDEN, features=f.numpy(), deepfake_logits=dl.numpy())
     print("features", f.shape, "abs-mean", f.abs().mean().item(), "max", f.abs().max().item(),
           "row-to-row diff", (f[0] - f[1]).abs().mean().item())
 

@@ -59,3 +59,52 @@ def vit_features(sd, x):
         h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
         t = t + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
     return F.layer_norm(t[:, 0], (DIM,), sd["vit.norm.weight"], sd["vit.norm.bias"], 1e-6)
+
+
+# ---- DeepfakeModel = ViT frame encoder + SimpleGCN + classifier (src/models.py:177-291; caller app.py:2225-2255) ----------
+def normalize_adjacency(A):
+    """src/utils.py:95-104: D^-1/2 (A + I) D^-1/2 (numpy, fp32)."""
+    import numpy as np
+    A = A.copy().astype(np.float32)
+    A = A + np.eye(A.shape[0], dtype=A.dtype)
+    d = np.power(np.sum(A, axis=1), -0.5)
+    d[np.isinf(d)] = 0.0
+    return np.diag(d) @ A @ np.diag(d)
+
+
+def chain_adjacency(n):
+    """app.py:2245-2250: consecutive frames are linked."""
+    import numpy as np
+    A = np.zeros((n, n), np.float32)
+    for i in range(n - 1):
+        A[i, i + 1] = A[i + 1, i] = 1.0
+    return torch.from_numpy(normalize_adjacency(A)).float()
+
+
+def synth_deepfake_state_dict(seed=0):
+    """DeepfakeModel schema: the ViT under `vit.vit.*` (models.py:223 wraps ViTFeatureExtractor) + gcn + classifier."""
+    sd = {"vit." + k: v for k, v in synth_state_dict(seed).items()}
+    g = torch.Generator().manual_seed(100 + seed)
+    r = lambda *s, std: torch.randn(*s, generator=g) * std
+    sd.update({"gcn.fc1.weight": r(256, DIM, std=0.05), "gcn.fc1.bias": r(256, std=0.1),
+               "gcn.fc2.weight": r(128, 256, std=0.08), "gcn.fc2.bias": r(128, std=0.1),
+               "classifier.0.weight": r(64, 128, std=0.12), "classifier.0.bias": r(64, std=0.1),
+               "classifier.3.weight": r(2, 64, std=0.3), "classifier.3.bias": r(2, std=0.1)})
+    return sd
+
+
+def gcn_head(sd, feats, A_norm):
+    """feats (B,N,768), A_norm (B,N,N) -> logits (B,2): models.py:186-197 (SimpleGCN) + :283-291 (mean pool, classifier)."""
+    h = torch.bmm(A_norm, feats)
+    h = F.relu(F.linear(h, sd["gcn.fc1.weight"], sd["gcn.fc1.bias"]))
+    h = F.relu(F.linear(h, sd["gcn.fc2.weight"], sd["gcn.fc2.bias"]))
+    p = h.mean(dim=1)
+    return F.linear(F.relu(F.linear(p, sd["classifier.0.weight"], sd["classifier.0.bias"])), sd["classifier.3.weight"], sd["classifier.3.bias"])
+
+
+def deepfake_forward(sd, images, A_norm):
+    """images (B,N,3,224,224), A_norm (B,N,N) -> logits (B,2)  (models.py:271-291)."""
+    B, N = images.shape[:2]
+    vit_sd = {k[4:]: v for k, v in sd.items() if k.startswith("vit.")}
+    feats = vit_features(vit_sd, images.reshape(B * N, *images.shape[2:])).view(B, N, -1)
+    return gcn_head(sd, feats, A_norm)

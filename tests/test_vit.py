@@ -96,3 +96,58 @@ def test_vit_cuda_batch_invariance_and_ragged_batches():
     assert torch.equal(full[perm.cuda()], shuffled)
     with pytest.raises(ValueError):
         m(torch.zeros(1, 3, 192, 192, device="cuda"))
+
+
+def test_deepfake_model_oracle_and_dropin_contract():
+    """DeepfakeModel = ViT + SimpleGCN + classifier (models.py:199-291): restatement vs goldens of the unmodified class."""
+    from deepfake_video_detection_b200.vit_model import DeepfakeModel
+    from oracle import vit_oracle as V
+    sd = V.synth_deepfake_state_dict(0)
+    imgs = V.synth_images(2, 8).view(2, 4, 3, 224, 224)
+    A = V.chain_adjacency(4).unsqueeze(0).repeat(2, 1, 1)
+    with torch.no_grad():
+        lg = V.deepfake_forward(sd, imgs, A)
+    g = np.load(GOLDEN)["deepfake_logits"]
+    assert np.abs(lg.numpy() - g).max() < 1e-4
+    m = DeepfakeModel()
+    assert set(m.state_dict()) == set(sd)                          # vit.vit.*, gcn.*, classifier.*
+    m.load_state_dict(sd, strict=True)
+    m.train(); m.gcn.dropout.p = 0.0; m.classifier[2].p = 0.0
+    with torch.no_grad():
+        assert (m(imgs[:1, :2], A[:1, :2, :2]) - V.deepfake_forward(sd, imgs[:1, :2], A[:1, :2, :2])).abs().max().item() < 1e-4
+    m.eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(imgs, A)
+    with pytest.raises(ValueError):
+        DeepfakeModel(backbone="clip")
+
+
+@pytest.mark.gpu
+def test_deepfake_model_cuda_matches_oracle():
+    from deepfake_video_detection_b200.vit_model import DeepfakeModel
+    from oracle import vit_oracle as V
+    sd = V.synth_deepfake_state_dict(0)
+    imgs = V.synth_images(2, 8).view(2, 4, 3, 224, 224)
+    A = V.chain_adjacency(4).unsqueeze(0).repeat(2, 1, 1)
+    m = DeepfakeModel().eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = m(imgs.cuda(), A.cuda()).cpu()
+        ref = V.deepfake_forward(sd, imgs, A)
+        # the fused head alone, on exact fp32 features: tight tolerance (only the summation order differs)
+        vit_sd = {k[4:]: v for k, v in sd.items() if k.startswith("vit.")}
+        feats = V.vit_features(vit_sd, imgs.reshape(8, 3, 224, 224)).view(2, 4, -1)
+    g = torch.from_numpy(np.load(GOLDEN)["deepfake_logits"])
+    print(f"deepfake model: max |dlogit| vs oracle {(out - ref).abs().max().item():.3e}, vs reference goldens {(out - g).abs().max().item():.3e}")
+    assert (out - ref).abs().max().item() <= 2e-2 and (out - g).abs().max().item() <= 2e-2
+    assert (out.argmax(1) == g.argmax(1)).all()
+    import ctypes as C
+    from deepfake_video_detection_b200 import _lib
+    from deepfake_video_detection_b200.engine import _stream_ptr
+    lib = _lib.load()
+    for n_nodes in (4, 1, 3):                                       # ragged node counts incl. a single-frame graph
+        f = feats[:, :n_nodes].contiguous().cuda(); a = V.chain_adjacency(n_nodes).unsqueeze(0).repeat(2, 1, 1).cuda()
+        o = torch.empty((2, 2), device="cuda")
+        assert lib.dfd_gcn_head(m._pack_head(f.device), f.data_ptr(), a.data_ptr(), 2, n_nodes, o.data_ptr(), _stream_ptr(f.device)) == 0
+        assert (o.cpu() - V.gcn_head(sd, f.cpu(), a.cpu())).abs().max().item() < 1e-4
+    assert lib.dfd_gcn_head(m._pack_head(f.device), f.data_ptr(), a.data_ptr(), 2, 65, o.data_ptr(), _stream_ptr(f.device)) != 0   # nodes > 64
