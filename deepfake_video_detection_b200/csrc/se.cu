@@ -9,17 +9,20 @@
 
 namespace dfd {
 
-constexpr int kSeThreads = 256;
+constexpr int kSeMaxThreads = 1024;
 
 template <int kSeFrames>
-__global__ void __launch_bounds__(kSeThreads)
+__global__ void __launch_bounds__(kSeMaxThreads)
 se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
           const float* __restrict__ w1, const float* __restrict__ b1,
           const float* __restrict__ w2t, const float* __restrict__ b2,
           float* __restrict__ gate, int64_t frames, int C, int rd) {
-    extern __shared__ float smem[];
-    float* s_mean = smem;                         // [kSeFrames][C]
-    float* s_r = smem + kSeFrames * C;            // [kSeFrames][rd]
+    extern __shared__ __align__(16) float smem[];
+    // frame-minor layouts: one 16-byte shared-memory load fetches 4 frames of a channel (the FC loops were bound by
+    // the number of shared-memory loads, 8 scalar loads per weight)
+    float* s_mean = smem;                         // [C][kSeFrames]
+    float* s_r = smem + kSeFrames * C;            // [rd][kSeFrames]
+    const int kSeThreads = blockDim.x;
     const int64_t f0 = (int64_t)blockIdx.x * kSeFrames;
     const int nf = (int)min((int64_t)kSeFrames, frames - f0);
 
@@ -39,7 +42,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
             }
             for (int u = 0; q < nparts; ++q, ++u) a[u] += p[(size_t)q * C];
         }
-        s_mean[i] = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) * inv_hw;
+        s_mean[c * kSeFrames + f] = (((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]))) * inv_hw;
     }
     __syncthreads();
 
@@ -52,8 +55,16 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
 #pragma unroll 4
         for (int c = lane; c < C; c += 32) {
             const float wv = __ldg(wr + c);
+            float m[kSeFrames];
+            if constexpr (kSeFrames % 4 == 0) {
 #pragma unroll
-            for (int f = 0; f < kSeFrames; ++f) acc[f] = fmaf(wv, s_mean[f * C + c], acc[f]);
+                for (int f = 0; f < kSeFrames; f += 4) *reinterpret_cast<float4*>(&m[f]) = *reinterpret_cast<const float4*>(&s_mean[c * kSeFrames + f]);
+            } else {
+#pragma unroll
+                for (int f = 0; f < kSeFrames; ++f) m[f] = s_mean[c * kSeFrames + f];
+            }
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f) acc[f] = fmaf(wv, m[f], acc[f]);
         }
 #pragma unroll
         for (int f = 0; f < kSeFrames; ++f) {
@@ -63,7 +74,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
         if (lane == 0) {
             const float bj = __ldg(b1 + j);
 #pragma unroll
-            for (int f = 0; f < kSeFrames; ++f) s_r[f * rd + j] = silu_f(acc[f] + bj);
+            for (int f = 0; f < kSeFrames; ++f) s_r[j * kSeFrames + f] = silu_f(acc[f] + bj);
         }
     }
     __syncthreads();
@@ -76,8 +87,16 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
 #pragma unroll 8
         for (int j = 0; j < rd; ++j) {
             const float wv = __ldg(w2t + (size_t)j * C + c);
+            float r[kSeFrames];
+            if constexpr (kSeFrames % 4 == 0) {
 #pragma unroll
-            for (int f = 0; f < kSeFrames; ++f) acc[f] = fmaf(wv, s_r[f * rd + j], acc[f]);
+                for (int f = 0; f < kSeFrames; f += 4) *reinterpret_cast<float4*>(&r[f]) = *reinterpret_cast<const float4*>(&s_r[j * kSeFrames + f]);
+            } else {
+#pragma unroll
+                for (int f = 0; f < kSeFrames; ++f) r[f] = s_r[j * kSeFrames + f];
+            }
+#pragma unroll
+            for (int f = 0; f < kSeFrames; ++f) acc[f] = fmaf(wv, r[f], acc[f]);
         }
 #pragma unroll
         for (int f = 0; f < kSeFrames; ++f)
@@ -93,7 +112,9 @@ static cudaError_t launch_se_t(const float* partials, int nparts, float inv_hw, 
     cudaError_t e = cudaFuncSetAttribute(se_kernel<FPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((frames + FPB - 1) / FPB);
-    se_kernel<FPB><<<grid, kSeThreads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
+    // the kernel is instruction-latency-bound (IPC 0.66 at 8 warps per SM): wide layers get 32 warps per CTA
+    const int threads = C >= 480 ? 1024 : (C >= 144 ? 512 : 256);
+    se_kernel<FPB><<<grid, threads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
     return cudaGetLastError();
 }
 
