@@ -527,7 +527,10 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
     const size_t budget = 227 * 1024;
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
-    const size_t res_limit = 152 * 1024;                              // leaves >= 3 A stages
+    static const size_t env_res = getenv("DFD_GEMM_RESLIM") ? (size_t)atol(getenv("DFD_GEMM_RESLIM")) : 0;      // experiments only
+    // Weights stay resident only up to 60 KB: beyond that the shared memory is worth more as pipeline stages (W blocks then
+    // stream from L2 by TMA).  Measured: 672->112 gated 233 -> 178 us, 112->672 expand 88 -> 78 us per 2048 / 1024 frames.
+    const size_t res_limit = env_res ? env_res : 60 * 1024;
     a.b_resident = 0;
     if (a.tpf == 0) {
         if (bres <= res_limit) a.b_resident = 1;
