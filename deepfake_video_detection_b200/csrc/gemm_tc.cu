@@ -9,20 +9,22 @@
 //   R   residual input of the block (stride-1, Cin == Cout blocks)
 //   pool variant: conv_head + BN + SiLU + global average pool -> features fp32 [frames][N]
 //
-// Structure (one persistent CTA per SM, 17 warps, warp-specialised):
-//   loaders      cp.async (LDGSTS, 16 B, L1 bypass) global -> shared memory straight into the UMMA canonical
-//                K-major no-swizzle layout (8-row x 16-byte core matrices).  Completion is tracked by the
-//                stage mbarrier itself (`cp.async.mbarrier.arrive`), so a loader never waits for data: up to
-//                16 stages are in flight.  Weights that fit (<= 120 KB) are loaded once per CTA and stay
-//                resident; larger ones stream through the stage ring.
-//   transformers (gated project layers only) wait for a landed stage, multiply it in place by the per-frame
-//                squeeze-excite gate (the gate slice travels with the stage), `fence.proxy.async`, then hand
-//                the stage to the MMA warp.  They hold no outstanding cp.async, so the proxy fence is cheap.
-//   warp  8      MMA issuer: one elected thread issues tcgen05.mma (M=128, N=NBp, K=16) per 16-wide K step,
-//                accumulators in TMEM (double buffered), tcgen05.commit releases smem stages / signals epilogue
-//   warps 0..7   epilogue: tcgen05.ld (32 lanes x 16 columns), +bias, SiLU, +residual, pack, store
-// Almost every layer is HBM-bound: the design goal is "read A once, write D once, keep
-// enough bytes in flight", not tensor-pipe occupancy.
+// Structure (one persistent CTA per SM, warp-specialised; roles are template parameters):
+//   TMA issuer   ONE thread issues the copies of a pipeline stage with cp.async.bulk.tensor.2d: the A tile (64 K-elements
+//                x 128 rows) and, when the weights are not resident, the W block (64 x N) — both land in the 128-byte
+//                swizzled K-major UMMA layout, out-of-range K / M is zero-filled by the copy engine, completion is counted
+//                in bytes on the stage mbarrier (`mbarrier.arrive.expect_tx`).  Up to 13 stages are in flight.
+//                Weights up to 60 KB are loaded once per CTA (cp.async, no-swizzle layout) and stay resident.
+//   transformers (gated project layers on small maps) wait for a landed stage, multiply the A tile in place by the
+//                per-frame squeeze-excite gate (gate slice staged beside the tile by two loader warps), issue
+//                `fence.proxy.async` and hand the stage to the MMA warp; the warps form groups that take alternate stages.
+//   MMA issuer   one elected thread issues tcgen05.mma (M=128, N<=256, K=16) per 16-wide K step with descriptors that only
+//                add to the 14-bit start-address field; accumulators in TMEM (ring of up to 8), tcgen05.commit releases
+//                smem stages / signals the epilogue.
+//   epilogue     8-16 warps in sets that take alternate tiles: tcgen05.ld (32 lanes x 16 columns), +bias, SiLU / exact GELU,
+//                +residual (16-bit, or fp32 in place), pack, 32-byte stores; head variant: SiLU + average pool.
+// Almost every EfficientNet layer is HBM-bound: the design goal there is "read A once, write D once, keep
+// enough bytes in flight"; the ViT contractions are tensor-bound and reuse the same kernel with streamed weights.
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda.h>
@@ -59,7 +61,6 @@ struct GemmArgs {
                                     //    8 skip the transformers' proxy fence, 16 per-thread (not per-warp) arrivals,
                                     //    32 per-role wait accounting, 64 transformers skip the tile, 128 transformers skip the stores
     int xg;                         // gated: transformer warp groups taking alternate stages
-    int cshift;                     // log2 of the 16-byte chunk columns a loader thread group spans (K < 64: fewer than 8)
     uint32_t lbo_b, stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
     // unit strides of the persistent loops, decomposed on the host so that no role divides per tile
@@ -502,9 +503,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.NBp = (a.NB + 15) & ~15;
     a.lbo_b = (uint32_t)a.NBp * 16 + 16;
     a.kchunks_pad = ((a.K >> 3) + 1) & ~1;
-    const int kcp_max = a.kchunks_pad < 8 ? a.kchunks_pad : 8;       // 16-byte chunk columns a stage can hold
     { static const int env_dbg = getenv("DFD_GEMM_DBG") ? atoi(getenv("DFD_GEMM_DBG")) : 0; a.dbg = env_dbg; }
-    a.cshift = kcp_max <= 2 ? 1 : (kcp_max <= 4 ? 2 : 3);
     {   static const int env_xg = getenv("DFD_GEMM_XG") ? atoi(getenv("DFD_GEMM_XG")) : 4;
         a.xg = xform_warps > 0 ? env_xg : 1;
         if (a.xg < 1 || a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1; }
