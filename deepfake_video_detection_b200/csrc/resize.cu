@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/dfd_b200.h"
+#include "../../include/dfd_b200_kernels.h"
 
 namespace {
 
@@ -192,6 +193,16 @@ int dfd_crop_resize_u8(const uint8_t* d_frames, const dfd_crop_box* h_boxes, int
     e = cudaGetLastError();
     if (e != cudaSuccess) return rsfail(DFD_ECUDA, std::string("dfd_crop_resize_u8: launch: ") + cudaGetErrorString(e));
     return DFD_OK;
+}
+
+int dfd_k_resize_coeffs(int in_size, int out_size, int32_t* h_bounds, int32_t* h_coeffs, int* ksize) {
+    if (in_size <= 0 || out_size <= 0 || !ksize) return rsfail(DFD_EINVAL, "dfd_k_resize_coeffs: bad argument");
+    std::vector<int> tab; int b_off = 0, k_off = 0, ks = 0;
+    build_coeffs(in_size, out_size, tab, b_off, k_off, ks);
+    *ksize = ks;
+    if (h_bounds) memcpy(h_bounds, tab.data() + b_off, (size_t)out_size * 2 * sizeof(int));
+    if (h_coeffs) memcpy(h_coeffs, tab.data() + k_off, (size_t)out_size * ks * sizeof(int));
+    return ks;
 }
 
 #pragma GCC visibility pop

@@ -47,6 +47,12 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
 int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K,
                     int N, int HW, int dtype, int impl, void* stream);
 
+/* HOST-ONLY (no GPU needed): the fixed-point bicubic coefficient table the resize kernels use for one axis
+ * (Pillow's precompute_coeffs + normalize_coeffs_8bpc).  h_bounds int32 [out_size][2] = (first source index, taps),
+ * h_coeffs int32 [out_size][*ksize] (row stride = *ksize, unused taps 0); h_coeffs may be NULL to query *ksize only.
+ * Returns the number of coefficients per row, or a negative DFD_E* code. */
+int dfd_k_resize_coeffs(int in_size, int out_size, int32_t* h_bounds, int32_t* h_coeffs, int* ksize);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,41 @@ def test_abi_argument_errors_without_gpu():
     assert lib.dfd_preprocess_u8hwc_to_nchw(None, None, 1, 224, 224, 1, None) == -1
 
 
+def test_new_entry_points_validate_arguments_without_gpu():
+    """ViT / GCN / crop-resize ABI: size queries and argument errors are host logic."""
+    from deepfake_video_detection_b200 import _lib
+    lib = _lib.load()
+    n = C.c_size_t()
+    assert lib.dfd_vit_workspace_bytes(4, C.byref(n)) == 0 and 4 * 2_000_000 < n.value < 4 * 2_300_000     # 2.1 MB per image
+    assert lib.dfd_vit_workspace_bytes(0, C.byref(n)) == -1
+    assert lib.dfd_vit_pack_weights(0, None, None, None, 1, None) == -1 and lib.dfd_gcn_pack_weights(0, None, None, None, 2, None) == -1
+    assert lib.dfd_gcn_head(None, None, None, 1, 4, None, None) == -1
+    boxes = (_lib.CropBox * 2)(_lib.CropBox(0, 640, 480, 10, 20, 300, 400), _lib.CropBox(640 * 480 * 3, 640, 480, 0, 0, 640, 480))
+    assert lib.dfd_crop_resize_workspace_bytes(boxes, 2, 224, C.byref(n)) == 0 and n.value > (380 + 480) * 224 * 3
+    bad = (_lib.CropBox * 1)(_lib.CropBox(0, 640, 480, 10, 20, 10, 400))                                       # empty box
+    assert lib.dfd_crop_resize_workspace_bytes(bad, 1, 224, C.byref(n)) == -1 and b"clamp" in lib.dfd_resize_last_error()
+    bad = (_lib.CropBox * 1)(_lib.CropBox(0, 640, 480, 10, 20, 700, 400))                                      # outside the frame
+    assert lib.dfd_crop_resize_workspace_bytes(bad, 1, 224, C.byref(n)) == -1
+
+
+def test_resize_coefficient_tables_match_the_pillow_oracle():
+    """The C++ table builder (host code of csrc/resize.cu) against oracle/pil_resize_oracle.py, which is pinned on Pillow."""
+    import numpy as np
+    from deepfake_video_detection_b200 import _lib
+    from oracle.pil_resize_oracle import coeffs
+    lib = _lib.load()
+    for in_size, out_size in [(1, 224), (2, 224), (31, 224), (223, 224), (224, 224), (225, 224), (300, 224), (447, 224), (448, 224),
+                              (1080, 224), (1919, 224), (77, 96), (500, 64)]:
+        ks = C.c_int()
+        assert lib.dfd_k_resize_coeffs(in_size, out_size, None, None, C.byref(ks)) == ks.value > 0
+        b = np.zeros((out_size, 2), np.int32); k = np.zeros((out_size, ks.value), np.int32)
+        assert lib.dfd_k_resize_coeffs(in_size, out_size, b.ctypes.data, k.ctypes.data, C.byref(ks)) == ks.value
+        rb, rk = coeffs(in_size, out_size)
+        assert rk.shape[1] == ks.value and np.array_equal(b, rb) and np.array_equal(k, rk), (in_size, out_size)
+        assert (k.sum(1) - (1 << 22)).__abs__().max() <= ks.value                 # rows sum to 1.0 in 22-bit fixed point (rounding)
+    assert lib.dfd_k_resize_coeffs(0, 224, None, None, C.byref(ks)) < 0
+
+
 def test_module_contract_matches_reference(synth_sd):
     from deepfake_video_detection_b200 import EnsembleDetector, PretrainedBackboneDetector
     m = PretrainedBackboneDetector("efficientnet_b0", pretrained=False, num_classes=2, dropout_rate=0.5, use_temporal_attention=True)
