@@ -645,6 +645,15 @@ int dfd_k_stem_tc(const uint8_t* d_in, const float* h_w27x32, const float* d_bia
     if (e2 != cudaSuccess) return cuda_fail(e2, "stem kernel (tcgen05) sync");
     return DFD_OK;
 }
+int dfd_k_pack_stem_row(const float* h_w27x32, const float* h_bias32, uint16_t* h_wrow, float* h_bias4) {
+    if (!h_w27x32 || !h_bias32 || !h_wrow || !h_bias4) return fail(DFD_EINVAL, "dfd_k_pack_stem_row: null pointer");
+    HostArena a;
+    size_t w_off = 0, b4_off = 0;
+    pack_stem_row(a, h_w27x32, h_bias32, w_off, b4_off);
+    memcpy(h_wrow, a.bytes.data() + w_off, 2 * 32 * 32 * 2);
+    memcpy(h_bias4, a.bytes.data() + b4_off, 4 * 32 * 4);
+    return DFD_OK;
+}
 void dfd_k_set_dw_channel_block(int cb) { dfd::dw_march_set_cb(cb); }
 int dfd_k_dw_num_partials(int OH, int OW, int C, int k, int stride) { return dfd::dw_num_partials(OH, OW, C, k, stride); }
 int dfd_k_dwconv(const void* d_in, const float* d_w, const float* d_bias, void* d_out, float* d_partials,

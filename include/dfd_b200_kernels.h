@@ -47,6 +47,12 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
 int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K,
                     int N, int HW, int dtype, int impl, void* stream);
 
+/* HOST-ONLY (no GPU needed): the operands dfd_pack_weights builds for the row-variant stem (stem_tc.cu) from BN-folded
+ * weights h_w27x32 fp32 [(ky*3+kx)*3+c][32] and bias h_bias32: h_wrow fp16 bits [hi|lo][32 oc][32 k] with
+ * k = ky*10 + kx*3 + c holding 256*w/(255*std_c) split in two fp16 terms, h_bias4 fp32 [top*2+left][32] = bias minus
+ * sum over the in-bounds taps of w*mean_c/std_c (the tensor prep of app.py:1772-1780 folded into the conv). */
+int dfd_k_pack_stem_row(const float* h_w27x32, const float* h_bias32, uint16_t* h_wrow, float* h_bias4);
+
 /* HOST-ONLY (no GPU needed): the fixed-point bicubic coefficient table the resize kernels use for one axis
  * (Pillow's precompute_coeffs + normalize_coeffs_8bpc).  h_bounds int32 [out_size][2] = (first source index, taps),
  * h_coeffs int32 [out_size][*ksize] (row stride = *ksize, unused taps 0); h_coeffs may be NULL to query *ksize only.

@@ -70,6 +70,39 @@ def test_resize_coefficient_tables_match_the_pillow_oracle():
     assert lib.dfd_k_resize_coeffs(0, 224, None, None, C.byref(ks)) < 0
 
 
+def test_row_stem_operands_fold_the_tensor_prep_exactly():
+    """CPU emulation of the row-variant stem arithmetic (stem_tc.cu): raw uint8 window x (w_hi + w_lo) / 256 + the bias
+    vector of the border case must equal conv3x3(s2, p1) over the reference's normalised input (app.py:2084-2085)."""
+    import numpy as np
+    import torch.nn.functional as F
+    from deepfake_video_detection_b200 import _lib
+    from oracle import effnet_b0_oracle as O
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(32, generator=g) * 0.2
+    wp = w.permute(2, 3, 1, 0).reshape(27, 32).contiguous()                       # [(ky*3+kx)*3+c][oc], BN already folded
+    wrow = np.zeros((2, 32, 32), np.uint16); bias4 = np.zeros((4, 32), np.float32)
+    assert lib.dfd_k_pack_stem_row(wp.data_ptr(), b.contiguous().data_ptr(), wrow.ctypes.data, bias4.ctypes.data) == 0
+    wsum = wrow.view(np.float16).astype(np.float64).sum(0)                        # (w_hi + w_lo)[oc][k], k = ky*10 + kx*3 + c
+    assert np.all(wsum[:, [9, 19, 29, 30, 31]] == 0)                              # padding columns of the K layout
+    u8 = torch.randint(0, 256, (1, 16, 16, 3), dtype=torch.uint8, generator=g)
+    ref = F.conv2d(O.prep_u8_hwc(u8), w, b, 2, 1)[0].permute(1, 2, 0).double().numpy()   # (8, 8, 32)
+    img = u8[0].numpy().astype(np.float64)
+    worst = 0.0
+    for oy in range(8):
+        for ox in range(8):
+            a = np.zeros(32)
+            for ky in range(3):
+                for kx in range(3):
+                    iy, ix = 2 * oy - 1 + ky, 2 * ox - 1 + kx
+                    if 0 <= iy < 16 and 0 <= ix < 16:
+                        a[ky * 10 + kx * 3: ky * 10 + kx * 3 + 3] = img[iy, ix]  # zero padding: the tap stays 0
+            y = wsum @ a / 256.0 + bias4[(2 if oy == 0 else 0) + (1 if ox == 0 else 0)]
+            worst = max(worst, np.abs(y - ref[oy, ox]).max())
+    assert worst < 2e-5, worst                                                    # fp32 rounding of the reference itself
+
+
 def test_module_contract_matches_reference(synth_sd):
     from deepfake_video_detection_b200 import EnsembleDetector, PretrainedBackboneDetector
     m = PretrainedBackboneDetector("efficientnet_b0", pretrained=False, num_classes=2, dropout_rate=0.5, use_temporal_attention=True)
