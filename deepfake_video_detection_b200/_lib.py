@@ -40,6 +40,11 @@ _SIGNATURES = {
     "dfd_vit_free_weights": (None, [_vp]),
     "dfd_vit_workspace_bytes": (_int, [_i64, C.POINTER(C.c_size_t)]),
     "dfd_vit_features": (_int, [_vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
+    "dfd_resnet_last_error": (C.c_char_p, []),
+    "dfd_resnet50_pack_weights": (_int, [_int, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _int, C.POINTER(_vp)]),
+    "dfd_resnet50_free_weights": (None, [_vp]),
+    "dfd_resnet50_workspace_bytes": (_int, [_i64, C.POINTER(C.c_size_t)]),
+    "dfd_resnet50_score_videos": (_int, [_vp, _vp, _vp, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "dfd_gcn_pack_weights": (_int, [_int, C.POINTER(C.c_char_p), C.POINTER(_vp), C.POINTER(_i64), _int, C.POINTER(_vp)]),
     "dfd_gcn_free_weights": (None, [_vp]),
     "dfd_gcn_head": (_int, [_vp, _vp, _vp, _i64, _int, _vp, _vp]),

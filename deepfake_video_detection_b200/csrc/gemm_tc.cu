@@ -99,7 +99,7 @@ struct TileIter {
     }
 };
 
-// ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
+// ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP), 3 ReLU applied AFTER the residual add (ResNet bottleneck: relu(bn(conv) + identity)).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
 template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
@@ -421,6 +421,10 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                             v[2 * i] += a.x; v[2 * i + 1] += a.y;
                         }
                     }
+                    if (ACT == 3) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
                     U32x8 o;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o.v[i] = Half16<T>::pack(v[2 * i], v[2 * i + 1]);
@@ -585,6 +589,8 @@ static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     if (gate && !res && !act) return run(gemm_tc_kernel<T, true, 0, false, false, 8, 4, 8>, a, 8, 4, 8, s);
     if (!gate && !res && act == 1) return run(gemm_tc_kernel<T, false, 1, false, false, 16, 4, 0>, a, 16, 4, 0, s);
     if (!gate && !res && act == 2) return run(gemm_tc_kernel<T, false, 2, false, false, 16, 4, 0>, a, 16, 4, 0, s);
+    if (!gate && !res && act == 3) return run(gemm_tc_kernel<T, false, 3, false, false, 8, 4, 0>, a, 8, 4, 0, s);
+    if (!gate && res && act == 3) return run(gemm_tc_kernel<T, false, 3, true, false, 8, 4, 0>, a, 8, 4, 0, s);
     if (!gate && !res && !act) return run(gemm_tc_kernel<T, false, 0, false, false, 8, 4, 0>, a, 8, 4, 0, s);
     if (!gate && res && !act) return run(gemm_tc_kernel<T, false, 0, true, false, 8, 4, 0>, a, 8, 4, 0, s);
     return cudaErrorInvalidValue;

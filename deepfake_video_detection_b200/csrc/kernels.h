@@ -40,7 +40,7 @@ cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const flo
                       const float* w2t, const float* b2, float* gate, int64_t frames, int C, int rd, cudaStream_t s);
 
 // K3 (gemm_tc.cu): pointwise conv as tcgen05/TMEM GEMM.  D[M,N] = act((A .* gate)[M,K] * W[N,K]^T + bias) (+ R)
-// A, W, R, D 16-bit; bias fp32 [N]; gate fp32 [M/HW][K] or null; R [M,N] or null; act: 0 none, 1 SiLU, 2 exact GELU.
+// A, W, R, D 16-bit; bias fp32 [N]; gate fp32 [M/HW][K] or null; R [M,N] or null; act: 0 none, 1 SiLU, 2 exact GELU, 3 ReLU after the residual add.
 cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, const float* gate, const void* R,
                            void* D, int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s);
 // gated project conv for big maps (HW >= 784): fold the SE gate into per-frame weights, then an ungated GEMM on

@@ -112,15 +112,20 @@ class PretrainedBackboneDetector(nn.Module):
         self.num_classes = num_classes
         self.use_temporal_attention = use_temporal_attention
         self.precision = precision
-        if backbone_name != "efficientnet_b0":
-            # resnet*/vit*/other efficientnets of the reference (:38-56) are outside this path
-            raise ValueError(f"Unsupported backbone: {backbone_name} (the B200 path implements efficientnet_b0)")
+        if backbone_name not in ("efficientnet_b0", "resnet50"):
+            # resnet18/34, vit* and the other efficientnets of the reference (:38-56) are outside this path
+            raise ValueError(f"Unsupported backbone: {backbone_name} (the B200 path implements efficientnet_b0 and resnet50)")
         if num_classes != 2:
             raise ValueError("the B200 head kernel implements num_classes=2 (the reference's only use)")
         # `pretrained=True` means "download ImageNet weights" in the reference; there is no network here and
         # every reference caller loads a checkpoint afterwards, so the flag only selects the init below.
-        self.backbone = _efficientnet_b0_trunk()
-        self.feature_dim = 1280                                               # :49
+        if backbone_name == "resnet50":                                       # :38-41 (the ensemble's default second member)
+            import torchvision                                                # the reference builds this trunk from torchvision itself
+            self.backbone = nn.Sequential(*list(torchvision.models.resnet50(weights=None).children())[:-1])
+            self.feature_dim = 2048
+        else:
+            self.backbone = _efficientnet_b0_trunk()
+            self.feature_dim = 1280                                           # :49
         if freeze_backbone:                                                   # :58-61
             for p in self.backbone.parameters():
                 p.requires_grad = False
@@ -140,7 +145,8 @@ class PretrainedBackboneDetector(nn.Module):
         nn.init.constant_(self.fc2.bias, 0)
 
     def unfreeze_backbone(self, num_blocks: int = 2):                         # :87-101 (stage granularity)
-        for stage in list(self.backbone[2])[-num_blocks:]:
+        stages = list(self.backbone.children()) if self.backbone_name == "resnet50" else list(self.backbone[2])
+        for stage in stages[-num_blocks:]:
             for p in stage.parameters():
                 p.requires_grad = True
 
@@ -150,13 +156,17 @@ class PretrainedBackboneDetector(nn.Module):
         key = (str(device), self.precision, tuple((t.data_ptr(), t._version) for _, t in tensors))
         if self._scorer is None or key != self._scorer_key:
             if self._scorer is not None:
-                self._scorer.weights.free()
+                (self._scorer if self.backbone_name == "resnet50" else self._scorer.weights).free()
             sd = {k: v for k, v in tensors}
             if not self.use_temporal_attention:     # mean mode has no attention MLP; the packer wants the keys
                 z = torch.zeros
-                sd.update({"temporal_attention.0.weight": z(64, 1280), "temporal_attention.0.bias": z(64),
+                sd.update({"temporal_attention.0.weight": z(64, self.feature_dim), "temporal_attention.0.bias": z(64),
                            "temporal_attention.2.weight": z(1, 64), "temporal_attention.2.bias": z(1)})
-            self._scorer = FrameScorer(sd, self.precision, device, self.use_temporal_attention)
+            if self.backbone_name == "resnet50":
+                from .resnet_model import ResNet50Scorer
+                self._scorer = ResNet50Scorer(sd, self.precision, device, self.use_temporal_attention)
+            else:
+                self._scorer = FrameScorer(sd, self.precision, device, self.use_temporal_attention)
             self._scorer_key = key
         return self._scorer
 
@@ -175,6 +185,9 @@ class PretrainedBackboneDetector(nn.Module):
         if x_flat.dtype != torch.float32 and x_flat.dtype != {"fp16": torch.float16, "bf16": torch.bfloat16}[self.precision]:
             x_flat = x_flat.float()
         offsets = torch.arange(0, (batch_size + 1) * num_frames, num_frames, dtype=torch.int32, device=x.device)
+        if self.backbone_name == "resnet50":
+            logits, scores = eng.score(x_flat.float(), offsets, num_frames, self.use_temporal_attention)
+            return logits, scores.view(batch_size, num_frames)
         logits, scores = eng.score(x_flat, offsets, self.use_temporal_attention)
         return logits, scores.view(batch_size, num_frames)
 
@@ -192,8 +205,8 @@ class PretrainedBackboneDetector(nn.Module):
 
 
 class EnsembleDetector(nn.Module):
-    """Reference: src/pretrained_detector.py:146-218.  Members are limited to `efficientnet_b0` here
-    (the reference's default second member, resnet50, is SURVEY.md §8f next-1)."""
+    """Reference: src/pretrained_detector.py:146-218.  Members: `efficientnet_b0` and `resnet50` (the reference's default
+    pair, app.py:1597)."""
 
     def __init__(self, backbone_names: List[str], pretrained: bool = True, num_classes: int = 2,
                  dropout_rate: float = 0.5, ensemble_method: str = "average", precision: str = DEFAULT_PRECISION):

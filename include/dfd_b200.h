@@ -127,6 +127,22 @@ int dfd_vit_workspace_bytes(int64_t images, size_t* bytes);
 int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t images, float* d_features,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- `resnet50` ensemble member: src/pretrained_detector.py:38-41 (torchvision trunk), :103-143 ------
+ * Weights by reference state_dict key ("backbone.0.weight" = conv1, "backbone.1.*" = bn1, "backbone.{4..7}.{b}.conv{1,2,3}.weight",
+ * ".bn{1,2,3}.*", ".downsample.{0,1}.*", "temporal_attention.{0,2}.*", "fc1.*", "fc2.*"), HOST fp32; BatchNorm is folded in fp32.
+ * dfd_resnet50_score_videos: d_in fp32 (frames,3,224,224) already normalised (what forward() receives), d_offsets int32
+ * (videos+1), max_frames_per_video >= the longest video -> d_logits fp32 (videos,2), d_frame_scores fp32 (frames) or NULL,
+ * d_features_out fp32 (frames,2048) or NULL.  Workspace: dfd_resnet50_workspace_bytes(frames). */
+typedef struct dfd_resnet_weights dfd_resnet_weights_t;
+const char* dfd_resnet_last_error(void);
+int dfd_resnet50_pack_weights(int n_tensors, const char* const* names, const float* const* data, const int64_t* numel,
+                              int dtype, dfd_resnet_weights_t** out);
+void dfd_resnet50_free_weights(dfd_resnet_weights_t* w);
+int dfd_resnet50_workspace_bytes(int64_t frames, size_t* bytes);
+int dfd_resnet50_score_videos(const dfd_resnet_weights_t* w, const float* d_in, const int32_t* d_offsets, int64_t videos, int64_t frames,
+                              int max_frames_per_video, int use_attention, float* d_logits, float* d_frame_scores, float* d_features_out,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- DeepfakeModel head: src/models.py:177-197 SimpleGCN + :283-291 mean pool + classifier ------
  * logits = classifier(mean_n relu(fc2(relu(fc1(A_norm @ H))))) on the ViT frame features H of each video.
  * Weights by reference state_dict key ("gcn.fc1.*", "gcn.fc2.*", "classifier.0.*", "classifier.3.*"), HOST fp32; built for

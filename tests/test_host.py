@@ -120,7 +120,7 @@ def test_module_contract_matches_reference(synth_sd):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 2, 3, 224, 224))
     with pytest.raises(ValueError):
-        PretrainedBackboneDetector("resnet50", pretrained=False)
+        PretrainedBackboneDetector("resnet18", pretrained=False)
     e = EnsembleDetector(["efficientnet_b0", "efficientnet_b0"], pretrained=False, ensemble_method="weighted")
     assert hasattr(e, "models") and e.weights.shape == (2,)
 
