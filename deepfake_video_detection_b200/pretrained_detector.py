@@ -1,4 +1,4 @@
-"""Drop-in for the reference's `src/pretrained_detector.py` on the EfficientNet-B0 path.
+"""Drop-in for the reference's `src/pretrained_detector.py` (EfficientNet-B0 path + the `resnet50` ensemble member).
 
 Same class names, constructor keywords, attributes, `forward(x) -> (logits, frame_scores)` contract and
 state_dict schema (366 keys) as the reference (`src/pretrained_detector.py:15-143`,
