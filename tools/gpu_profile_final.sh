@@ -10,6 +10,7 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$tag.json 2
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>/dev/null; cat gpurun_out/bench_ref_$tag.json
 timeout 300 python tools/bench_vit.py --batch 512 --iters 5 > gpurun_out/bench_vit_$tag.json 2>&1; cat gpurun_out/bench_vit_$tag.json
 timeout 300 python tools/bench_rnn.py > gpurun_out/bench_rnn_$tag.json 2>&1; cat gpurun_out/bench_rnn_$tag.json
+timeout 300 python tools/bench_resnet.py > gpurun_out/bench_resnet_$tag.json 2>&1; cat gpurun_out/bench_resnet_$tag.json
 CMD="python tools/prof_step.py --videos 64 --frames 32 --iters 2"
 timeout 300 $CMD > gpurun_out/prof_plain_$tag.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 71 -c 71 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
