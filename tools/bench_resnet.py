@@ -1,5 +1,5 @@
 """`resnet50` ensemble member (and the weighted ensemble with efficientnet_b0): device time per batch of videos.
-Not measured in round 1 (GPU budget spent) — first thing to run in round 2:  python tools/bench_resnet.py"""
+Round 1 took one short run (profiles/r01_bench_resnet.json); a longer one belongs in the next evidence run."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
