@@ -15,6 +15,7 @@
 #include "../../include/dfd_b200.h"
 #include "../../include/dfd_b200_kernels.h"
 #include "kernels.h"
+#include "conv_map.h"
 
 namespace {
 
@@ -694,6 +695,38 @@ int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float
     if (impl == 1) DFD_LAUNCH(dfd::launch_gemm_simt(d_A, d_W, d_bias, nullptr, nullptr, nullptr, d_feat, M, K, N, HW, 1, dtype, (cudaStream_t)stream), "head (simt)");
     else DFD_LAUNCH(dfd::launch_gemm_tc_pool(d_A, d_W, d_bias, d_feat, M, K, N, HW, dtype, (cudaStream_t)stream), "head (tcgen05)");
     return DFD_OK;
+}
+
+// relu(conv3x3(relu(conv1x1(x)))) of a resnet bottleneck through the haloed-map path (gemm_tc.cu CONV variants): one memset,
+// one scattering pointwise GEMM, one implicit 3x3 GEMM.  Test / profiling aid for DFD_RESNET_IMPLICIT.
+int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2, void* d_out,
+                          int64_t frames, int H, int W, int K, int C, int N, int dtype, void* d_pad, size_t pad_bytes, void* stream) {
+    g_launches = 0;
+    if (!d_in || !d_w1 || !d_b1 || !d_w2 || !d_b2 || !d_out || !d_pad) return fail(DFD_EINVAL, "dfd_k_conv1x1_conv3x3: null pointer");
+    if (frames <= 0 || H <= 0 || W <= 0 || (C % 64) || (K & 7) || (N & 7)) return fail(DFD_EINVAL, "dfd_k_conv1x1_conv3x3: C must be a multiple of 64, K and N of 8");
+    const size_t need = (size_t)dfd::conv3x3_padded_rows(frames, H, W) * C * 2;
+    if (pad_bytes < need) return fail(DFD_ENOMEM, "dfd_k_conv1x1_conv3x3: haloed map needs " + std::to_string(need) + " bytes");
+    DFD_CUDA(cudaMemsetAsync(d_pad, 0, need, (cudaStream_t)stream), "cudaMemsetAsync(haloed map)");
+    DFD_LAUNCH(dfd::launch_gemm_tc_padout(d_in, d_w1, d_b1, d_pad, frames, H, W, K, C, dtype, (cudaStream_t)stream), "conv1x1 -> haloed map");
+    DFD_LAUNCH(dfd::launch_gemm_tc_conv3x3(d_pad, d_w2, d_b2, d_out, frames, H, W, C, N, dtype, (cudaStream_t)stream), "implicit conv3x3");
+    return DFD_OK;
+}
+
+// HOST-ONLY: the row maps of the haloed layout, computed by the functions the kernels use (csrc/conv_map.h)
+int64_t dfd_k_conv3x3_maps(int frames, int H, int W, int cpk, int64_t* h_pad_row, int64_t* h_out_row, int32_t* h_tap_row, int32_t* h_tap_col) {
+    if (frames <= 0 || H <= 0 || W <= 0 || cpk <= 0) return fail(DFD_EINVAL, "dfd_k_conv3x3_maps: bad geometry");
+    if (h_pad_row)
+        for (int64_t m = 0; m < (int64_t)frames * H * W; ++m) h_pad_row[m] = dfd::conv_pad_row((uint32_t)m, (uint32_t)H, (uint32_t)W);
+    if (h_out_row)
+        for (int64_t p = 0; p < (int64_t)frames * (H + 2) * (W + 2); ++p) {
+            int64_t o;
+            h_out_row[p] = dfd::conv_unpad_row((uint32_t)p, (uint32_t)H, (uint32_t)W, &o) ? o : -1;
+        }
+    if (h_tap_row && h_tap_col) {
+        dfd::ConvTapIter it; it.init(0);
+        for (int kb = 0; kb < 9 * cpk; ++kb) { h_tap_row[kb] = it.row; h_tap_col[kb] = it.ck * 64; it.next(cpk, W); }
+    }
+    return dfd::conv3x3_padded_rows(frames, H, W);
 }
 
 #pragma GCC visibility pop

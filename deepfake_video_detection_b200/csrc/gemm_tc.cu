@@ -27,6 +27,7 @@
 // enough bytes in flight"; the ViT contractions are tensor-bound and reuse the same kernel with streamed weights.
 #include "common.cuh"
 #include "kernels.h"
+#include "conv_map.h"
 #include <cuda.h>
 #include <cstdlib>
 #include <cstring>
@@ -47,8 +48,12 @@ struct GemmArgs {
     int64_t M; int K; int N; int HW;
     int NB, NBp, n_chunks;          // columns per work unit, padded to 16, units along N
     int rows_per_tile;              // 128, or frames_per_tile*HW for the pooled head
+    int conv_h;                     // CONV variants (3x3 convolution over a zero-haloed map, see launch_gemm_tc_conv3x3): map height.
+                                    //    The three conv_* fields sit in alignment holes, so the parameter layout (and the
+                                    //    generated code) of the CONV == 0 kernels is exactly what was verified on the GPU.
     int64_t m_tiles;
     int tpf;                        // > 0: frame-aligned tiling (tpf tiles per frame, the last one partial) with per-frame weights
+    int conv_w;                     // CONV variants: map width (the padded map is (conv_h + 2) x (conv_w + 2))
     int64_t w_frame_stride;         // elements between the weight matrices of consecutive frames (frame-aligned mode)
     int stages;
     int nacc, na;                   // TMEM accumulator buffers; epilogue group sets that take alternate tiles
@@ -63,11 +68,13 @@ struct GemmArgs {
     int xg;                         // gated: transformer warp groups taking alternate stages
     uint32_t lbo_b, stage_bytes, b_stage_bytes, b_chunk_bytes, b_res_bytes, tmem_cols;
     float inv_hw;
+    int conv_cpk;                   // CONV == 2: 64-element k-blocks per filter tap (= input channels / 64)
     // unit strides of the persistent loops, decomposed on the host so that no role divides per tile
     int64_t stride1, strideE;       // grid, na * grid
     int64_t d1_mt, dE_mt, d1_frame, dE_frame;
     int d1_nc, dE_nc, d1_t, dE_t;
 };
+static_assert(sizeof(GemmArgs) == 256, "GemmArgs layout is part of the verified kernels' parameter space");
 
 // Walks the work units u = u0, u0 + stride, ... of one warp role: (M tile, N chunk) and, for frame-aligned tiling
 // (per-frame weights), (frame, tile inside the frame).  Divisions happen once in init(); advance() only adds.
@@ -99,10 +106,17 @@ struct TileIter {
     }
 };
 
+// CONV (3x3 stride-1 pad-1 convolutions of the resnet50 member without a gathered operand; the map between two such
+// launches lives in a zero-haloed layout [frames][H+2][W+2][C] preceded by a guard of W+3 rows, so that filter tap (ky,kx)
+// of padded pixel p is the plain row p + ky*(W+2) + kx of a 2-D tensor map and every tap tile is ONE ordinary TMA box):
+//   1  pointwise GEMM whose output rows are scattered into that layout (interior pixels only; the halo stays zero)
+//   2  implicit GEMM over it: k-block kb = (tap, 64-channel slice), A box at row m0 + ky*(W+2) + kx; M runs over the padded
+//      pixels, halo rows are computed and dropped, interior rows are stored to the ordinary [frames*H*W][N] layout
 // ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP), 3 ReLU applied AFTER the residual add (ResNet bottleneck: relu(bn(conv) + identity)).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
-template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false>
+template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false, int CONV = 0>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
+    static_assert(CONV == 0 || (!GATE && !RES && !POOL && !F32OUT), "CONV variants: plain 16-bit epilogue only");
     constexpr int kProdThreads = kProdWarps * 32;
     constexpr int kXformThreads = kXformWarps * 32;
     constexpr int kGemmThreads = (kEpiWarps + 1 + kProdWarps + kXformWarps) * 32;
@@ -186,15 +200,18 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             for (; it.u < units; it.next1(p)) {
                 const int m0 = (int)it.m0(p);
                 const int wrow = (int)it.frame * p.N + it.nc * p.NB;       // per-frame weights when tpf > 0
+                ConvTapIter tap; tap.init(m0);                             // CONV == 2: (64-channel slice, row) of the k-block's A box
                 for (int kb = 0; kb < num_kb; ++kb) {
                     DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
                     const uint32_t a_base = smem_base + stage * stage_bytes;
                     const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
                     mbar_arrive_expect_tx(bar, (p.dbg & 1) ? 0u : tx_bytes);
                     if (!(p.dbg & 1)) {
-                        tma_load_2d(a_base, &tmA, kb * kKB, m0, bar);
+                        if (CONV == 2) tma_load_2d(a_base, &tmA, tap.ck * kKB, tap.row, bar);
+                        else tma_load_2d(a_base, &tmA, kb * kKB, m0, bar);
                         if (!p.b_resident) tma_load_2d(a_base + kAStageBytes, &tmB, kb * kKB, wrow, bar);
                     }
+                    if (CONV == 2) tap.next(p.conv_cpk, p.conv_w);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -333,8 +350,15 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             const int rows_valid = it.rows_valid(p, m0);
             const int n0 = nc * p.NB;
             const int nb_valid = min(p.NB, p.N - n0);
-            const bool valid = row < rows_valid;
-            const int64_t m = m0 + row;
+            bool valid = row < rows_valid;
+            int64_t m = m0 + row;
+            if (CONV == 1) {           // rows are interior pixels: scatter into the zero-haloed layout
+                m = conv_pad_row((uint32_t)m, (uint32_t)p.conv_h, (uint32_t)p.conv_w);
+            } else if (CONV == 2) {    // rows are padded pixels: only interior ones are outputs
+                int64_t mo;
+                const bool interior = conv_unpad_row((uint32_t)m, (uint32_t)p.conv_h, (uint32_t)p.conv_w, &mo);
+                valid = valid && interior; m = mo;
+            }
             DFD_TWAIT(w0, bar_tfull + 8 * acc, acc_phase)
             tc_fence_after_sync();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
@@ -567,7 +591,10 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
         split(a.strideE, a.dE_mt, a.dE_nc, a.dE_frame, a.dE_t);
     }
     CUtensorMap tmA, tmB;
-    e = make_tmap(a.A, a.M, a.K, kBM, &tmA);
+    if (a.conv_cpk > 0)     // CONV == 2: A is the zero-haloed map, guard rows before and after: [M + 2 (W+3)][channels]
+        e = make_tmap(a.A, a.M + 2 * (int64_t)(a.conv_w + 3), a.conv_cpk * kKB, kBM, &tmA);
+    else
+        e = make_tmap(a.A, a.M, a.K, kBM, &tmA);
     if (e != cudaSuccess) return e;
     if (!a.b_resident) {
         if (a.tpf > 0 && a.w_frame_stride != (int64_t)a.N * a.K) return cudaErrorInvalidValue;
@@ -606,6 +633,38 @@ cudaError_t launch_gemm_tc(const void* A, const void* W, const float* bias, cons
     a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
     if (dtype == kDtypeFP16) return launch_t<__half>(a, act, s);
     return launch_t<__nv_bfloat16>(a, act, s);
+}
+
+// ---- 3x3 stride-1 pad-1 convolution without a gathered operand (resnet50 bottleneck conv2; DFD_RESNET_IMPLICIT=1) ------
+// The producer (conv1, a pointwise GEMM) scatters its rows into the zero-haloed layout described at the kernel template;
+// the consumer reads nine shifted boxes of it per 64-channel slice.  Element counts of that buffer:
+int64_t conv3x3_padded_rows(int64_t frames, int H, int Wd) { return frames * (int64_t)(H + 2) * (Wd + 2) + 2 * (int64_t)(Wd + 3); }
+
+// D_pad[guard + padded(f,y,x)][N] = relu(A[(f,y,x)][K] * W[N,K]^T + bias); halo and guard rows are never written (the
+// caller zeroes the buffer once per geometry).
+cudaError_t launch_gemm_tc_padout(const void* A, const void* W, const float* bias, void* Dpad, int64_t frames, int H, int Wd,
+                                  int K, int N, int dtype, cudaStream_t s) {
+    if (frames <= 0) return cudaSuccess;
+    if ((K & 7) || (N & 7) || K < 8 || N < 8 || H <= 0 || Wd <= 0 || frames * (int64_t)(H + 2) * (Wd + 2) > (1ll << 30)) return cudaErrorInvalidValue;
+    GemmArgs a{};
+    a.A = A; a.W = W; a.bias = bias; a.D = Dpad;
+    a.M = frames * H * Wd; a.K = K; a.N = N; a.HW = H * Wd; a.conv_h = H; a.conv_w = Wd;
+    a.rows_per_tile = kBM; a.m_tiles = (a.M + kBM - 1) / kBM;
+    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 3, false, false, 8, 4, 0, false, 1>, a, 8, 4, 0, s);
+    return run(gemm_tc_kernel<__nv_bfloat16, false, 3, false, false, 8, 4, 0, false, 1>, a, 8, 4, 0, s);
+}
+
+// D[(f,y,x)][N] = relu(sum over taps (ky,kx) and channels c of Apad[padded(f, y+ky-1, x+kx-1)][c] * W[N][(ky*3+kx)*C + c] + bias)
+cudaError_t launch_gemm_tc_conv3x3(const void* Apad, const void* W, const float* bias, void* D, int64_t frames, int H, int Wd,
+                                   int C, int N, int dtype, cudaStream_t s) {
+    if (frames <= 0) return cudaSuccess;
+    if ((C % kKB) || (N & 7) || N < 8 || H <= 0 || Wd <= 0 || frames * (int64_t)(H + 2) * (Wd + 2) > (1ll << 30)) return cudaErrorInvalidValue;
+    GemmArgs a{};
+    a.A = Apad; a.W = W; a.bias = bias; a.D = D;
+    a.M = frames * (int64_t)(H + 2) * (Wd + 2); a.K = 9 * C; a.N = N; a.HW = H * Wd; a.conv_h = H; a.conv_w = Wd; a.conv_cpk = C / kKB;
+    a.rows_per_tile = kBM; a.m_tiles = (a.M + kBM - 1) / kBM;
+    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 3, false, false, 8, 4, 0, false, 2>, a, 8, 4, 0, s);
+    return run(gemm_tc_kernel<__nv_bfloat16, false, 3, false, false, 8, 4, 0, false, 2>, a, 8, 4, 0, s);
 }
 
 // Project conv with the SE gate folded into per-frame weights Wf[frame][N][K] (scale_weights kernel): tiles are

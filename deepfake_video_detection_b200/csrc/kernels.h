@@ -56,6 +56,14 @@ cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bia
 // conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
                                 int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
+// 3x3 stride-1 pad-1 convolution + bias + ReLU as an implicit GEMM (resnet50 conv2, behind DFD_RESNET_IMPLICIT=1): the
+// producing pointwise conv scatters its rows into a zero-haloed map of conv3x3_padded_rows(frames,H,W) x N elements (zeroed
+// by the caller once per geometry), the 3x3 conv reads nine shifted TMA boxes of it.  Weights [N][(ky*3+kx)*C + c].
+int64_t conv3x3_padded_rows(int64_t frames, int H, int W);
+cudaError_t launch_gemm_tc_padout(const void* A, const void* W, const float* bias, void* Dpad, int64_t frames, int H, int Wd,
+                                  int K, int N, int dtype, cudaStream_t s);
+cudaError_t launch_gemm_tc_conv3x3(const void* Apad, const void* W, const float* bias, void* D, int64_t frames, int H, int Wd,
+                                   int C, int N, int dtype, cudaStream_t s);
 // straightforward CUDA-core GEMM with the same contract; bring-up / bisecting aid (DFD_GEMM_IMPL=simt)
 cudaError_t launch_gemm_simt(const void* A, const void* W, const float* bias, const float* gate, const void* R,
                              void* D, float* pool_feat, int64_t M, int K, int N, int HW, int act, int dtype,

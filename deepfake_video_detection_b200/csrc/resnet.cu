@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -342,15 +343,32 @@ static int rn_trunk_chunk(const dfd_resnet_weights* w, const float* x, int64_t n
         else rn_maxpool_kernel<__nv_bfloat16><<<pgrid, 256, 0, s>>>((const __nv_bfloat16*)buf[0], (__nv_bfloat16*)buf[1], 112, 112, 64, 56, 56, ptotal);
         RN_CK(cudaGetLastError(), "resnet maxpool");
     }
+    // DFD_RESNET_IMPLICIT=1 (experimental, off by default until it has been verified on a GPU): the 13 stride-1 3x3 convs
+    // run as implicit GEMMs — conv1 scatters its rows into a zero-haloed map kept in `col`, conv2 reads nine shifted TMA
+    // boxes of it (gemm_tc.cu, CONV variants) — instead of gathering a 9x larger operand.  The halo is zeroed once per
+    // (H, C) geometry: inside a layer only interior rows are ever rewritten.
+    const char* env_implicit = getenv("DFD_RESNET_IMPLICIT");
+    const bool implicit = env_implicit && atoi(env_implicit) != 0;
+    int pad_h = 0, pad_c = 0;
     int cur = 1, H = 56;                                           // buf[cur] holds the block input [n][H][H][cin]
     for (const RnBlock& b : w->blocks) {
         const int s2 = b.c2.stride, OH = (H + 2 - 3) / s2 + 1;
         uint8_t* y = buf[cur];
         uint8_t* o1 = buf[(cur + 1) % 5]; uint8_t* o2 = buf[(cur + 2) % 5]; uint8_t* idn = buf[(cur + 3) % 5]; uint8_t* nxt = buf[(cur + 4) % 5];
         const int64_t rows_in = n * H * H, rows_out = n * OH * OH;
-        RN_CK(launch_gemm_tc(y, b.c1.w, b.c1.b, nullptr, nullptr, o1, rows_in, b.c1.cin, b.c1.cout, 1, 3, dt, s), "resnet conv1");
-        RN_CK(im2col(o1, col, H, H, b.c2.cin, OH, OH, 3, s2), "resnet conv2 gather");
-        RN_CK(launch_gemm_tc(col, b.c2.w, b.c2.b, nullptr, nullptr, o2, rows_out, 9 * b.c2.cin, b.c2.cout, 1, 3, dt, s), "resnet conv2");
+        if (implicit && s2 == 1 && (b.c2.cin % 64) == 0) {
+            if (pad_h != H || pad_c != b.c2.cin) {
+                RN_CK(cudaMemsetAsync(col, 0, (size_t)conv3x3_padded_rows(n, H, H) * b.c2.cin * 2, s), "resnet halo memset");
+                pad_h = H; pad_c = b.c2.cin;
+            }
+            RN_CK(launch_gemm_tc_padout(y, b.c1.w, b.c1.b, col, n, H, H, b.c1.cin, b.c1.cout, dt, s), "resnet conv1 (haloed output)");
+            RN_CK(launch_gemm_tc_conv3x3(col, b.c2.w, b.c2.b, o2, n, H, H, b.c2.cin, b.c2.cout, dt, s), "resnet conv2 (implicit)");
+        } else {
+            RN_CK(launch_gemm_tc(y, b.c1.w, b.c1.b, nullptr, nullptr, o1, rows_in, b.c1.cin, b.c1.cout, 1, 3, dt, s), "resnet conv1");
+            RN_CK(im2col(o1, col, H, H, b.c2.cin, OH, OH, 3, s2), "resnet conv2 gather");
+            RN_CK(launch_gemm_tc(col, b.c2.w, b.c2.b, nullptr, nullptr, o2, rows_out, 9 * b.c2.cin, b.c2.cout, 1, 3, dt, s), "resnet conv2");
+            pad_h = 0;                                             // the gather overwrote the haloed map
+        }
         const void* res = y;
         if (b.has_ds) {
             const void* a = y;

@@ -47,6 +47,19 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
 int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K,
                     int N, int HW, int dtype, int impl, void* stream);
 
+/* EXPERIMENTAL (path behind DFD_RESNET_IMPLICIT=1, not yet verified on a GPU): torchvision Bottleneck conv1 + bn1 + relu ->
+ * conv2 (3x3, stride 1, pad 1) + bn2 + relu (reference trunk: src/pretrained_detector.py:38-41) without a gathered operand.
+ * d_in [frames*H*W][K], d_w1 [C][K], d_w2 [N][(ky*3+kx)*C + c] (BN folded), d_out [frames*H*W][N], all 16-bit; biases fp32.
+ * d_pad: scratch for the zero-haloed intermediate map, dfd_k_conv3x3_maps(frames,H,W,..) * C * 2 bytes. */
+int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2, void* d_out,
+                          int64_t frames, int H, int W, int K, int C, int N, int dtype, void* d_pad, size_t pad_bytes, void* stream);
+
+/* HOST-ONLY (no GPU needed): row maps of that zero-haloed layout, computed by the very functions the kernels use
+ * (csrc/conv_map.h).  h_pad_row [frames*H*W]: physical row of every interior pixel; h_out_row [frames*(H+2)*(W+2)]: output
+ * row of every padded pixel, -1 for halo pixels; h_tap_row / h_tap_col [9*cpk]: row offset and channel column of the A box
+ * of k-block kb = tap*cpk + slice.  Any pointer may be NULL.  Returns the number of rows of the layout (guards included). */
+int64_t dfd_k_conv3x3_maps(int frames, int H, int W, int cpk, int64_t* h_pad_row, int64_t* h_out_row, int32_t* h_tap_row, int32_t* h_tap_col);
+
 /* HOST-ONLY (no GPU needed): the operands dfd_pack_weights builds for the row-variant stem (stem_tc.cu) from BN-folded
  * weights h_w27x32 fp32 [(ky*3+kx)*3+c][32] and bias h_bias32: h_wrow fp16 bits [hi|lo][32 oc][32 k] with
  * k = ky*10 + kx*3 + c holding 256*w/(255*std_c) split in two fp16 terms, h_bias4 fp32 [top*2+left][32] = bias minus

@@ -2,6 +2,7 @@
 16-bit-rounded inputs.  Tolerances are one output rounding of the storage type plus accumulation noise:
 fp16 2^-10, bf16 2^-7 relative (written next to each check)."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -232,3 +233,40 @@ def test_head_gemm_pool(lib, prec, impl, frames):
                                  frames * HW, K, N, HW, code, impl, stream()))
     ref = F.silu(A.double() @ Wt.double().t() + bias.double()).view(frames, HW, N).mean(1)
     close(feat.cpu(), ref.float(), 1e-5, abs_=1e-5)
+
+
+# ---- experimental paths: compiled and CPU-checked, but not yet run on a GPU; they are off by default in the product and these
+# ---- tests only run with DFD_EXPERIMENTAL=1 (the first thing to do with the next GPU session: tools/gpu_experimental.sh)
+experimental = pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
+
+
+@experimental
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("frames,H,W,K,C,N", [(2, 7, 7, 256, 128, 64), (3, 14, 14, 64, 64, 64), (2, 56, 56, 64, 64, 64),
+                                              (1, 28, 28, 512, 128, 128), (5, 7, 7, 2048, 512, 512), (1, 9, 5, 64, 64, 8)])
+def test_conv1x1_conv3x3_implicit(lib, prec, frames, H, W, K, C, N):
+    """resnet50 bottleneck conv1 -> conv2 through the zero-haloed map (implicit 3x3 GEMM): against F.conv2d on the same
+    16-bit-rounded operands, with the intermediate rounded to the storage type as the kernel stores it."""
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(H * 1000 + C)
+    x = torch.randn(frames, H, W, K, generator=g).to(tdt)
+    w1 = (torch.randn(C, K, generator=g) / K ** 0.5).to(tdt); b1 = torch.randn(C, generator=g) * 0.2
+    w2 = (torch.randn(N, 3, 3, C, generator=g) / (9 * C) ** 0.5 * 2).to(tdt); b2 = torch.randn(N, generator=g) * 0.2
+    rows = lib.dfd_k_conv3x3_maps(frames, H, W, C // 64, None, None, None, None)
+    pad = torch.full((rows * C,), float("nan"), dtype=tdt, device="cuda")          # the entry point zeroes it itself
+    out = torch.full((frames * H * W, N), float("nan"), dtype=tdt, device="cuda")
+    dev = [t.cuda() for t in (x, w1, b1, w2.reshape(N, 9 * C).contiguous(), b2)]
+    chk(lib, lib.dfd_k_conv1x1_conv3x3(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
+                                       out.data_ptr(), frames, H, W, K, C, N, code, pad.data_ptr(), pad.numel() * 2, stream()))
+    mid = torch.relu(x.double().reshape(-1, K) @ w1.double().t() + b1.double()).to(tdt)          # stored 16-bit
+    mid = mid.double().view(frames, H, W, C).permute(0, 3, 1, 2)
+    ref = torch.relu(F.conv2d(mid, w2.double().permute(0, 3, 1, 2), b2.double(), padding=1)).permute(0, 2, 3, 1).reshape(-1, N)
+    assert torch.isfinite(out).all()
+    close(out.cpu(), ref.float(), 2 * rel)
+    halo = pad.view(rows, C).float().cpu()
+    interior = torch.zeros(rows, dtype=torch.bool)
+    import numpy as np
+    pr = np.zeros(frames * H * W, np.int64)
+    lib.dfd_k_conv3x3_maps(frames, H, W, C // 64, pr.ctypes.data, None, None, None)
+    interior[torch.from_numpy(pr)] = True
+    assert (halo[~interior] == 0).all()                                             # halo and guards untouched by the scatter

@@ -103,6 +103,50 @@ def test_row_stem_operands_fold_the_tensor_prep_exactly():
     assert worst < 2e-5, worst                                                    # fp32 rounding of the reference itself
 
 
+@pytest.mark.parametrize("frames,H,W,C,N", [(2, 7, 7, 128, 16), (3, 14, 9, 64, 8), (1, 56, 56, 64, 8)])
+def test_haloed_map_scheme_reproduces_conv3x3(frames, H, W, C, N):
+    """Implicit 3x3 convolution of the resnet50 member (gemm_tc.cu CONV variants, behind DFD_RESNET_IMPLICIT): the row maps
+    come from the C++ functions the kernels use (csrc/conv_map.h via dfd_k_conv3x3_maps); emulating the GEMM over them on the
+    CPU — scatter into the zero-haloed map, nine shifted row blocks per 64-channel slice, drop halo rows — must reproduce
+    F.conv2d(padding=1) exactly in structure (fp64, so only the indexing is under test)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from deepfake_video_detection_b200 import _lib
+    lib = _lib.load()
+    cpk = C // 64
+    pad_row = np.zeros(frames * H * W, np.int64)
+    out_row = np.zeros(frames * (H + 2) * (W + 2), np.int64)
+    tap_row, tap_col = np.zeros(9 * cpk, np.int32), np.zeros(9 * cpk, np.int32)
+    rows = lib.dfd_k_conv3x3_maps(frames, H, W, cpk, pad_row.ctypes.data, out_row.ctypes.data, tap_row.ctypes.data, tap_col.ctypes.data)
+    assert rows == frames * (H + 2) * (W + 2) + 2 * (W + 3)
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(frames, H, W, C, generator=g, dtype=torch.float64)
+    w = torch.randn(N, 3, 3, C, generator=g, dtype=torch.float64)                   # packed layout: [N][(ky*3+kx)*C + c]
+    buf = torch.full((rows, C), float("nan"), dtype=torch.float64)                  # guards stay NaN: they must never reach an output
+    buf[W + 3: W + 3 + frames * (H + 2) * (W + 2)] = 0.0                            # the memset (guards are zeroed too in the product; NaN here is stricter)
+    assert len(set(pad_row.tolist())) == len(pad_row) and pad_row.min() >= W + 3 and pad_row.max() < rows - (W + 3)
+    buf[torch.from_numpy(pad_row)] = x.reshape(-1, C)                               # conv1's scattered store
+    Mp = frames * (H + 2) * (W + 2)
+    wk = w.reshape(N, 9 * C)
+    interior = out_row >= 0
+    assert interior.sum() == frames * H * W and sorted(out_row[interior].tolist()) == list(range(frames * H * W))
+    out = torch.zeros(frames * H * W, N, dtype=torch.float64)
+    for m0 in range(0, Mp, 128):                                                     # tiles of 128 padded pixels
+        nrow = min(128, Mp - m0)
+        acc = torch.zeros(nrow, N, dtype=torch.float64)
+        keep = torch.from_numpy(interior[m0:m0 + nrow])
+        for kb in range(9 * cpk):
+            r0, c0 = m0 + int(tap_row[kb]), int(tap_col[kb])
+            assert r0 >= 0 and r0 + nrow <= rows                                     # every box lies inside the tensor map
+            a = buf[r0:r0 + nrow, c0:c0 + 64]
+            part = torch.nan_to_num(a, nan=1e30) @ wk[:, kb * 64:(kb + 1) * 64].T    # a NaN guard row would poison a kept row as 1e30
+            acc += part
+        out[torch.from_numpy(out_row[m0:m0 + nrow][interior[m0:m0 + nrow]])] = acc[keep]
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1).reshape(-1, N)
+    assert (out - ref).abs().max().item() < 1e-9
+
+
 def test_module_contract_matches_reference(synth_sd):
     from deepfake_video_detection_b200 import EnsembleDetector, PretrainedBackboneDetector
     m = PretrainedBackboneDetector("efficientnet_b0", pretrained=False, num_classes=2, dropout_rate=0.5, use_temporal_attention=True)
