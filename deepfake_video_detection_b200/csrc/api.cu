@@ -23,9 +23,9 @@ thread_local std::string g_err;
 thread_local int g_launches = 0;
 
 // ---- optional per-launch profiling (dfd_profile_*): CUDA events around every launch on the launch stream
-enum KClass { KC_PREPROCESS = 0, KC_STEM, KC_DWCONV, KC_SE, KC_GEMM_EXPAND, KC_GEMM_PROJECT, KC_GEMM_HEAD_POOL, KC_POOL_HEAD, KC_COUNT };
+enum KClass { KC_PREPROCESS = 0, KC_STEM, KC_DWCONV, KC_SE, KC_GEMM_EXPAND, KC_GEMM_PROJECT, KC_GEMM_HEAD_POOL, KC_POOL_HEAD, KC_MBCONV_FUSED, KC_COUNT };
 const char* const kClassNames[KC_COUNT] = {"preprocess", "stem", "dwconv_se_squeeze", "se_gate", "gemm_expand", "gemm_project",
-                                           "gemm_head_pool", "attn_pool_head"};
+                                           "gemm_head_pool", "attn_pool_head", "expand_dwconv_fused"};
 struct ProfRec { int cls; cudaEvent_t a, b; double bytes, flops; };
 thread_local bool g_prof_on = false;
 thread_local std::vector<ProfRec> g_prof;
@@ -474,11 +474,18 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, w->stem_wrow, w->stem_b4, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
     else
         DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
+    // DFD_FUSE_EXPAND=1 (experimental, off by default until it has been verified on a GPU): the early HBM-bound blocks run
+    // expand 1x1 + depthwise as ONE kernel (mbconv_fused.cu); the expanded tensor never goes to HBM.
+    const char* env_fuse = getenv("DFD_FUSE_EXPAND");
+    const bool fuse = env_fuse && atoi(env_fuse) != 0 && !use_simt_gemm();
     for (int i = 0; i < kNumBlocks; ++i) {
         const BlockW& B = w->blocks[i];
         const void* x = io[cur];
         const void* e = x;
-        if (B.has_expand) {
+        const bool fused = fuse && B.has_expand && dfd::mbconv_fused_supported(h, wd, B.cin, B.mid, B.k, B.stride) &&
+                           dfd::dw_num_partials((h + 2 * (B.k / 2) - B.k) / B.stride + 1, (wd + 2 * (B.k / 2) - B.k) / B.stride + 1, B.mid, B.k, B.stride) ==
+                               dfd::dw_march_slots((h + 2 * (B.k / 2) - B.k) / B.stride + 1, (wd + 2 * (B.k / 2) - B.k) / B.stride + 1);
+        if (B.has_expand && !fused) {
             const int r = (B.exp_pack > 1 && !use_simt_gemm() && (h * wd) % B.exp_pack == 0) ? B.exp_pack : 1;
             int rc = run_gemm(x, r > 1 ? B.exp_wp : B.exp_w, r > 1 ? B.exp_bp : B.exp_b, nullptr, nullptr, bufE,
                               frames * h * wd, B.cin, B.mid, h * wd, 1, dt, s, r);
@@ -487,8 +494,15 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         }
         const int pad = B.k / 2;
         const int oh = (h + 2 * pad - B.k) / B.stride + 1, ow = (wd + 2 * pad - B.k) / B.stride + 1;
-        prof_next(KC_DWCONV, (double)frames * B.mid * ((double)h * wd + (double)oh * ow) * 2, 2.0 * frames * oh * ow * B.mid * B.k * B.k, s);
-        DFD_LAUNCH(dfd::launch_dwconv(e, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.mid, B.k, B.stride, dt, s), "depthwise kernel");
+        if (fused) {
+            prof_next(KC_MBCONV_FUSED, (double)frames * ((double)h * wd * B.cin + (double)oh * ow * B.mid) * 2,
+                      2.0 * frames * ((double)h * wd * B.cin * B.mid + (double)oh * ow * B.mid * B.k * B.k), s);
+            DFD_LAUNCH(dfd::launch_mbconv_fused(x, B.exp_w, B.exp_b, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.cin, B.mid, B.k, B.stride, dt, s),
+                       "fused expand + depthwise kernel");
+        } else {
+            prof_next(KC_DWCONV, (double)frames * B.mid * ((double)h * wd + (double)oh * ow) * 2, 2.0 * frames * oh * ow * B.mid * B.k * B.k, s);
+            DFD_LAUNCH(dfd::launch_dwconv(e, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.mid, B.k, B.stride, dt, s), "depthwise kernel");
+        }
         const int nparts = dfd::dw_num_partials(oh, ow, B.mid, B.k, B.stride);
         prof_next(KC_SE, (double)frames * B.mid * (nparts + 1) * 4, 4.0 * frames * B.mid * B.rd, s);
         DFD_LAUNCH(dfd::launch_se(part, nparts, 1.0f / (float)(oh * ow), B.se_w1, B.se_b1, B.se_w2t, B.se_b2, gate,
@@ -711,6 +725,18 @@ int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1,
     DFD_LAUNCH(dfd::launch_gemm_tc_conv3x3(d_pad, d_w2, d_b2, d_out, frames, H, W, C, N, dtype, (cudaStream_t)stream), "implicit conv3x3");
     return DFD_OK;
 }
+
+// EXPERIMENTAL: expand 1x1 + BN + SiLU fused into the row-marching depthwise kernel (mbconv_fused.cu)
+int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, const float* d_w, const float* d_bias, void* d_out,
+                       float* d_partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype, void* stream) {
+    g_launches = 0;
+    if (!d_x || !d_we || !d_be || !d_w || !d_bias || !d_out || !d_partials) return fail(DFD_EINVAL, "dfd_k_mbconv_fused: null pointer");
+    if (!dfd::mbconv_fused_supported(H, W, cin, mid, k, stride)) return fail(DFD_EINVAL, "dfd_k_mbconv_fused: unsupported block shape");
+    DFD_LAUNCH(dfd::launch_mbconv_fused(d_x, d_we, d_be, d_w, d_bias, d_out, d_partials, frames, H, W, cin, mid, k, stride, dtype, (cudaStream_t)stream),
+               "fused expand + depthwise kernel");
+    return DFD_OK;
+}
+int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) { return dfd::mbconv_fused_supported(H, W, cin, mid, k, stride) ? 1 : 0; }
 
 // HOST-ONLY: the row maps of the haloed layout, computed by the functions the kernels use (csrc/conv_map.h)
 int64_t dfd_k_conv3x3_maps(int frames, int H, int W, int cpk, int64_t* h_pad_row, int64_t* h_out_row, int32_t* h_tap_row, int32_t* h_tap_col) {

@@ -34,6 +34,14 @@ void dw_march_set_cb(int cb);      // tuning aid: force the channel block of the
 cudaError_t launch_dwconv_march(const void* in, const float* w, const float* bias, void* out, float* partials,
                                 int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
 
+// K2' (mbconv_fused.cu, behind DFD_FUSE_EXPAND=1): expand 1x1 + BN + SiLU fused into the row-marching depthwise kernel for the
+// early HBM-bound blocks.  x [frames][H][W][cin] 16-bit, we [mid][cin] 16-bit + be fp32 [mid]; the rest as launch_dwconv_march
+// (partials: dw_march_slots rows).
+bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride);
+cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
+                                float* partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype,
+                                cudaStream_t s);
+
 // K2 tail (se.cu): mean -> FC(C->rd)+bias -> SiLU -> FC(rd->C)+bias -> sigmoid.  gate fp32 [frames][C].
 // w1 fp32 [rd][C], w2t fp32 [rd][C] (conv_expand transposed), b1 [rd], b2 [C].
 cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,

@@ -1,0 +1,284 @@
+// K2' (EXPERIMENTAL, off by default: DFD_FUSE_EXPAND=1; written without GPU access) — MBConv expand 1x1 + BN + SiLU fused
+// into the row-marching depthwise kernel (dwconv_march.cu) for the early, HBM-bound InvertedResidual blocks
+// (timm `conv_pw` + `bn1` -> `conv_dw` + `bn2` + SqueezeExcite's mean; reference call site pretrained_detector.py:116).
+//
+// Why: on the 112x112 / 56x56 maps the expanded tensor (6x the block input) is written by the expand GEMM and read back
+// by the depthwise kernel — 8.4 MB of the 28 MB a frame moves, at kernels that already run at the HBM roofline.  Here the
+// expanded rows never leave the SM: the CTA that marches down the rows of (frame, channel block) computes each expanded
+// row itself, one row ahead of the depthwise stencil, from the 6x smaller block input.
+//
+// Structure (one CTA = frame x block of CB expanded channels, whole map width, marching down the rows):
+//   x ring     block-input rows [W][Cin] 16-bit staged by cp.async kXR-1 rows ahead (rows padded to 16-pixel tiles and to
+//              Cin+8 halves per pixel: conflict-free fragment loads, zero K padding)
+//   expand     all warps: mma.sync m16n8k16 tiles (16 pixels x 8 channels, K = Cin padded to 16/32) of row r+1 against the
+//              CTA's [CB][Cin] weight slice in shared memory, + bias, SiLU (same tanh.approx form as the GEMM epilogue),
+//              rounded to the storage type — the same rounding point as the HBM round trip it replaces — and written to
+//              slot (r+1)&1 of a two-row expanded ring laid out exactly like the march kernel's staged rows
+//   depthwise  unchanged march: one thread = 2 channels x 7 output columns, k*k weight pairs and the accumulator ring in
+//              registers, packed fma.rn.f32x2, SiLU, SE partial sums, 16-bit stores
+// One __syncthreads per input row, as before: expanded row r was written during step r-1; slot (r+1)&1 was last read in
+// step r-1.  Partial-sum layout = dw_march_slots, so se.cu and the project GEMM are unchanged.
+#include "common.cuh"
+#include "kernels.h"
+#include <cstdlib>
+#include <type_traits>
+
+namespace dfd {
+
+namespace {
+constexpr int kFTW = 7;              // output columns per thread (as dwconv_march.cu)
+constexpr int kXR = 6;               // x-row ring depth
+
+template <typename T>
+__device__ __forceinline__ void mma16816_f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    if constexpr (Half16<T>::kCode == kDtypeFP16)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+}  // namespace
+
+// Geometry is compile-time: CIN block input channels, C expanded channels, W x W map, CB channels per CTA.
+template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
+__global__ void __launch_bounds__(((W + 2 * (KS / 2) - KS) / S + 1) / kFTW * (CB / 2), 1) __maxnreg__(MAXREG)
+mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const float* __restrict__ be,
+                    const float* __restrict__ w, const float* __restrict__ bias,
+                    T* __restrict__ out, float* __restrict__ partials) {
+    constexpr int TW = kFTW, PAD = KS / 2, H = W;
+    constexpr int OW = (W + 2 * PAD - KS) / S + 1, OH = OW;
+    constexpr int strips = OW / TW;
+    static_assert(OW % TW == 0, "whole strips only");
+    static_assert(CB % 16 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
+    constexpr int THREADS = strips * (CB / 2), WARPS = THREADS / 32;
+    static_assert(THREADS % 32 == 0, "whole warps");
+    constexpr int NCOL = (TW - 1) * S + KS;
+    constexpr int RING = (KS + S - 1) / S, PERIOD = S * RING;
+    constexpr int pixw = ((strips * TW - 1) * S + KS) > W + 2 * PAD ? ((strips * TW - 1) * S + KS) : W + 2 * PAD;
+    constexpr int KP = (CIN + 15) & ~15, KSTEPS = KP / 16;       // K padded to whole mma k-steps
+    constexpr int XP = KP + 8;                                    // halves per staged x pixel / weight row (conflict-free)
+    constexpr int PXT = (W + 15) / 16;                            // 16-pixel tiles per row
+    constexpr int NTL = CB / 8;                                   // 8-channel tiles of the channel block
+    constexpr uint32_t rsb = (uint32_t)pixw * CB * 2;             // bytes per expanded row slot
+    constexpr uint32_t xsb = (uint32_t)PXT * 16 * XP * 2;         // bytes per x row slot
+    constexpr uint32_t wsb = (uint32_t)CB * XP * 2;               // bytes of the weight slice
+    constexpr int rps = OH > 56 ? 56 : OH;                        // = march_rps(OH)
+    constexpr int segs = (OH + rps - 1) / rps;
+    constexpr int XCH = W * (CIN / 8);                            // 16-byte chunks of an x row
+    constexpr int XK = (XCH + THREADS - 1) / THREADS;
+
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    const uint32_t sm_e = smem_u32(fz_smem);                      // [2][pixw][CB]      expanded ring
+    const uint32_t sm_x = sm_e + 2 * rsb;                         // [kXR][PXT*16][XP]  x ring
+    const uint32_t sm_w = sm_x + kXR * xsb;                       // [CB][XP]           expand weights of this channel block
+    float* s_be = reinterpret_cast<float*>(fz_smem + 2 * rsb + kXR * xsb + wsb);   // [CB] expand bias
+
+    constexpr int ncb = C / CB;
+    const int cb = blockIdx.x % ncb;
+    const int fs = blockIdx.x / ncb;
+    const int seg = fs % segs;
+    const int64_t frame = fs / segs;
+    constexpr int CB2 = CB >> 1;
+    const int cpl = threadIdx.x % CB2, strip = threadIdx.x / CB2;
+    const int c0 = cb * CB + 2 * cpl;
+    const int oy0 = seg * rps;
+    const int nrows = min(rps, OH - oy0);
+    const int ox0 = strip * TW;
+    const int iy_start = oy0 * S - PAD;
+    const int rend = S * (nrows - 1) + KS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+    // zero everything once: padding columns of the expanded slots, K padding / tile padding of the x slots and weights
+    for (uint32_t i = threadIdx.x * 16; i < 2 * rsb + kXR * xsb + wsb; i += THREADS * 16) sts16(sm_e + i, make_uint4(0, 0, 0, 0));
+    __syncthreads();
+    // expand weights [CB][CIN] (BN folded, 16-bit, K-major) and bias of this channel block
+    for (int i = threadIdx.x; i < CB * (CIN / 8); i += THREADS) {
+        const int r = i / (CIN / 8), q = i - r * (CIN / 8);
+        sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8));
+    }
+    for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = be[cb * CB + i];
+
+    uint64_t wr[KS * KS];
+    const uint64_t half2 = f2_pack(0.5f, 0.5f);
+#pragma unroll
+    for (int i = 0; i < KS * KS; ++i) wr[i] = mul2(__ldg(reinterpret_cast<const unsigned long long*>(w + (size_t)i * C + c0)), half2);
+    const uint64_t b2 = mul2(__ldg(reinterpret_cast<const unsigned long long*>(bias + c0)), half2);
+
+    // x-row stager: chunk i -> pixel i / (CIN/8), 8-channel group i % (CIN/8)
+    uint32_t g_off[XK], s_off[XK];
+#pragma unroll
+    for (int k = 0; k < XK; ++k) {
+        const int i = threadIdx.x + k * THREADS;
+        const int px = i / (CIN / 8), sub = i - px * (CIN / 8);
+        g_off[k] = (uint32_t)(px * CIN + sub * 8) * 2;
+        s_off[k] = i < XCH ? (uint32_t)(px * XP + sub * 8) * 2 : 0xffffffffu;
+    }
+    constexpr size_t xpitch_b = (size_t)W * CIN * 2;
+    int iy_i = iy_start, left_i = rend;
+    uint32_t xs_i = sm_x;
+    const char* gp_i = reinterpret_cast<const char*>(x + (size_t)frame * H * W * CIN) + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b;
+    auto issue_row = [&]() {
+        if (left_i > 0 && (unsigned)iy_i < (unsigned)H) {
+#pragma unroll
+            for (int k = 0; k < XK; ++k)
+                if (s_off[k] != 0xffffffffu) cp_async16(xs_i + s_off[k], gp_i + g_off[k], true);
+        }
+        cp_async_commit();
+        ++iy_i; --left_i; gp_i += xpitch_b;
+        xs_i += xsb; if (xs_i == sm_x + kXR * xsb) xs_i = sm_x;
+    };
+
+    // expand one input row (index k of this CTA's walk, image row iy) from its x slot into expanded slot k & 1
+    auto expand_row = [&](int k, int iy) {
+        if (k >= rend || (unsigned)iy >= (unsigned)H) return;            // CTA-uniform
+        const uint32_t xs = sm_x + (uint32_t)(k % kXR) * xsb;
+        const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
+        for (int tile = warp; tile < PXT * NTL; tile += WARPS) {
+            const int pt = tile / NTL, nt = tile - pt * NTL;
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            const uint32_t ar = xs + (uint32_t)((pt * 16 + g) * XP + 2 * t) * 2;
+            const uint32_t br = sm_w + (uint32_t)((nt * 8 + g) * XP + 2 * t) * 2;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                uint32_t a[4];
+                a[0] = lds32(ar + ks * 32);                 a[1] = lds32(ar + ks * 32 + 8 * XP * 2);
+                a[2] = lds32(ar + ks * 32 + 16);            a[3] = lds32(ar + ks * 32 + 8 * XP * 2 + 16);
+                mma16816_f<T>(c, a, lds32(br + ks * 32), lds32(br + ks * 32 + 16));
+            }
+            const float2 bb = *reinterpret_cast<const float2*>(&s_be[nt * 8 + 2 * t]);
+            const int px0 = pt * 16 + g, px1 = px0 + 8;
+            const uint32_t ea = es + (uint32_t)((px0 + PAD) * CB + nt * 8 + 2 * t) * 2;
+            if (px0 < W) sts32(ea, Half16<T>::pack(silu_tanh(c[0] + bb.x), silu_tanh(c[1] + bb.y)));
+            if (px1 < W) sts32(ea + 8 * CB * 2, Half16<T>::pack(silu_tanh(c[2] + bb.x), silu_tanh(c[3] + bb.y)));
+        }
+    };
+
+#pragma unroll
+    for (int r = 0; r < kXR - 1; ++r) issue_row();
+    cp_async_wait<kXR - 2>();                // x row 0 has landed (this thread's copies) ...
+    __syncthreads();                         // ... and everybody's; weights and bias are visible too
+    issue_row();                             // row kXR-1 into the free slot
+    expand_row(0, iy_start);
+
+    uint64_t acc[RING][TW];
+#pragma unroll
+    for (int s = 0; s < RING; ++s)
+#pragma unroll
+        for (int j = 0; j < TW; ++j) acc[s][j] = 0ull;
+    uint64_t sums = 0ull;
+    T* obase = out + (((size_t)frame * OH) * OW + ox0) * C + c0;
+    uint32_t ro = (uint32_t)(oy0 * OW) * (uint32_t)C;
+    constexpr uint32_t ro_step = (uint32_t)OW * (uint32_t)C;
+    constexpr uint32_t pix_b = (uint32_t)CB * 2;
+    const uint32_t sb_c0 = sm_e + (uint32_t)(ox0 * S * CB + 2 * cpl) * 2;   // window column 0 of this thread in slot 0
+    int iy = iy_start;
+
+    for (int rb = 0; rb < rend; rb += PERIOD) {
+#pragma unroll
+        for (int p = 0; p < PERIOD; ++p) {
+            const int r = rb + p;
+            if (r < rend) {
+                cp_async_wait<kXR - 2>();                // x row r+1 has landed (this thread's copies) ...
+                __syncthreads();                         // ... and everybody's; expanded row r is complete; row r-1 consumed
+                issue_row();                             // x row r+kXR into the slot of x row r (expanded in step r-1)
+                expand_row(r + 1, iy + 1);
+                const uint32_t sb_c = sb_c0 + (uint32_t)(r & 1) * rsb;
+                if ((unsigned)iy < (unsigned)H) {
+#pragma unroll
+                    for (int jj = 0; jj < NCOL; ++jj) {
+                        const uint32_t raw = lds32(sb_c + jj * pix_b);
+                        const float2 xf = Half16<T>::unpack(raw);
+                        const uint64_t xv = f2_pack(xf.x, xf.y);
+#pragma unroll
+                        for (int ky = 0; ky < KS; ++ky) {
+                            const int dd = p - ky + 2 * PERIOD;
+                            if (dd % S != 0) continue;
+                            const int slot = (dd / S) % RING;
+#pragma unroll
+                            for (int kx = 0; kx < KS; ++kx) {
+                                const int dj = jj - kx;
+                                if (dj < 0 || (dj % S) != 0 || dj / S >= TW) continue;
+                                const int j = dj / S;
+                                if (ky == 0 && kx == 0) acc[slot][j] = fma2(xv, wr[0], b2);
+                                else acc[slot][j] = fma2(xv, wr[ky * KS + kx], acc[slot][j]);
+                            }
+                        }
+                    }
+                } else if (p % S == 0) {
+                    const int slot = (p / S) % RING;
+#pragma unroll
+                    for (int j = 0; j < TW; ++j) acc[slot][j] = b2;
+                }
+                ++iy;
+                if ((p - (KS - 1) + 2 * PERIOD) % S == 0) {
+                    const int slot = ((p - (KS - 1) + 2 * PERIOD) / S) % RING;
+                    if (r >= KS - 1) {
+#pragma unroll
+                        for (int j = 0; j < TW; ++j) {
+                            const float2 a = f2_unpack(acc[slot][j]);
+                            const float y0 = fmaf(a.x, tanh_approx(a.x), a.x), y1 = fmaf(a.y, tanh_approx(a.y), a.y);
+                            sums = add2(sums, f2_pack(y0, y1));
+                            *reinterpret_cast<uint32_t*>(obase + (ro + (uint32_t)(j * C))) = Half16<T>::pack(y0, y1);
+                        }
+                        ro += ro_step;
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    float* dst = partials + (((size_t)frame * segs + seg) * strips + strip) * C + c0;
+    *reinterpret_cast<float2*>(dst) = f2_unpack(sums);
+}
+
+// The early InvertedResidual blocks of the 224x224 network: (Cin, mid, map, k, stride)
+//   2.1.0: 16 -> 96 @112 k3 s2     2.1.1: 24 -> 144 @56 k3 s1     2.2.0: 24 -> 144 @56 k5 s2
+bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) {
+    if (H != W) return false;
+    return (cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
+           (cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
+           (cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2);
+}
+
+template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
+static cudaError_t fused_go(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
+                            float* partials, int64_t frames, cudaStream_t s) {
+    constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, strips = OW / kFTW;
+    constexpr int THREADS = strips * (CB / 2);
+    constexpr int pixw = ((strips * kFTW - 1) * S + KS) > W + 2 * PAD ? ((strips * kFTW - 1) * S + KS) : W + 2 * PAD;
+    constexpr int KP = (CIN + 15) & ~15, XP = KP + 8, PXT = (W + 15) / 16;
+    constexpr size_t smem = (size_t)2 * pixw * CB * 2 + (size_t)kXR * PXT * 16 * XP * 2 + (size_t)CB * XP * 2 + (size_t)CB * 4;
+    constexpr int rps = OW > 56 ? 56 : OW, segs = (OW + rps - 1) / rps;
+    auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG>;
+    if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    const int64_t grid = frames * segs * (C / CB);
+    if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
+    kern<<<(unsigned)grid, THREADS, smem, s>>>((const T*)x, (const T*)we, be, w, bias, (T*)out, partials);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_fused_t(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
+                                  float* partials, int64_t frames, int W, int cin, int k, int stride, cudaStream_t s) {
+    if (cin == 16 && W == 112) return fused_go<T, 3, 2, 16, 96, 112, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 24 && k == 3) return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
+}
+
+// x [frames][H][W][cin], we [mid][cin] + be [mid] (expand conv, BN folded), w [k*k][mid] fp32 + bias [mid] (depthwise, BN
+// folded) -> out [frames][OH][OW][mid], partials [frames][dw_march_slots(OH,OW)][mid]
+cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
+                                float* partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype,
+                                cudaStream_t s) {
+    if (frames <= 0) return cudaSuccess;
+    if (!mbconv_fused_supported(H, W, cin, mid, k, stride)) return cudaErrorInvalidValue;
+    if (dtype == kDtypeFP16) return launch_fused_t<__half>(x, we, be, w, bias, out, partials, frames, W, cin, k, stride, s);
+    return launch_fused_t<__nv_bfloat16>(x, we, be, w, bias, out, partials, frames, W, cin, k, stride, s);
+}
+
+}  // namespace dfd

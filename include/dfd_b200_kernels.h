@@ -54,6 +54,15 @@ int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float
 int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2, void* d_out,
                           int64_t frames, int H, int W, int K, int C, int N, int dtype, void* d_pad, size_t pad_bytes, void* stream);
 
+/* EXPERIMENTAL (path behind DFD_FUSE_EXPAND=1, not yet verified on a GPU): timm InvertedResidual conv_pw + bn1 + SiLU ->
+ * conv_dw + bn2 + SiLU (+ squeeze-excite sums) as ONE kernel for the early blocks of the 224x224 network
+ * ((cin, mid, map, k, stride) = (16,96,112,3,2), (24,144,56,3,1), (24,144,56,5,2); dfd_k_mbconv_fused_supported tells):
+ * the expanded tensor stays in shared memory.  d_x [frames*H*W][cin], d_we [mid][cin] 16-bit, d_be fp32 [mid]; d_w, d_bias,
+ * d_out, d_partials as dfd_k_dwconv. */
+int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride);
+int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, const float* d_w, const float* d_bias, void* d_out,
+                       float* d_partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype, void* stream);
+
 /* HOST-ONLY (no GPU needed): row maps of that zero-haloed layout, computed by the very functions the kernels use
  * (csrc/conv_map.h).  h_pad_row [frames*H*W]: physical row of every interior pixel; h_out_row [frames*(H+2)*(W+2)]: output
  * row of every padded pixel, -1 for halo pixels; h_tap_row / h_tap_col [9*cpk]: row offset and channel column of the A box

@@ -270,3 +270,38 @@ def test_conv1x1_conv3x3_implicit(lib, prec, frames, H, W, K, C, N):
     lib.dfd_k_conv3x3_maps(frames, H, W, C // 64, pr.ctypes.data, None, None, None)
     interior[torch.from_numpy(pr)] = True
     assert (halo[~interior] == 0).all()                                             # halo and guards untouched by the scatter
+
+
+@experimental
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("cin,mid,H,k,s", [(16, 96, 112, 3, 2), (24, 144, 56, 3, 1), (24, 144, 56, 5, 2)])
+def test_mbconv_fused_expand_depthwise(lib, prec, cin, mid, H, k, s):
+    """Expand 1x1 + SiLU fused into the marching depthwise kernel (mbconv_fused.cu): against fp32 PyTorch with the expanded
+    tensor rounded to the storage type (the rounding point the kernel keeps), and against the two verified kernels it replaces."""
+    code, tdt, rel = DT[prec]
+    assert lib.dfd_k_mbconv_fused_supported(H, H, cin, mid, k, s) == 1 and lib.dfd_k_mbconv_fused_supported(H, H, cin, mid, k, 3 - s) == 0
+    g = torch.Generator().manual_seed(cin * 7 + k + s)
+    frames = 3
+    x = torch.randn(frames, H, H, cin, generator=g).to(tdt)
+    we = (torch.randn(mid, cin, generator=g) / cin ** 0.5).to(tdt); be = torch.randn(mid, generator=g) * 0.3
+    w = torch.randn(mid, 1, k, k, generator=g) * (1.0 / k); b = torch.randn(mid, generator=g) * 0.2
+    OH = (H + 2 * (k // 2) - k) // s + 1
+    nparts = lib.dfd_k_dw_num_partials(OH, OH, mid, k, s)
+    wp = w.reshape(mid, k * k).t().contiguous().cuda()
+    xd, wed, bed, bd = x.cuda(), we.cuda(), be.cuda(), b.cuda()
+    out = torch.full((frames, OH, OH, mid), float("nan"), dtype=tdt, device="cuda")
+    parts = torch.full((frames, nparts, mid), float("nan"), device="cuda")
+    chk(lib, lib.dfd_k_mbconv_fused(xd.data_ptr(), wed.data_ptr(), bed.data_ptr(), wp.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                                    parts.data_ptr(), frames, H, H, cin, mid, k, s, code, stream()))
+    e = F.silu(x.double().reshape(-1, cin) @ we.double().t() + be.double()).to(tdt).float().view(frames, H, H, mid)
+    ref = F.silu(F.conv2d(e.permute(0, 3, 1, 2), w, b, s, k // 2, 1, mid))
+    assert torch.isfinite(out).all()
+    close(out.cpu(), ref.permute(0, 2, 3, 1), 2 * rel)
+    close(parts.sum(1).cpu(), ref.sum((2, 3)), 1e-3, abs_=5e-2)
+    # the unfused pair: expand GEMM (tcgen05) -> marching depthwise
+    E = torch.empty((frames * H * H, mid), dtype=tdt, device="cuda")
+    chk(lib, lib.dfd_k_gemm(xd.data_ptr(), wed.data_ptr(), bed.data_ptr(), None, None, E.data_ptr(), frames * H * H, cin, mid, H * H, 1, code, 0, stream()))
+    out2 = torch.empty_like(out); parts2 = torch.empty_like(parts)
+    chk(lib, lib.dfd_k_dwconv(E.data_ptr(), wp.data_ptr(), bd.data_ptr(), out2.data_ptr(), parts2.data_ptr(), frames, H, H, mid, k, s, code, stream()))
+    close(out.cpu(), out2.cpu(), rel)                                               # same rounding points; only the MMA accumulation order differs
+    close(parts.cpu(), parts2.cpu(), 1e-3, abs_=5e-2)
