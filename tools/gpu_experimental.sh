@@ -20,7 +20,7 @@ run resnet_implicit env DFD_RESNET_IMPLICIT=1 python tools/bench_resnet.py --vid
 # 3. one ncu --set full capture of the new kernels (only after the runs above exited 0 without ncu)
 if grep -q "passed" gpurun_out/exp_fused_path.log 2>/dev/null; then
   CMD="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
-  DFD_FUSE_EXPAND=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mbconv_fused|dwconv_march|gemm_tc" -s 68 -c 12 -f -o /tmp/full_fused \
+  DFD_FUSE_EXPAND=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mbconv_fused -c 6 -f -o /tmp/full_fused \
       env DFD_FUSE_EXPAND=1 $CMD > gpurun_out/exp_ncu_fused.log 2>&1
   ncu -i /tmp/full_fused.ncu-rep --page raw --csv > gpurun_out/exp_full_fused_raw.csv 2>/dev/null
   python tools/ncu_table.py gpurun_out/exp_full_fused_raw.csv > gpurun_out/exp_full_fused_table.txt 2>&1; cat gpurun_out/exp_full_fused_table.txt
