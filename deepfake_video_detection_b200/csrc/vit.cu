@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -249,6 +250,149 @@ __global__ void __launch_bounds__(128) vit_attention_kernel(const T* __restrict_
 
 constexpr size_t kAttSmem = (size_t)(2 * kTokPad * kQKStride + kHd * kVtStride) * 2;
 
+// ---- attention, second variant (EXPERIMENTAL, DFD_VIT_ATTN_V2=1; written without GPU access, off by default) ----------------
+// Same contract as vit_attention_kernel.  Differences, all aimed at the latency / LSU limits the first variant shows (8 warps
+// per SM, two 32-bit shared-memory loads per MMA, an 8-way bank-conflicted V^T scatter while staging):
+//   * Q, K and V are all staged row-major with 16-byte stores (pitch 72 halves: conflict-free for ldmatrix);
+//   * fragments come from `ldmatrix.x4` (one instruction feeds two MMAs); the V operand of P V uses `.trans`, so no
+//     transposed copy of V is ever written;
+//   * keys are processed in blocks of 64 with the online-softmax recurrence (fp32 running max / sum, accumulator rescaled
+//     when the max moves), so a thread holds 32 score registers instead of 104: 256 threads per CTA and 2 CTAs per SM
+//     (16 warps per SM instead of 8).  Scores are pre-multiplied by log2(e)/8 and exponentiated with ex2.approx.
+template <typename T>
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T>
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+constexpr int kAtt2Warps = 8;
+constexpr int kAtt2KeyBlock = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(kAtt2Warps * 32, 2) vit_attention_v2_kernel(const T* __restrict__ qkv, T* __restrict__ o) {
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    T* sQ = reinterpret_cast<T*>(att_smem);                       // [208][72]
+    T* sK = sQ + kTokPad * kQKStride;                             // [208][72]
+    T* sV = sK + kTokPad * kQKStride;                             // [208][72]  row-major (read through ldmatrix.trans)
+    const int head = blockIdx.x % kHeads;
+    const int64_t img = blockIdx.x / kHeads;
+    const T* base = qkv + (size_t)img * kTokens * (3 * kDim) + head * kHd;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kTokPad * 8; i += kAtt2Warps * 32) {
+        const int tok = i >> 3, ch = (i & 7) * 8;
+        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+        if (tok < kTokens) {
+            const T* row = base + (size_t)tok * (3 * kDim) + ch;
+            q = *reinterpret_cast<const uint4*>(row);
+            k = *reinterpret_cast<const uint4*>(row + kDim);
+            v = *reinterpret_cast<const uint4*>(row + 2 * kDim);
+        }
+        *reinterpret_cast<uint4*>(sQ + tok * kQKStride + ch) = q;
+        *reinterpret_cast<uint4*>(sK + tok * kQKStride + ch) = k;
+        *reinterpret_cast<uint4*>(sV + tok * kQKStride + ch) = v;
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31, t = lane & 3;
+    const uint32_t sq = smem_u32(sQ), sk = smem_u32(sK), sv = smem_u32(sV);
+    constexpr uint32_t kRowB = kQKStride * 2;                                     // bytes per staged row
+    // per-lane row / column offsets of the three ldmatrix address patterns (see the fragment layouts of mma.m16n8k16):
+    //   A (Q):        matrices (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15) (rows 8-15, k 8-15)
+    //   B (K, S=QK^T): matrices (keys 0-7, d 0-7) (keys 0-7, d 8-15) (keys 0-7, d 16-23) (keys 0-7, d 24-31)
+    //   B (V, O=PV):   .trans of (keys 0-7, d 0-7) (keys 8-15, d 0-7) (keys 0-7, d 8-15) (keys 8-15, d 8-15)
+    const uint32_t a_off = (uint32_t)(lane & 15) * kRowB + (uint32_t)(lane >> 4) * 16;
+    const uint32_t k_off = (uint32_t)(lane & 7) * kRowB + (uint32_t)(lane >> 3) * 16;
+    const uint32_t v_off = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * kRowB + (uint32_t)(lane >> 4) * 16;
+    const float kScale = 0.125f * 1.4426950408889634f;                            // 1/sqrt(64) * log2(e)
+
+    for (int qt = warp; qt < kTokPad / 16; qt += kAtt2Warps) {
+        const int q0 = qt * 16;
+        uint32_t aq[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldsm_x4<T>(aq[ks], sq + (uint32_t)q0 * kRowB + a_off + ks * 32);
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float acc[kHd / 8][4];
+#pragma unroll
+        for (int dt = 0; dt < kHd / 8; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
+#pragma unroll 1
+        for (int kb0 = 0; kb0 < kTokPad; kb0 += kAtt2KeyBlock) {
+            const int nkt = min(kAtt2KeyBlock, kTokPad - kb0) / 8;                // 8-key tiles in this block: 8, 8, 8, 2
+            float s[kAtt2KeyBlock / 8][4];
+#pragma unroll
+            for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+                if (nt < nkt) {
+                    uint32_t b0[4], b1[4];
+                    const uint32_t ka = sk + (uint32_t)(kb0 + nt * 8) * kRowB + k_off;
+                    ldsm_x4<T>(b0, ka); ldsm_x4<T>(b1, ka + 64);                  // head dims 0-31, 32-63
+                    mma16816<T>(s[nt], aq[0], b0[0], b0[1]); mma16816<T>(s[nt], aq[1], b0[2], b0[3]);
+                    mma16816<T>(s[nt], aq[2], b1[0], b1[1]); mma16816<T>(s[nt], aq[3], b1[2], b1[3]);
+                }
+            }
+            // scale, mask the padding keys, block maxima of rows g (c0,c1) and g+8 (c2,c3)
+            float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool ok = nt < nkt && kb0 + nt * 8 + 2 * t + j < kTokens;
+                    s[nt][j] = ok ? s[nt][j] * kScale : -INFINITY;
+                    s[nt][2 + j] = ok ? s[nt][2 + j] * kScale : -INFINITY;
+                    bm0 = fmaxf(bm0, s[nt][j]); bm1 = fmaxf(bm1, s[nt][2 + j]);
+                }
+            }
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+            const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);                 // finite: every block holds a valid key
+            const float al0 = ex2_approx(m0 - n0), al1 = ex2_approx(m1 - n1);     // first block: ex2(-inf) = 0
+            m0 = n0; m1 = n1;
+            float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    s[nt][j] = ex2_approx(s[nt][j] - n0); s[nt][2 + j] = ex2_approx(s[nt][2 + j] - n1);
+                    r0 += s[nt][j]; r1 += s[nt][2 + j];
+                }
+            }
+            l0 = l0 * al0 + r0; l1 = l1 * al1 + r1;                               // per-lane partial sums; quad-reduced at the end
+#pragma unroll
+            for (int dt = 0; dt < kHd / 8; ++dt) { acc[dt][0] *= al0; acc[dt][1] *= al0; acc[dt][2] *= al1; acc[dt][3] *= al1; }
+            // O += P V: two adjacent 8-key score tiles are one 16-key A fragment
+#pragma unroll
+            for (int kk = 0; kk < kAtt2KeyBlock / 16; ++kk) {
+                if (2 * kk < nkt) {
+                    uint32_t ap[4];
+                    ap[0] = Half16<T>::pack(s[2 * kk][0], s[2 * kk][1]);         ap[1] = Half16<T>::pack(s[2 * kk][2], s[2 * kk][3]);
+                    ap[2] = Half16<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]); ap[3] = Half16<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+                    const uint32_t va = sv + (uint32_t)(kb0 + kk * 16) * kRowB + v_off;
+#pragma unroll
+                    for (int dp = 0; dp < kHd / 16; ++dp) {
+                        uint32_t bv[4];
+                        ldsm_x4_trans<T>(bv, va + dp * 32);
+                        mma16816<T>(acc[2 * dp], ap, bv[0], bv[1]);
+                        mma16816<T>(acc[2 * dp + 1], ap, bv[2], bv[3]);
+                    }
+                }
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
+        T* ob = o + (size_t)img * kTokens * kDim + head * kHd + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < kHd / 8; ++dt) {
+            if (r0 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * kDim + dt * 8) = Half16<T>::pack(acc[dt][0] * i0, acc[dt][1] * i0);
+            if (r1 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * kDim + dt * 8) = Half16<T>::pack(acc[dt][2] * i1, acc[dt][3] * i1);
+        }
+    }
+}
+constexpr size_t kAtt2Smem = (size_t)(3 * kTokPad * kQKStride) * 2;
+
 // ---- DeepfakeModel head (src/models.py:199-291): SimpleGCN over the frame graph + mean pool + classifier ------------
 //   g = relu(fc2(relu(fc1(A_norm @ H))));  logits = Linear(64 -> C)(relu(Linear(128 -> 64)(mean_n g)))      (:186-197, :283-291)
 // One CTA per video, fp32.  fc1(A @ H) is evaluated as A @ (H W1^T) + b1 (same function, N x 256 intermediate instead
@@ -454,11 +598,21 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
     }
     if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAttSmem), "vit attention smem");
     else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAttSmem), "vit attention smem");
+    // DFD_VIT_ATTN_V2=1 (experimental, off by default until it has been verified on a GPU): ldmatrix + online-softmax attention
+    const char* env_att = getenv("DFD_VIT_ATTN_V2");
+    const bool att_v2 = env_att && atoi(env_att) != 0;
+    if (att_v2) {
+        if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention v2 smem");
+        else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention v2 smem");
+    }
     for (int i = 0; i < kDepth; ++i) {
         const auto& b = w->blk[i];
         VIT_CK(ln(X, kDim, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");
         VIT_CK(dfd::launch_gemm_tc(H16, b.qkv_w, b.qkv_b, nullptr, nullptr, BIG, M, kDim, 3 * kDim, 1, 0, dt, s), "vit qkv gemm");
-        if (f16) dfd::vit_attention_kernel<__half><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __half*)BIG, (__half*)H16);
+        if (att_v2) {
+            if (f16) dfd::vit_attention_v2_kernel<__half><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __half*)BIG, (__half*)H16);
+            else dfd::vit_attention_v2_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
+        } else if (f16) dfd::vit_attention_kernel<__half><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __half*)BIG, (__half*)H16);
         else dfd::vit_attention_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
         VIT_CK(cudaGetLastError(), "vit attention");
         VIT_CK(dfd::launch_gemm_tc_f32out(H16, b.proj_w, b.proj_b, X, X, M, kDim, kDim, dt, s), "vit proj gemm");

@@ -17,7 +17,11 @@ run conv_kernel  env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.
 run conv_member  env DFD_EXPERIMENTAL=1 python -m pytest tests/test_resnet.py -m gpu -q -x -s -k implicit
 run resnet_gather   python tools/bench_resnet.py --videos 8 --frames 32 --iters 5
 run resnet_implicit env DFD_RESNET_IMPLICIT=1 python tools/bench_resnet.py --videos 8 --frames 32 --iters 5
-# 3. one ncu --set full capture of the new kernels (only after the runs above exited 0 without ncu)
+# 3. ViT attention, second variant (vit.cu, DFD_VIT_ATTN_V2=1)
+run vit_att2_test env DFD_EXPERIMENTAL=1 python -m pytest tests/test_vit.py -m gpu -q -x -s -k attention_v2
+run vit_base      python tools/bench_vit.py --batch 512 --iters 5
+run vit_att2      env DFD_VIT_ATTN_V2=1 python tools/bench_vit.py --batch 512 --iters 5
+# 4. one ncu --set full capture of the new kernels (only after the runs above exited 0 without ncu)
 if grep -q "passed" gpurun_out/exp_fused_path.log 2>/dev/null; then
   CMD="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
   DFD_FUSE_EXPAND=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mbconv_fused -c 6 -f -o /tmp/full_fused \
