@@ -305,3 +305,27 @@ def test_mbconv_fused_expand_depthwise(lib, prec, cin, mid, H, k, s):
     chk(lib, lib.dfd_k_dwconv(E.data_ptr(), wp.data_ptr(), bd.data_ptr(), out2.data_ptr(), parts2.data_ptr(), frames, H, H, mid, k, s, code, stream()))
     close(out.cpu(), out2.cpu(), rel)                                               # same rounding points; only the MMA accumulation order differs
     close(parts.cpu(), parts2.cpu(), 1e-3, abs_=5e-2)
+
+
+@experimental
+@pytest.mark.parametrize("C_,rd,nparts,frames", [(32, 8, 32, 3), (96, 4, 8, 9), (144, 6, 8, 16), (240, 10, 4, 5), (480, 20, 2, 8),
+                                                  (672, 28, 2, 13), (1152, 48, 1, 17), (1152, 47, 3, 1)])
+def test_se_gate_v2(lib, C_, rd, nparts, frames, monkeypatch):
+    """DFD_SE_V2=1 (packed fp32x2 FMAs, 16-byte weight loads, two FC1 rows per warp pass): against the fp32 reference and the
+    first variant (FC1 sums in another fixed order: agreement to rounding noise); odd rd exercises the duplicated last row."""
+    g = torch.Generator().manual_seed(C_ + rd)
+    parts = torch.randn(frames, nparts, C_, generator=g)
+    w1 = torch.randn(rd, C_, generator=g) * 0.1; b1 = torch.randn(rd, generator=g) * 0.1
+    w2 = torch.randn(C_, rd, generator=g) * 0.3; b2 = torch.randn(C_, generator=g) * 0.3
+    inv = 1.0 / 123.0
+    dev = [t.cuda() for t in (parts, w1, b1, w2.t().contiguous(), b2)]
+    run = lambda out: chk(lib, lib.dfd_k_se(dev[0].data_ptr(), nparts, C.c_float(inv), dev[1].data_ptr(), dev[2].data_ptr(),
+                                            dev[3].data_ptr(), dev[4].data_ptr(), out.data_ptr(), frames, C_, rd, stream()))
+    g1 = torch.full((frames, C_), float("nan"), device="cuda"); g2 = g1.clone(); g3 = g1.clone()
+    run(g1)
+    monkeypatch.setenv("DFD_SE_V2", "1")
+    run(g2); run(g3)
+    ref = torch.sigmoid(F.linear(F.silu(F.linear(parts.sum(1) * inv, w1, b1)), w2, b2))
+    close(g2.cpu(), ref, 1e-5, abs_=2e-6)
+    close(g2.cpu(), g1.cpu(), 1e-6, abs_=1e-6)
+    assert torch.equal(g2, g3)

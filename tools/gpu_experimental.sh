@@ -21,7 +21,12 @@ run resnet_implicit env DFD_RESNET_IMPLICIT=1 python tools/bench_resnet.py --vid
 run vit_att2_test env DFD_EXPERIMENTAL=1 python -m pytest tests/test_vit.py -m gpu -q -x -s -k attention_v2
 run vit_base      python tools/bench_vit.py --batch 512 --iters 5
 run vit_att2      env DFD_VIT_ATTN_V2=1 python tools/bench_vit.py --batch 512 --iters 5
-# 4. one ncu --set full capture of the new kernels (only after the runs above exited 0 without ncu)
+# 4. squeeze-excite gate, second variant (se.cu, DFD_SE_V2=1)
+run se2_kernel env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k se_gate_v2
+run se2_path   env DFD_SE_V2=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x
+run bench_se2  env DFD_SE_V2=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run bench_all  env DFD_SE_V2=1 DFD_FUSE_EXPAND=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+# 5. one ncu --set full capture of the new kernels (only after the runs above exited 0 without ncu)
 if grep -q "passed" gpurun_out/exp_fused_path.log 2>/dev/null; then
   CMD="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
   DFD_FUSE_EXPAND=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:mbconv_fused -c 6 -f -o /tmp/full_fused \
