@@ -54,7 +54,7 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     constexpr int OW = (W + 2 * PAD - KS) / S + 1, OH = OW;
     constexpr int strips = OW / TW;
     static_assert(OW % TW == 0, "whole strips only");
-    static_assert(CB % 16 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
+    static_assert(CB % 8 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
     constexpr int THREADS = strips * (CB / 2), WARPS = THREADS / 32;
     static_assert(THREADS % 32 == 0, "whole warps");
     constexpr int NCOL = (TW - 1) * S + KS;
@@ -265,8 +265,19 @@ static cudaError_t fused_go(const void* x, const void* we, const float* be, cons
 template <typename T>
 static cudaError_t launch_fused_t(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                                   float* partials, int64_t frames, int W, int cin, int k, int stride, cudaStream_t s) {
-    if (cin == 16 && W == 112) return fused_go<T, 3, 2, 16, 96, 112, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
-    if (cin == 24 && k == 3) return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    // channel block per CTA: 48 by default; DFD_FUSE_CB=1 picks the wider alternative of each shape (fewer re-reads of the
+    // block input, more warps per CTA) for the first GPU sweep
+    const char* env_cb = getenv("DFD_FUSE_CB");
+    const bool wide = env_cb && atoi(env_cb) != 0;
+    if (cin == 16 && W == 112) {
+        if (wide) return fused_go<T, 3, 2, 16, 96, 112, 96, 128>(x, we, be, w, bias, out, partials, frames, s);
+        return fused_go<T, 3, 2, 16, 96, 112, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    }
+    if (cin == 24 && k == 3) {
+        if (wide) return fused_go<T, 3, 1, 24, 144, 56, 72, 128>(x, we, be, w, bias, out, partials, frames, s);
+        return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    }
+    if (wide) return fused_go<T, 5, 2, 24, 144, 56, 144, 168>(x, we, be, w, bias, out, partials, frames, s);
     return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
 }
 

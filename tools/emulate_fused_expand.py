@@ -70,5 +70,6 @@ def check(KS, S, CIN, C, W, CB):
     print(f"k{KS} s{S} cin{CIN} mid{C} W{W} CB{CB}: {WARPS} warps, {PXT * NTL} tiles, slot {pixw}x{CB}, max err {err:.2e} ok")
 
 
-for spec in [(3, 2, 16, 96, 112, 48), (3, 1, 24, 144, 56, 48), (5, 2, 24, 144, 56, 48)]:
+for spec in [(3, 2, 16, 96, 112, 48), (3, 1, 24, 144, 56, 48), (5, 2, 24, 144, 56, 48),
+             (3, 2, 16, 96, 112, 96), (3, 1, 24, 144, 56, 72), (5, 2, 24, 144, 56, 144)]:      # DFD_FUSE_CB=1 alternatives
     check(*spec)
