@@ -477,12 +477,13 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
     // DFD_FUSE_EXPAND=1 (experimental, off by default until it has been verified on a GPU): the early HBM-bound blocks run
     // expand 1x1 + depthwise as ONE kernel (mbconv_fused.cu); the expanded tensor never goes to HBM.
     const char* env_fuse = getenv("DFD_FUSE_EXPAND");
-    const bool fuse = env_fuse && atoi(env_fuse) != 0 && !use_simt_gemm();
+    const int fuse = (env_fuse && !use_simt_gemm()) ? atoi(env_fuse) : 0;       // 1: the three early blocks; 2: every block mbconv_fused.cu supports
     for (int i = 0; i < kNumBlocks; ++i) {
         const BlockW& B = w->blocks[i];
         const void* x = io[cur];
         const void* e = x;
-        const bool fused = fuse && B.has_expand && dfd::mbconv_fused_supported(h, wd, B.cin, B.mid, B.k, B.stride) &&
+        const int fuse_level = dfd::mbconv_fused_level(h, wd, B.cin, B.mid, B.k, B.stride);
+        const bool fused = fuse > 0 && B.has_expand && fuse_level > 0 && fuse_level <= fuse &&
                            dfd::dw_num_partials((h + 2 * (B.k / 2) - B.k) / B.stride + 1, (wd + 2 * (B.k / 2) - B.k) / B.stride + 1, B.mid, B.k, B.stride) ==
                                dfd::dw_march_slots((h + 2 * (B.k / 2) - B.k) / B.stride + 1, (wd + 2 * (B.k / 2) - B.k) / B.stride + 1);
         if (B.has_expand && !fused) {

@@ -38,6 +38,7 @@ cudaError_t launch_dwconv_march(const void* in, const float* w, const float* bia
 // early HBM-bound blocks.  x [frames][H][W][cin] 16-bit, we [mid][cin] 16-bit + be fp32 [mid]; the rest as launch_dwconv_march
 // (partials: dw_march_slots rows).
 bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride);
+int mbconv_fused_level(int H, int W, int cin, int mid, int k, int stride);      // 0 unsupported, 1 early HBM-bound blocks, 2 later memory-bound blocks
 cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                                 float* partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype,
                                 cudaStream_t s);

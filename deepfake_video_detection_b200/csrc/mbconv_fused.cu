@@ -46,7 +46,7 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile(
 
 // Geometry is compile-time: CIN block input channels, C expanded channels, W x W map, CB channels per CTA.
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
-__global__ void __launch_bounds__(((W + 2 * (KS / 2) - KS) / S + 1) / kFTW * (CB / 2), 1) __maxnreg__(MAXREG)
+__global__ void __launch_bounds__((((W + 2 * (KS / 2) - KS) / S + 1) / kFTW * (CB / 2) + 31) / 32 * 32, 1) __maxnreg__(MAXREG)
 mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const float* __restrict__ be,
                     const float* __restrict__ w, const float* __restrict__ bias,
                     T* __restrict__ out, float* __restrict__ partials) {
@@ -55,8 +55,11 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     constexpr int strips = OW / TW;
     static_assert(OW % TW == 0, "whole strips only");
     static_assert(CB % 8 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
-    constexpr int THREADS = strips * (CB / 2), WARPS = THREADS / 32;
-    static_assert(THREADS % 32 == 0, "whole warps");
+    // DWT threads own the depthwise work (2 channels x 7 columns each); the CTA is rounded up to whole warps, and the few
+    // extra threads (they take part in staging, in the expand MMAs and in the barriers) shadow the first depthwise threads
+    // with their stores suppressed
+    constexpr int DWT = strips * (CB / 2), THREADS = (DWT + 31) / 32 * 32, WARPS = THREADS / 32;
+    static_assert(THREADS - DWT < DWT, "shadow threads map onto real ones");
     constexpr int NCOL = (TW - 1) * S + KS;
     constexpr int RING = (KS + S - 1) / S, PERIOD = S * RING;
     constexpr int pixw = ((strips * TW - 1) * S + KS) > W + 2 * PAD ? ((strips * TW - 1) * S + KS) : W + 2 * PAD;
@@ -84,7 +87,9 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     const int seg = fs % segs;
     const int64_t frame = fs / segs;
     constexpr int CB2 = CB >> 1;
-    const int cpl = threadIdx.x % CB2, strip = threadIdx.x / CB2;
+    const bool dw_active = (int)threadIdx.x < DWT;
+    const int tdw = dw_active ? (int)threadIdx.x : (int)threadIdx.x - DWT;
+    const int cpl = tdw % CB2, strip = tdw / CB2;
     const int c0 = cb * CB + 2 * cpl;
     const int oy0 = seg * rps;
     const int nrows = min(rps, OH - oy0);
@@ -223,7 +228,7 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
                             const float2 a = f2_unpack(acc[slot][j]);
                             const float y0 = fmaf(a.x, tanh_approx(a.x), a.x), y1 = fmaf(a.y, tanh_approx(a.y), a.y);
                             sums = add2(sums, f2_pack(y0, y1));
-                            *reinterpret_cast<uint32_t*>(obase + (ro + (uint32_t)(j * C))) = Half16<T>::pack(y0, y1);
+                            if (dw_active) *reinterpret_cast<uint32_t*>(obase + (ro + (uint32_t)(j * C))) = Half16<T>::pack(y0, y1);
                         }
                         ro += ro_step;
                     }
@@ -233,23 +238,34 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     }
     cp_async_wait<0>();
     float* dst = partials + (((size_t)frame * segs + seg) * strips + strip) * C + c0;
-    *reinterpret_cast<float2*>(dst) = f2_unpack(sums);
+    if (dw_active) *reinterpret_cast<float2*>(dst) = f2_unpack(sums);
 }
 
-// The early InvertedResidual blocks of the 224x224 network: (Cin, mid, map, k, stride)
-//   2.1.0: 16 -> 96 @112 k3 s2     2.1.1: 24 -> 144 @56 k3 s1     2.2.0: 24 -> 144 @56 k5 s2
-bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) {
-    if (H != W) return false;
-    return (cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
-           (cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
-           (cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2);
+// InvertedResidual blocks of the 224x224 network this kernel is instantiated for: (Cin, mid, map, k, stride)
+//   level 1 — the early blocks, whose expand GEMM and depthwise kernel both run at the HBM roofline:
+//     2.1.0: 16 -> 96 @112 k3 s2     2.1.1: 24 -> 144 @56 k3 s1     2.2.0: 24 -> 144 @56 k5 s2
+//   level 2 — later blocks whose depthwise kernel is still memory-bound (3x3, or stride 2); the 5x5 stride-1 blocks are
+//   FMA-issue-bound and would only get slower with more instructions in the same CTA:
+//     2.3.0: 40 -> 240 @28 k3 s2    2.3.1/2: 80 -> 480 @14 k3 s1    2.5.0: 112 -> 672 @14 k5 s2    2.6.0: 192 -> 1152 @7 k3 s1
+// Returns 0 (not supported), 1 or 2.
+int mbconv_fused_level(int H, int W, int cin, int mid, int k, int stride) {
+    if (H != W) return 0;
+    if ((cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
+        (cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
+        (cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2)) return 1;
+    if ((cin == 40 && mid == 240 && W == 28 && k == 3 && stride == 2) ||
+        (cin == 80 && mid == 480 && W == 14 && k == 3 && stride == 1) ||
+        (cin == 112 && mid == 672 && W == 14 && k == 5 && stride == 2) ||
+        (cin == 192 && mid == 1152 && W == 7 && k == 3 && stride == 1)) return 2;
+    return 0;
 }
+bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) { return mbconv_fused_level(H, W, cin, mid, k, stride) > 0; }
 
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
 static cudaError_t fused_go(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                             float* partials, int64_t frames, cudaStream_t s) {
     constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, strips = OW / kFTW;
-    constexpr int THREADS = strips * (CB / 2);
+    constexpr int THREADS = (strips * (CB / 2) + 31) / 32 * 32;
     constexpr int pixw = ((strips * kFTW - 1) * S + KS) > W + 2 * PAD ? ((strips * kFTW - 1) * S + KS) : W + 2 * PAD;
     constexpr int KP = (CIN + 15) & ~15, XP = KP + 8, PXT = (W + 15) / 16;
     constexpr size_t smem = (size_t)2 * pixw * CB * 2 + (size_t)kXR * PXT * 16 * XP * 2 + (size_t)CB * XP * 2 + (size_t)CB * 4;
@@ -277,8 +293,14 @@ static cudaError_t launch_fused_t(const void* x, const void* we, const float* be
         if (wide) return fused_go<T, 3, 1, 24, 144, 56, 72, 128>(x, we, be, w, bias, out, partials, frames, s);
         return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
     }
-    if (wide) return fused_go<T, 5, 2, 24, 144, 56, 144, 168>(x, we, be, w, bias, out, partials, frames, s);
-    return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 24) {
+        if (wide) return fused_go<T, 5, 2, 24, 144, 56, 144, 168>(x, we, be, w, bias, out, partials, frames, s);
+        return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
+    }
+    if (cin == 40) return fused_go<T, 3, 2, 40, 240, 28, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 80) return fused_go<T, 3, 1, 80, 480, 14, 96, 128>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 112) return fused_go<T, 5, 2, 112, 672, 14, 96, 168>(x, we, be, w, bias, out, partials, frames, s);
+    return fused_go<T, 3, 1, 192, 1152, 7, 128, 128>(x, we, be, w, bias, out, partials, frames, s);
 }
 
 // x [frames][H][W][cin], we [mid][cin] + be [mid] (expand conv, BN folded), w [k*k][mid] fp32 + bias [mid] (depthwise, BN

@@ -274,7 +274,8 @@ def test_conv1x1_conv3x3_implicit(lib, prec, frames, H, W, K, C, N):
 
 @experimental
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("cin,mid,H,k,s", [(16, 96, 112, 3, 2), (24, 144, 56, 3, 1), (24, 144, 56, 5, 2)])
+@pytest.mark.parametrize("cin,mid,H,k,s", [(16, 96, 112, 3, 2), (24, 144, 56, 3, 1), (24, 144, 56, 5, 2),
+                                           (40, 240, 28, 3, 2), (80, 480, 14, 3, 1), (112, 672, 14, 5, 2), (192, 1152, 7, 3, 1)])
 def test_mbconv_fused_expand_depthwise(lib, prec, cin, mid, H, k, s):
     """Expand 1x1 + SiLU fused into the marching depthwise kernel (mbconv_fused.cu): against fp32 PyTorch with the expanded
     tensor rounded to the storage type (the rounding point the kernel keeps), and against the two verified kernels it replaces."""

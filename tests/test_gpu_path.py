@@ -213,7 +213,8 @@ def test_npz_batch_scorer_cli(tmp_path, synth_sd, golden, golden_crops):
 
 
 @pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
-def test_fused_expand_path_matches_default_path_and_goldens(synth_sd, golden, golden_crops, monkeypatch):
+@pytest.mark.parametrize("level,folded", [(1, 3), (2, 8)])
+def test_fused_expand_path_matches_default_path_and_goldens(synth_sd, golden, golden_crops, monkeypatch, level, folded):
     """DFD_FUSE_EXPAND=1 (expand 1x1 fused into the depthwise kernel on the three early blocks) against the verified default
     path and the reference goldens: same rounding points, so features agree to MMA accumulation-order noise."""
     from deepfake_video_detection_b200 import FrameScorer, make_offsets
@@ -223,9 +224,9 @@ def test_fused_expand_path_matches_default_path_and_goldens(synth_sd, golden, go
     d = torch.from_numpy(crops).cuda()
     base, _ = scorer.score(d, make_offsets(lens, "cuda"))
     n_base = scorer.last_launch_count
-    monkeypatch.setenv("DFD_FUSE_EXPAND", "1")
+    monkeypatch.setenv("DFD_FUSE_EXPAND", str(level))
     logits, scores = scorer.score(d, make_offsets(lens, "cuda"))
-    assert scorer.last_launch_count == n_base - 3                                   # three expand GEMMs folded away
+    assert scorer.last_launch_count == n_base - folded                              # expand GEMMs folded away (level 1: 3, level 2: 8)
     err = (logits.cpu() - torch.from_numpy(golden["logits"])).abs().max().item()
     print(f"fused expand: max |dlogit| vs goldens {err:.3e}, vs default path {(logits - base).abs().max().item():.3e}")
     assert err <= TOL_LOGITS_FP16 and (logits - base).abs().max().item() <= 1e-2

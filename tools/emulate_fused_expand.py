@@ -11,7 +11,7 @@ def check(KS, S, CIN, C, W, CB):
     PAD, TW = KS // 2, 7
     OW = (W + 2 * PAD - KS) // S + 1
     strips = OW // TW
-    THREADS = strips * (CB // 2); WARPS = THREADS // 32
+    THREADS = (strips * (CB // 2) + 31) // 32 * 32; WARPS = THREADS // 32
     pixw = max((strips * TW - 1) * S + KS, W + 2 * PAD)
     KP = (CIN + 15) & ~15; KSTEPS = KP // 16; XP = KP + 8
     PXT = (W + 15) // 16; NTL = CB // 8
@@ -71,5 +71,6 @@ def check(KS, S, CIN, C, W, CB):
 
 
 for spec in [(3, 2, 16, 96, 112, 48), (3, 1, 24, 144, 56, 48), (5, 2, 24, 144, 56, 48),
-             (3, 2, 16, 96, 112, 96), (3, 1, 24, 144, 56, 72), (5, 2, 24, 144, 56, 144)]:      # DFD_FUSE_CB=1 alternatives
+             (3, 2, 16, 96, 112, 96), (3, 1, 24, 144, 56, 72), (5, 2, 24, 144, 56, 144),       # DFD_FUSE_CB=1 alternatives
+             (3, 2, 40, 240, 28, 48), (3, 1, 80, 480, 14, 96), (5, 2, 112, 672, 14, 96), (3, 1, 192, 1152, 7, 128)]:   # level 2
     check(*spec)

@@ -12,6 +12,7 @@ run fused_path   env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_path.py 
 run fused_all    env DFD_FUSE_EXPAND=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x
 run bench_base   python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run bench_fused  env DFD_FUSE_EXPAND=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run bench_fused2 env DFD_FUSE_EXPAND=2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run fused_wide_t env DFD_FUSE_EXPAND=1 DFD_FUSE_CB=1 DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_path.py -m gpu -q -x -k "mbconv_fused or fused_expand"
 run bench_fusedw env DFD_FUSE_EXPAND=1 DFD_FUSE_CB=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 # 2. implicit 3x3 convolution of the resnet50 member (gemm_tc.cu CONV variants, resnet.cu switch DFD_RESNET_IMPLICIT=1)
