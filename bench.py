@@ -37,6 +37,27 @@ METRIC = "frames/sec EfficientNet-B0 inference at 1/2/4/8 B200, % roofline, vs C
 WORKLOAD = "per-video scoring: 64 videos x 32 uint8 224x224 face crops per GPU -> fused preprocess + EfficientNet-B0 + attention pool + head"
 
 
+_saved_stdout_fd = None
+
+
+def stdout_to_stderr():
+    """Anything C libraries (NCCL's version banner, ...) write to fd 1 while the bench runs goes to stderr, so that stdout
+    carries exactly the one JSON line."""
+    global _saved_stdout_fd
+    sys.stdout.flush()
+    _saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
+
+def restore_stdout():
+    global _saved_stdout_fd
+    if _saved_stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(_saved_stdout_fd, 1)
+        os.close(_saved_stdout_fd)
+        _saved_stdout_fd = None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -152,6 +173,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    stdout_to_stderr()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -283,7 +305,9 @@ def main():
                                     "sample": f"1 video x 32 crops (BASELINE configs[0]), median of {len(ts_all)} runs ({sum(ts_all):.1f} s) after 1 warm-up, "
                                               "oracle port of the reference CPU path, fp32, all host threads",
                                     "value_1_thread": fps_1, "sample_1_thread": f"median of {len(ts_1)} runs ({sum(ts_1):.1f} s), torch.set_num_threads(1) as the reference deploys (app.py:5-8)"}
-        print(json.dumps(line))
+        restore_stdout()
+        print(json.dumps(line), flush=True)
+        stdout_to_stderr()
     if world > 1:
         dist.destroy_process_group()
 
