@@ -18,10 +18,14 @@
 //              registers, packed fma.rn.f32x2, SiLU, SE partial sums, 16-bit stores
 // One __syncthreads per input row, as before: expanded row r was written during step r-1; slot (r+1)&1 was last read in
 // step r-1.  Partial-sum layout = dw_march_slots, so se.cu and the project GEMM are unchanged.
+// tools/host_emul/ compiles the kernel below (everything between the DFD_FUSED_KERNEL markers) for the CPU with stand-ins for
+// the device helpers, one std::thread per CUDA thread, to check its indexing and barrier placement without a GPU.
+#ifndef DFD_HOST_EMUL
 #include "common.cuh"
 #include "kernels.h"
 #include <cstdlib>
 #include <type_traits>
+#endif
 
 namespace dfd {
 
@@ -29,6 +33,7 @@ namespace {
 constexpr int kFTW = 7;              // output columns per thread (as dwconv_march.cu)
 constexpr int kXR = 6;               // x-row ring depth
 
+#ifndef DFD_HOST_EMUL
 template <typename T>
 __device__ __forceinline__ void mma16816_f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
     if constexpr (Half16<T>::kCode == kDtypeFP16)
@@ -42,8 +47,10 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+#endif
 }  // namespace
 
+// DFD_FUSED_KERNEL_BEGIN
 // Geometry is compile-time: CIN block input channels, C expanded channels, W x W map, CB channels per CTA.
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
 __global__ void __launch_bounds__((((W + 2 * (KS / 2) - KS) / S + 1) / kFTW * (CB / 2) + 31) / 32 * 32, 1) __maxnreg__(MAXREG)
@@ -240,6 +247,8 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     float* dst = partials + (((size_t)frame * segs + seg) * strips + strip) * C + c0;
     if (dw_active) *reinterpret_cast<float2*>(dst) = f2_unpack(sums);
 }
+
+// DFD_FUSED_KERNEL_END
 
 // InvertedResidual blocks of the 224x224 network this kernel is instantiated for: (Cin, mid, map, k, stride)
 //   level 1 — the early blocks, whose expand GEMM and depthwise kernel both run at the HBM roofline:

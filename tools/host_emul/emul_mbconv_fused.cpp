@@ -1,0 +1,197 @@
+// CPU emulation of mbconv_fused_kernel (deepfake_video_detection_b200/csrc/mbconv_fused.cu): the kernel text between the
+// DFD_FUSED_KERNEL markers is compiled UNCHANGED with host stand-ins for the device helpers; every CUDA thread of a CTA is
+// a std::thread, __syncthreads is a std::barrier, mma.sync exchanges fragments through a per-warp buffer and applies the
+// m16n8k16 definition, cp.async is modelled in two modes — LAZY (the copy happens only when a wait_group forces it: catches
+// reads before the wait) and EAGER (the copy happens at issue: catches slots overwritten while still being read).
+// Built with -fsanitize=thread the run also reports shared-memory accesses that no barrier orders.
+// The result is compared with a straightforward fp32 reference (expanded tensor rounded to fp16, as the kernel stores it).
+// Build + run: python tools/host_emul/run.py
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define DFD_HOST_EMUL 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __maxnreg__(...)
+#define __align__(x)
+#define __shared__
+
+struct Dim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local Dim3 threadIdx, blockIdx;
+struct float2 { float x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline float2 make_float2(float a, float b) { return {a, b}; }
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return {a, b, c, d}; }
+using std::min;
+
+typedef _Float16 __half;
+struct __nv_bfloat16 { uint16_t v; };
+
+static bool g_eager = false;                         // cp.async completion model
+static std::barrier<>* g_cta_bar = nullptr;
+static void __syncthreads() { g_cta_bar->arrive_and_wait(); }
+
+namespace dfd {
+alignas(16) uint8_t fz_smem[232 * 1024];            // the CTA's dynamic shared memory (the kernel declares it extern)
+enum : int { kDtypeBF16 = 0, kDtypeFP16 = 1 };
+template <typename T> struct Half16;
+template <> struct Half16<__half> {
+    static constexpr int kCode = kDtypeFP16;
+    static float2 unpack(uint32_t v) { _Float16 h[2]; memcpy(h, &v, 4); return {(float)h[0], (float)h[1]}; }
+    static uint32_t pack(float a, float b) { _Float16 h[2] = {(_Float16)a, (_Float16)b}; uint32_t v; memcpy(&v, h, 4); return v; }
+};
+static inline uint64_t f2_pack(float a, float b) { float2 v{a, b}; uint64_t u; memcpy(&u, &v, 8); return u; }
+static inline float2 f2_unpack(uint64_t u) { float2 v; memcpy(&v, &u, 8); return v; }
+static inline uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { float2 x = f2_unpack(a), y = f2_unpack(b), z = f2_unpack(c); return f2_pack(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y)); }
+static inline uint64_t mul2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y = f2_unpack(b); return f2_pack(x.x * y.x, x.y * y.y); }
+static inline uint64_t add2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y = f2_unpack(b); return f2_pack(x.x + y.x, x.y + y.y); }
+static inline float tanh_approx(float x) { return tanhf(x); }
+static inline float silu_tanh(float x) { const float h = 0.5f * x; return fmaf(h, tanhf(h), h); }
+template <typename P> static inline P __ldg(const P* p) { return *p; }
+static inline uint4 ldg16(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - fz_smem); }
+static inline void sts16(uint32_t a, const uint4& v) { memcpy(fz_smem + a, &v, 16); }
+static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, fz_smem + a, 4); return v; }
+static inline void sts32(uint32_t a, uint32_t v) { memcpy(fz_smem + a, &v, 4); }
+
+// cp.async: per-thread list of committed groups
+struct CpOp { uint32_t dst; const void* src; };
+static thread_local std::vector<std::vector<CpOp>> t_groups;
+static thread_local std::vector<CpOp> t_open;
+static inline void cp_async16(uint32_t saddr, const void* g, bool valid) {
+    if (!valid) return;
+    if (g_eager) memcpy(fz_smem + saddr, g, 16); else t_open.push_back({saddr, g});
+}
+static inline void cp_async_commit() { t_groups.push_back(std::move(t_open)); t_open.clear(); }
+template <int N> static inline void cp_async_wait() {
+    while ((int)t_groups.size() > N) {
+        for (const CpOp& o : t_groups.front()) memcpy(fz_smem + o.dst, o.src, 16);
+        t_groups.erase(t_groups.begin());
+    }
+}
+
+// mma.sync m16n8k16 (row.col, fp16 x fp16 -> fp32): fragments exchanged through a per-warp buffer
+struct WarpX { uint32_t a[32][4], b[32][2]; float c[32][4]; std::barrier<> bar{32}; };
+static std::vector<std::unique_ptr<WarpX>> g_warps;
+template <typename T> static inline void mma16816_f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    WarpX& w = *g_warps[threadIdx.x >> 5];
+    for (int i = 0; i < 4; ++i) { w.a[lane][i] = a[i]; w.c[lane][i] = c[i]; }
+    w.b[lane][0] = b0; w.b[lane][1] = b1;
+    w.bar.arrive_and_wait();
+    // D[row][col] = C + sum_k A[row][k] B[k][col]; A[g|g+8][2t'..] in lane g*4+t' regs (0|1: k 0-7, 2|3: k 8-15); B[k][n] in lane n*4+t'
+    for (int half = 0; half < 2; ++half)
+        for (int j = 0; j < 2; ++j) {
+            const int col = 2 * t + j;
+            float acc = w.c[lane][half * 2 + j];
+            for (int tp = 0; tp < 4; ++tp) {
+                const float2 alo = Half16<T>::unpack(w.a[g * 4 + tp][half]), ahi = Half16<T>::unpack(w.a[g * 4 + tp][2 + half]);
+                const float2 blo = Half16<T>::unpack(w.b[col * 4 + tp][0]), bhi = Half16<T>::unpack(w.b[col * 4 + tp][1]);
+                acc += alo.x * blo.x + alo.y * blo.y + ahi.x * bhi.x + ahi.y * bhi.y;
+            }
+            c[half * 2 + j] = acc;
+        }
+    w.bar.arrive_and_wait();
+}
+
+namespace { constexpr int kFTW = 7; constexpr int kXR = 6; }
+#include "mbconv_fused_kernel.inc"
+}  // namespace dfd
+
+template <int KS, int S, int CIN, int C, int W, int CB>
+static int run_case(int frames) {
+    constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, OH = OW, strips = OW / 7;
+    constexpr int THREADS = (strips * (CB / 2) + 31) / 32 * 32;
+    constexpr int rps = OH > 56 ? 56 : OH, segs = (OH + rps - 1) / rps;
+    std::vector<_Float16> x((size_t)frames * W * W * CIN), we((size_t)C * CIN), out((size_t)frames * OH * OW * C);
+    std::vector<float> be(C), w((size_t)KS * KS * C), bias(C), parts((size_t)frames * segs * strips * C, NAN);
+    uint32_t seed = 12345u + KS * 7 + CIN;
+    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xffff) / 32768.0f - 1.0f; };
+    for (auto& v : x) v = (_Float16)rnd();
+    for (auto& v : we) v = (_Float16)(rnd() / sqrtf((float)CIN) * 1.5f);
+    for (auto& v : be) v = 0.3f * rnd();
+    for (auto& v : w) v = rnd() / KS;
+    for (auto& v : bias) v = 0.2f * rnd();
+    // reference
+    std::vector<float> e((size_t)frames * W * W * C), ref((size_t)frames * OH * OW * C);
+    for (size_t p = 0; p < (size_t)frames * W * W; ++p)
+        for (int c = 0; c < C; ++c) {
+            float a = 0.f;
+            for (int k = 0; k < CIN; ++k) a += (float)x[p * CIN + k] * (float)we[(size_t)c * CIN + k];
+            e[p * C + c] = (float)(_Float16)dfd::silu_tanh(a + be[c]);
+        }
+    for (int f = 0; f < frames; ++f)
+        for (int oy = 0; oy < OH; ++oy)
+            for (int ox = 0; ox < OW; ++ox)
+                for (int c = 0; c < C; ++c) {
+                    float a = bias[c];
+                    for (int ky = 0; ky < KS; ++ky)
+                        for (int kx = 0; kx < KS; ++kx) {
+                            const int iy = oy * S + ky - PAD, ix = ox * S + kx - PAD;
+                            if (iy >= 0 && iy < W && ix >= 0 && ix < W) a += e[(((size_t)f * W + iy) * W + ix) * C + c] * w[(size_t)(ky * KS + kx) * C + c];
+                        }
+                    ref[(((size_t)f * OH + oy) * OW + ox) * C + c] = dfd::silu_tanh(a);
+                }
+    // kernel, one CTA at a time
+    const int grid = frames * segs * (C / CB);
+    for (int b = 0; b < grid; ++b) {
+        memset(dfd::fz_smem, 0xff, sizeof(dfd::fz_smem));                  // NaN patterns: nothing may rely on zero-initialised shared memory
+        std::barrier<> bar(THREADS);
+        g_cta_bar = &bar;
+        dfd::g_warps.clear();
+        for (int i = 0; i < THREADS / 32; ++i) dfd::g_warps.emplace_back(new dfd::WarpX());
+        std::vector<std::thread> th;
+        for (int t = 0; t < THREADS; ++t)
+            th.emplace_back([&, t, b]() {
+                threadIdx.x = t; blockIdx.x = b;
+                dfd::t_groups.clear(); dfd::t_open.clear();
+                dfd::mbconv_fused_kernel<__half, KS, S, CIN, C, W, CB, 128>(x.data(), we.data(), be.data(), w.data(), bias.data(), out.data(), parts.data());
+            });
+        for (auto& t : th) t.join();
+    }
+    double max_err = 0, max_ref = 0, sum_err = 0;
+    for (size_t i = 0; i < ref.size(); ++i) { max_err = fmax(max_err, fabs((float)out[i] - ref[i])); max_ref = fmax(max_ref, fabs(ref[i])); }
+    for (int f = 0; f < frames; ++f)
+        for (int c = 0; c < C; ++c) {
+            double s = 0, r = 0;
+            for (int q = 0; q < segs * strips; ++q) s += parts[((size_t)f * segs * strips + q) * C + c];
+            for (int p = 0; p < OH * OW; ++p) r += ref[((size_t)f * OH * OW + p) * C + c];
+            sum_err = fmax(sum_err, fabs(s - r));
+        }
+    const bool ok = max_err <= 2e-3 * fmax(1.0, max_ref) && sum_err < 5e-2 && std::isfinite(sum_err);
+    printf("k%d s%d cin%d mid%d W%d CB%d %s: %d CTAs x %d threads, max |err| %.2e (scale %.2f), max |SE sum err| %.2e -> %s\n", KS, S, CIN, C, W, CB,
+           g_eager ? "eager" : "lazy ", grid, THREADS, max_err, max_ref, sum_err, ok ? "ok" : "MISMATCH");
+    return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+    int rc = 0;
+    const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    for (int mode = 0; mode < 2; ++mode) {
+        g_eager = mode == 1;
+        rc |= run_case<3, 1, 80, 480, 14, 96>(1);
+        rc |= run_case<5, 2, 112, 672, 14, 96>(1);
+        rc |= run_case<3, 1, 192, 1152, 7, 128>(1);
+        rc |= run_case<3, 2, 40, 240, 28, 48>(1);
+        if (quick) continue;
+        rc |= run_case<3, 1, 24, 144, 56, 48>(1);
+        rc |= run_case<5, 2, 24, 144, 56, 48>(1);
+        rc |= run_case<3, 2, 16, 96, 112, 48>(1);
+        rc |= run_case<3, 1, 24, 144, 56, 72>(1);
+        rc |= run_case<5, 2, 24, 144, 56, 144>(1);
+        rc |= run_case<3, 2, 16, 96, 112, 96>(1);
+    }
+    return rc;
+}
