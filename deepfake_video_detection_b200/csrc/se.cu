@@ -111,6 +111,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
 // fp32x2 FMAs (sm_100 needs the .f32x2 form for the full fp32 rate), 16-byte weight loads, two FC1 rows per warp pass (each
 // staged mean is read once for two rows) and two channels per thread in FC2 (one pass instead of two half-empty ones):
 // about 2.3x fewer instructions.
+// DFD_SE2_KERNEL_BEGIN   (tools/host_emul/ compiles the kernel up to the END marker unchanged for the CPU)
 template <int kSeFrames>
 __global__ void __launch_bounds__(kSeMaxThreads)
 se_kernel_v2(const float* __restrict__ partials, int nparts, float inv_hw,
@@ -212,6 +213,8 @@ se_kernel_v2(const float* __restrict__ partials, int nparts, float inv_hw,
         }
     }
 }
+
+// DFD_SE2_KERNEL_END
 
 template <int FPB>
 static cudaError_t launch_se_t(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,

@@ -259,6 +259,7 @@ constexpr size_t kAttSmem = (size_t)(2 * kTokPad * kQKStride + kHd * kVtStride) 
 //   * keys are processed in blocks of 64 with the online-softmax recurrence (fp32 running max / sum, accumulator rescaled
 //     when the max moves), so a thread holds 32 score registers instead of 104: 256 threads per CTA and 2 CTAs per SM
 //     (16 warps per SM instead of 8).  Scores are pre-multiplied by log2(e)/8 and exponentiated with ex2.approx.
+// (tools/host_emul/ compiles the kernel between the DFD_ATT2_KERNEL markers unchanged for the CPU, with its own ldmatrix / mma.)
 template <typename T>
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -268,6 +269,7 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
+// DFD_ATT2_KERNEL_BEGIN
 constexpr int kAtt2Warps = 8;
 constexpr int kAtt2KeyBlock = 64;
 
@@ -391,6 +393,7 @@ __global__ void __launch_bounds__(kAtt2Warps * 32, 2) vit_attention_v2_kernel(co
         }
     }
 }
+// DFD_ATT2_KERNEL_END
 constexpr size_t kAtt2Smem = (size_t)(3 * kTokPad * kQKStride) * 2;
 
 // ---- DeepfakeModel head (src/models.py:199-291): SimpleGCN over the frame graph + mean pool + classifier ------------

@@ -1,17 +1,24 @@
-"""Build and run the CPU emulation of mbconv_fused_kernel: extracts the kernel text between the DFD_FUSED_KERNEL markers of
-csrc/mbconv_fused.cu (unchanged) and compiles it with tools/host_emul/emul_mbconv_fused.cpp.
-    python tools/host_emul/run.py [quick] [tsan]"""
+"""Build and run the CPU emulations of the experimental kernels: the kernel text between the emulation markers of the .cu file
+is extracted UNCHANGED and compiled with the matching harness in this directory.
+    python tools/host_emul/run.py [fused|attention|all] [quick] [tsan]"""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-src = open(os.path.join(ROOT, "deepfake_video_detection_b200", "csrc", "mbconv_fused.cu")).read()
-kernel = src[src.index("// DFD_FUSED_KERNEL_BEGIN"):src.index("// DFD_FUSED_KERNEL_END")]
-out = os.path.join(ROOT, "build", "host_emul")
-os.makedirs(out, exist_ok=True)
-open(os.path.join(out, "mbconv_fused_kernel.inc"), "w").write(kernel)
+OUT = os.path.join(ROOT, "build", "host_emul")
+os.makedirs(OUT, exist_ok=True)
+CASES = {"fused": ("mbconv_fused.cu", "DFD_FUSED_KERNEL", "mbconv_fused_kernel.inc", "emul_mbconv_fused.cpp"),
+         "attention": ("vit.cu", "DFD_ATT2_KERNEL", "vit_attention_v2_kernel.inc", "emul_vit_attention_v2.cpp"),
+         "se": ("se.cu", "DFD_SE2_KERNEL", "se_kernel_v2.inc", "emul_se_v2.cpp")}
+which = [a for a in sys.argv[1:] if a in CASES] or (list(CASES) if "all" in sys.argv else ["fused"])
 tsan = "tsan" in sys.argv
-exe = os.path.join(out, "emul_mbconv_fused" + ("_tsan" if tsan else ""))
-cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I", out, os.path.join(ROOT, "tools", "host_emul", "emul_mbconv_fused.cpp"), "-o", exe]
-if tsan:
-    cmd += ["-fsanitize=thread"]
-subprocess.check_call(cmd)
-sys.exit(subprocess.call([exe] + (["quick"] if "quick" in sys.argv else [])))
+rc = 0
+for name in which:
+    cu, marker, inc, cpp = CASES[name]
+    if not os.path.exists(os.path.join(ROOT, "tools", "host_emul", cpp)):
+        continue
+    src = open(os.path.join(ROOT, "deepfake_video_detection_b200", "csrc", cu)).read()
+    open(os.path.join(OUT, inc), "w").write(src[src.index(f"// {marker}_BEGIN"):src.index(f"// {marker}_END")])
+    exe = os.path.join(OUT, cpp[:-4] + ("_tsan" if tsan else ""))
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I", OUT, os.path.join(ROOT, "tools", "host_emul", cpp), "-o", exe]
+    subprocess.check_call(cmd + (["-fsanitize=thread"] if tsan else []))
+    rc |= subprocess.call([exe] + (["quick"] if "quick" in sys.argv else []))
+sys.exit(rc)
