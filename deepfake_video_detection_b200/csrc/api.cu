@@ -469,15 +469,21 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
     const int dt = w->dtype;
 
     int h = H / 2, wd = W / 2, cur = 0;
-    prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
-    if (in_kind == DFD_IN_U8_HWC && !use_simt_stem())
-        DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, w->stem_wrow, w->stem_b4, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
-    else
-        DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
     // DFD_FUSE_EXPAND=1 (experimental, off by default until it has been verified on a GPU): the early HBM-bound blocks run
     // expand 1x1 + depthwise as ONE kernel (mbconv_fused.cu); the expanded tensor never goes to HBM.
     const char* env_fuse = getenv("DFD_FUSE_EXPAND");
-    const int fuse = (env_fuse && !use_simt_gemm()) ? atoi(env_fuse) : 0;       // 1: the three early blocks; 2: every block mbconv_fused.cu supports
+    // 1: the three early blocks; 2: every block mbconv_fused.cu supports; 3: also the stem fused with block 0's depthwise conv
+    const int fuse = (env_fuse && !use_simt_gemm()) ? atoi(env_fuse) : 0;
+    const bool stem_fused = fuse >= 3 && in_kind == DFD_IN_U8_HWC && !use_simt_stem() && H == 224 && W == 224 && w->stem_wrow && w->stem_b4 &&
+                            !w->blocks[0].has_expand && w->blocks[0].k == 3 && w->blocks[0].stride == 1 && w->blocks[0].mid == 32 &&
+                            dfd::dw_num_partials(112, 112, 32, 3, 1) == dfd::dw_march_slots(112, 112);
+    if (!stem_fused) {
+        prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
+        if (in_kind == DFD_IN_U8_HWC && !use_simt_stem())
+            DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, w->stem_wrow, w->stem_b4, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
+        else
+            DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
+    }
     for (int i = 0; i < kNumBlocks; ++i) {
         const BlockW& B = w->blocks[i];
         const void* x = io[cur];
@@ -495,7 +501,12 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         }
         const int pad = B.k / 2;
         const int oh = (h + 2 * pad - B.k) / B.stride + 1, ow = (wd + 2 * pad - B.k) / B.stride + 1;
-        if (fused) {
+        if (i == 0 && stem_fused) {
+            prof_next(KC_MBCONV_FUSED, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)oh * ow * B.mid * 2),
+                      2.0 * frames * ((double)h * wd * 27 * 32 + (double)oh * ow * B.mid * B.k * B.k), s);
+            DFD_LAUNCH(dfd::launch_stem_dw_fused(reinterpret_cast<const uint8_t*>(in), w->stem_wrow, w->stem_b4, B.dw_w, B.dw_b, bufD, part, frames, H, W, dt, s),
+                       "fused stem + depthwise kernel");
+        } else if (fused) {
             prof_next(KC_MBCONV_FUSED, (double)frames * ((double)h * wd * B.cin + (double)oh * ow * B.mid) * 2,
                       2.0 * frames * ((double)h * wd * B.cin * B.mid + (double)oh * ow * B.mid * B.k * B.k), s);
             DFD_LAUNCH(dfd::launch_mbconv_fused(x, B.exp_w, B.exp_b, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.cin, B.mid, B.k, B.stride, dt, s),
@@ -735,6 +746,29 @@ int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, con
     if (!dfd::mbconv_fused_supported(H, W, cin, mid, k, stride)) return fail(DFD_EINVAL, "dfd_k_mbconv_fused: unsupported block shape");
     DFD_LAUNCH(dfd::launch_mbconv_fused(d_x, d_we, d_be, d_w, d_bias, d_out, d_partials, frames, H, W, cin, mid, k, stride, dtype, (cudaStream_t)stream),
                "fused expand + depthwise kernel");
+    return DFD_OK;
+}
+// EXPERIMENTAL: stem (h_w27x32 / h_bias32 as dfd_k_pack_stem_row takes them, packed and uploaded inside; synchronous) fused with
+// the depthwise 3x3 of block 0
+int dfd_k_stem_dw_fused(const uint8_t* d_in, const float* h_w27x32, const float* h_bias32, const float* d_w, const float* d_bias,
+                        void* d_out, float* d_partials, int64_t frames, int H, int W, int dtype, void* stream) {
+    g_launches = 0;
+    if (!d_in || !h_w27x32 || !h_bias32 || !d_w || !d_bias || !d_out || !d_partials) return fail(DFD_EINVAL, "dfd_k_stem_dw_fused: null pointer");
+    if (H != 224 || W != 224) return fail(DFD_EINVAL, "dfd_k_stem_dw_fused: 224x224 crops only");
+    HostArena a; size_t w_off = 0, b_off = 0;
+    pack_stem_row(a, h_w27x32, h_bias32, w_off, b_off);
+    void* dw = nullptr;
+    DFD_CUDA(cudaMalloc(&dw, a.bytes.size()), "cudaMalloc(stem operands)");
+    cudaError_t e = cudaMemcpy(dw, a.bytes.data(), a.bytes.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        e = dfd::launch_stem_dw_fused(d_in, reinterpret_cast<uint8_t*>(dw) + w_off, reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(dw) + b_off),
+                                      d_w, d_bias, d_out, d_partials, frames, H, W, dtype, (cudaStream_t)stream);
+        g_launches = 1;
+    }
+    const cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(dw);
+    if (e != cudaSuccess) return cuda_fail(e, "fused stem + depthwise kernel");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "fused stem + depthwise kernel sync");
     return DFD_OK;
 }
 int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) { return dfd::mbconv_fused_supported(H, W, cin, mid, k, stride) ? 1 : 0; }

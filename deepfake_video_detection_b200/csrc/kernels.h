@@ -43,6 +43,11 @@ cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, 
                                 float* partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype,
                                 cudaStream_t s);
 
+// stem + block 0's depthwise conv as one kernel (mbconv_fused.cu STEM producer, behind DFD_FUSE_EXPAND=3): uint8 224x224 crops ->
+// [frames][112][112][32] + SE partials; wrow / bias4 are the row-variant stem operands of launch_stem_tc
+cudaError_t launch_stem_dw_fused(const uint8_t* in, const void* wrow, const float* bias4, const float* w, const float* bias, void* out,
+                                 float* partials, int64_t frames, int H, int W, int dtype, cudaStream_t s);
+
 // K2 tail (se.cu): mean -> FC(C->rd)+bias -> SiLU -> FC(rd->C)+bias -> sigmoid.  gate fp32 [frames][C].
 // w1 fp32 [rd][C], w2t fp32 [rd][C] (conv_expand transposed), b1 [rd], b2 [C].
 cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,

@@ -47,21 +47,36 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
+}
+// two bytes -> the fp16 pair (b0, b1), exactly: 0x6400 | b is the half 1024 + b (stem_tc.cu uses the same magic)
+__device__ __forceinline__ uint32_t u8pair_to_half2(uint32_t b0, uint32_t b1) {
+    uint32_t p = b0 | (b1 << 16) | 0x64006400u;
+    const __half2 v = __hsub2(*reinterpret_cast<__half2*>(&p), __floats2half2_rn(1024.f, 1024.f));
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
 #endif
 }  // namespace
 
 // DFD_FUSED_KERNEL_BEGIN
 // Geometry is compile-time: CIN block input channels, C expanded channels, W x W map, CB channels per CTA.
-template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
+// STEM: the producer is not an expand conv but the network's stem (conv3x3 s2 p1 3 -> 32 + BN + SiLU on uint8 crops, tensor prep
+// folded into the weights exactly as stem_tc.cu's row variant does): x = uint8 crops (frames, 2W, 2W, 3), we = fp16 [hi|lo][32][32]
+// (k = ky*10 + kx*3 + c), be = fp32 [top*2+left][32]; the consumer is block 0's depthwise 3x3.  CIN is unused then.
+template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG, bool STEM = false>
 __global__ void __launch_bounds__((((W + 2 * (KS / 2) - KS) / S + 1) / kFTW * (CB / 2) + 31) / 32 * 32, 1) __maxnreg__(MAXREG)
-mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const float* __restrict__ be,
+mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, const float* __restrict__ be,
                     const float* __restrict__ w, const float* __restrict__ bias,
                     T* __restrict__ out, float* __restrict__ partials) {
+    const T* x = reinterpret_cast<const T*>(xv);
+    const T* we = reinterpret_cast<const T*>(wev);
     constexpr int TW = kFTW, PAD = KS / 2, H = W;
     constexpr int OW = (W + 2 * PAD - KS) / S + 1, OH = OW;
     constexpr int strips = OW / TW;
     static_assert(OW % TW == 0, "whole strips only");
-    static_assert(CB % 8 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
+    static_assert(CB % 8 == 0 && C % CB == 0 && (STEM || CIN % 8 == 0), "channel blocks");
+    static_assert(!STEM || (C == 32 && CB == 32 && KS == 3 && S == 1 && W % 16 == 0), "stem producer: block 0 of the network");
     // DWT threads own the depthwise work (2 channels x 7 columns each); the CTA is rounded up to whole warps, and the few
     // extra threads (they take part in staging, in the expand MMAs and in the barriers) shadow the first depthwise threads
     // with their stores suppressed
@@ -70,23 +85,26 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     constexpr int NCOL = (TW - 1) * S + KS;
     constexpr int RING = (KS + S - 1) / S, PERIOD = S * RING;
     constexpr int pixw = ((strips * TW - 1) * S + KS) > W + 2 * PAD ? ((strips * TW - 1) * S + KS) : W + 2 * PAD;
-    constexpr int KP = (CIN + 15) & ~15, KSTEPS = KP / 16;       // K padded to whole mma k-steps
+    constexpr int KP = STEM ? 32 : (CIN + 15) & ~15, KSTEPS = KP / 16;       // K padded to whole mma k-steps
     constexpr int XP = KP + 8;                                    // halves per staged x pixel / weight row (conflict-free)
+    constexpr uint32_t RB = 2 * W * 3;                            // STEM: bytes per raw crop row
     constexpr int PXT = (W + 15) / 16;                            // 16-pixel tiles per row
     constexpr int NTL = CB / 8;                                   // 8-channel tiles of the channel block
     constexpr uint32_t rsb = (uint32_t)pixw * CB * 2;             // bytes per expanded row slot
-    constexpr uint32_t xsb = (uint32_t)PXT * 16 * XP * 2;         // bytes per x row slot
-    constexpr uint32_t wsb = (uint32_t)CB * XP * 2;               // bytes of the weight slice
+    // x row slot: [PXT*16 pixels][XP]; STEM: [16 zero bytes][raw rows 2iy-1, 2iy, 2iy+1][pad to 16]
+    constexpr uint32_t xsb = STEM ? ((16u + 3u * RB + 15u) & ~15u) : (uint32_t)PXT * 16 * XP * 2;
+    constexpr uint32_t wsb = (STEM ? 2u : 1u) * CB * XP * 2;      // bytes of the weight slice (STEM: hi and lo)
     constexpr int rps = OH > 56 ? 56 : OH;                        // = march_rps(OH)
     constexpr int segs = (OH + rps - 1) / rps;
-    constexpr int XCH = W * (CIN / 8);                            // 16-byte chunks of an x row
+    constexpr int XCH = STEM ? (int)(3 * RB / 16) : W * (CIN / 8);   // 16-byte chunks of an x row
+    static_assert(!STEM || (3 * RB) % 16 == 0, "raw rows are whole 16-byte chunks");
     constexpr int XK = (XCH + THREADS - 1) / THREADS;
 
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const uint32_t sm_e = smem_u32(fz_smem);                      // [2][pixw][CB]      expanded ring
     const uint32_t sm_x = sm_e + 2 * rsb;                         // [kXR][PXT*16][XP]  x ring
     const uint32_t sm_w = sm_x + kXR * xsb;                       // [CB][XP]           expand weights of this channel block
-    float* s_be = reinterpret_cast<float*>(fz_smem + 2 * rsb + kXR * xsb + wsb);   // [CB] expand bias
+    float* s_be = reinterpret_cast<float*>(fz_smem + 2 * rsb + kXR * xsb + wsb);   // [CB] expand bias (STEM: [4][32])
 
     constexpr int ncb = C / CB;
     const int cb = blockIdx.x % ncb;
@@ -109,11 +127,19 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
     for (uint32_t i = threadIdx.x * 16; i < 2 * rsb + kXR * xsb + wsb; i += THREADS * 16) sts16(sm_e + i, make_uint4(0, 0, 0, 0));
     __syncthreads();
     // expand weights [CB][CIN] (BN folded, 16-bit, K-major) and bias of this channel block
-    for (int i = threadIdx.x; i < CB * (CIN / 8); i += THREADS) {
-        const int r = i / (CIN / 8), q = i - r * (CIN / 8);
-        sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8));
+    if constexpr (STEM) {
+        for (int i = threadIdx.x; i < 2 * 32 * 4; i += THREADS) {                      // [hi|lo][32 oc][32 k] -> pitch XP
+            const int r = i >> 2, q = i & 3;
+            sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(reinterpret_cast<const uint16_t*>(wev) + (size_t)r * 32 + q * 8));
+        }
+        for (int i = threadIdx.x; i < 4 * 32; i += THREADS) s_be[i] = be[i];
+    } else {
+        for (int i = threadIdx.x; i < CB * (CIN / 8); i += THREADS) {
+            const int r = i / (CIN / 8), q = i - r * (CIN / 8);
+            sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8));
+        }
+        for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = be[cb * CB + i];
     }
-    for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = be[cb * CB + i];
 
     uint64_t wr[KS * KS];
     const uint64_t half2 = f2_pack(0.5f, 0.5f);
@@ -126,19 +152,27 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
 #pragma unroll
     for (int k = 0; k < XK; ++k) {
         const int i = threadIdx.x + k * THREADS;
-        const int px = i / (CIN / 8), sub = i - px * (CIN / 8);
-        g_off[k] = (uint32_t)(px * CIN + sub * 8) * 2;
-        s_off[k] = i < XCH ? (uint32_t)(px * XP + sub * 8) * 2 : 0xffffffffu;
+        if constexpr (STEM) {
+            g_off[k] = (uint32_t)i * 16;
+            s_off[k] = i < XCH ? 16u + (uint32_t)i * 16 : 0xffffffffu;
+        } else {
+            const int px = i / (CIN / 8), sub = i - px * (CIN / 8);
+            g_off[k] = (uint32_t)(px * CIN + sub * 8) * 2;
+            s_off[k] = i < XCH ? (uint32_t)(px * XP + sub * 8) * 2 : 0xffffffffu;
+        }
     }
-    constexpr size_t xpitch_b = (size_t)W * CIN * 2;
+    // bytes between the sources of consecutive x rows; STEM: x row iy = raw rows 2iy-1 .. 2iy+1 (3*RB contiguous bytes)
+    constexpr size_t xpitch_b = STEM ? (size_t)2 * RB : (size_t)W * CIN * 2;
     int iy_i = iy_start, left_i = rend;
     uint32_t xs_i = sm_x;
-    const char* gp_i = reinterpret_cast<const char*>(x + (size_t)frame * H * W * CIN) + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b;
+    const char* gp_i = STEM ? reinterpret_cast<const char*>(xv) + (size_t)frame * (2 * H) * RB + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b - (ptrdiff_t)RB
+                            : reinterpret_cast<const char*>(x + (size_t)frame * H * W * CIN) + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b;
     auto issue_row = [&]() {
         if (left_i > 0 && (unsigned)iy_i < (unsigned)H) {
 #pragma unroll
             for (int k = 0; k < XK; ++k)
-                if (s_off[k] != 0xffffffffu) cp_async16(xs_i + s_off[k], gp_i + g_off[k], true);
+                if (s_off[k] != 0xffffffffu && !(STEM && iy_i == 0 && g_off[k] < RB))      // STEM: raw row -1 is padding
+                    cp_async16(xs_i + s_off[k], gp_i + g_off[k], true);
         }
         cp_async_commit();
         ++iy_i; --left_i; gp_i += xpitch_b;
@@ -150,6 +184,55 @@ mbconv_fused_kernel(const T* __restrict__ x, const T* __restrict__ we, const flo
         if (k >= rend || (unsigned)iy >= (unsigned)H) return;            // CTA-uniform
         const uint32_t xs = sm_x + (uint32_t)(k % kXR) * xsb;
         const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
+        if constexpr (STEM) {
+            // stem output row iy: one warp pass = 16 pixels x all 32 channels.  A = the raw bytes as exact fp16 values, pair
+            // i = (k = 2i, 2i+1) with k = r*10 + kx*3 + c taken from byte 2*(i%5) of the 9-byte window of raw row r = i/5;
+            // lane (g, t) needs pairs t, t+4 (k-step 0) and t+8, t+12 (k-step 1) of pixels g and g+8.
+            const bool top = iy == 0;
+            for (int pt = warp; pt < PXT; pt += WARPS) {
+                uint32_t a[2][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = t + 4 * j, r = i / 5, ii = i - 5 * r;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int px = pt * 16 + g + 8 * hf;
+                        uint32_t v = 0u;
+                        if (i < 15 && !(r == 0 && top)) {
+                            const uint32_t s0 = xs + 16u + (uint32_t)r * RB + 6u * (uint32_t)px - 3u + 2u * (uint32_t)ii;
+                            uint32_t b0 = lds_u8(s0), b1 = ii < 4 ? lds_u8(s0 + 1) : 0u;
+                            if (px == 0) {                                    // left padding column: the kx = 0 taps (window bytes 0..2)
+                                if (ii == 0) { b0 = 0u; b1 = 0u; } else if (ii == 1) b0 = 0u;
+                            }
+                            v = u8pair_to_half2(b0, b1);
+                        }
+                        a[j >> 1][(j & 1) * 2 + hf] = v;
+                    }
+                }
+                float c[4][4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl) {                          // W_hi then W_lo into the same accumulator
+                        const uint32_t br = sm_w + (uint32_t)(((hl * 32 + nt * 8 + g) * XP) + 2 * t) * 2;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) mma16816_f<__half>(c[nt], a[ks], lds32(br + ks * 32), lds32(br + ks * 32 + 16));
+                    }
+                }
+                const int px0 = pt * 16 + g;
+                const float* bs0 = s_be + ((top ? 2 : 0) + (px0 == 0 ? 1 : 0)) * 32;      // pixel px0 (may be the left column)
+                const float* bs1 = s_be + (top ? 2 : 0) * 32;                             // pixel px0 + 8 (never the left column)
+                const uint32_t ea = es + (uint32_t)((px0 + PAD) * CB + 2 * t) * 2;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int ch = nt * 8 + 2 * t;
+                    sts32(ea + nt * 16, Half16<T>::pack(silu_tanh(fmaf(c[nt][0], 0.00390625f, bs0[ch])), silu_tanh(fmaf(c[nt][1], 0.00390625f, bs0[ch + 1]))));
+                    sts32(ea + nt * 16 + 8 * CB * 2, Half16<T>::pack(silu_tanh(fmaf(c[nt][2], 0.00390625f, bs1[ch])), silu_tanh(fmaf(c[nt][3], 0.00390625f, bs1[ch + 1]))));
+                }
+            }
+            return;
+        }
         for (int tile = warp; tile < PXT * NTL; tile += WARPS) {
             const int pt = tile / NTL, nt = tile - pt * NTL;
             float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -270,20 +353,21 @@ int mbconv_fused_level(int H, int W, int cin, int mid, int k, int stride) {
 }
 bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) { return mbconv_fused_level(H, W, cin, mid, k, stride) > 0; }
 
-template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
+template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG, bool STEM = false>
 static cudaError_t fused_go(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                             float* partials, int64_t frames, cudaStream_t s) {
     constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, strips = OW / kFTW;
     constexpr int THREADS = (strips * (CB / 2) + 31) / 32 * 32;
     constexpr int pixw = ((strips * kFTW - 1) * S + KS) > W + 2 * PAD ? ((strips * kFTW - 1) * S + KS) : W + 2 * PAD;
-    constexpr int KP = (CIN + 15) & ~15, XP = KP + 8, PXT = (W + 15) / 16;
-    constexpr size_t smem = (size_t)2 * pixw * CB * 2 + (size_t)kXR * PXT * 16 * XP * 2 + (size_t)CB * XP * 2 + (size_t)CB * 4;
+    constexpr int KP = STEM ? 32 : (CIN + 15) & ~15, XP = KP + 8, PXT = (W + 15) / 16;
+    constexpr size_t xsb = STEM ? ((16 + 3 * (2 * W * 3) + 15) & ~15) : (size_t)PXT * 16 * XP * 2;       // as in the kernel
+    constexpr size_t smem = (size_t)2 * pixw * CB * 2 + (size_t)kXR * xsb + (size_t)(STEM ? 2 : 1) * CB * XP * 2 + (size_t)(STEM ? 4 * 32 : CB) * 4;
     constexpr int rps = OW > 56 ? 56 : OW, segs = (OW + rps - 1) / rps;
-    auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG>;
+    auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG, STEM>;
     if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     const int64_t grid = frames * segs * (C / CB);
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-    kern<<<(unsigned)grid, THREADS, smem, s>>>((const T*)x, (const T*)we, be, w, bias, (T*)out, partials);
+    kern<<<(unsigned)grid, THREADS, smem, s>>>(x, we, be, w, bias, (T*)out, partials);
     return cudaGetLastError();
 }
 
@@ -321,6 +405,19 @@ cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, 
     if (!mbconv_fused_supported(H, W, cin, mid, k, stride)) return cudaErrorInvalidValue;
     if (dtype == kDtypeFP16) return launch_fused_t<__half>(x, we, be, w, bias, out, partials, frames, W, cin, k, stride, s);
     return launch_fused_t<__nv_bfloat16>(x, we, be, w, bias, out, partials, frames, W, cin, k, stride, s);
+}
+
+
+// Stem (conv3x3 s2 + BN + SiLU on uint8 224x224 crops, tensor prep folded into wrow / bias4 as in stem_tc.cu's row variant)
+// fused with block 0's depthwise 3x3 + BN + SiLU + SE sums: the stem output (0.8 MB per frame) never goes to HBM.
+// in uint8 (frames,224,224,3); wrow fp16 [hi|lo][32][32]; bias4 fp32 [4][32]; w fp32 [9][32], bias [32];
+// out [frames][112][112][32], partials [frames][dw_march_slots(112,112)][32].  DFD_FUSE_EXPAND=3.
+cudaError_t launch_stem_dw_fused(const uint8_t* in, const void* wrow, const float* bias4, const float* w, const float* bias, void* out,
+                                 float* partials, int64_t frames, int H, int W, int dtype, cudaStream_t s) {
+    if (frames <= 0) return cudaSuccess;
+    if (H != 224 || W != 224 || !wrow || !bias4) return cudaErrorInvalidValue;
+    if (dtype == kDtypeFP16) return fused_go<__half, 3, 1, 8, 32, 112, 32, 128, true>(in, wrow, bias4, w, bias, out, partials, frames, s);
+    return fused_go<__nv_bfloat16, 3, 1, 8, 32, 112, 32, 128, true>(in, wrow, bias4, w, bias, out, partials, frames, s);
 }
 
 }  // namespace dfd

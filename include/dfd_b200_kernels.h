@@ -63,6 +63,13 @@ int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stri
 int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, const float* d_w, const float* d_bias, void* d_out,
                        float* d_partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype, void* stream);
 
+/* EXPERIMENTAL (engine switch DFD_FUSE_EXPAND=3): timm conv_stem + bn1 + SiLU on uint8 224x224 crops (tensor prep of app.py:1772-1780,
+ * 2084-2085 folded into the weights as in dfd_k_stem_tc's row variant) fused with block 0's conv_dw + bn1 + SiLU + squeeze-excite sums.
+ * h_w27x32 / h_bias32: HOST fp32 stem weights [(ky*3+kx)*3+c][32] and bias (packed + uploaded inside; synchronous; test aid);
+ * d_w fp32 [9][32], d_bias [32]: depthwise; d_out [frames][112][112][32] 16-bit; d_partials as dfd_k_dwconv for (112,112,32,3,1). */
+int dfd_k_stem_dw_fused(const uint8_t* d_in, const float* h_w27x32, const float* h_bias32, const float* d_w, const float* d_bias,
+                        void* d_out, float* d_partials, int64_t frames, int H, int W, int dtype, void* stream);
+
 /* HOST-ONLY (no GPU needed): row maps of that zero-haloed layout, computed by the very functions the kernels use
  * (csrc/conv_map.h).  h_pad_row [frames*H*W]: physical row of every interior pixel; h_out_row [frames*(H+2)*(W+2)]: output
  * row of every padded pixel, -1 for halo pixels; h_tap_row / h_tap_col [9*cpk]: row offset and channel column of the A box

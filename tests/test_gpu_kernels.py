@@ -330,3 +330,36 @@ def test_se_gate_v2(lib, C_, rd, nparts, frames, monkeypatch):
     close(g2.cpu(), ref, 1e-5, abs_=2e-6)
     close(g2.cpu(), g1.cpu(), 1e-6, abs_=1e-6)
     assert torch.equal(g2, g3)
+
+
+@experimental
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_stem_dw_fused(lib, prec):
+    """Stem (uint8 crops, prep folded into the weights) fused with block 0's depthwise 3x3 (mbconv_fused.cu STEM producer): against
+    fp32 PyTorch with the stem output rounded to the storage type, and against the two verified kernels it replaces."""
+    from oracle import effnet_b0_oracle as O
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(11)
+    frames = 2
+    u8 = torch.randint(0, 256, (frames, 224, 224, 3), dtype=torch.uint8, generator=g)
+    u8[0, 0, :, :] = torch.arange(224 * 3, dtype=torch.int64).remainder(256).to(torch.uint8).view(224, 3)
+    ws = torch.randn(32, 3, 3, 3, generator=g) * 0.3; bs = torch.randn(32, generator=g) * 0.2
+    w = torch.randn(32, 1, 3, 3, generator=g) / 3; b = torch.randn(32, generator=g) * 0.2
+    wp27 = ws.permute(2, 3, 1, 0).reshape(27, 32).contiguous()
+    wp = w.reshape(32, 9).t().contiguous().cuda(); bd = b.cuda(); u8d = u8.cuda()
+    nparts = lib.dfd_k_dw_num_partials(112, 112, 32, 3, 1)
+    out = torch.full((frames, 112, 112, 32), float("nan"), dtype=tdt, device="cuda")
+    parts = torch.full((frames, nparts, 32), float("nan"), device="cuda")
+    chk(lib, lib.dfd_k_stem_dw_fused(u8d.data_ptr(), wp27.data_ptr(), bs.contiguous().data_ptr(), wp.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                                     parts.data_ptr(), frames, 224, 224, code, stream()))
+    e = F.silu(F.conv2d(O.prep_u8_hwc(u8), ws, bs, 2, 1)).to(tdt).float()
+    ref = F.silu(F.conv2d(e, w, b, 1, 1, 1, 32))
+    assert torch.isfinite(out).all()
+    close(out.cpu(), ref.permute(0, 2, 3, 1), 2 * rel)
+    close(parts.sum(1).cpu(), ref.sum((2, 3)), 1e-3, abs_=5e-2)
+    mid = torch.empty((frames, 112, 112, 32), dtype=tdt, device="cuda")
+    wp27d, bsd = wp27.cuda(), bs.cuda()
+    chk(lib, lib.dfd_k_stem(u8d.data_ptr(), 0, wp27d.data_ptr(), bsd.data_ptr(), mid.data_ptr(), frames, 224, 224, code, stream()))
+    out2 = torch.empty_like(out); parts2 = torch.empty_like(parts)
+    chk(lib, lib.dfd_k_dwconv(mid.data_ptr(), wp.data_ptr(), bd.data_ptr(), out2.data_ptr(), parts2.data_ptr(), frames, 112, 112, 32, 3, 1, code, stream()))
+    close(out.cpu(), out2.cpu(), 2 * rel)

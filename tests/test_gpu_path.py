@@ -213,7 +213,7 @@ def test_npz_batch_scorer_cli(tmp_path, synth_sd, golden, golden_crops):
 
 
 @pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
-@pytest.mark.parametrize("level,folded", [(1, 3), (2, 8)])
+@pytest.mark.parametrize("level,folded", [(1, 3), (2, 8), (3, 9)])
 def test_fused_expand_path_matches_default_path_and_goldens(synth_sd, golden, golden_crops, monkeypatch, level, folded):
     """DFD_FUSE_EXPAND=1 (expand 1x1 fused into the depthwise kernel on the three early blocks) against the verified default
     path and the reference goldens: same rounding points, so features agree to MMA accumulation-order noise."""
@@ -226,7 +226,7 @@ def test_fused_expand_path_matches_default_path_and_goldens(synth_sd, golden, go
     n_base = scorer.last_launch_count
     monkeypatch.setenv("DFD_FUSE_EXPAND", str(level))
     logits, scores = scorer.score(d, make_offsets(lens, "cuda"))
-    assert scorer.last_launch_count == n_base - folded                              # expand GEMMs folded away (level 1: 3, level 2: 8)
+    assert scorer.last_launch_count == n_base - folded                              # expand GEMMs folded away (level 1: 3, level 2: 8; level 3 also merges the stem into block 0's depthwise kernel)
     err = (logits.cpu() - torch.from_numpy(golden["logits"])).abs().max().item()
     print(f"fused expand: max |dlogit| vs goldens {err:.3e}, vs default path {(logits - base).abs().max().item():.3e}")
     assert err <= TOL_LOGITS_FP16 and (logits - base).abs().max().item() <= 1e-2

@@ -25,6 +25,10 @@ def test_fused_expand_depthwise_kernel_source_on_cpu():
     assert out.count("-> ok") == 8
 
 
+def test_stem_dw_fused_kernel_source_on_cpu():
+    assert _run("fused", "stem").count("-> ok") == 2      # uint8 crops -> stem -> depthwise 3x3, both cp.async models
+
+
 def test_attention_v2_kernel_source_on_cpu():
     assert "-> ok" in _run("attention")
 

@@ -7,12 +7,13 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 run() { name=$1; shift; echo "=== $name: $*"; timeout 600 "$@" > gpurun_out/exp_$name.log 2>&1; echo "=== $name exit $?"; tail -n 12 gpurun_out/exp_$name.log; }
 # 1. expand 1x1 fused into the marching depthwise kernel (mbconv_fused.cu, engine switch DFD_FUSE_EXPAND=1)
-run fused_kernel env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k mbconv_fused
+run fused_kernel env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "mbconv_fused or stem_dw_fused"
 run fused_path   env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x -s -k fused_expand
 run fused_all    env DFD_FUSE_EXPAND=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x
 run bench_base   python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run bench_fused  env DFD_FUSE_EXPAND=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run bench_fused2 env DFD_FUSE_EXPAND=2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run bench_fused3 env DFD_FUSE_EXPAND=3 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 run fused_wide_t env DFD_FUSE_EXPAND=1 DFD_FUSE_CB=1 DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_path.py -m gpu -q -x -k "mbconv_fused or fused_expand"
 run bench_fusedw env DFD_FUSE_EXPAND=1 DFD_FUSE_CB=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 # 2. implicit 3x3 convolution of the resnet50 member (gemm_tc.cu CONV variants, resnet.cu switch DFD_RESNET_IMPLICIT=1)
@@ -28,7 +29,7 @@ run vit_att2      env DFD_VIT_ATTN_V2=1 python tools/bench_vit.py --batch 512 --
 run se2_kernel env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k se_gate_v2
 run se2_path   env DFD_SE_V2=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x
 run bench_se2  env DFD_SE_V2=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
-run bench_all  env DFD_SE_V2=1 DFD_FUSE_EXPAND=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run bench_all  env DFD_SE_V2=1 DFD_FUSE_EXPAND=3 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 # 5. one ncu --set full capture of the new kernels (only after the runs above exited 0 without ncu)
 if grep -q "passed" gpurun_out/exp_fused_path.log 2>/dev/null; then
   CMD="python tools/prof_step.py --videos 16 --frames 32 --iters 2"

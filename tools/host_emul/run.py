@@ -20,5 +20,5 @@ for name in which:
     exe = os.path.join(OUT, cpp[:-4] + ("_tsan" if tsan else ""))
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I", OUT, os.path.join(ROOT, "tools", "host_emul", cpp), "-o", exe]
     subprocess.check_call(cmd + (["-fsanitize=thread"] if tsan else []))
-    rc |= subprocess.call([exe] + (["quick"] if "quick" in sys.argv else []))
+    rc |= subprocess.call([exe] + (["quick"] if "quick" in sys.argv else []) + (["stem"] if "stem" in sys.argv and name == "fused" else []))
 sys.exit(rc)
