@@ -714,6 +714,18 @@ cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bia
     a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = R; a.D = D; a.feat = nullptr;
     a.M = M; a.K = K; a.N = N; a.HW = 1;
     a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
+    // DFD_GEMM_F32_EPI16=1 (experimental, off by default until it has been timed on a GPU): 16 epilogue warps for the fp32-output
+    // variants.  The ViT attention-projection GEMM (K = 768: 12 k-blocks per tile) runs at 410 TFLOP/s against 1.0-1.1 PFLOP/s of
+    // the qkv / fc2 GEMMs: its epilogue (fp32 residual read + write, 8 warps) is as long as its main loop.
+    const char* env_e16 = getenv("DFD_GEMM_F32_EPI16");
+    if (env_e16 && atoi(env_e16) != 0) {
+        if (R) {
+            if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, true, false, 16, 4, 0, true>, a, 16, 4, 0, s);
+            return run(gemm_tc_kernel<__nv_bfloat16, false, 0, true, false, 16, 4, 0, true>, a, 16, 4, 0, s);
+        }
+        if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, false, false, 16, 4, 0, true>, a, 16, 4, 0, s);
+        return run(gemm_tc_kernel<__nv_bfloat16, false, 0, false, false, 16, 4, 0, true>, a, 16, 4, 0, s);
+    }
     if (R) {
         if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, true, false, 8, 4, 0, true>, a, 8, 4, 0, s);
         return run(gemm_tc_kernel<__nv_bfloat16, false, 0, true, false, 8, 4, 0, true>, a, 8, 4, 0, s);

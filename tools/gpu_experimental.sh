@@ -25,6 +25,9 @@ run resnet_implicit env DFD_RESNET_IMPLICIT=1 python tools/bench_resnet.py --vid
 run vit_att2_test env DFD_EXPERIMENTAL=1 python -m pytest tests/test_vit.py -m gpu -q -x -s -k attention_v2
 run vit_base      python tools/bench_vit.py --batch 512 --iters 5
 run vit_att2      env DFD_VIT_ATTN_V2=1 python tools/bench_vit.py --batch 512 --iters 5
+run vit_epi16_t   env DFD_EXPERIMENTAL=1 python -m pytest tests/test_vit.py tests/test_rnn.py -m gpu -q -x -k "epilogue_warps or rnn"
+run vit_epi16     env DFD_GEMM_F32_EPI16=1 python tools/bench_vit.py --batch 512 --iters 5
+run vit_both      env DFD_GEMM_F32_EPI16=1 DFD_VIT_ATTN_V2=1 python tools/bench_vit.py --batch 512 --iters 5
 # 4. squeeze-excite gate, second variant (se.cu, DFD_SE_V2=1)
 run se2_kernel env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k se_gate_v2
 run se2_path   env DFD_SE_V2=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x
