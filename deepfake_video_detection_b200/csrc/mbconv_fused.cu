@@ -231,25 +231,59 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
                     sts32(ea + nt * 16 + 8 * CB * 2, Half16<T>::pack(silu_tanh(fmaf(c[nt][2], 0.00390625f, bs1[ch])), silu_tanh(fmaf(c[nt][3], 0.00390625f, bs1[ch + 1]))));
                 }
             }
-            return;
-        }
-        for (int tile = warp; tile < PXT * NTL; tile += WARPS) {
-            const int pt = tile / NTL, nt = tile - pt * NTL;
-            float c[4] = {0.f, 0.f, 0.f, 0.f};
-            const uint32_t ar = xs + (uint32_t)((pt * 16 + g) * XP + 2 * t) * 2;
-            const uint32_t br = sm_w + (uint32_t)((nt * 8 + g) * XP + 2 * t) * 2;
+        } else {
+        // A warp owns NTL / WARPS channel tiles (8 / strips of them: always whole) and walks the pixel tiles of the row: the
+        // weight fragments are loaded once per row, every offset below is a compile-time constant, and the unrolled pixel
+        // tiles give the scheduler independent load -> MMA -> SiLU -> store chains.
+        static_assert(NTL % WARPS == 0, "whole channel tiles per warp");
+        constexpr int NPW = NTL / WARPS;
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) {
-                uint32_t a[4];
-                a[0] = lds32(ar + ks * 32);                 a[1] = lds32(ar + ks * 32 + 8 * XP * 2);
-                a[2] = lds32(ar + ks * 32 + 16);            a[3] = lds32(ar + ks * 32 + 8 * XP * 2 + 16);
-                mma16816_f<T>(c, a, lds32(br + ks * 32), lds32(br + ks * 32 + 16));
+        for (int q = 0; q < NPW; ++q) {
+            const int nt = warp * NPW + q;
+            const uint32_t br = sm_w + (uint32_t)((nt * 8 + g) * XP + 2 * t) * 2;
+            uint32_t bf[KSTEPS][2];
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) { bf[ks][0] = lds32(br + ks * 32); bf[ks][1] = lds32(br + ks * 32 + 16); }
+            // h = (acc + bias) / 2 in one FMA; SiLU(x) = h + h tanh(h)
+            const float hbx = 0.5f * s_be[nt * 8 + 2 * t], hby = 0.5f * s_be[nt * 8 + 2 * t + 1];
+            const uint32_t ar0 = xs + (uint32_t)(g * XP + 2 * t) * 2;
+            const uint32_t ea0 = es + (uint32_t)((g + PAD) * CB + nt * 8 + 2 * t) * 2;
+            // the fragment loads of pixel tile pt+1 are issued before the MMA -> SiLU -> store chain of tile pt (the volatile
+            // shared-memory accesses keep their program order, so the overlap has to be written out)
+            constexpr bool PREF = KSTEPS <= 3;
+            uint32_t an[PREF ? KSTEPS : 1][4];
+            auto load_a = [&](int pt, uint32_t (*dst)[4]) {
+                const uint32_t ar = ar0 + (uint32_t)(pt * 16 * XP) * 2;
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    dst[ks][0] = lds32(ar + ks * 32);                 dst[ks][1] = lds32(ar + ks * 32 + 8 * XP * 2);
+                    dst[ks][2] = lds32(ar + ks * 32 + 16);            dst[ks][3] = lds32(ar + ks * 32 + 8 * XP * 2 + 16);
+                }
+            };
+            if (PREF) load_a(0, an);
+#pragma unroll
+            for (int pt = 0; pt < PXT; ++pt) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t a[KSTEPS][4];
+                if (PREF) {
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ++ks)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) a[ks][i] = an[ks][i];
+                    if (pt + 1 < PXT) load_a(pt + 1, an);
+                } else {
+                    load_a(pt, a);
+                }
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) mma16816_f<T>(c, a[ks], bf[ks][0], bf[ks][1]);
+                const float h0 = fmaf(c[0], 0.5f, hbx), h1 = fmaf(c[1], 0.5f, hby), h2 = fmaf(c[2], 0.5f, hbx), h3 = fmaf(c[3], 0.5f, hby);
+                const uint32_t ea = ea0 + (uint32_t)(pt * 16 * CB) * 2;
+                if (pt * 16 + 8 <= W || pt * 16 + g < W)
+                    sts32(ea, Half16<T>::pack(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1)));
+                if (pt * 16 + 16 <= W || pt * 16 + 8 + g < W)
+                    sts32(ea + 8 * CB * 2, Half16<T>::pack(fmaf(h2, tanh_approx(h2), h2), fmaf(h3, tanh_approx(h3), h3)));
             }
-            const float2 bb = *reinterpret_cast<const float2*>(&s_be[nt * 8 + 2 * t]);
-            const int px0 = pt * 16 + g, px1 = px0 + 8;
-            const uint32_t ea = es + (uint32_t)((px0 + PAD) * CB + nt * 8 + 2 * t) * 2;
-            if (px0 < W) sts32(ea, Half16<T>::pack(silu_tanh(c[0] + bb.x), silu_tanh(c[1] + bb.y)));
-            if (px1 < W) sts32(ea + 8 * CB * 2, Half16<T>::pack(silu_tanh(c[2] + bb.x), silu_tanh(c[3] + bb.y)));
+        }
         }
     };
 
