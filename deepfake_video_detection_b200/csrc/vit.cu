@@ -323,13 +323,21 @@ __global__ void __launch_bounds__(kAtt2Warps * 32, 2) vit_attention_v2_kernel(co
         for (int kb0 = 0; kb0 < kTokPad; kb0 += kAtt2KeyBlock) {
             const int nkt = min(kAtt2KeyBlock, kTokPad - kb0) / 8;                // 8-key tiles in this block: 8, 8, 8, 2
             float s[kAtt2KeyBlock / 8][4];
+            // the K fragments of key tile nt+1 are requested before the MMAs of tile nt (the asm statements keep their program
+            // order, so the load / MMA overlap inside a warp has to be written out)
+            uint32_t kn0[4], kn1[4];
+            ldsm_x4<T>(kn0, sk + (uint32_t)kb0 * kRowB + k_off); ldsm_x4<T>(kn1, sk + (uint32_t)kb0 * kRowB + k_off + 64);   // head dims 0-31, 32-63
 #pragma unroll
             for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
                 s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
                 if (nt < nkt) {
                     uint32_t b0[4], b1[4];
-                    const uint32_t ka = sk + (uint32_t)(kb0 + nt * 8) * kRowB + k_off;
-                    ldsm_x4<T>(b0, ka); ldsm_x4<T>(b1, ka + 64);                  // head dims 0-31, 32-63
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { b0[i] = kn0[i]; b1[i] = kn1[i]; }
+                    if (nt + 1 < nkt) {
+                        const uint32_t ka = sk + (uint32_t)(kb0 + (nt + 1) * 8) * kRowB + k_off;
+                        ldsm_x4<T>(kn0, ka); ldsm_x4<T>(kn1, ka + 64);
+                    }
                     mma16816<T>(s[nt], aq[0], b0[0], b0[1]); mma16816<T>(s[nt], aq[1], b0[2], b0[3]);
                     mma16816<T>(s[nt], aq[2], b1[0], b1[1]); mma16816<T>(s[nt], aq[3], b1[2], b1[3]);
                 }
@@ -371,10 +379,14 @@ __global__ void __launch_bounds__(kAtt2Warps * 32, 2) vit_attention_v2_kernel(co
                     ap[0] = Half16<T>::pack(s[2 * kk][0], s[2 * kk][1]);         ap[1] = Half16<T>::pack(s[2 * kk][2], s[2 * kk][3]);
                     ap[2] = Half16<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]); ap[3] = Half16<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
                     const uint32_t va = sv + (uint32_t)(kb0 + kk * 16) * kRowB + v_off;
+                    uint32_t vn[4];
+                    ldsm_x4_trans<T>(vn, va);
 #pragma unroll
                     for (int dp = 0; dp < kHd / 16; ++dp) {
                         uint32_t bv[4];
-                        ldsm_x4_trans<T>(bv, va + dp * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) bv[i] = vn[i];
+                        if (dp + 1 < kHd / 16) ldsm_x4_trans<T>(vn, va + (dp + 1) * 32);      // next pair of head-dim tiles
                         mma16816<T>(acc[2 * dp], ap, bv[0], bv[1]);
                         mma16816<T>(acc[2 * dp + 1], ap, bv[2], bv[3]);
                     }
