@@ -210,15 +210,28 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
                     }
                 }
                 float c[4][4];
+                // weight fragments [hi|lo][k-step][2] of channel tile nt+1 are requested before the MMAs of tile nt
+                uint32_t bn[2][2][2];
+                auto load_b = [&](int nt) {
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl) {
+                        const uint32_t br = sm_w + (uint32_t)(((hl * 32 + nt * 8 + g) * XP) + 2 * t) * 2;
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) { bn[hl][ks][0] = lds32(br + ks * 32); bn[hl][ks][1] = lds32(br + ks * 32 + 16); }
+                    }
+                };
+                load_b(0);
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+                    uint32_t bc[2][2][2];
 #pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {                          // W_hi then W_lo into the same accumulator
-                        const uint32_t br = sm_w + (uint32_t)(((hl * 32 + nt * 8 + g) * XP) + 2 * t) * 2;
+                    for (int i = 0; i < 8; ++i) (&bc[0][0][0])[i] = (&bn[0][0][0])[i];
+                    if (nt + 1 < 4) load_b(nt + 1);
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) mma16816_f<__half>(c[nt], a[ks], lds32(br + ks * 32), lds32(br + ks * 32 + 16));
-                    }
+                    for (int hl = 0; hl < 2; ++hl)                            // W_hi then W_lo into the same accumulator
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) mma16816_f<__half>(c[nt], a[ks], bc[hl][ks][0], bc[hl][ks][1]);
                 }
                 const int px0 = pt * 16 + g;
                 const float* bs0 = s_be + ((top ? 2 : 0) + (px0 == 0 ? 1 : 0)) * 32;      // pixel px0 (may be the left column)
