@@ -6,6 +6,8 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 run() { name=$1; shift; echo "=== $name: $*"; timeout 600 "$@" > gpurun_out/exp_$name.log 2>&1; echo "=== $name exit $?"; tail -n 12 gpurun_out/exp_$name.log; }
+# 0. is bench.py's e2e bound by the host->device copy or by the kernels?
+run h2d python tools/probe_h2d.py
 # 1. expand 1x1 fused into the marching depthwise kernel (mbconv_fused.cu, engine switch DFD_FUSE_EXPAND=1)
 run fused_kernel env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "mbconv_fused or stem_dw_fused"
 run fused_path   env DFD_EXPERIMENTAL=1 python -m pytest tests/test_gpu_path.py -m gpu -q -x -s -k fused_expand
