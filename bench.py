@@ -293,7 +293,8 @@ def main():
             "dtype": precision, "data": "synthetic",
             "config": {"workload": WORKLOAD, "videos_per_gpu": V, "frames_per_video": T, "crop": SIZE, "l2": "inputs (308 MB/GPU) and every activation tensor exceed the 126 MB L2",
                        "weights": "calibrated synthetic checkpoint, reference state_dict schema (366 tensors)",
-                       "chunk_frames": int(os.environ.get("DFD_CHUNK_FRAMES", "2048")), "parallelism": f"videos sharded over {world} GPU(s), one all-gather of logits"},
+                       "chunk_frames": int(os.environ.get("DFD_CHUNK_FRAMES", "2048")), "parallelism": f"videos sharded over {world} GPU(s), one all-gather of logits",
+                       "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("DFD_")}},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches_per_step * args.steps + (0),
             "gpu_launches_per_step": launches_per_step, "roofline": roofline, "kernels": kernels,
         }
