@@ -24,14 +24,20 @@ def gather_video_logits(local_logits: torch.Tensor, num_videos: int, group=None)
     dropped after the collective (all_gather needs equal shapes)."""
     world = dist.get_world_size(group)
     max_local = (num_videos + world - 1) // world
-    buf = local_logits.new_zeros((max_local, local_logits.shape[1]))
-    buf[: local_logits.shape[0]] = local_logits
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
+    n, c = local_logits.shape
+    if n == max_local:
+        buf = local_logits.contiguous()                       # full shard: no padding copy
+    else:
+        buf = local_logits.new_zeros((max_local, c))
+        buf[:n] = local_logits
+    out = local_logits.new_empty((world * max_local, c))      # concatenation layout (what gloo and NCCL both accept)
+    dist.all_gather_into_tensor(out, buf, group=group)        # ONE collective, no per-rank list copies
+    if num_videos == world * max_local:
+        return out                                            # equal shards: rank order is global video order
     parts = []
     for r in range(world):
         lo, hi = shard_bounds(num_videos, world, r)
-        parts.append(out[r][: hi - lo])
+        parts.append(out[r * max_local: r * max_local + hi - lo])
     return torch.cat(parts, dim=0)
 
 
