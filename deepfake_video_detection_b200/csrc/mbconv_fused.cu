@@ -61,41 +61,54 @@ __device__ __forceinline__ uint32_t u8pair_to_half2(uint32_t b0, uint32_t b1) {
 
 // DFD_FUSED_KERNEL_BEGIN
 // Geometry is compile-time: CIN block input channels, C expanded channels, W x W map, CB channels per CTA.
+// Launch geometry and shared-memory carve-up: ONE definition for the kernel and for its launcher.
+template <int KS, int S, int CIN, int C, int W, int CB, bool STEM>
+struct FusedGeom {
+    static constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, OH = OW, strips = OW / kFTW;
+    // DWT threads own the depthwise work (2 channels x 7 columns each); the CTA is rounded up to whole warps, and the few
+    // extra threads (they take part in staging, in the expand MMAs and in the barriers) shadow the first depthwise threads
+    // with their stores suppressed
+    static constexpr int DWT = strips * (CB / 2), THREADS = (DWT + 31) / 32 * 32, WARPS = THREADS / 32;
+    static constexpr int pixw = ((strips * kFTW - 1) * S + KS) > W + 2 * PAD ? ((strips * kFTW - 1) * S + KS) : W + 2 * PAD;
+    static constexpr int KP = STEM ? 32 : (CIN + 15) & ~15;        // K padded to whole mma k-steps
+    static constexpr int XP = KP + 8;                               // halves per staged x pixel / weight row (conflict-free)
+    static constexpr uint32_t RB = 2 * W * 3;                       // STEM: bytes per raw crop row
+    static constexpr int PXT = (W + 15) / 16;                       // 16-pixel tiles per row
+    static constexpr uint32_t rsb = (uint32_t)pixw * CB * 2;        // bytes per expanded row slot
+    // x row slot: [PXT*16 pixels][XP]; STEM: [16 zero bytes][raw rows 2iy-1, 2iy, 2iy+1][pad to 16]
+    static constexpr uint32_t xsb = STEM ? ((16u + 3u * RB + 15u) & ~15u) : (uint32_t)PXT * 16 * XP * 2;
+    static constexpr uint32_t wsb = (STEM ? 2u : 1u) * CB * XP * 2; // bytes of the weight slice (STEM: hi and lo)
+    static constexpr uint32_t bias_floats = STEM ? 4u * 32u : (uint32_t)CB;
+    static constexpr size_t smem_bytes = (size_t)2 * rsb + (size_t)kXR * xsb + wsb + (size_t)bias_floats * 4;
+    static constexpr int rps = OH > 56 ? 56 : OH;                   // = march_rps(OH)
+    static constexpr int segs = (OH + rps - 1) / rps;
+    static constexpr int ctas_per_frame = segs * (C / CB);
+    static_assert(OW % kFTW == 0, "whole strips only");
+    static_assert(CB % 8 == 0 && C % CB == 0 && (STEM || CIN % 8 == 0), "channel blocks");
+    static_assert(THREADS - DWT < DWT, "shadow threads map onto real ones");
+};
+
 // STEM: the producer is not an expand conv but the network's stem (conv3x3 s2 p1 3 -> 32 + BN + SiLU on uint8 crops, tensor prep
 // folded into the weights exactly as stem_tc.cu's row variant does): x = uint8 crops (frames, 2W, 2W, 3), we = fp16 [hi|lo][32][32]
 // (k = ky*10 + kx*3 + c), be = fp32 [top*2+left][32]; the consumer is block 0's depthwise 3x3.  CIN is unused then.
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG, bool STEM = false>
-__global__ void __launch_bounds__((((W + 2 * (KS / 2) - KS) / S + 1) / kFTW * (CB / 2) + 31) / 32 * 32, 1) __maxnreg__(MAXREG)
+__global__ void __launch_bounds__((FusedGeom<KS, S, CIN, C, W, CB, STEM>::THREADS), 1) __maxnreg__(MAXREG)
 mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, const float* __restrict__ be,
                     const float* __restrict__ w, const float* __restrict__ bias,
                     T* __restrict__ out, float* __restrict__ partials) {
+    using G = FusedGeom<KS, S, CIN, C, W, CB, STEM>;
     const T* x = reinterpret_cast<const T*>(xv);
     const T* we = reinterpret_cast<const T*>(wev);
-    constexpr int TW = kFTW, PAD = KS / 2, H = W;
-    constexpr int OW = (W + 2 * PAD - KS) / S + 1, OH = OW;
-    constexpr int strips = OW / TW;
-    static_assert(OW % TW == 0, "whole strips only");
-    static_assert(CB % 8 == 0 && C % CB == 0 && (STEM || CIN % 8 == 0), "channel blocks");
+    constexpr int TW = kFTW, PAD = G::PAD, H = W;
+    constexpr int OW = G::OW, OH = G::OH, strips = G::strips;
     static_assert(!STEM || (C == 32 && CB == 32 && KS == 3 && S == 1 && W % 16 == 0), "stem producer: block 0 of the network");
-    // DWT threads own the depthwise work (2 channels x 7 columns each); the CTA is rounded up to whole warps, and the few
-    // extra threads (they take part in staging, in the expand MMAs and in the barriers) shadow the first depthwise threads
-    // with their stores suppressed
-    constexpr int DWT = strips * (CB / 2), THREADS = (DWT + 31) / 32 * 32, WARPS = THREADS / 32;
-    static_assert(THREADS - DWT < DWT, "shadow threads map onto real ones");
+    constexpr int DWT = G::DWT, THREADS = G::THREADS, WARPS = G::WARPS;
     constexpr int NCOL = (TW - 1) * S + KS;
     constexpr int RING = (KS + S - 1) / S, PERIOD = S * RING;
-    constexpr int pixw = ((strips * TW - 1) * S + KS) > W + 2 * PAD ? ((strips * TW - 1) * S + KS) : W + 2 * PAD;
-    constexpr int KP = STEM ? 32 : (CIN + 15) & ~15, KSTEPS = KP / 16;       // K padded to whole mma k-steps
-    constexpr int XP = KP + 8;                                    // halves per staged x pixel / weight row (conflict-free)
-    constexpr uint32_t RB = 2 * W * 3;                            // STEM: bytes per raw crop row
-    constexpr int PXT = (W + 15) / 16;                            // 16-pixel tiles per row
+    constexpr int pixw = G::pixw, KP = G::KP, KSTEPS = KP / 16, XP = G::XP, PXT = G::PXT;
+    constexpr uint32_t RB = G::RB, rsb = G::rsb, xsb = G::xsb, wsb = G::wsb;
     constexpr int NTL = CB / 8;                                   // 8-channel tiles of the channel block
-    constexpr uint32_t rsb = (uint32_t)pixw * CB * 2;             // bytes per expanded row slot
-    // x row slot: [PXT*16 pixels][XP]; STEM: [16 zero bytes][raw rows 2iy-1, 2iy, 2iy+1][pad to 16]
-    constexpr uint32_t xsb = STEM ? ((16u + 3u * RB + 15u) & ~15u) : (uint32_t)PXT * 16 * XP * 2;
-    constexpr uint32_t wsb = (STEM ? 2u : 1u) * CB * XP * 2;      // bytes of the weight slice (STEM: hi and lo)
-    constexpr int rps = OH > 56 ? 56 : OH;                        // = march_rps(OH)
-    constexpr int segs = (OH + rps - 1) / rps;
+    constexpr int rps = G::rps, segs = G::segs;
     constexpr int XCH = STEM ? (int)(3 * RB / 16) : W * (CIN / 8);   // 16-byte chunks of an x row
     static_assert(!STEM || (3 * RB) % 16 == 0, "raw rows are whole 16-byte chunks");
     constexpr int XK = (XCH + THREADS - 1) / THREADS;
@@ -403,16 +416,12 @@ bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) {
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG, bool STEM = false>
 static cudaError_t fused_go(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                             float* partials, int64_t frames, cudaStream_t s) {
-    constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, strips = OW / kFTW;
-    constexpr int THREADS = (strips * (CB / 2) + 31) / 32 * 32;
-    constexpr int pixw = ((strips * kFTW - 1) * S + KS) > W + 2 * PAD ? ((strips * kFTW - 1) * S + KS) : W + 2 * PAD;
-    constexpr int KP = STEM ? 32 : (CIN + 15) & ~15, XP = KP + 8, PXT = (W + 15) / 16;
-    constexpr size_t xsb = STEM ? ((16 + 3 * (2 * W * 3) + 15) & ~15) : (size_t)PXT * 16 * XP * 2;       // as in the kernel
-    constexpr size_t smem = (size_t)2 * pixw * CB * 2 + (size_t)kXR * xsb + (size_t)(STEM ? 2 : 1) * CB * XP * 2 + (size_t)(STEM ? 4 * 32 : CB) * 4;
-    constexpr int rps = OW > 56 ? 56 : OW, segs = (OW + rps - 1) / rps;
+    using G = FusedGeom<KS, S, CIN, C, W, CB, STEM>;
+    constexpr int THREADS = G::THREADS;
+    constexpr size_t smem = G::smem_bytes;
     auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG, STEM>;
     if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-    const int64_t grid = frames * segs * (C / CB);
+    const int64_t grid = frames * G::ctas_per_frame;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
     kern<<<(unsigned)grid, THREADS, smem, s>>>(x, we, be, w, bias, (T*)out, partials);
     return cudaGetLastError();

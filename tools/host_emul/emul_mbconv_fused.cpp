@@ -114,9 +114,8 @@ namespace { constexpr int kFTW = 7; constexpr int kXR = 6; }
 
 template <int KS, int S, int CIN, int C, int W, int CB>
 static int run_case(int frames) {
-    constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, OH = OW, strips = OW / 7;
-    constexpr int THREADS = (strips * (CB / 2) + 31) / 32 * 32;
-    constexpr int rps = OH > 56 ? 56 : OH, segs = (OH + rps - 1) / rps;
+    using G = dfd::FusedGeom<KS, S, CIN, C, W, CB, false>;          // the launcher's geometry (fused_go uses the same struct)
+    constexpr int PAD = KS / 2, OW = G::OW, OH = G::OH, strips = G::strips, THREADS = G::THREADS, segs = G::segs;
     std::vector<_Float16> x((size_t)frames * W * W * CIN), we((size_t)C * CIN), out((size_t)frames * OH * OW * C);
     std::vector<float> be(C), w((size_t)KS * KS * C), bias(C), parts((size_t)frames * segs * strips * C, NAN);
     uint32_t seed = 12345u + KS * 7 + CIN;
@@ -147,9 +146,11 @@ static int run_case(int frames) {
                     ref[(((size_t)f * OH + oy) * OW + ox) * C + c] = dfd::silu_tanh(a);
                 }
     // kernel, one CTA at a time
-    const int grid = frames * segs * (C / CB);
+    const int grid = frames * G::ctas_per_frame;
+    bool overrun = false;
     for (int b = 0; b < grid; ++b) {
         memset(dfd::fz_smem, 0xff, sizeof(dfd::fz_smem));                  // NaN patterns: nothing may rely on zero-initialised shared memory
+        memset(dfd::fz_smem + G::smem_bytes, 0xA5, 4096);                  // guard behind the launcher's allocation
         std::barrier<> bar(THREADS);
         g_cta_bar = &bar;
         dfd::g_warps.clear();
@@ -162,6 +163,7 @@ static int run_case(int frames) {
                 dfd::mbconv_fused_kernel<__half, KS, S, CIN, C, W, CB, 128>(x.data(), we.data(), be.data(), w.data(), bias.data(), out.data(), parts.data());
             });
         for (auto& t : th) t.join();
+        for (int i = 0; i < 4096; ++i) overrun |= dfd::fz_smem[G::smem_bytes + i] != 0xA5;
     }
     double max_err = 0, max_ref = 0, sum_err = 0;
     for (size_t i = 0; i < ref.size(); ++i) { max_err = fmax(max_err, fabs((float)out[i] - ref[i])); max_ref = fmax(max_ref, fabs(ref[i])); }
@@ -172,7 +174,8 @@ static int run_case(int frames) {
             for (int p = 0; p < OH * OW; ++p) r += ref[((size_t)f * OH * OW + p) * C + c];
             sum_err = fmax(sum_err, fabs(s - r));
         }
-    const bool ok = max_err <= 2e-3 * fmax(1.0, max_ref) && sum_err < 5e-2 && std::isfinite(sum_err);
+    const bool ok = max_err <= 2e-3 * fmax(1.0, max_ref) && sum_err < 5e-2 && std::isfinite(sum_err) && !overrun;
+    if (overrun) printf("shared-memory write behind the %zu bytes the launcher allocates\n", (size_t)G::smem_bytes);
     printf("k%d s%d cin%d mid%d W%d CB%d %s: %d CTAs x %d threads, max |err| %.2e (scale %.2f), max |SE sum err| %.2e -> %s\n", KS, S, CIN, C, W, CB,
            g_eager ? "eager" : "lazy ", grid, THREADS, max_err, max_ref, sum_err, ok ? "ok" : "MISMATCH");
     return ok ? 0 : 1;
@@ -181,7 +184,9 @@ static int run_case(int frames) {
 // STEM producer: uint8 crops -> stem (prep folded into hi/lo weights + 4 bias vectors, packed as api.cu pack_stem_row does)
 // -> block 0's depthwise 3x3.  Reference: the reference's own arithmetic order (u8/255, (x-mean)/std, zero-padded conv) in double.
 static int run_stem_case(int frames) {
-    constexpr int W = 112, C = 32, KS = 3, OW = 112, OH = 112, strips = 16, THREADS = 256, segs = 2, RAW = 224;
+    using G = dfd::FusedGeom<3, 1, 8, 32, 112, 32, true>;
+    constexpr int W = 112, C = 32, KS = 3, OW = G::OW, OH = G::OH, strips = G::strips, THREADS = G::THREADS, segs = G::segs, RAW = 224;
+    static_assert(THREADS == 256 && segs == 2 && strips == 16, "block 0 geometry");
     std::vector<uint8_t> in((size_t)frames * RAW * RAW * 3);
     std::vector<float> w27((size_t)27 * 32), b32(32), w((size_t)9 * C), bias(C), parts((size_t)frames * segs * strips * C, NAN), b4(4 * 32);
     std::vector<_Float16> wrow(2 * 32 * 32, (_Float16)0.f), out((size_t)frames * OH * OW * C);
@@ -224,9 +229,11 @@ static int run_stem_case(int frames) {
         }
         ref[(((size_t)f * OH + oy) * OW + ox) * C + c] = dfd::silu_tanh(a);
     }
-    const int grid = frames * segs;
+    const int grid = frames * G::ctas_per_frame;
+    bool overrun = false;
     for (int b = 0; b < grid; ++b) {
         memset(dfd::fz_smem, 0xff, sizeof(dfd::fz_smem));
+        memset(dfd::fz_smem + G::smem_bytes, 0xA5, 4096);
         std::barrier<> bar(THREADS); g_cta_bar = &bar;
         dfd::g_warps.clear();
         for (int i = 0; i < THREADS / 32; ++i) dfd::g_warps.emplace_back(new dfd::WarpX());
@@ -237,8 +244,9 @@ static int run_stem_case(int frames) {
                 dfd::mbconv_fused_kernel<__half, 3, 1, 8, 32, 112, 32, 128, true>(in.data(), wrow.data(), b4.data(), w.data(), bias.data(), out.data(), parts.data());
             });
         for (auto& t : th) t.join();
+        for (int i = 0; i < 4096; ++i) overrun |= dfd::fz_smem[G::smem_bytes + i] != 0xA5;
     }
-    double max_err = 0, max_ref = 0, sum_err = 0; size_t bad = 0;
+    double max_err = 0, max_ref = 0, sum_err = 0; size_t bad = overrun ? 1 : 0;
     for (size_t i = 0; i < ref.size(); ++i) {
         const double d = fabs((float)out[i] - ref[i]);
         max_err = fmax(max_err, d); max_ref = fmax(max_ref, fabs(ref[i])); if (d > 3e-3 * fmax(1.0, fabs(ref[i]))) ++bad;
