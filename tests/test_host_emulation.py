@@ -21,8 +21,8 @@ def _run(*args):
 
 
 def test_fused_expand_depthwise_kernel_source_on_cpu():
-    out = _run("fused", "quick")                     # the four level-2 shapes (small maps), both cp.async models
-    assert out.count("-> ok") == 8
+    out = _run("fused", "quick")                     # the four level-2 shapes (small maps) + one bf16 case, both cp.async models
+    assert out.count("-> ok") == 10
 
 
 def test_stem_dw_fused_kernel_source_on_cpu():

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <type_traits>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -51,6 +52,12 @@ template <> struct Half16<__half> {
     static constexpr int kCode = kDtypeFP16;
     static float2 unpack(uint32_t v) { _Float16 h[2]; memcpy(h, &v, 4); return {(float)h[0], (float)h[1]}; }
     static uint32_t pack(float a, float b) { _Float16 h[2] = {(_Float16)a, (_Float16)b}; uint32_t v; memcpy(&v, h, 4); return v; }
+};
+template <> struct Half16<__nv_bfloat16> {
+    static constexpr int kCode = kDtypeBF16;
+    static uint16_t rn(float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7fffu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); }   // finite inputs only
+    static float2 unpack(uint32_t v) { uint32_t lo = v << 16, hi = v & 0xffff0000u; float2 r; memcpy(&r.x, &lo, 4); memcpy(&r.y, &hi, 4); return r; }
+    static uint32_t pack(float a, float b) { return (uint32_t)rn(a) | ((uint32_t)rn(b) << 16); }
 };
 static inline uint64_t f2_pack(float a, float b) { float2 v{a, b}; uint64_t u; memcpy(&u, &v, 8); return u; }
 static inline float2 f2_unpack(uint64_t u) { float2 v; memcpy(&v, &u, 8); return v; }
@@ -112,16 +119,22 @@ namespace { constexpr int kFTW = 7; constexpr int kXR = 6; }
 #include "mbconv_fused_kernel.inc"
 }  // namespace dfd
 
-template <int KS, int S, int CIN, int C, int W, int CB>
+template <typename ST> struct Store;                      // host-side view of the 16-bit storage type
+template <> struct Store<__half> { static uint16_t enc(float f) { _Float16 h = (_Float16)f; uint16_t u; memcpy(&u, &h, 2); return u; }
+                                   static float dec(uint16_t u) { _Float16 h; memcpy(&h, &u, 2); return (float)h; } static constexpr double tol = 2e-3; };
+template <> struct Store<__nv_bfloat16> { static uint16_t enc(float f) { return dfd::Half16<__nv_bfloat16>::rn(f); }
+                                          static float dec(uint16_t u) { uint32_t v = (uint32_t)u << 16; float f; memcpy(&f, &v, 4); return f; } static constexpr double tol = 1.6e-2; };
+
+template <int KS, int S, int CIN, int C, int W, int CB, typename ST = __half>
 static int run_case(int frames) {
     using G = dfd::FusedGeom<KS, S, CIN, C, W, CB, false>;          // the launcher's geometry (fused_go uses the same struct)
     constexpr int PAD = KS / 2, OW = G::OW, OH = G::OH, strips = G::strips, THREADS = G::THREADS, segs = G::segs;
-    std::vector<_Float16> x((size_t)frames * W * W * CIN), we((size_t)C * CIN), out((size_t)frames * OH * OW * C);
+    std::vector<uint16_t> x((size_t)frames * W * W * CIN), we((size_t)C * CIN), out((size_t)frames * OH * OW * C);
     std::vector<float> be(C), w((size_t)KS * KS * C), bias(C), parts((size_t)frames * segs * strips * C, NAN);
     uint32_t seed = 12345u + KS * 7 + CIN;
     auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xffff) / 32768.0f - 1.0f; };
-    for (auto& v : x) v = (_Float16)rnd();
-    for (auto& v : we) v = (_Float16)(rnd() / sqrtf((float)CIN) * 1.5f);
+    for (auto& v : x) v = Store<ST>::enc(rnd());
+    for (auto& v : we) v = Store<ST>::enc(rnd() / sqrtf((float)CIN) * 1.5f);
     for (auto& v : be) v = 0.3f * rnd();
     for (auto& v : w) v = rnd() / KS;
     for (auto& v : bias) v = 0.2f * rnd();
@@ -130,8 +143,8 @@ static int run_case(int frames) {
     for (size_t p = 0; p < (size_t)frames * W * W; ++p)
         for (int c = 0; c < C; ++c) {
             float a = 0.f;
-            for (int k = 0; k < CIN; ++k) a += (float)x[p * CIN + k] * (float)we[(size_t)c * CIN + k];
-            e[p * C + c] = (float)(_Float16)dfd::silu_tanh(a + be[c]);
+            for (int k = 0; k < CIN; ++k) a += Store<ST>::dec(x[p * CIN + k]) * Store<ST>::dec(we[(size_t)c * CIN + k]);
+            e[p * C + c] = Store<ST>::dec(Store<ST>::enc(dfd::silu_tanh(a + be[c])));
         }
     for (int f = 0; f < frames; ++f)
         for (int oy = 0; oy < OH; ++oy)
@@ -160,13 +173,13 @@ static int run_case(int frames) {
             th.emplace_back([&, t, b]() {
                 threadIdx.x = t; blockIdx.x = b;
                 dfd::t_groups.clear(); dfd::t_open.clear();
-                dfd::mbconv_fused_kernel<__half, KS, S, CIN, C, W, CB, 128>(x.data(), we.data(), be.data(), w.data(), bias.data(), out.data(), parts.data());
+                dfd::mbconv_fused_kernel<ST, KS, S, CIN, C, W, CB, 128>(x.data(), we.data(), be.data(), w.data(), bias.data(), reinterpret_cast<ST*>(out.data()), parts.data());
             });
         for (auto& t : th) t.join();
         for (int i = 0; i < 4096; ++i) overrun |= dfd::fz_smem[G::smem_bytes + i] != 0xA5;
     }
     double max_err = 0, max_ref = 0, sum_err = 0;
-    for (size_t i = 0; i < ref.size(); ++i) { max_err = fmax(max_err, fabs((float)out[i] - ref[i])); max_ref = fmax(max_ref, fabs(ref[i])); }
+    for (size_t i = 0; i < ref.size(); ++i) { max_err = fmax(max_err, fabs(Store<ST>::dec(out[i]) - ref[i])); max_ref = fmax(max_ref, fabs(ref[i])); }
     for (int f = 0; f < frames; ++f)
         for (int c = 0; c < C; ++c) {
             double s = 0, r = 0;
@@ -174,9 +187,9 @@ static int run_case(int frames) {
             for (int p = 0; p < OH * OW; ++p) r += ref[((size_t)f * OH * OW + p) * C + c];
             sum_err = fmax(sum_err, fabs(s - r));
         }
-    const bool ok = max_err <= 2e-3 * fmax(1.0, max_ref) && sum_err < 5e-2 && std::isfinite(sum_err) && !overrun;
+    const bool ok = max_err <= Store<ST>::tol * fmax(1.0, max_ref) && sum_err < 5e-2 && std::isfinite(sum_err) && !overrun;
     if (overrun) printf("shared-memory write behind the %zu bytes the launcher allocates\n", (size_t)G::smem_bytes);
-    printf("k%d s%d cin%d mid%d W%d CB%d %s: %d CTAs x %d threads, max |err| %.2e (scale %.2f), max |SE sum err| %.2e -> %s\n", KS, S, CIN, C, W, CB,
+    printf("%s k%d s%d cin%d mid%d W%d CB%d %s: %d CTAs x %d threads, max |err| %.2e (scale %.2f), max |SE sum err| %.2e -> %s\n", sizeof(ST) && std::is_same<ST, __half>::value ? "fp16" : "bf16", KS, S, CIN, C, W, CB,
            g_eager ? "eager" : "lazy ", grid, THREADS, max_err, max_ref, sum_err, ok ? "ok" : "MISMATCH");
     return ok ? 0 : 1;
 }
@@ -274,7 +287,9 @@ int main(int argc, char** argv) {
         rc |= run_case<5, 2, 112, 672, 14, 96>(1);
         rc |= run_case<3, 1, 192, 1152, 7, 128>(1);
         rc |= run_case<3, 2, 40, 240, 28, 48>(1);
+        rc |= run_case<3, 1, 80, 480, 14, 96, __nv_bfloat16>(1);
         if (quick) continue;
+        rc |= run_case<3, 1, 24, 144, 56, 48, __nv_bfloat16>(1);
         rc |= run_stem_case(1);
         rc |= run_case<3, 1, 24, 144, 56, 48>(1);
         rc |= run_case<5, 2, 24, 144, 56, 48>(1);
