@@ -11,6 +11,7 @@ namespace dfd {
 
 constexpr int kSeMaxThreads = 1024;
 
+// DFD_SE1_KERNEL_BEGIN   (tools/host_emul/ also runs this kernel, unchanged, on CPU threads)
 template <int kSeFrames>
 __global__ void __launch_bounds__(kSeMaxThreads)
 se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
@@ -104,6 +105,8 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
     }
 }
 
+
+// DFD_SE1_KERNEL_END
 
 // Second variant (EXPERIMENTAL, DFD_SE_V2=1; written without GPU access, off by default).  Same contract, same phase 1, same
 // FC2 summation order; FC1 sums its channels in a different (still fixed) order.  The first variant is bound by instruction
