@@ -149,6 +149,8 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// DFD_ATT1_KERNEL_BEGIN   (tools/host_emul/ also runs this GPU-verified kernel, unchanged, on CPU threads: it pins the emulated
+// mma.sync fragment layout to what the hardware does)
 template <typename T>
 __global__ void __launch_bounds__(128) vit_attention_kernel(const T* __restrict__ qkv, T* __restrict__ o) {
     extern __shared__ __align__(16) uint8_t att_smem[];
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(128) vit_attention_kernel(const T* __restrict_
     }
 }
 
+// DFD_ATT1_KERNEL_END
 constexpr size_t kAttSmem = (size_t)(2 * kTokPad * kQKStride + kHd * kVtStride) * 2;
 
 // ---- attention, second variant (EXPERIMENTAL, DFD_VIT_ATTN_V2=1; written without GPU access, off by default) ----------------

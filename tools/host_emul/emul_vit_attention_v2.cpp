@@ -90,11 +90,16 @@ template <typename T> static inline void mma16816(float* c, const uint32_t* a, u
     w.bar.arrive_and_wait();
 }
 constexpr int kDim = 768, kHeads = 12, kHd = 64, kTokens = 197;
-constexpr int kTokPad = 208, kQKStride = 72;
+constexpr int kTokPad = 208, kQKStride = 72, kVtStride = 216;
+static inline float __expf(float x) { return expf(x); }
+#include "vit_attention_v1_kernel.inc"
 #include "vit_attention_v2_kernel.inc"
 }  // namespace dfd
 
-int main() {
+template <bool V2> static int run();
+int main() { return run<true>() | run<false>(); }
+
+template <bool V2> static int run() {
     using namespace dfd;
     const int images = 2;
     std::vector<_Float16> qkv((size_t)images * kTokens * 3 * kDim), o((size_t)images * kTokens * kDim);
@@ -105,13 +110,14 @@ int main() {
     double max_err = 0, scale = 0;
     for (int b : heads_to_run) {
         memset(att_smem, 0xff, sizeof(att_smem));
-        const int threads = kAtt2Warps * 32;
+        const int threads = V2 ? kAtt2Warps * 32 : 128;
         std::barrier<> bar(threads); g_cta_bar = &bar;
         g_warps.clear();
-        for (int i = 0; i < kAtt2Warps; ++i) g_warps.emplace_back(new WarpX());
+        for (int i = 0; i < threads / 32; ++i) g_warps.emplace_back(new WarpX());
         std::vector<std::thread> th;
         for (int t = 0; t < threads; ++t)
-            th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b; vit_attention_v2_kernel<__half>(qkv.data(), o.data()); });
+            th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b;
+                if (V2) vit_attention_v2_kernel<__half>(qkv.data(), o.data()); else vit_attention_kernel<__half>(qkv.data(), o.data()); });
         for (auto& t : th) t.join();
         const int head = b % kHeads, img = b / kHeads;
         for (int q = 0; q < kTokens; ++q) {
@@ -132,6 +138,7 @@ int main() {
         }
     }
     const bool ok = max_err < 4e-3 && std::isfinite(max_err);
-    printf("vit_attention_v2_kernel: 3 (image, head) CTAs x %d threads, max |err| %.2e (scale %.2f) -> %s\n", kAtt2Warps * 32, max_err, scale, ok ? "ok" : "MISMATCH");
+    printf("%s: 3 (image, head) CTAs x %d threads, max |err| %.2e (scale %.2f) -> %s\n", V2 ? "vit_attention_v2_kernel" : "vit_attention_kernel (GPU-verified)",
+           V2 ? kAtt2Warps * 32 : 128, max_err, scale, ok ? "ok" : "MISMATCH");
     return ok ? 0 : 1;
 }

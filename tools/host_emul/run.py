@@ -17,6 +17,8 @@ for name in which:
         continue
     src = open(os.path.join(ROOT, "deepfake_video_detection_b200", "csrc", cu)).read()
     open(os.path.join(OUT, inc), "w").write(src[src.index(f"// {marker}_BEGIN"):src.index(f"// {marker}_END")])
+    if name == "attention":                            # the GPU-verified first attention kernel goes through the same harness
+        open(os.path.join(OUT, "vit_attention_v1_kernel.inc"), "w").write(src[src.index("// DFD_ATT1_KERNEL_BEGIN"):src.index("// DFD_ATT1_KERNEL_END")])
     if name == "se":                                   # the default SE kernel goes through the same harness
         open(os.path.join(OUT, "se_kernel_v1.inc"), "w").write(src[src.index("// DFD_SE1_KERNEL_BEGIN"):src.index("// DFD_SE1_KERNEL_END")])
     exe = os.path.join(OUT, cpp[:-4] + ("_tsan" if tsan else ""))
