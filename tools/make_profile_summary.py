@@ -13,6 +13,7 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
 def klass(name):
+    if "mbconv_fused" in name: return "expand_dwconv_fused"   # bench.py's class name for the fused producer + depthwise kernel
     if "dwconv" in name: return "dwconv_se_squeeze"
     if "se_kernel" in name: return "se_gate"
     if "stem" in name: return "stem"
