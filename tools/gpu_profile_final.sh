@@ -12,15 +12,17 @@ timeout 300 python tools/bench_vit.py --batch 512 --iters 5 > gpurun_out/bench_v
 timeout 300 python tools/bench_rnn.py > gpurun_out/bench_rnn_$tag.json 2>&1; cat gpurun_out/bench_rnn_$tag.json
 timeout 300 python tools/bench_resnet.py > gpurun_out/bench_resnet_$tag.json 2>&1; cat gpurun_out/bench_resnet_$tag.json
 CMD="python tools/prof_step.py --videos 64 --frames 32 --iters 2"
-timeout 300 $CMD > gpurun_out/prof_plain_$tag.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 71 -c 71 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
+timeout 300 $CMD > gpurun_out/prof_plain_$tag.log 2>&1
+L=$(grep -o '[0-9]* launches' gpurun_out/prof_plain_$tag.log | tail -1 | cut -d' ' -f1); L=${L:-71}     # launches per forward pass (71 by default, fewer with DFD_FUSE_EXPAND)
+echo "launches per pass: $L"
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s $L -c $L --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_list_$tag.log 2>&1
 echo "launch list rc=$?"
 CMDV="python tools/bench_vit.py --batch 128 --iters 1"
 timeout 300 $CMDV > /dev/null 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_tensor.sum --clock-control none -s 176 -c 88 --csv --log-file gpurun_out/launches_vit_$tag.csv $CMDV > gpurun_out/ncu_list_vit_$tag.log 2>&1
 echo "vit launch list rc=$?"
 CMD2="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
-timeout 300 $CMD2 > /dev/null 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"dwconv|mbconv_fused|gemm_tc|stem|se_kernel|pool_head" -s 66 -c 66 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
+timeout 300 $CMD2 > /dev/null 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"dwconv|mbconv_fused|gemm_tc|stem|se_kernel|pool_head" -c 200 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full rc=$?"
 ncu -i /tmp/full_$tag.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.csv 2>/dev/null
 du -sh gpurun_out
