@@ -22,7 +22,7 @@ timeout 300 $CMDV > /dev/null 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__inst_executed_pipe_tensor.sum --clock-control none -s 176 -c 88 --csv --log-file gpurun_out/launches_vit_$tag.csv $CMDV > gpurun_out/ncu_list_vit_$tag.log 2>&1
 echo "vit launch list rc=$?"
 CMD2="python tools/prof_step.py --videos 16 --frames 32 --iters 2"
-timeout 300 $CMD2 > /dev/null 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"dwconv|mbconv_fused|gemm_tc|stem|se_kernel|pool_head" -c 200 -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
+timeout 300 $CMD2 > /dev/null 2>&1 && timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"dwconv|mbconv_fused|gemm_tc|stem|se_kernel|pool_head" -s $((L-5)) -c $((L-5)) -f -o /tmp/full_$tag $CMD2 > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full rc=$?"
 ncu -i /tmp/full_$tag.ncu-rep --page raw --csv > gpurun_out/full_${tag}_raw.csv 2>/dev/null
 du -sh gpurun_out
