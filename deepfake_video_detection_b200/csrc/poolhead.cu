@@ -9,6 +9,7 @@
 
 namespace dfd {
 
+// DFD_POOLHEAD_KERNEL_BEGIN   (tools/host_emul/ runs the kernel below, unchanged, on CPU threads)
 constexpr int kPhThreads = 512;
 constexpr int kFeat = 1280, kAttHidden = 64, kFc1 = 256;
 constexpr int kMaxT = 1024;
@@ -126,6 +127,8 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
         if (lane == 0) logits[(size_t)v * 2 + warp] = acc + __ldg(hw.fc2_b + warp);
     }
 }
+
+// DFD_POOLHEAD_KERNEL_END
 
 cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos,
                              int use_attention, float* logits, float* frame_scores, cudaStream_t s) {

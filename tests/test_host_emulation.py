@@ -35,3 +35,9 @@ def test_attention_v2_kernel_source_on_cpu():
 
 def test_se_gate_v2_kernel_source_on_cpu():
     assert _run("se").count("-> ok") == 11              # 8 cases of the second variant + 3 of the default kernel
+
+
+def test_pool_head_kernel_source_on_cpu():
+    """Rows a6 / a7 (attention pool + head, pretrained_detector.py:123-141): the default kernel's source against the reference
+    arithmetic in double, ragged videos incl. an empty one, both pooling modes."""
+    assert _run("poolhead").count("-> ok") == 2
