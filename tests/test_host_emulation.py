@@ -16,6 +16,8 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ (
 
 def _run(*args):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "host_emul", "run.py"), *args], capture_output=True, text=True, timeout=900)
+    if r.returncode != 0 and ("Resource temporarily unavailable" in r.stderr or "std::system_error" in r.stderr):
+        pytest.skip("this machine does not allow the ~1000 threads a CTA emulation needs")
     assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
 
