@@ -1,7 +1,7 @@
 """Build and run the CPU emulations of the experimental kernels: the kernel text between the emulation markers of the .cu file
 is extracted UNCHANGED and compiled with the matching harness in this directory.
     python tools/host_emul/run.py [fused|attention|se|poolhead|all] [quick] [tsan]"""
-import os, subprocess, sys
+import hashlib, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "build", "host_emul")
 os.makedirs(OUT, exist_ok=True)
@@ -26,8 +26,13 @@ for name in which:
         open(os.path.join(OUT, "vit_attention_v1_kernel.inc"), "w").write(src[src.index("// DFD_ATT1_KERNEL_BEGIN"):src.index("// DFD_ATT1_KERNEL_END")])
     if name == "se":                                   # the default SE kernel goes through the same harness
         open(os.path.join(OUT, "se_kernel_v1.inc"), "w").write(src[src.index("// DFD_SE1_KERNEL_BEGIN"):src.index("// DFD_SE1_KERNEL_END")])
-    exe = os.path.join(OUT, cpp[:-4] + ("_tsan" if tsan else ""))
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-pthread", "-I", OUT, os.path.join(ROOT, "tools", "host_emul", cpp), "-o", exe]
-    subprocess.check_call(cmd + (["-fsanitize=thread"] if tsan else []))
+    quick = "quick" in sys.argv or ("stem" in sys.argv and name == "fused")
+    flags = ["-std=c++20", "-O1", "-pthread"] + (["-DEMUL_QUICK"] if quick and name == "fused" else []) + (["-g", "-fsanitize=thread"] if tsan else [])
+    cpp_path = os.path.join(ROOT, "tools", "host_emul", cpp)
+    incs = "".join(open(os.path.join(OUT, f)).read() for f in sorted(os.listdir(OUT)) if f.endswith(".inc"))
+    key = hashlib.sha1((open(cpp_path).read() + incs + " ".join(flags)).encode()).hexdigest()[:12]
+    exe = os.path.join(OUT, f"{cpp[:-4]}_{key}")
+    if not os.path.exists(exe):                        # same sources + flags: reuse the binary of an earlier invocation
+        subprocess.check_call(["g++", *flags, "-I", OUT, cpp_path, "-o", exe])
     rc |= subprocess.call([exe] + (["quick"] if "quick" in sys.argv else []) + (["stem"] if "stem" in sys.argv and name == "fused" else []))
 sys.exit(rc)
