@@ -8,6 +8,7 @@
 
 namespace dfd {
 
+// DFD_PREP_KERNEL_BEGIN   (tools/host_emul/ runs this kernel, unchanged, on CPU threads)
 template <typename T>
 __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ in, T* __restrict__ out,
                                                          int64_t groups, int groups_per_frame, int HW) {
@@ -38,6 +39,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
         stg32(out + (frame * 3 + c) * HW + (int64_t)gi * 16, o);
     }
 }
+
+// DFD_PREP_KERNEL_END
 
 cudaError_t launch_preprocess(const uint8_t* in, void* out, int64_t frames, int H, int W, int dtype, cudaStream_t s) {
     const int HW = H * W;

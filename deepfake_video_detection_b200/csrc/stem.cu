@@ -11,6 +11,7 @@
 
 namespace dfd {
 
+// DFD_STEM_KERNEL_BEGIN   (tools/host_emul/ runs this kernel, unchanged, on CPU threads)
 template <typename T, int IN_KIND>
 __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ in_, const float* __restrict__ w,
                                                    const float* __restrict__ bias, T* __restrict__ out,
@@ -81,6 +82,8 @@ __global__ void __launch_bounds__(128) stem_kernel(const void* __restrict__ in_,
         stg32(dst + h * 16, o);
     }
 }
+
+// DFD_STEM_KERNEL_END
 
 template <typename T>
 static cudaError_t launch_stem_t(const void* in, int in_kind, const float* w, const float* bias, void* out,

@@ -43,3 +43,10 @@ def test_pool_head_kernel_source_on_cpu():
     """Rows a6 / a7 (attention pool + head, pretrained_detector.py:123-141): the default kernel's source against the reference
     arithmetic in double, ragged videos incl. an empty one, both pooling modes."""
     assert _run("poolhead").count("-> ok") == 2
+
+
+def test_preprocess_and_stem_kernel_sources_on_cpu():
+    """Row a1 (K1 tensor prep: bit-exact with the reference's fp32 arithmetic rounded once) and row a3 (CUDA-core stem for the fp32
+    NCHW input forward() receives, and for uint8 crops with the prep fused): the default kernels' sources on CPU threads."""
+    out = _run("prepstem")
+    assert out.count("-> ok") == 3 and "0 of 3072 values differ" in out

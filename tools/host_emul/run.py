@@ -1,6 +1,6 @@
 """Build and run the CPU emulations of the experimental kernels: the kernel text between the emulation markers of the .cu file
 is extracted UNCHANGED and compiled with the matching harness in this directory.
-    python tools/host_emul/run.py [fused|attention|se|poolhead|all] [quick] [tsan]"""
+    python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|all] [quick] [tsan]"""
 import hashlib, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "build", "host_emul")
@@ -8,7 +8,8 @@ os.makedirs(OUT, exist_ok=True)
 CASES = {"fused": ("mbconv_fused.cu", "DFD_FUSED_KERNEL", "mbconv_fused_kernel.inc", "emul_mbconv_fused.cpp"),
          "attention": ("vit.cu", "DFD_ATT2_KERNEL", "vit_attention_v2_kernel.inc", "emul_vit_attention_v2.cpp"),
          "se": ("se.cu", "DFD_SE2_KERNEL", "se_kernel_v2.inc", "emul_se_v2.cpp"),
-         "poolhead": ("poolhead.cu", "DFD_POOLHEAD_KERNEL", "pool_head_kernel.inc", "emul_pool_head.cpp")}
+         "poolhead": ("poolhead.cu", "DFD_POOLHEAD_KERNEL", "pool_head_kernel.inc", "emul_pool_head.cpp"),
+         "prepstem": ("preprocess.cu", "DFD_PREP_KERNEL", "preprocess_kernel.inc", "emul_prep_stem.cpp")}
 which = [a for a in sys.argv[1:] if a in CASES] or (list(CASES) if "all" in sys.argv else ["fused"])
 tsan = "tsan" in sys.argv
 rc = 0
@@ -22,6 +23,9 @@ for name in which:
         assert "extern __shared__ float s_f[];" in text
         text = text.replace("extern __shared__ float s_f[];", "float* s_f = g_dyn_smem;")
     open(os.path.join(OUT, inc), "w").write(text)
+    if name == "prepstem":
+        st = open(os.path.join(ROOT, "deepfake_video_detection_b200", "csrc", "stem.cu")).read()
+        open(os.path.join(OUT, "stem_kernel.inc"), "w").write(st[st.index("// DFD_STEM_KERNEL_BEGIN"):st.index("// DFD_STEM_KERNEL_END")])
     if name == "attention":                            # the GPU-verified first attention kernel goes through the same harness
         open(os.path.join(OUT, "vit_attention_v1_kernel.inc"), "w").write(src[src.index("// DFD_ATT1_KERNEL_BEGIN"):src.index("// DFD_ATT1_KERNEL_END")])
     if name == "se":                                   # the default SE kernel goes through the same harness
