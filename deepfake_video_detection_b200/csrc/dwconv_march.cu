@@ -33,6 +33,8 @@ constexpr int kMarchTW = 7;          // output columns per thread (odd: strips i
 constexpr int kMarchMaxThreads = 256;
 constexpr int kMarchMaxK = 4;        // 16-byte chunks a thread copies per input row (upper limit)
 
+// DFD_MARCH_KERNEL_BEGIN   (tools/host_emul/ runs this kernel on CPU threads; its one inline-asm shared-memory load is mapped
+// to the harness's load by run.py, everything else is the text below)
 // CC / WC / CBC: channels, (square) map size and channel block as compile-time constants for the network's own
 // layer shapes (every address offset becomes an immediate), 0 = run-time geometry.
 template <typename T, int KS, int S, int NR, int MAXREG, bool FULL, int MAXK, int CC = 0, int WC = 0, int CBC = 0>
@@ -182,6 +184,8 @@ dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const
     float* dst = partials + (((size_t)frame * segs + seg) * strips + strip) * C + c0;
     *reinterpret_cast<float2*>(dst) = f2_unpack(sums);
 }
+
+// DFD_MARCH_KERNEL_END
 
 // rows per segment: a function of the layer shape only (batch-invariant partial sums)
 static inline int march_rps(int OH) { return OH > 56 ? 56 : OH; }

@@ -50,3 +50,9 @@ def test_preprocess_and_stem_kernel_sources_on_cpu():
     NCHW input forward() receives, and for uint8 crops with the prep fused): the default kernels' sources on CPU threads."""
     out = _run("prepstem")
     assert out.count("-> ok") == 3 and "0 of 3072 values differ" in out
+
+
+def test_depthwise_march_kernel_source_on_cpu():
+    """Row a4, the dominant kernel of the step (depthwise kxk + BN + SiLU + squeeze-excite sums): the default kernel's source on CPU
+    threads for five of the network's own shapes (compile-time geometry) and two run-time-geometry shapes, both cp.async models."""
+    assert _run("march").count("-> ok") == 14

@@ -1,0 +1,133 @@
+// CPU emulation of dwconv_march_kernel (deepfake_video_detection_b200/csrc/dwconv_march.cu): the dominant kernel of the scoring
+// step (depthwise kxk + BN + SiLU + squeeze-excite sums, 39 % of the step), GPU-verified; its text between the
+// DFD_MARCH_KERNEL markers runs on CPU threads (run.py maps its one inline-asm `ld.shared.b32` to the harness's load).
+// cp.async is modelled lazily and eagerly, shared memory starts as NaN patterns.  Reference: fp32 depthwise conv on the same
+// fp16 inputs; SE partial sums against the reference sums.
+// Build + run: python tools/host_emul/run.py march
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __maxnreg__(...)
+#define __align__(x)
+#define __shared__
+struct Dim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local Dim3 threadIdx, blockIdx;
+static Dim3 blockDim;
+struct float2 { float x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return {a, b, c, d}; }
+using std::min;
+typedef _Float16 __half;
+static bool g_eager = false;
+static std::barrier<>* g_cta_bar = nullptr;
+static void __syncthreads() { g_cta_bar->arrive_and_wait(); }
+
+namespace dfd {
+alignas(16) uint8_t dw_smem[232 * 1024];
+template <typename T> struct Half16;
+template <> struct Half16<__half> {
+    static float2 unpack(uint32_t v) { _Float16 h[2]; memcpy(h, &v, 4); return {(float)h[0], (float)h[1]}; }
+    static uint32_t pack(float a, float b) { _Float16 h[2] = {(_Float16)a, (_Float16)b}; uint32_t v; memcpy(&v, h, 4); return v; }
+};
+static inline uint64_t f2_pack(float a, float b) { float2 v{a, b}; uint64_t u; memcpy(&u, &v, 8); return u; }
+static inline float2 f2_unpack(uint64_t u) { float2 v; memcpy(&v, &u, 8); return v; }
+static inline uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { float2 x = f2_unpack(a), y = f2_unpack(b), z = f2_unpack(c); return f2_pack(fmaf(x.x, y.x, z.x), fmaf(x.y, y.y, z.y)); }
+static inline uint64_t mul2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y = f2_unpack(b); return f2_pack(x.x * y.x, x.y * y.y); }
+static inline uint64_t add2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y = f2_unpack(b); return f2_pack(x.x + y.x, x.y + y.y); }
+static inline float tanh_approx(float x) { return tanhf(x); }
+template <typename P> static inline P __ldg(const P* p) { return *p; }
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - dw_smem); }
+static inline void sts16(uint32_t a, const uint4& v) { memcpy(dw_smem + a, &v, 16); }
+static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, dw_smem + a, 4); return v; }
+struct CpOp { uint32_t dst; const void* src; };
+static thread_local std::vector<std::vector<CpOp>> t_groups;
+static thread_local std::vector<CpOp> t_open;
+static inline void cp_async16(uint32_t saddr, const void* g, bool valid) {
+    if (!valid) return;
+    if (g_eager) memcpy(dw_smem + saddr, g, 16); else t_open.push_back({saddr, g});
+}
+static inline void cp_async_commit() { t_groups.push_back(std::move(t_open)); t_open.clear(); }
+template <int N> static inline void cp_async_wait() {
+    while ((int)t_groups.size() > N) { for (const CpOp& o : t_groups.front()) memcpy(dw_smem + o.dst, o.src, 16); t_groups.erase(t_groups.begin()); }
+}
+constexpr int kMarchTW = 7, kMarchMaxThreads = 256, kMarchMaxK = 4;
+#include "dwconv_march_kernel.inc"
+}  // namespace dfd
+
+// KS, S, C, W (square), CB; SPEC: compile-time geometry instantiation (as the network's own shapes use) or run-time geometry
+template <int KS, int S, int C, int W, int CB, bool SPEC>
+static int run_case() {
+    using namespace dfd;
+    constexpr int NR = 6, PAD = KS / 2, H = W, OW = (W + 2 * PAD - KS) / S + 1, OH = OW, strips = (OW + 6) / 7, frames = 2;
+    constexpr int rps = OH > 56 ? 56 : OH, segs = (OH + rps - 1) / rps, threads = strips * (CB / 2);
+    constexpr int need = (strips * 7 - 1) * S + KS, pixw = need > W + 2 * PAD ? need : W + 2 * PAD;
+    constexpr int chunks = W * (CB / 8), MAXK = (chunks <= 2 * threads) ? 2 : 4;
+    static_assert(OW % 7 == 0 && chunks <= MAXK * threads, "shape");
+    std::vector<_Float16> x((size_t)frames * H * W * C), out((size_t)frames * OH * OW * C);
+    std::vector<float> w((size_t)KS * KS * C), bias(C), parts((size_t)frames * segs * strips * C, NAN);
+    uint32_t seed = 17u + KS + C;
+    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xffff) / 32768.0f - 1.0f; };
+    for (auto& v : x) v = (_Float16)rnd();
+    for (auto& v : w) v = rnd() / KS;
+    for (auto& v : bias) v = 0.2f * rnd();
+    blockDim.x = threads;
+    const int grid = frames * segs * (C / CB);
+    for (int b = 0; b < grid; ++b) {
+        memset(dw_smem, 0xff, sizeof(dw_smem));
+        std::barrier<> bar(threads); g_cta_bar = &bar;
+        std::vector<std::thread> th;
+        for (int t = 0; t < threads; ++t)
+            th.emplace_back([&, t, b]() {
+                threadIdx.x = t; blockIdx.x = b; t_groups.clear(); t_open.clear();
+                if (SPEC) dwconv_march_kernel<__half, KS, S, NR, 128, true, MAXK, C, W, CB>(x.data(), w.data(), bias.data(), out.data(), parts.data(), H, W, C, OH, OW, CB, strips, rps, segs, pixw);
+                else dwconv_march_kernel<__half, KS, S, NR, 128, true, MAXK>(x.data(), w.data(), bias.data(), out.data(), parts.data(), H, W, C, OH, OW, CB, strips, rps, segs, pixw);
+            });
+        for (auto& t : th) t.join();
+    }
+    double max_err = 0, max_ref = 0, sum_err = 0;
+    std::vector<double> sums((size_t)frames * C, 0.0);
+    for (int f = 0; f < frames; ++f) for (int oy = 0; oy < OH; ++oy) for (int ox = 0; ox < OW; ++ox) for (int c = 0; c < C; ++c) {
+        float a = bias[c];
+        for (int ky = 0; ky < KS; ++ky) for (int kx = 0; kx < KS; ++kx) {
+            const int iy = oy * S + ky - PAD, ix = ox * S + kx - PAD;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) a += (float)x[(((size_t)f * H + iy) * W + ix) * C + c] * w[(size_t)(ky * KS + kx) * C + c];
+        }
+        const float r = a / (1.0f + expf(-a));
+        sums[(size_t)f * C + c] += r;
+        max_err = fmax(max_err, fabs((float)out[(((size_t)f * OH + oy) * OW + ox) * C + c] - r)); max_ref = fmax(max_ref, fabs(r));
+    }
+    for (int f = 0; f < frames; ++f) for (int c = 0; c < C; ++c) {
+        double s = 0;
+        for (int q = 0; q < segs * strips; ++q) s += parts[((size_t)f * segs * strips + q) * C + c];
+        sum_err = fmax(sum_err, fabs(s - sums[(size_t)f * C + c]));
+    }
+    const bool ok = max_err <= 2e-3 * fmax(1.0, max_ref) && sum_err < 5e-2 && std::isfinite(sum_err);
+    printf("dwconv_march k%d s%d C%d W%d CB%d %s %s: %d CTAs x %d threads, max |err| %.2e (scale %.2f), max |SE sum err| %.2e -> %s\n", KS, S, C, W, CB,
+           SPEC ? "compile-time geometry" : "run-time geometry", g_eager ? "eager" : "lazy ", grid, threads, max_err, max_ref, sum_err, ok ? "ok" : "MISMATCH");
+    return ok ? 0 : 1;
+}
+
+int main() {
+    int rc = 0;
+    for (int m = 0; m < 2; ++m) {
+        g_eager = m == 1;
+        rc |= run_case<3, 1, 480, 14, 32, true>();      // the network's own shapes with their tuned channel blocks
+        rc |= run_case<5, 1, 672, 14, 32, true>();
+        rc |= run_case<5, 2, 672, 14, 96, true>();
+        rc |= run_case<5, 1, 1152, 7, 64, true>();
+        rc |= run_case<3, 2, 240, 28, 48, true>();
+        rc |= run_case<5, 1, 240, 28, 16, false>();      // run-time geometry path
+        rc |= run_case<3, 1, 144, 56, 16, false>();
+    }
+    return rc;
+}

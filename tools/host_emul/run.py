@@ -1,6 +1,6 @@
 """Build and run the CPU emulations of the experimental kernels: the kernel text between the emulation markers of the .cu file
 is extracted UNCHANGED and compiled with the matching harness in this directory.
-    python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|all] [quick] [tsan]"""
+    python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|march|all] [quick] [tsan]"""
 import hashlib, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "build", "host_emul")
@@ -9,6 +9,7 @@ CASES = {"fused": ("mbconv_fused.cu", "DFD_FUSED_KERNEL", "mbconv_fused_kernel.i
          "attention": ("vit.cu", "DFD_ATT2_KERNEL", "vit_attention_v2_kernel.inc", "emul_vit_attention_v2.cpp"),
          "se": ("se.cu", "DFD_SE2_KERNEL", "se_kernel_v2.inc", "emul_se_v2.cpp"),
          "poolhead": ("poolhead.cu", "DFD_POOLHEAD_KERNEL", "pool_head_kernel.inc", "emul_pool_head.cpp"),
+         "march": ("dwconv_march.cu", "DFD_MARCH_KERNEL", "dwconv_march_kernel.inc", "emul_dwconv_march.cpp"),
          "prepstem": ("preprocess.cu", "DFD_PREP_KERNEL", "preprocess_kernel.inc", "emul_prep_stem.cpp")}
 which = [a for a in sys.argv[1:] if a in CASES] or (list(CASES) if "all" in sys.argv else ["fused"])
 tsan = "tsan" in sys.argv
@@ -19,6 +20,10 @@ for name in which:
         continue
     src = open(os.path.join(ROOT, "deepfake_video_detection_b200", "csrc", cu)).read()
     text = src[src.index(f"// {marker}_BEGIN"):src.index(f"// {marker}_END")]
+    if name == "march":                                # the kernel's one inline-asm statement (a 32-bit shared-memory load)
+        asm_line = 'asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(sb_c + jj * pix_b));'
+        assert text.count(asm_line) == 1
+        text = text.replace(asm_line, "raw = lds32(sb_c + jj * pix_b);")
     if name == "poolhead":                             # the one dynamic shared-memory array becomes a host buffer
         assert "extern __shared__ float s_f[];" in text
         text = text.replace("extern __shared__ float s_f[];", "float* s_f = g_dyn_smem;")
