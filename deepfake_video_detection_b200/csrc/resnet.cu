@@ -91,6 +91,7 @@ __global__ void rn_im2col_kernel(const T* __restrict__ in, T* __restrict__ a, in
     *reinterpret_cast<uint4*>(a + ((size_t)row * (k * k) + tap) * C + c8 * 8) = v;
 }
 
+// DFD_RESNET_SMALL_KERNELS_BEGIN   (tools/host_emul/ runs the three kernels below, unchanged, on CPU threads)
 // max-pool 3x3 s2 p1 on NHWC (padding never wins: -inf)
 template <typename T>
 __global__ void rn_maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, int OH, int OW, int64_t total) {
@@ -201,6 +202,8 @@ __global__ void __launch_bounds__(256) rn_pool_head_kernel(RnHead hw, const floa
         logits[(size_t)v * 2 + tid] = a;
     }
 }
+
+// DFD_RESNET_SMALL_KERNELS_END
 
 }  // namespace dfd
 

@@ -56,3 +56,8 @@ def test_depthwise_march_kernel_source_on_cpu():
     """Row a4, the dominant kernel of the step (depthwise kxk + BN + SiLU + squeeze-excite sums): the default kernel's source on CPU
     threads for five of the network's own shapes (compile-time geometry) and two run-time-geometry shapes, both cp.async models."""
     assert _run("march").count("-> ok") == 14
+
+
+def test_resnet_member_small_kernel_sources_on_cpu():
+    """Row a9 (`resnet50` ensemble member): its max-pool, average-pool and 2048-wide attention pool + head kernels on CPU threads."""
+    assert _run("resnet").count("-> ok") == 4
