@@ -54,6 +54,7 @@ __global__ void rnn_pack_x_kernel(const float* __restrict__ x, T* __restrict__ a
     }
 }
 
+// DFD_RNN_KERNELS_BEGIN   (tools/host_emul/ runs the two kernels below, unchanged, on CPU threads)
 // LogicCell gate math (RNNModel.py:24-39).  g fp32 [B][7H] = (and, or, forget, input, cell, output, not) pre-activations.
 template <typename T>
 __global__ void rnn_cell_kernel(const float* __restrict__ g, float* __restrict__ c, T* __restrict__ h16, int h16_stride,
@@ -131,6 +132,8 @@ __global__ void rnn_head_kernel(const float* __restrict__ outs, int Tn, int H,
     __syncthreads();
     if (j == 0) { float s = cb2[0]; for (int w = 0; w < nw; ++w) s += s_red[w]; prob[b] = 1.f / (1.f + expf(-s)); }
 }
+
+// DFD_RNN_KERNELS_END
 
 }  // namespace dfd
 

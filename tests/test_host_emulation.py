@@ -61,3 +61,8 @@ def test_depthwise_march_kernel_source_on_cpu():
 def test_resnet_member_small_kernel_sources_on_cpu():
     """Row a9 (`resnet50` ensemble member): its max-pool, average-pool and 2048-wide attention pool + head kernels on CPU threads."""
     assert _run("resnet").count("-> ok") == 4
+
+
+def test_rnn_head_kernel_sources_on_cpu():
+    """Row a10 (LogicRNNLSTM head, config 3): LogicCell gate math with the length mask, attention over time + classifier."""
+    assert _run("rnn").count("-> ok") == 2

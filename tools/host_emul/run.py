@@ -1,6 +1,6 @@
 """Build and run the CPU emulations of the experimental kernels: the kernel text between the emulation markers of the .cu file
 is extracted UNCHANGED and compiled with the matching harness in this directory.
-    python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|march|resnet|all] [quick] [tsan]"""
+    python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|march|resnet|rnn|all] [quick] [tsan]"""
 import hashlib, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "build", "host_emul")
@@ -11,6 +11,7 @@ CASES = {"fused": ("mbconv_fused.cu", "DFD_FUSED_KERNEL", "mbconv_fused_kernel.i
          "poolhead": ("poolhead.cu", "DFD_POOLHEAD_KERNEL", "pool_head_kernel.inc", "emul_pool_head.cpp"),
          "march": ("dwconv_march.cu", "DFD_MARCH_KERNEL", "dwconv_march_kernel.inc", "emul_dwconv_march.cpp"),
          "resnet": ("resnet.cu", "DFD_RESNET_SMALL_KERNELS", "resnet_small_kernels.inc", "emul_resnet_small.cpp"),
+         "rnn": ("rnn.cu", "DFD_RNN_KERNELS", "rnn_kernels.inc", "emul_rnn.cpp"),
          "prepstem": ("preprocess.cu", "DFD_PREP_KERNEL", "preprocess_kernel.inc", "emul_prep_stem.cpp")}
 which = [a for a in sys.argv[1:] if a in CASES] or (list(CASES) if "all" in sys.argv else ["fused"])
 tsan = "tsan" in sys.argv
@@ -25,6 +26,9 @@ for name in which:
         asm_line = 'asm volatile("ld.shared.b32 %0, [%1];" : "=r"(raw) : "r"(sb_c + jj * pix_b));'
         assert text.count(asm_line) == 1
         text = text.replace(asm_line, "raw = lds32(sb_c + jj * pix_b);")
+    if name == "rnn":
+        assert text.count("extern __shared__ float sm[];") == 1
+        text = text.replace("extern __shared__ float sm[];", "")
     if name == "resnet":                               # the pool head's dynamic shared memory is the harness's `sm` array
         assert text.count("extern __shared__ float sm[];") == 1
         text = text.replace("extern __shared__ float sm[];", "")
