@@ -89,7 +89,7 @@ struct HeadWeights {
     const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;       // [256][1280], [256], [2][256], [2]
 };
 // a video that is empty or longer than 1024 frames gets NaN logits
-cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos,
+cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,
                              int use_attention, float* logits, float* frame_scores, cudaStream_t s);
 
 }  // namespace dfd

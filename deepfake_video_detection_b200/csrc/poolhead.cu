@@ -29,7 +29,7 @@ constexpr int kPhChunk = 32;          // frames staged in shared memory at a tim
 
 __global__ void __launch_bounds__(kPhThreads)
 pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int32_t* __restrict__ offsets,
-                 int use_attention, float* __restrict__ logits, float* __restrict__ frame_scores) {
+                 int frames, int use_attention, float* __restrict__ logits, float* __restrict__ frame_scores) {
     extern __shared__ float s_f[];                 // [kPhChunk][kFeat] features of the current frame chunk
     __shared__ float s_w[kMaxT];
     __shared__ float s_hid[kPhChunk][kAttHidden + 1];
@@ -40,8 +40,10 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
     const int T = offsets[v + 1] - f0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int NW = kPhThreads / 32;
-    if (T <= 0 || T > kMaxT) {      // empty / over-long video: poison the outputs instead of guessing
-        if (threadIdx.x < 2) logits[(size_t)v * 2 + threadIdx.x] = __int_as_float(0x7fc00000);
+    if (T <= 0 || T > kMaxT || f0 < 0 || f0 + T > frames) {      // empty / over-long video or offsets outside the feature matrix:
+        if (threadIdx.x < 2) logits[(size_t)v * 2 + threadIdx.x] = __int_as_float(0x7fc00000);      // poison instead of guessing
+        if (frame_scores && T > 0 && f0 >= 0)
+            for (int t = threadIdx.x; t < T && f0 + t < frames; t += kPhThreads) frame_scores[f0 + t] = __int_as_float(0x7fc00000);
         return;
     }
     const float* fv = feat + (size_t)f0 * kFeat;
@@ -130,13 +132,13 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
 
 // DFD_POOLHEAD_KERNEL_END
 
-cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos,
+cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,
                              int use_attention, float* logits, float* frame_scores, cudaStream_t s) {
     if (videos <= 0) return cudaSuccess;
     const size_t smem = (size_t)kPhChunk * kFeat * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pool_head_kernel<<<(unsigned)videos, kPhThreads, smem, s>>>(hw, feat, offsets, use_attention, logits, frame_scores);
+    pool_head_kernel<<<(unsigned)videos, kPhThreads, smem, s>>>(hw, feat, offsets, (int)frames, use_attention, logits, frame_scores);
     return cudaGetLastError();
 }
 

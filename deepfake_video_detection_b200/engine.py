@@ -7,6 +7,7 @@ memory, streams and the caching allocator only — every arithmetic op runs in l
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Mapping, Optional, Sequence, Tuple
 
 import torch
@@ -16,6 +17,29 @@ from . import _lib
 PRECISIONS = {"fp16": _lib.DTYPE_FP16, "bf16": _lib.DTYPE_BF16}
 TORCH_DTYPE = {"fp16": torch.float16, "bf16": torch.bfloat16}
 DEFAULT_PRECISION = "fp16"      # bf16 storage misses the 2e-2 logit bar, fp16 meets it
+
+
+def normalize_key(key: str) -> str:
+    """Strip checkpoint wrappers the way the reference's `_normalize_state_dict_keys` does (app.py:1413-1432): 'module.',
+    'model.' and 'net.' prefixes are removed repeatedly until none is left ('model.module.backbone…' -> 'backbone…')."""
+    changed = True
+    while changed:
+        changed = False
+        for prefix in ("module.", "model.", "net."):
+            if key.startswith(prefix):
+                key = key[len(prefix):]
+                changed = True
+    return key
+
+
+def check_offsets(offsets_host: Sequence[int], frames: int) -> None:
+    """offsets must start at 0, never decrease, end at `frames` and describe videos of 1..1024 frames (the pool kernel's range)."""
+    off = [int(o) for o in offsets_host]
+    if not off or off[0] != 0 or off[-1] != frames:
+        raise ValueError(f"offsets must run from 0 to the number of frames ({frames}), got {off[:1]}..{off[-1:]}")
+    for a, b in zip(off, off[1:]):
+        if b - a < 1 or b - a > 1024:
+            raise ValueError("every video needs between 1 and 1024 frames")
 
 
 def _stream_ptr(device: torch.device) -> int:
@@ -44,10 +68,7 @@ class PackedWeights:
         for k, v in state_dict.items():
             if k.endswith("num_batches_tracked") or not torch.is_tensor(v):
                 continue
-            for prefix in ("module.", "model.", "net."):       # app.py:1413-1432 strips the same prefixes
-                if k.startswith(prefix):
-                    k = k[len(prefix):]
-            names.append(k.encode())
+            names.append(normalize_key(k).encode())
             keep.append(v.detach().to("cpu", torch.float32).contiguous())
         n = len(names)
         c_names = (C.c_char_p * n)(*names)
@@ -94,6 +115,24 @@ class FrameScorer:
         self.use_temporal_attention = bool(use_temporal_attention)
         self._lib = _lib.load()
         self.last_launch_count = 0
+        self._ws = {}                       # stream handle -> persistent workspace (grown on demand, reused across calls)
+        self._ws_lock = threading.Lock()
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        """Persistent per-(device, stream) workspace: calls on one stream run in stream order, so they can share it; calls on
+        different streams (re-entrant use from several request threads) get their own.  A regrow frees the old
+        block through the caching allocator on the stream that used it, i.e. behind the kernels still reading it."""
+        if torch.cuda.is_current_stream_capturing():        # a captured call owns its workspace (graph-private memory pool)
+            return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        key = _stream_ptr(self.device)
+        with self._ws_lock:
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < nbytes:
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                if len(self._ws) > 16:
+                    self._ws.clear()
+                self._ws[key] = ws
+        return ws
 
     # ---- helpers -----------------------------------------------------------------------------
     def _classify_input(self, frames: torch.Tensor) -> Tuple[int, int, int, int]:
@@ -136,7 +175,7 @@ class FrameScorer:
             return feat
         nbytes = C.c_size_t()
         _lib.check(self._lib.dfd_workspace_bytes(F, H, W, C.byref(nbytes)), "workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        ws = self._workspace(nbytes.value)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.dfd_effnet_b0_features(self.weights.handle, frames.data_ptr(), kind, F, H, W,
                                                         feat.data_ptr(), ws.data_ptr(), nbytes.value,
@@ -177,7 +216,7 @@ class FrameScorer:
             return (logits, scores, feat) if return_features else (logits, scores)
         nbytes = C.c_size_t()
         _lib.check(self._lib.dfd_score_workspace_bytes(F, H, W, C.byref(nbytes)), "score_workspace_bytes")
-        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        ws = self._workspace(nbytes.value)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.dfd_score_videos(self.weights.handle, frames.data_ptr(), kind, offsets.data_ptr(), V, F,
                                                   H, W, int(att), logits.data_ptr(), scores.data_ptr(), _ptr(feat),
@@ -217,9 +256,15 @@ class FrameScorer:
         need = max(b - a for _, _, a, b in chunks) * host_crops[0].numel()
         st = getattr(self, "_staging", None)
         if st is None or st["bytes"] < need:
-            st = {"bytes": need, "copy_stream": torch.cuda.Stream(self.device), "turn": 0,
+            # The staging buffers come from the caching allocator on the MAIN stream, so they may alias a block that earlier
+            # main-stream work (a previous score(), the old staging buffers of a smaller call) is still using: the copy
+            # stream's first write into each slot must wait for everything queued on main so far.
+            seed = torch.cuda.Event()
+            cs = st["copy_stream"] if st is not None else torch.cuda.Stream(self.device)
+            st = {"bytes": need, "copy_stream": cs, "turn": 0,
                   "buf": [torch.empty(need, dtype=torch.uint8, device=self.device) for _ in range(2)],
-                  "freed": [None, None]}
+                  "freed": [seed, seed]}
+            seed.record(main)
             self._staging = st
         cs = st["copy_stream"]
         frame_shape = tuple(host_crops.shape[1:])
@@ -228,8 +273,7 @@ class FrameScorer:
             st["turn"] += 1
             dst = st["buf"][slot][: (fb - fa) * host_crops[0].numel()].view((fb - fa,) + frame_shape)
             with torch.cuda.stream(cs):
-                if st["freed"][slot] is not None:
-                    cs.wait_event(st["freed"][slot])               # the batch that last used this buffer has been scored
+                cs.wait_event(st["freed"][slot])                   # the batch that last used this buffer has been scored
                 dst.copy_(host_crops[fa:fb], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(cs)

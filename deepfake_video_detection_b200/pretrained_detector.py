@@ -137,6 +137,8 @@ class PretrainedBackboneDetector(nn.Module):
         self._init_head_weights()
         self._scorer: Optional[FrameScorer] = None
         self._scorer_key = None
+        self._generation = 0             # bumped by _apply() (.to / .half / .cuda replace tensor storage)
+        self._flat = None                # cached [tensor, ...] of the state_dict, rebuilt when the generation changes
 
     def _init_head_weights(self):                                             # :80-85
         nn.init.kaiming_normal_(self.fc1.weight, mode="fan_out", nonlinearity="relu")
@@ -151,12 +153,24 @@ class PretrainedBackboneDetector(nn.Module):
                 p.requires_grad = True
 
     # ---- CUDA engine plumbing ----------------------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        self._generation += 1
+        self._flat = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _engine(self, device: torch.device) -> FrameScorer:
-        tensors = list(self.state_dict(keep_vars=True).items())
-        key = (str(device), self.precision, tuple((t.data_ptr(), t._version) for _, t in tensors))
+        # Cheap change detection (the reference calls forward once per request, app.py:2089): in-place updates (load_state_dict,
+        # optimiser steps, `.add_`) bump the tensors' version counters, storage moves go through _apply().  Walking the
+        # module tree (state_dict) only happens when the key changes; replacing a submodule by assignment needs `refresh()`.
+        if self._flat is None or self._flat[0] != self._generation:
+            self._flat = (self._generation, [t for t in self.state_dict(keep_vars=True).values()])
+        key = (str(device), self.precision, self._generation, sum(t._version for t in self._flat[1]))
         if self._scorer is None or key != self._scorer_key:
             if self._scorer is not None:
                 (self._scorer if self.backbone_name == "resnet50" else self._scorer.weights).free()
+            tensors = list(self.state_dict(keep_vars=True).items())
+            self._flat = (self._generation, [t for _, t in tensors])
+            key = (str(device), self.precision, self._generation, sum(t._version for t in self._flat[1]))
             sd = {k: v for k, v in tensors}
             if not self.use_temporal_attention:     # mean mode has no attention MLP; the packer wants the keys
                 z = torch.zeros
@@ -170,11 +184,18 @@ class PretrainedBackboneDetector(nn.Module):
             self._scorer_key = key
         return self._scorer
 
+    def refresh(self) -> None:
+        """Force a repack of the weights on the next forward (after replacing a submodule or a Parameter object)."""
+        self._generation += 1
+        self._flat = None
+
     def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """x (B,T,C,H,W) float -> logits (B,num_classes), frame_scores (B,T)   (:103-143)."""
         batch_size, num_frames, c, h, w = x.shape
         if self.training:
             return self._forward_eager(x)
+        if num_frames < 1 or num_frames > 1024:
+            raise ValueError(f"forward: between 1 and 1024 frames per video, got {num_frames} (the reference serves at most 64, app.py:2053)")
         if x.device.type != "cuda":
             raise RuntimeError("PretrainedBackboneDetector (B200 build): inference needs a CUDA tensor; "
                                "there is no CPU fallback (move model and input to cuda)")

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .engine import PRECISIONS, _stream_ptr
+from .engine import PRECISIONS, _stream_ptr, normalize_key
 
 FEATURE_DIM = 2048
 
@@ -20,7 +20,7 @@ class ResNet50Scorer:
             raise RuntimeError("ResNet50Scorer: a CUDA device is required; there is no CPU fallback")
         self.use_temporal_attention = use_temporal_attention
         lib = _lib.load()
-        keep = [(k.encode(), v.detach().to("cpu", torch.float32).contiguous()) for k, v in state_dict.items()
+        keep = [(normalize_key(k).encode(), v.detach().to("cpu", torch.float32).contiguous()) for k, v in state_dict.items()
                 if torch.is_tensor(v) and v.is_floating_point()]
         n = len(keep)
         names = (C.c_char_p * n)(*[k for k, _ in keep])
@@ -36,6 +36,12 @@ class ResNet50Scorer:
         if self.handle:
             _lib.load().dfd_resnet50_free_weights(self.handle)
             self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
     def score(self, x_flat: torch.Tensor, offsets: torch.Tensor, max_frames: int, use_temporal_attention=None):
         """x_flat fp32 (F,3,224,224) on the device, offsets int32 (V+1) -> logits (V,2), frame_scores (F)."""

@@ -65,6 +65,14 @@ class LogicRNNLSTM(nn.Module):                  # RNNModel.py:43-147
         self._handle, self._key = h, key
         return h
 
+    def __del__(self):                    # release the packed device weights with the module
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().dfd_rnn_free_weights(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
     def forward(self, x, lengths=None):
         batch_size, seq_length, _ = x.size()
         if lengths is not None:                                   # :92-95 (outputs stay in sorted order, as in the reference)

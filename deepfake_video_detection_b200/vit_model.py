@@ -102,6 +102,14 @@ class ViTFeatureExtractor(nn.Module):            # models.py:88-107
         self._handle, self._key = h, key
         return h
 
+    def __del__(self):                    # release the packed device weights with the module
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().dfd_vit_free_weights(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
     def forward(self, x):
         if self.training:
             return self.vit(x)
@@ -182,6 +190,14 @@ class DeepfakeModel(nn.Module):
             raise RuntimeError(f"dfd_gcn_pack_weights failed ({rc}): {lib.dfd_vit_last_error().decode()}")
         self._head, self._head_key = h, key
         return h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_head", None) is not None:
+                _lib.load().dfd_gcn_free_weights(self._head)
+                self._head = None
+        except Exception:
+            pass
 
     def forward(self, images, A_norm):
         B, N, Cc, H, W = images.shape

@@ -185,3 +185,22 @@ def fold_bn(w: torch.Tensor, sd, bn_prefix: str):
     """w' = w·γ/√(σ²+eps), b' = β − μ·γ/√(σ²+eps)  (fp32)."""
     scale = sd[bn_prefix + ".weight"] / torch.sqrt(sd[bn_prefix + ".running_var"] + BN_EPS)
     return w * scale.view(-1, *([1] * (w.dim() - 1))), sd[bn_prefix + ".bias"] - sd[bn_prefix + ".running_mean"] * scale
+
+
+def score_ragged_batched(sd, crops_u8, offsets, use_temporal_attention: bool = True, chunk: int = 256):
+    """`score_ragged` for large samples: the trunk (per-frame independent, pretrained_detector.py:116) runs over chunks of
+    frames instead of one call per video; pool + head stay one B=1 call per video (:123-141).  Pinned against `score_ragged`
+    in tests/test_oracle.py."""
+    F_total = int(offsets[-1])
+    feats = []
+    with torch.no_grad():
+        for a in range(0, F_total, chunk):
+            feats.append(trunk_features(sd, prep_u8_hwc(crops_u8[a:min(F_total, a + chunk)])))
+        feats = torch.cat(feats) if feats else torch.zeros(0, 1280)
+        logits, scores = [], []
+        for v in range(len(offsets) - 1):
+            a, b = int(offsets[v]), int(offsets[v + 1])
+            lg, fs = attention_pool_head(sd, feats[a:b].unsqueeze(0), use_temporal_attention)
+            logits.append(lg[0])
+            scores.append(fs[0])
+    return torch.stack(logits), torch.cat(scores), feats

@@ -130,6 +130,45 @@ def test_score_host_matches_device_path(scorer, golden_crops):
             assert torch.equal(lg, ref_l) and torch.equal(sc, ref_s)
 
 
+def test_score_host_right_after_score_and_staging_regrow(scorer, golden_crops):
+    """No synchronisation between calls: score() leaves work in flight on the main stream, then score_host() allocates its
+    staging buffers (which may alias memory that work still uses) and copies on a side stream; a later, larger call regrows
+    the staging buffers while the previous call is still running.  Results must be the bits of the synchronous path."""
+    from deepfake_video_detection_b200 import FrameScorer, make_offsets
+    crops, offsets = golden_crops
+    lens = np.diff(offsets).tolist()
+    dev = torch.from_numpy(crops).cuda()
+    off = make_offsets(lens, "cuda")
+    ref_l, ref_s = scorer.score(dev, off)
+    ref_small, _ = scorer.score(dev[: offsets[2]], make_offsets(lens[:2], "cuda"))
+    torch.cuda.synchronize()
+    host_small = torch.from_numpy(crops[: offsets[2]]).pin_memory()
+    host_all = torch.from_numpy(crops).pin_memory()
+    for _ in range(3):
+        fresh = FrameScorer.__new__(FrameScorer)                  # same packed weights, no staging / workspace yet
+        fresh.__dict__.update({k: v for k, v in scorer.__dict__.items() if k not in ("_staging", "_ws", "_offsets_cache")})
+        fresh._ws = {}
+        big = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        big.fill_(7)                                              # in flight on main; freed right away -> reusable block
+        del big
+        a, _ = fresh.score(dev, off)                              # in flight on main
+        b, _ = fresh.score_host(host_small, lens[:2])             # first staging allocation, no sync before it
+        c, cs = fresh.score_host(host_all, lens)                  # staging regrow while the previous call is in flight
+        d, _ = fresh.score_host(host_small, lens[:2])
+        torch.cuda.synchronize()
+        assert torch.equal(a, ref_l) and torch.equal(b, ref_small) and torch.equal(c, ref_l) and torch.equal(cs, ref_s) and torch.equal(d, ref_small)
+
+
+def test_bad_offsets_poison_instead_of_reading_out_of_bounds(scorer, golden_crops):
+    """Offsets that run past the feature matrix give NaN logits / frame scores for that video, never an out-of-bounds read."""
+    crops, offsets = golden_crops
+    feat = scorer.features(torch.from_numpy(crops[:6]).cuda())
+    bad = torch.tensor([0, 4, 9], dtype=torch.int32, device="cuda")          # second video claims frames 4..8 of a 6-frame batch
+    logits, scores = scorer.pool_head(feat, bad)
+    good, _ = scorer.pool_head(feat[:4], torch.tensor([0, 4], dtype=torch.int32, device="cuda"))
+    assert torch.equal(logits[0], good[0]) and torch.isnan(logits[1]).all() and torch.isnan(scores[4:6]).all()
+
+
 def test_full_c2_batch_properties(scorer, synth_sd):
     """BASELINE configs[1] size (64 videos x 32 crops): size-independent properties + spot parity against the oracle."""
     from deepfake_video_detection_b200 import decide, make_offsets

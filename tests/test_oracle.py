@@ -112,3 +112,13 @@ def test_fp16_storage_meets_logit_bar_and_bf16_does_not(synth_sd):
         lbf, _ = O.attention_pool_head(synth_sd, E.trunk_features_bf16(synth_sd, x).view(4, 4, -1))
     assert (l16 - l32).abs().max().item() < 2e-2
     assert (lbf - l32).abs().max().item() > (l16 - l32).abs().max().item()
+
+
+def test_batched_oracle_scorer_matches_per_video_calls(synth_sd, golden, golden_crops):
+    """`score_ragged_batched` (large parity samples) against `score_ragged` (one reference B=1 call per video) and the goldens."""
+    crops, offsets = golden_crops
+    lg, fs, feats = O.score_ragged_batched(synth_sd, crops, offsets, chunk=7)
+    lg1, fs1 = O.score_ragged(synth_sd, crops, offsets)
+    assert (lg - lg1).abs().max().item() < 1e-5 and (fs - fs1).abs().max().item() < 1e-6
+    assert np.abs(lg.numpy() - golden["logits"]).max() < 1e-4
+    assert np.abs(feats.numpy() - golden["features"]).max() < 1e-4

@@ -73,7 +73,7 @@ int main() {
             for (int i = 0; i < kPhThreads / 32; ++i) g_warps.emplace_back(new WarpX());
             std::vector<std::thread> th;
             for (int t = 0; t < kPhThreads; ++t)
-                th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b; pool_head_kernel(hw, feat.data(), off.data(), att, logits.data(), scores.data()); });
+                th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b; pool_head_kernel(hw, feat.data(), off.data(), (int)(feat.size() / 1280), att, logits.data(), scores.data()); });
             for (auto& t : th) t.join();
         }
         double max_l = 0, max_s = 0; bool nan_ok = true;
