@@ -64,7 +64,6 @@ _SIGNATURES = {
     "dfd_k_conv1x1_conv3x3": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp, C.c_size_t, _vp]),
     "dfd_k_mbconv_fused_supported": (_int, [_int, _int, _int, _int, _int, _int]),
     "dfd_k_mbconv_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _int, _vp]),
-    "dfd_k_stem_dw_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp]),
     "dfd_k_conv3x3_maps": (_i64, [_int, _int, _int, _int, _vp, _vp, _vp, _vp]),
     "dfd_k_pack_stem_row": (_int, [_vp, _vp, _vp, _vp]),
     "dfd_k_resize_coeffs": (_int, [_int, _int, _vp, _vp, C.POINTER(_int)]),

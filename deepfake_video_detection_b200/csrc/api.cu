@@ -85,16 +85,7 @@ struct BlockW {
 // r = pixels per GEMM row for a pointwise layer with K input channels (r*K <= 64)
 int pack_factor(int K) { return K <= 16 ? 4 : (K <= 32 ? 2 : 1); }
 
-bool use_simt_stem() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DFD_STEM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
-    return v == 1;
-}
-bool use_simt_gemm() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DFD_GEMM_IMPL"); v = (e && strcmp(e, "simt") == 0) ? 1 : 0; }
-    return v == 1;
-}
+// frames per pass of the trunk (bounds the workspace; results do not depend on it: tests/test_gpu_path.py)
 int64_t chunk_frames() {
     const char* e = getenv("DFD_CHUNK_FRAMES");
     long v = e ? atol(e) : 0;
@@ -450,8 +441,7 @@ int run_gemm(const void* A, const void* Wt, const float* bias, const float* gate
              int64_t M, int K, int N, int HW, int act, int dtype, cudaStream_t s, int r = 1) {
     prof_next(gate ? KC_GEMM_PROJECT : KC_GEMM_EXPAND, (double)M * (K + N + (R ? N : 0)) * 2, 2.0 * M * K * N, s);
     M /= r; K *= r; N *= r; HW /= r;
-    if (use_simt_gemm()) DFD_LAUNCH(dfd::launch_gemm_simt(A, Wt, bias, gate, R, D, nullptr, M, K, N, HW, act, dtype, s), "gemm (simt)");
-    else DFD_LAUNCH(dfd::launch_gemm_tc(A, Wt, bias, gate, R, D, M, K, N, HW, act, dtype, s), "gemm (tcgen05)");
+    DFD_LAUNCH(dfd::launch_gemm_tc(A, Wt, bias, gate, R, D, M, K, N, HW, act, dtype, s), "gemm (tcgen05)");
     return DFD_OK;
 }
 
@@ -469,31 +459,20 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
     const int dt = w->dtype;
 
     int h = H / 2, wd = W / 2, cur = 0;
-    // DFD_FUSE_EXPAND=1 (experimental, off by default until it has been verified on a GPU): the early HBM-bound blocks run
-    // expand 1x1 + depthwise as ONE kernel (mbconv_fused.cu); the expanded tensor never goes to HBM.
-    const char* env_fuse = getenv("DFD_FUSE_EXPAND");
-    // 1: the three early blocks; 2: every block mbconv_fused.cu supports; 3: also the stem fused with block 0's depthwise conv
-    const int fuse = (env_fuse && !use_simt_gemm()) ? atoi(env_fuse) : 0;
-    const bool stem_fused = fuse >= 3 && in_kind == DFD_IN_U8_HWC && !use_simt_stem() && H == 224 && W == 224 && w->stem_wrow && w->stem_b4 &&
-                            !w->blocks[0].has_expand && w->blocks[0].k == 3 && w->blocks[0].stride == 1 && w->blocks[0].mid == 32 &&
-                            dfd::dw_num_partials(112, 112, 32, 3, 1) == dfd::dw_march_slots(112, 112);
-    if (!stem_fused) {
-        prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
-        if (in_kind == DFD_IN_U8_HWC && !use_simt_stem())
-            DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, w->stem_wrow, w->stem_b4, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
-        else
-            DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
-    }
+    prof_next(KC_STEM, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)h * wd * 32 * 2), 2.0 * frames * h * wd * 27 * 32, s);
+    if (in_kind == DFD_IN_U8_HWC)      // uint8 crops: tensor prep folded into the tcgen05 stem; float inputs (the module's forward): CUDA-core stem
+        DFD_LAUNCH(dfd::launch_stem_tc(reinterpret_cast<const uint8_t*>(in), w->stem_w16, w->stem_b, w->stem_wrow, w->stem_b4, io[cur], frames, H, W, dt, s), "stem kernel (tcgen05)");
+    else
+        DFD_LAUNCH(dfd::launch_stem(in, in_kind, w->stem_w, w->stem_b, io[cur], frames, H, W, dt, s), "stem kernel");
     for (int i = 0; i < kNumBlocks; ++i) {
         const BlockW& B = w->blocks[i];
         const void* x = io[cur];
         const void* e = x;
-        const int fuse_level = dfd::mbconv_fused_level(h, wd, B.cin, B.mid, B.k, B.stride);
-        const bool fused = fuse > 0 && B.has_expand && fuse_level > 0 && fuse_level <= fuse &&
-                           dfd::dw_num_partials((h + 2 * (B.k / 2) - B.k) / B.stride + 1, (wd + 2 * (B.k / 2) - B.k) / B.stride + 1, B.mid, B.k, B.stride) ==
-                               dfd::dw_march_slots((h + 2 * (B.k / 2) - B.k) / B.stride + 1, (wd + 2 * (B.k / 2) - B.k) / B.stride + 1);
+        // the early, HBM-bound blocks of the 224x224 network run expand 1x1 + depthwise as ONE kernel (mbconv_fused.cu): the
+        // expanded tensor never goes to HBM; same rounding points, same partial-sum layout
+        const bool fused = B.has_expand && dfd::mbconv_fused_supported(h, wd, B.cin, B.mid, B.k, B.stride);
         if (B.has_expand && !fused) {
-            const int r = (B.exp_pack > 1 && !use_simt_gemm() && (h * wd) % B.exp_pack == 0) ? B.exp_pack : 1;
+            const int r = (B.exp_pack > 1 && (h * wd) % B.exp_pack == 0) ? B.exp_pack : 1;
             int rc = run_gemm(x, r > 1 ? B.exp_wp : B.exp_w, r > 1 ? B.exp_bp : B.exp_b, nullptr, nullptr, bufE,
                               frames * h * wd, B.cin, B.mid, h * wd, 1, dt, s, r);
             if (rc) return rc;
@@ -501,12 +480,7 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         }
         const int pad = B.k / 2;
         const int oh = (h + 2 * pad - B.k) / B.stride + 1, ow = (wd + 2 * pad - B.k) / B.stride + 1;
-        if (i == 0 && stem_fused) {
-            prof_next(KC_MBCONV_FUSED, (double)frames * (in_frame_bytes(in_kind, H, W) + (double)oh * ow * B.mid * 2),
-                      2.0 * frames * ((double)h * wd * 27 * 32 + (double)oh * ow * B.mid * B.k * B.k), s);
-            DFD_LAUNCH(dfd::launch_stem_dw_fused(reinterpret_cast<const uint8_t*>(in), w->stem_wrow, w->stem_b4, B.dw_w, B.dw_b, bufD, part, frames, H, W, dt, s),
-                       "fused stem + depthwise kernel");
-        } else if (fused) {
+        if (fused) {
             prof_next(KC_MBCONV_FUSED, (double)frames * ((double)h * wd * B.cin + (double)oh * ow * B.mid) * 2,
                       2.0 * frames * ((double)h * wd * B.cin * B.mid + (double)oh * ow * B.mid * B.k * B.k), s);
             DFD_LAUNCH(dfd::launch_mbconv_fused(x, B.exp_w, B.exp_b, B.dw_w, B.dw_b, bufD, part, frames, h, wd, B.cin, B.mid, B.k, B.stride, dt, s),
@@ -519,7 +493,7 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         prof_next(KC_SE, (double)frames * B.mid * (nparts + 1) * 4, 4.0 * frames * B.mid * B.rd, s);
         DFD_LAUNCH(dfd::launch_se(part, nparts, 1.0f / (float)(oh * ow), B.se_w1, B.se_b1, B.se_w2t, B.se_b2, gate,
                                   frames, B.mid, B.rd, s), "squeeze-excite kernel");
-        if (oh * ow >= kFrameWeightsMinHW && !use_simt_gemm()) {
+        if (oh * ow >= kFrameWeightsMinHW) {
             // big maps: SE gate folded into per-frame weights, ungated GEMM on frame-aligned tiles
             prof_next(KC_GEMM_PROJECT, (double)frames * B.cout * B.mid * 2 * 2, 0, s);
             const int r = (B.proj_pack > 1 && (oh * ow) % B.proj_pack == 0) ? B.proj_pack : 1;
@@ -535,10 +509,7 @@ int run_trunk_chunk(const dfd_weights* w, const void* in, int in_kind, int64_t f
         cur ^= 1; h = oh; wd = ow;
     }
     prof_next(KC_GEMM_HEAD_POOL, (double)frames * h * wd * 320 * 2 + (double)frames * 1280 * 4, 2.0 * frames * h * wd * 320 * 1280, s);
-    if (use_simt_gemm())
-        DFD_LAUNCH(dfd::launch_gemm_simt(io[cur], w->head_w, w->head_b, nullptr, nullptr, nullptr, feat, frames * h * wd, 320, 1280, h * wd, 1, dt, s), "head (simt)");
-    else
-        DFD_LAUNCH(dfd::launch_gemm_tc_pool(io[cur], w->head_w, w->head_b, feat, frames * h * wd, 320, 1280, h * wd, dt, s), "head (tcgen05)");
+    DFD_LAUNCH(dfd::launch_gemm_tc_pool(io[cur], w->head_w, w->head_b, feat, frames * h * wd, 320, 1280, h * wd, dt, s), "head (tcgen05)");
     return DFD_OK;
 }
 
@@ -710,20 +681,20 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
         if (e2 != cudaSuccess) return cuda_fail(e2, "gemm (tcgen05, per-frame weights) sync");
         return DFD_OK;
     }
-    if (impl == 1) DFD_LAUNCH(dfd::launch_gemm_simt(d_A, d_W, d_bias, d_gate, d_R, d_D, nullptr, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (simt)");
-    else DFD_LAUNCH(dfd::launch_gemm_tc(d_A, d_W, d_bias, d_gate, d_R, d_D, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (tcgen05)");
+    if (impl != 0) return fail(DFD_EINVAL, "dfd_k_gemm: impl must be 0 (tcgen05 GEMM) or 2 (per-frame weights)");
+    DFD_LAUNCH(dfd::launch_gemm_tc(d_A, d_W, d_bias, d_gate, d_R, d_D, M, K, N, HW, act, dtype, (cudaStream_t)stream), "gemm (tcgen05)");
     return DFD_OK;
 }
 int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K, int N,
                     int HW, int dtype, int impl, void* stream) {
     g_launches = 0;
-    if (impl == 1) DFD_LAUNCH(dfd::launch_gemm_simt(d_A, d_W, d_bias, nullptr, nullptr, nullptr, d_feat, M, K, N, HW, 1, dtype, (cudaStream_t)stream), "head (simt)");
-    else DFD_LAUNCH(dfd::launch_gemm_tc_pool(d_A, d_W, d_bias, d_feat, M, K, N, HW, dtype, (cudaStream_t)stream), "head (tcgen05)");
+    if (impl != 0) return fail(DFD_EINVAL, "dfd_k_gemm_pool: impl must be 0 (tcgen05 GEMM)");
+    DFD_LAUNCH(dfd::launch_gemm_tc_pool(d_A, d_W, d_bias, d_feat, M, K, N, HW, dtype, (cudaStream_t)stream), "head (tcgen05)");
     return DFD_OK;
 }
 
 // relu(conv3x3(relu(conv1x1(x)))) of a resnet bottleneck through the haloed-map path (gemm_tc.cu CONV variants): one memset,
-// one scattering pointwise GEMM, one implicit 3x3 GEMM.  Test / profiling aid for DFD_RESNET_IMPLICIT.
+// one scattering pointwise GEMM, one implicit 3x3 GEMM (the path resnet.cu runs for its 13 stride-1 3x3 convolutions).
 int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2, void* d_out,
                           int64_t frames, int H, int W, int K, int C, int N, int dtype, void* d_pad, size_t pad_bytes, void* stream) {
     g_launches = 0;
@@ -737,7 +708,7 @@ int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1,
     return DFD_OK;
 }
 
-// EXPERIMENTAL: expand 1x1 + BN + SiLU fused into the row-marching depthwise kernel (mbconv_fused.cu)
+// expand 1x1 + BN + SiLU fused into the row-marching depthwise kernel (mbconv_fused.cu): the early blocks of the trunk
 int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, const float* d_w, const float* d_bias, void* d_out,
                        float* d_partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype, void* stream) {
     g_launches = 0;
@@ -745,29 +716,6 @@ int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, con
     if (!dfd::mbconv_fused_supported(H, W, cin, mid, k, stride)) return fail(DFD_EINVAL, "dfd_k_mbconv_fused: unsupported block shape");
     DFD_LAUNCH(dfd::launch_mbconv_fused(d_x, d_we, d_be, d_w, d_bias, d_out, d_partials, frames, H, W, cin, mid, k, stride, dtype, (cudaStream_t)stream),
                "fused expand + depthwise kernel");
-    return DFD_OK;
-}
-// EXPERIMENTAL: stem (h_w27x32 / h_bias32 as dfd_k_pack_stem_row takes them, packed and uploaded inside; synchronous) fused with
-// the depthwise 3x3 of block 0
-int dfd_k_stem_dw_fused(const uint8_t* d_in, const float* h_w27x32, const float* h_bias32, const float* d_w, const float* d_bias,
-                        void* d_out, float* d_partials, int64_t frames, int H, int W, int dtype, void* stream) {
-    g_launches = 0;
-    if (!d_in || !h_w27x32 || !h_bias32 || !d_w || !d_bias || !d_out || !d_partials) return fail(DFD_EINVAL, "dfd_k_stem_dw_fused: null pointer");
-    if (H != 224 || W != 224) return fail(DFD_EINVAL, "dfd_k_stem_dw_fused: 224x224 crops only");
-    HostArena a; size_t w_off = 0, b_off = 0;
-    pack_stem_row(a, h_w27x32, h_bias32, w_off, b_off);
-    void* dw = nullptr;
-    DFD_CUDA(cudaMalloc(&dw, a.bytes.size()), "cudaMalloc(stem operands)");
-    cudaError_t e = cudaMemcpy(dw, a.bytes.data(), a.bytes.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        e = dfd::launch_stem_dw_fused(d_in, reinterpret_cast<uint8_t*>(dw) + w_off, reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(dw) + b_off),
-                                      d_w, d_bias, d_out, d_partials, frames, H, W, dtype, (cudaStream_t)stream);
-        g_launches = 1;
-    }
-    const cudaError_t e2 = cudaStreamSynchronize((cudaStream_t)stream);
-    cudaFree(dw);
-    if (e != cudaSuccess) return cuda_fail(e, "fused stem + depthwise kernel");
-    if (e2 != cudaSuccess) return cuda_fail(e2, "fused stem + depthwise kernel sync");
     return DFD_OK;
 }
 int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) { return dfd::mbconv_fused_supported(H, W, cin, mid, k, stride) ? 1 : 0; }

@@ -1,4 +1,4 @@
-// K2 (row-marching variant) — MBConv depthwise conv kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU,
+// K2 — MBConv depthwise conv kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU,
 // NHWC 16-bit, fused with the squeeze-excite spatial sums (timm `conv_dw` + `bn1` + SqueezeExcite's
 // `x.mean((2,3))`; reference call site pretrained_detector.py:116).
 //
@@ -17,7 +17,7 @@
 //
 // The row loop is unrolled over one period of the accumulator ring (PERIOD = stride * RING input rows) so that
 // every ring slot index is a compile-time constant.  For every output the taps are added in (ky, kx) order
-// starting from the bias, exactly like the window-per-row kernel in dwconv.cu, so both give the same bits.
+// starting from the bias.
 //
 // SE squeeze: a thread sums its SiLU outputs (fp32, before the 16-bit rounding) over its segment and strip and
 // writes its own 2-channel slice of partial row (segment, strip): no atomics, fixed order; se.cu adds the
@@ -241,9 +241,8 @@ bool dw_march_supported(int H, int W, int C, int k, int stride) {
 template <typename T>
 static cudaError_t launch_march_t(const void* in, const float* w, const float* bias, void* out, float* partials,
                                   int64_t frames, int H, int W, int C, int k, int stride, cudaStream_t s) {
-    static const int max_threads = getenv("DFD_DW_MAXT") ? atoi(getenv("DFD_DW_MAXT")) : 128;
-    const int env_cb = g_march_cb_override;                                              // sweeps only
-    static const bool no_spec = getenv("DFD_DW_NOSPEC") != nullptr;
+    constexpr int max_threads = 128;
+    const int env_cb = g_march_cb_override;                                              // sweeps only (dfd_k_set_dw_channel_block)
     constexpr int NR = 6;
     const int pad = k / 2;
     const int OH = (H + 2 * pad - k) / stride + 1, OW = (W + 2 * pad - k) / stride + 1;
@@ -268,7 +267,7 @@ static cudaError_t launch_march_t(const void* in, const float* w, const float* b
         return cudaGetLastError(); }
     // the network's own layer shapes at 224x224, fp16: compile-time geometry
 #define DFD_MARCH_SPEC(KS, ST, MR, CC_, WW_, CB_) \
-    if constexpr (std::is_same<T, __half>::value) if (!no_spec && k == KS && stride == ST && C == CC_ && W == WW_ && H == WW_ && CB == CB_) { \
+    if constexpr (std::is_same<T, __half>::value) if (k == KS && stride == ST && C == CC_ && W == WW_ && H == WW_ && CB == CB_) { \
         constexpr int kOW = (WW_ + 2 * (KS / 2) - KS) / ST + 1; \
         static_assert(kOW % kMarchTW == 0, "specialised shapes have whole strips"); \
         constexpr int kMK = (WW_ * (CB_ / 8) <= 2 * (kOW / kMarchTW) * (CB_ / 2)) ? 2 : 4; \
@@ -286,8 +285,10 @@ static cudaError_t launch_march_t(const void* in, const float* w, const float* b
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_dwconv_march(const void* in, const float* w, const float* bias, void* out, float* partials,
-                                int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s) {
+int dw_num_partials(int OH, int OW, int C, int k, int stride) { (void)C; (void)k; (void)stride; return dw_march_slots(OH, OW); }
+
+cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, void* out, float* partials,
+                          int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s) {
     if (dtype == kDtypeFP16) return launch_march_t<__half>(in, w, bias, out, partials, frames, H, W, C, k, stride, s);
     return launch_march_t<__nv_bfloat16>(in, w, bias, out, partials, frames, H, W, C, k, stride, s);
 }

@@ -532,9 +532,8 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.lbo_b = (uint32_t)a.NBp * 16 + 16;
     a.kchunks_pad = ((a.K >> 3) + 1) & ~1;
     { static const int env_dbg = getenv("DFD_GEMM_DBG") ? atoi(getenv("DFD_GEMM_DBG")) : 0; a.dbg = env_dbg; }
-    {   static const int env_xg = getenv("DFD_GEMM_XG") ? atoi(getenv("DFD_GEMM_XG")) : 4;
-        a.xg = xform_warps > 0 ? env_xg : 1;
-        if (a.xg < 1 || a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1; }
+    a.xg = xform_warps > 0 ? 4 : 1;                                // transformer warp groups (take alternate stages)
+    if (a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1;
     a.b_stage_bytes = (uint32_t)a.NBp * 128u;                      // streamed W block: NBp rows x 64 elements, 128-byte swizzle
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
     {   // accumulator ring: as many buffers as fit in the 512 TMEM columns (<= 8); epilogue groups take alternate tiles
@@ -542,8 +541,6 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
         int na = groups; while (na > fit) na >>= 1;
         a.na = na;
         int nacc = (fit / na) * na; if (nacc > 8) nacc = 8 / na * na;
-        static const int env_nacc = getenv("DFD_GEMM_NACC") ? atoi(getenv("DFD_GEMM_NACC")) : 0;         // experiments only
-        if (env_nacc >= na && nacc > env_nacc) nacc = env_nacc / na * na;
         a.nacc = nacc;
     }
     uint32_t cols = 32; while (cols < (uint32_t)(a.nacc * a.NBp)) cols <<= 1;
@@ -554,10 +551,9 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
     const size_t budget = 227 * 1024;
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
-    static const size_t env_res = getenv("DFD_GEMM_RESLIM") ? (size_t)atol(getenv("DFD_GEMM_RESLIM")) : 0;      // experiments only
     // Weights stay resident only up to 60 KB: beyond that the shared memory is worth more as pipeline stages (W blocks then
     // stream from L2 by TMA).  Measured: 672->112 gated 233 -> 178 us, 112->672 expand 88 -> 78 us per 2048 / 1024 frames.
-    const size_t res_limit = env_res ? env_res : 60 * 1024;
+    const size_t res_limit = 60 * 1024;
     a.b_resident = 0;
     if (a.tpf == 0) {
         if (bres <= res_limit) a.b_resident = 1;
@@ -569,8 +565,6 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     const size_t bres_pad = ((size_t)a.b_res_bytes + 1023) & ~size_t(1023);      // + worst-case alignment of the stage ring
     int stages = (int)((budget - fixed - bres_pad - 1024) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
-    static const int env_stages = getenv("DFD_GEMM_STAGES") ? atoi(getenv("DFD_GEMM_STAGES")) : 0;     // experiments only
-    if (env_stages >= 3 && stages > env_stages) stages = env_stages;
     if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
     while (a.xg > 1 && (a.xg > stages || a.xg > 4)) a.xg >>= 1;      // groups take alternate stages: never more groups than stages
@@ -714,24 +708,14 @@ cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bia
     a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = R; a.D = D; a.feat = nullptr;
     a.M = M; a.K = K; a.N = N; a.HW = 1;
     a.rows_per_tile = kBM; a.m_tiles = (M + kBM - 1) / kBM; a.inv_hw = 0.f;
-    // DFD_GEMM_F32_EPI16=1 (experimental, off by default until it has been timed on a GPU): 16 epilogue warps for the fp32-output
-    // variants.  The ViT attention-projection GEMM (K = 768: 12 k-blocks per tile) runs at 410 TFLOP/s against 1.0-1.1 PFLOP/s of
-    // the qkv / fc2 GEMMs: its epilogue (fp32 residual read + write, 8 warps) is as long as its main loop.
-    const char* env_e16 = getenv("DFD_GEMM_F32_EPI16");
-    if (env_e16 && atoi(env_e16) != 0) {
-        if (R) {
-            if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, true, false, 16, 4, 0, true>, a, 16, 4, 0, s);
-            return run(gemm_tc_kernel<__nv_bfloat16, false, 0, true, false, 16, 4, 0, true>, a, 16, 4, 0, s);
-        }
-        if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, false, false, 16, 4, 0, true>, a, 16, 4, 0, s);
-        return run(gemm_tc_kernel<__nv_bfloat16, false, 0, false, false, 16, 4, 0, true>, a, 16, 4, 0, s);
-    }
+    // 16 epilogue warps: with 12 k-blocks per tile (ViT attention projection, K = 768) the fp32 residual read + write of an
+    // 8-warp epilogue is as long as the main loop (measured on B200: ViT-B/16 at batch 512 28.73 -> 28.57 ms)
     if (R) {
-        if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, true, false, 8, 4, 0, true>, a, 8, 4, 0, s);
-        return run(gemm_tc_kernel<__nv_bfloat16, false, 0, true, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+        if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, true, false, 16, 4, 0, true>, a, 16, 4, 0, s);
+        return run(gemm_tc_kernel<__nv_bfloat16, false, 0, true, false, 16, 4, 0, true>, a, 16, 4, 0, s);
     }
-    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
-    return run(gemm_tc_kernel<__nv_bfloat16, false, 0, false, false, 8, 4, 0, true>, a, 8, 4, 0, s);
+    if (dtype == kDtypeFP16) return run(gemm_tc_kernel<__half, false, 0, false, false, 16, 4, 0, true>, a, 16, 4, 0, s);
+    return run(gemm_tc_kernel<__nv_bfloat16, false, 0, false, false, 16, 4, 0, true>, a, 16, 4, 0, s);
 }
 
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,

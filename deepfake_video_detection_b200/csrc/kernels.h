@@ -20,33 +20,24 @@ cudaError_t launch_stem(const void* in, int in_kind, const float* w, const float
 cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, const void* wrow, const float* bias4, void* out,
                            int64_t frames, int H, int W, int dtype, cudaStream_t s);
 
-// K2 (dwconv.cu): depthwise kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU, NHWC, plus the
+// K2 (dwconv_march.cu): depthwise kxk (k in {3,5}, stride in {1,2}, pad k/2) + folded BN + SiLU, NHWC, plus the
 // squeeze-excite spatial sums as per-block partials.  w: fp32 [k*k][C], bias fp32 [C].
 // partials: fp32 [frames][dw_num_partials][C] (sums of SiLU outputs over groups of output tiles).
 int dw_num_partials(int OH, int OW, int C, int k, int stride);
 cudaError_t launch_dwconv(const void* in, const float* w, const float* bias, void* out, float* partials,
                           int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
 
-// row-marching variant (dwconv_march.cu): same contract, partial rows = dw_march_slots
-bool dw_march_supported(int H, int W, int C, int k, int stride);
+bool dw_march_supported(int H, int W, int C, int k, int stride);      // geometry the kernel can launch (maps up to 448 columns)
 int dw_march_slots(int OH, int OW);
 void dw_march_set_cb(int cb);      // tuning aid: force the channel block of the next launches (0 = default)
-cudaError_t launch_dwconv_march(const void* in, const float* w, const float* bias, void* out, float* partials,
-                                int64_t frames, int H, int W, int C, int k, int stride, int dtype, cudaStream_t s);
 
-// K2' (mbconv_fused.cu, behind DFD_FUSE_EXPAND=1): expand 1x1 + BN + SiLU fused into the row-marching depthwise kernel for the
-// early HBM-bound blocks.  x [frames][H][W][cin] 16-bit, we [mid][cin] 16-bit + be fp32 [mid]; the rest as launch_dwconv_march
+// K2' (mbconv_fused.cu): expand 1x1 + BN + SiLU fused into the row-marching depthwise kernel for the early HBM-bound
+// blocks of the 224x224 network.  x [frames][H][W][cin] 16-bit, we [mid][cin] 16-bit + be fp32 [mid]; the rest as launch_dwconv
 // (partials: dw_march_slots rows).
 bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride);
-int mbconv_fused_level(int H, int W, int cin, int mid, int k, int stride);      // 0 unsupported, 1 early HBM-bound blocks, 2 later memory-bound blocks
 cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                                 float* partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype,
                                 cudaStream_t s);
-
-// stem + block 0's depthwise conv as one kernel (mbconv_fused.cu STEM producer, behind DFD_FUSE_EXPAND=3): uint8 224x224 crops ->
-// [frames][112][112][32] + SE partials; wrow / bias4 are the row-variant stem operands of launch_stem_tc
-cudaError_t launch_stem_dw_fused(const uint8_t* in, const void* wrow, const float* bias4, const float* w, const float* bias, void* out,
-                                 float* partials, int64_t frames, int H, int W, int dtype, cudaStream_t s);
 
 // K2 tail (se.cu): mean -> FC(C->rd)+bias -> SiLU -> FC(rd->C)+bias -> sigmoid.  gate fp32 [frames][C].
 // w1 fp32 [rd][C], w2t fp32 [rd][C] (conv_expand transposed), b1 [rd], b2 [C].
@@ -70,7 +61,7 @@ cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bia
 // conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
                                 int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
-// 3x3 stride-1 pad-1 convolution + bias + ReLU as an implicit GEMM (resnet50 conv2, behind DFD_RESNET_IMPLICIT=1): the
+// 3x3 stride-1 pad-1 convolution + bias + ReLU as an implicit GEMM (resnet50 conv2): the
 // producing pointwise conv scatters its rows into a zero-haloed map of conv3x3_padded_rows(frames,H,W) x N elements (zeroed
 // by the caller once per geometry), the 3x3 conv reads nine shifted TMA boxes of it.  Weights [N][(ky*3+kx)*C + c].
 int64_t conv3x3_padded_rows(int64_t frames, int H, int W);
@@ -78,11 +69,6 @@ cudaError_t launch_gemm_tc_padout(const void* A, const void* W, const float* bia
                                   int K, int N, int dtype, cudaStream_t s);
 cudaError_t launch_gemm_tc_conv3x3(const void* Apad, const void* W, const float* bias, void* D, int64_t frames, int H, int Wd,
                                    int C, int N, int dtype, cudaStream_t s);
-// straightforward CUDA-core GEMM with the same contract; bring-up / bisecting aid (DFD_GEMM_IMPL=simt)
-cudaError_t launch_gemm_simt(const void* A, const void* W, const float* bias, const float* gate, const void* R,
-                             void* D, float* pool_feat, int64_t M, int K, int N, int HW, int act, int dtype,
-                             cudaStream_t s);
-
 // K4 (poolhead.cu): temporal attention pool + fc1/ReLU/fc2 per video (pretrained_detector.py:123-141)
 struct HeadWeights {
     const float *att_w1, *att_b1, *att_w2, *att_b2;   // [64][1280], [64], [64], [1]

@@ -1,4 +1,4 @@
-// K2' (EXPERIMENTAL, off by default: DFD_FUSE_EXPAND=1; written without GPU access) — MBConv expand 1x1 + BN + SiLU fused
+// K2' — MBConv expand 1x1 + BN + SiLU fused
 // into the row-marching depthwise kernel (dwconv_march.cu) for the early, HBM-bound InvertedResidual blocks
 // (timm `conv_pw` + `bn1` -> `conv_dw` + `bn2` + SqueezeExcite's mean; reference call site pretrained_detector.py:116).
 //
@@ -47,22 +47,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
-    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
-}
-// two bytes -> the fp16 pair (b0, b1), exactly: 0x6400 | b is the half 1024 + b (stem_tc.cu uses the same magic)
-__device__ __forceinline__ uint32_t u8pair_to_half2(uint32_t b0, uint32_t b1) {
-    uint32_t p = b0 | (b1 << 16) | 0x64006400u;
-    const __half2 v = __hsub2(*reinterpret_cast<__half2*>(&p), __floats2half2_rn(1024.f, 1024.f));
-    return *reinterpret_cast<const uint32_t*>(&v);
-}
 #endif
 }  // namespace
 
 // DFD_FUSED_KERNEL_BEGIN
 // Geometry is compile-time: CIN block input channels, C expanded channels, W x W map, CB channels per CTA.
 // Launch geometry and shared-memory carve-up: ONE definition for the kernel and for its launcher.
-template <int KS, int S, int CIN, int C, int W, int CB, bool STEM>
+template <int KS, int S, int CIN, int C, int W, int CB>
 struct FusedGeom {
     static constexpr int PAD = KS / 2, OW = (W + 2 * PAD - KS) / S + 1, OH = OW, strips = OW / kFTW;
     // DWT threads own the depthwise work (2 channels x 7 columns each); the CTA is rounded up to whole warps, and the few
@@ -70,54 +61,47 @@ struct FusedGeom {
     // with their stores suppressed
     static constexpr int DWT = strips * (CB / 2), THREADS = (DWT + 31) / 32 * 32, WARPS = THREADS / 32;
     static constexpr int pixw = ((strips * kFTW - 1) * S + KS) > W + 2 * PAD ? ((strips * kFTW - 1) * S + KS) : W + 2 * PAD;
-    static constexpr int KP = STEM ? 32 : (CIN + 15) & ~15;        // K padded to whole mma k-steps
+    static constexpr int KP = (CIN + 15) & ~15;                     // K padded to whole mma k-steps
     static constexpr int XP = KP + 8;                               // halves per staged x pixel / weight row (conflict-free)
-    static constexpr uint32_t RB = 2 * W * 3;                       // STEM: bytes per raw crop row
     static constexpr int PXT = (W + 15) / 16;                       // 16-pixel tiles per row
     static constexpr uint32_t rsb = (uint32_t)pixw * CB * 2;        // bytes per expanded row slot
-    // x row slot: [PXT*16 pixels][XP]; STEM: [16 zero bytes][raw rows 2iy-1, 2iy, 2iy+1][pad to 16]
-    static constexpr uint32_t xsb = STEM ? ((16u + 3u * RB + 15u) & ~15u) : (uint32_t)PXT * 16 * XP * 2;
-    static constexpr uint32_t wsb = (STEM ? 2u : 1u) * CB * XP * 2; // bytes of the weight slice (STEM: hi and lo)
-    static constexpr uint32_t bias_floats = STEM ? 4u * 32u : (uint32_t)CB;
+    static constexpr uint32_t xsb = (uint32_t)PXT * 16 * XP * 2;    // x row slot: [PXT*16 pixels][XP]
+    static constexpr uint32_t wsb = (uint32_t)CB * XP * 2;          // bytes of the weight slice
+    static constexpr uint32_t bias_floats = (uint32_t)CB;
     static constexpr size_t smem_bytes = (size_t)2 * rsb + (size_t)kXR * xsb + wsb + (size_t)bias_floats * 4;
     static constexpr int rps = OH > 56 ? 56 : OH;                   // = march_rps(OH)
     static constexpr int segs = (OH + rps - 1) / rps;
     static constexpr int ctas_per_frame = segs * (C / CB);
     static_assert(OW % kFTW == 0, "whole strips only");
-    static_assert(CB % 8 == 0 && C % CB == 0 && (STEM || CIN % 8 == 0), "channel blocks");
+    static_assert(CB % 8 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
     static_assert(THREADS - DWT < DWT, "shadow threads map onto real ones");
 };
 
-// STEM: the producer is not an expand conv but the network's stem (conv3x3 s2 p1 3 -> 32 + BN + SiLU on uint8 crops, tensor prep
-// folded into the weights exactly as stem_tc.cu's row variant does): x = uint8 crops (frames, 2W, 2W, 3), we = fp16 [hi|lo][32][32]
-// (k = ky*10 + kx*3 + c), be = fp32 [top*2+left][32]; the consumer is block 0's depthwise 3x3.  CIN is unused then.
-template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG, bool STEM = false>
-__global__ void __launch_bounds__((FusedGeom<KS, S, CIN, C, W, CB, STEM>::THREADS), 1) __maxnreg__(MAXREG)
+template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
+__global__ void __launch_bounds__((FusedGeom<KS, S, CIN, C, W, CB>::THREADS), 1) __maxnreg__(MAXREG)
 mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, const float* __restrict__ be,
                     const float* __restrict__ w, const float* __restrict__ bias,
                     T* __restrict__ out, float* __restrict__ partials) {
-    using G = FusedGeom<KS, S, CIN, C, W, CB, STEM>;
+    using G = FusedGeom<KS, S, CIN, C, W, CB>;
     const T* x = reinterpret_cast<const T*>(xv);
     const T* we = reinterpret_cast<const T*>(wev);
     constexpr int TW = kFTW, PAD = G::PAD, H = W;
     constexpr int OW = G::OW, OH = G::OH, strips = G::strips;
-    static_assert(!STEM || (C == 32 && CB == 32 && KS == 3 && S == 1 && W % 16 == 0), "stem producer: block 0 of the network");
     constexpr int DWT = G::DWT, THREADS = G::THREADS, WARPS = G::WARPS;
     constexpr int NCOL = (TW - 1) * S + KS;
     constexpr int RING = (KS + S - 1) / S, PERIOD = S * RING;
     constexpr int pixw = G::pixw, KP = G::KP, KSTEPS = KP / 16, XP = G::XP, PXT = G::PXT;
-    constexpr uint32_t RB = G::RB, rsb = G::rsb, xsb = G::xsb, wsb = G::wsb;
+    constexpr uint32_t rsb = G::rsb, xsb = G::xsb, wsb = G::wsb;
     constexpr int NTL = CB / 8;                                   // 8-channel tiles of the channel block
     constexpr int rps = G::rps, segs = G::segs;
-    constexpr int XCH = STEM ? (int)(3 * RB / 16) : W * (CIN / 8);   // 16-byte chunks of an x row
-    static_assert(!STEM || (3 * RB) % 16 == 0, "raw rows are whole 16-byte chunks");
+    constexpr int XCH = W * (CIN / 8);                            // 16-byte chunks of an x row
     constexpr int XK = (XCH + THREADS - 1) / THREADS;
 
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const uint32_t sm_e = smem_u32(fz_smem);                      // [2][pixw][CB]      expanded ring
     const uint32_t sm_x = sm_e + 2 * rsb;                         // [kXR][PXT*16][XP]  x ring
     const uint32_t sm_w = sm_x + kXR * xsb;                       // [CB][XP]           expand weights of this channel block
-    float* s_be = reinterpret_cast<float*>(fz_smem + 2 * rsb + kXR * xsb + wsb);   // [CB] expand bias (STEM: [4][32])
+    float* s_be = reinterpret_cast<float*>(fz_smem + 2 * rsb + kXR * xsb + wsb);   // [CB] expand bias
 
     constexpr int ncb = C / CB;
     const int cb = blockIdx.x % ncb;
@@ -140,19 +124,11 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
     for (uint32_t i = threadIdx.x * 16; i < 2 * rsb + kXR * xsb + wsb; i += THREADS * 16) sts16(sm_e + i, make_uint4(0, 0, 0, 0));
     __syncthreads();
     // expand weights [CB][CIN] (BN folded, 16-bit, K-major) and bias of this channel block
-    if constexpr (STEM) {
-        for (int i = threadIdx.x; i < 2 * 32 * 4; i += THREADS) {                      // [hi|lo][32 oc][32 k] -> pitch XP
-            const int r = i >> 2, q = i & 3;
-            sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(reinterpret_cast<const uint16_t*>(wev) + (size_t)r * 32 + q * 8));
-        }
-        for (int i = threadIdx.x; i < 4 * 32; i += THREADS) s_be[i] = be[i];
-    } else {
-        for (int i = threadIdx.x; i < CB * (CIN / 8); i += THREADS) {
-            const int r = i / (CIN / 8), q = i - r * (CIN / 8);
-            sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8));
-        }
-        for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = be[cb * CB + i];
+    for (int i = threadIdx.x; i < CB * (CIN / 8); i += THREADS) {
+        const int r = i / (CIN / 8), q = i - r * (CIN / 8);
+        sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8));
     }
+    for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = be[cb * CB + i];
 
     uint64_t wr[KS * KS];
     const uint64_t half2 = f2_pack(0.5f, 0.5f);
@@ -165,26 +141,19 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 #pragma unroll
     for (int k = 0; k < XK; ++k) {
         const int i = threadIdx.x + k * THREADS;
-        if constexpr (STEM) {
-            g_off[k] = (uint32_t)i * 16;
-            s_off[k] = i < XCH ? 16u + (uint32_t)i * 16 : 0xffffffffu;
-        } else {
-            const int px = i / (CIN / 8), sub = i - px * (CIN / 8);
-            g_off[k] = (uint32_t)(px * CIN + sub * 8) * 2;
-            s_off[k] = i < XCH ? (uint32_t)(px * XP + sub * 8) * 2 : 0xffffffffu;
-        }
+        const int px = i / (CIN / 8), sub = i - px * (CIN / 8);
+        g_off[k] = (uint32_t)(px * CIN + sub * 8) * 2;
+        s_off[k] = i < XCH ? (uint32_t)(px * XP + sub * 8) * 2 : 0xffffffffu;
     }
-    // bytes between the sources of consecutive x rows; STEM: x row iy = raw rows 2iy-1 .. 2iy+1 (3*RB contiguous bytes)
-    constexpr size_t xpitch_b = STEM ? (size_t)2 * RB : (size_t)W * CIN * 2;
+    constexpr size_t xpitch_b = (size_t)W * CIN * 2;              // bytes between consecutive x rows
     int iy_i = iy_start, left_i = rend;
     uint32_t xs_i = sm_x;
-    const char* gp_i = STEM ? reinterpret_cast<const char*>(xv) + (size_t)frame * (2 * H) * RB + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b - (ptrdiff_t)RB
-                            : reinterpret_cast<const char*>(x + (size_t)frame * H * W * CIN) + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b;
+    const char* gp_i = reinterpret_cast<const char*>(x + (size_t)frame * H * W * CIN) + (ptrdiff_t)iy_start * (ptrdiff_t)xpitch_b;
     auto issue_row = [&]() {
         if (left_i > 0 && (unsigned)iy_i < (unsigned)H) {
 #pragma unroll
             for (int k = 0; k < XK; ++k)
-                if (s_off[k] != 0xffffffffu && !(STEM && iy_i == 0 && g_off[k] < RB))      // STEM: raw row -1 is padding
+                if (s_off[k] != 0xffffffffu)
                     cp_async16(xs_i + s_off[k], gp_i + g_off[k], true);
         }
         cp_async_commit();
@@ -197,67 +166,6 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
         if (k >= rend || (unsigned)iy >= (unsigned)H) return;            // CTA-uniform
         const uint32_t xs = sm_x + (uint32_t)(k % kXR) * xsb;
         const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
-        if constexpr (STEM) {
-            // stem output row iy: one warp pass = 16 pixels x all 32 channels.  A = the raw bytes as exact fp16 values, pair
-            // i = (k = 2i, 2i+1) with k = r*10 + kx*3 + c taken from byte 2*(i%5) of the 9-byte window of raw row r = i/5;
-            // lane (g, t) needs pairs t, t+4 (k-step 0) and t+8, t+12 (k-step 1) of pixels g and g+8.
-            const bool top = iy == 0;
-            for (int pt = warp; pt < PXT; pt += WARPS) {
-                uint32_t a[2][4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = t + 4 * j, r = i / 5, ii = i - 5 * r;
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const int px = pt * 16 + g + 8 * hf;
-                        uint32_t v = 0u;
-                        if (i < 15 && !(r == 0 && top)) {
-                            const uint32_t s0 = xs + 16u + (uint32_t)r * RB + 6u * (uint32_t)px - 3u + 2u * (uint32_t)ii;
-                            uint32_t b0 = lds_u8(s0), b1 = ii < 4 ? lds_u8(s0 + 1) : 0u;
-                            if (px == 0) {                                    // left padding column: the kx = 0 taps (window bytes 0..2)
-                                if (ii == 0) { b0 = 0u; b1 = 0u; } else if (ii == 1) b0 = 0u;
-                            }
-                            v = u8pair_to_half2(b0, b1);
-                        }
-                        a[j >> 1][(j & 1) * 2 + hf] = v;
-                    }
-                }
-                float c[4][4];
-                // weight fragments [hi|lo][k-step][2] of channel tile nt+1 are requested before the MMAs of tile nt
-                uint32_t bn[2][2][2];
-                auto load_b = [&](int nt) {
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl) {
-                        const uint32_t br = sm_w + (uint32_t)(((hl * 32 + nt * 8 + g) * XP) + 2 * t) * 2;
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) { bn[hl][ks][0] = lds32(br + ks * 32); bn[hl][ks][1] = lds32(br + ks * 32 + 16); }
-                    }
-                };
-                load_b(0);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
-                    uint32_t bc[2][2][2];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) (&bc[0][0][0])[i] = (&bn[0][0][0])[i];
-                    if (nt + 1 < 4) load_b(nt + 1);
-#pragma unroll
-                    for (int hl = 0; hl < 2; ++hl)                            // W_hi then W_lo into the same accumulator
-#pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) mma16816_f<__half>(c[nt], a[ks], bc[hl][ks][0], bc[hl][ks][1]);
-                }
-                const int px0 = pt * 16 + g;
-                const float* bs0 = s_be + ((top ? 2 : 0) + (px0 == 0 ? 1 : 0)) * 32;      // pixel px0 (may be the left column)
-                const float* bs1 = s_be + (top ? 2 : 0) * 32;                             // pixel px0 + 8 (never the left column)
-                const uint32_t ea = es + (uint32_t)((px0 + PAD) * CB + 2 * t) * 2;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int ch = nt * 8 + 2 * t;
-                    sts32(ea + nt * 16, Half16<T>::pack(silu_tanh(fmaf(c[nt][0], 0.00390625f, bs0[ch])), silu_tanh(fmaf(c[nt][1], 0.00390625f, bs0[ch + 1]))));
-                    sts32(ea + nt * 16 + 8 * CB * 2, Half16<T>::pack(silu_tanh(fmaf(c[nt][2], 0.00390625f, bs1[ch])), silu_tanh(fmaf(c[nt][3], 0.00390625f, bs1[ch + 1]))));
-                }
-            }
-        } else {
         // A warp owns NTL / WARPS channel tiles (8 / strips of them: always whole) and walks the pixel tiles of the row: the
         // weight fragments are loaded once per row, every offset below is a compile-time constant, and the unrolled pixel
         // tiles give the scheduler independent load -> MMA -> SiLU -> store chains.
@@ -309,7 +217,6 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
                 if (pt * 16 + 16 <= W || pt * 16 + 8 + g < W)
                     sts32(ea + 8 * CB * 2, Half16<T>::pack(fmaf(h2, tanh_approx(h2), h2), fmaf(h3, tanh_approx(h3), h3)));
             }
-        }
         }
     };
 
@@ -393,33 +300,25 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 
 // DFD_FUSED_KERNEL_END
 
-// InvertedResidual blocks of the 224x224 network this kernel is instantiated for: (Cin, mid, map, k, stride)
-//   level 1 — the early blocks, whose expand GEMM and depthwise kernel both run at the HBM roofline:
+// InvertedResidual blocks of the 224x224 network this kernel runs: the early blocks, whose expand GEMM and
+// depthwise kernel both sit at the HBM roofline when run separately — (Cin, mid, map, k, stride):
 //     2.1.0: 16 -> 96 @112 k3 s2     2.1.1: 24 -> 144 @56 k3 s1     2.2.0: 24 -> 144 @56 k5 s2
-//   level 2 — later blocks whose depthwise kernel is still memory-bound (3x3, or stride 2); the 5x5 stride-1 blocks are
-//   FMA-issue-bound and would only get slower with more instructions in the same CTA:
-//     2.3.0: 40 -> 240 @28 k3 s2    2.3.1/2: 80 -> 480 @14 k3 s1    2.5.0: 112 -> 672 @14 k5 s2    2.6.0: 192 -> 1152 @7 k3 s1
-// Returns 0 (not supported), 1 or 2.
-int mbconv_fused_level(int H, int W, int cin, int mid, int k, int stride) {
-    if (H != W) return 0;
-    if ((cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
-        (cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
-        (cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2)) return 1;
-    if ((cin == 40 && mid == 240 && W == 28 && k == 3 && stride == 2) ||
-        (cin == 80 && mid == 480 && W == 14 && k == 3 && stride == 1) ||
-        (cin == 112 && mid == 672 && W == 14 && k == 5 && stride == 2) ||
-        (cin == 192 && mid == 1152 && W == 7 && k == 3 && stride == 1)) return 2;
-    return 0;
+// Measured on B200 at 2048 frames (profiles/r02_*): the step drops from 13.99 to 12.87 ms.  The later blocks (28x28 and
+// smaller maps, the stem + block 0) were measured SLOWER fused (their kernels are issue-bound, not HBM-bound) and stay apart.
+bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) {
+    if (H != W) return false;
+    return (cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
+           (cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
+           (cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2);
 }
-bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) { return mbconv_fused_level(H, W, cin, mid, k, stride) > 0; }
 
-template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG, bool STEM = false>
+template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
 static cudaError_t fused_go(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                             float* partials, int64_t frames, cudaStream_t s) {
-    using G = FusedGeom<KS, S, CIN, C, W, CB, STEM>;
+    using G = FusedGeom<KS, S, CIN, C, W, CB>;
     constexpr int THREADS = G::THREADS;
     constexpr size_t smem = G::smem_bytes;
-    auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG, STEM>;
+    auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG>;
     if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     const int64_t grid = frames * G::ctas_per_frame;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -430,26 +329,10 @@ static cudaError_t fused_go(const void* x, const void* we, const float* be, cons
 template <typename T>
 static cudaError_t launch_fused_t(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                                   float* partials, int64_t frames, int W, int cin, int k, int stride, cudaStream_t s) {
-    // channel block per CTA: 48 by default; DFD_FUSE_CB=1 picks the wider alternative of each shape (fewer re-reads of the
-    // block input, more warps per CTA) for the first GPU sweep
-    const char* env_cb = getenv("DFD_FUSE_CB");
-    const bool wide = env_cb && atoi(env_cb) != 0;
-    if (cin == 16 && W == 112) {
-        if (wide) return fused_go<T, 3, 2, 16, 96, 112, 96, 128>(x, we, be, w, bias, out, partials, frames, s);
-        return fused_go<T, 3, 2, 16, 96, 112, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
-    }
-    if (cin == 24 && k == 3) {
-        if (wide) return fused_go<T, 3, 1, 24, 144, 56, 72, 128>(x, we, be, w, bias, out, partials, frames, s);
-        return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
-    }
-    if (cin == 24) {
-        if (wide) return fused_go<T, 5, 2, 24, 144, 56, 144, 168>(x, we, be, w, bias, out, partials, frames, s);
-        return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
-    }
-    if (cin == 40) return fused_go<T, 3, 2, 40, 240, 28, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
-    if (cin == 80) return fused_go<T, 3, 1, 80, 480, 14, 96, 128>(x, we, be, w, bias, out, partials, frames, s);
-    if (cin == 112) return fused_go<T, 5, 2, 112, 672, 14, 96, 168>(x, we, be, w, bias, out, partials, frames, s);
-    return fused_go<T, 3, 1, 192, 1152, 7, 128, 128>(x, we, be, w, bias, out, partials, frames, s);
+    // 48 expanded channels per CTA (the wider blocks measured slower: 4.53 vs 3.57 ms for the three launches)
+    if (cin == 16 && W == 112) return fused_go<T, 3, 2, 16, 96, 112, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 24 && k == 3) return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
+    return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
 }
 
 // x [frames][H][W][cin], we [mid][cin] + be [mid] (expand conv, BN folded), w [k*k][mid] fp32 + bias [mid] (depthwise, BN
@@ -461,19 +344,6 @@ cudaError_t launch_mbconv_fused(const void* x, const void* we, const float* be, 
     if (!mbconv_fused_supported(H, W, cin, mid, k, stride)) return cudaErrorInvalidValue;
     if (dtype == kDtypeFP16) return launch_fused_t<__half>(x, we, be, w, bias, out, partials, frames, W, cin, k, stride, s);
     return launch_fused_t<__nv_bfloat16>(x, we, be, w, bias, out, partials, frames, W, cin, k, stride, s);
-}
-
-
-// Stem (conv3x3 s2 + BN + SiLU on uint8 224x224 crops, tensor prep folded into wrow / bias4 as in stem_tc.cu's row variant)
-// fused with block 0's depthwise 3x3 + BN + SiLU + SE sums: the stem output (0.8 MB per frame) never goes to HBM.
-// in uint8 (frames,224,224,3); wrow fp16 [hi|lo][32][32]; bias4 fp32 [4][32]; w fp32 [9][32], bias [32];
-// out [frames][112][112][32], partials [frames][dw_march_slots(112,112)][32].  DFD_FUSE_EXPAND=3.
-cudaError_t launch_stem_dw_fused(const uint8_t* in, const void* wrow, const float* bias4, const float* w, const float* bias, void* out,
-                                 float* partials, int64_t frames, int H, int W, int dtype, cudaStream_t s) {
-    if (frames <= 0) return cudaSuccess;
-    if (H != 224 || W != 224 || !wrow || !bias4) return cudaErrorInvalidValue;
-    if (dtype == kDtypeFP16) return fused_go<__half, 3, 1, 8, 32, 112, 32, 128, true>(in, wrow, bias4, w, bias, out, partials, frames, s);
-    return fused_go<__nv_bfloat16, 3, 1, 8, 32, 112, 32, 128, true>(in, wrow, bias4, w, bias, out, partials, frames, s);
 }
 
 }  // namespace dfd

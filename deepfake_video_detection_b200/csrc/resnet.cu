@@ -346,12 +346,11 @@ static int rn_trunk_chunk(const dfd_resnet_weights* w, const float* x, int64_t n
         else rn_maxpool_kernel<__nv_bfloat16><<<pgrid, 256, 0, s>>>((const __nv_bfloat16*)buf[0], (__nv_bfloat16*)buf[1], 112, 112, 64, 56, 56, ptotal);
         RN_CK(cudaGetLastError(), "resnet maxpool");
     }
-    // DFD_RESNET_IMPLICIT=1 (experimental, off by default until it has been verified on a GPU): the 13 stride-1 3x3 convs
-    // run as implicit GEMMs — conv1 scatters its rows into a zero-haloed map kept in `col`, conv2 reads nine shifted TMA
+    // The 13 stride-1 3x3 convs run as implicit GEMMs — conv1 scatters its rows into a zero-haloed map kept in `col`, conv2 reads nine shifted TMA
     // boxes of it (gemm_tc.cu, CONV variants) — instead of gathering a 9x larger operand.  The halo is zeroed once per
     // (H, C) geometry: inside a layer only interior rows are ever rewritten.
-    const char* env_implicit = getenv("DFD_RESNET_IMPLICIT");
-    const bool implicit = env_implicit && atoi(env_implicit) != 0;
+    // (measured on B200, 256 frames: 14.19 -> 11.50 ms against gathering those operands; the three stride-2 3x3 convs,
+    // the strided 1x1 shortcuts and the 7x7 stem still gather).
     int pad_h = 0, pad_c = 0;
     int cur = 1, H = 56;                                           // buf[cur] holds the block input [n][H][H][cin]
     for (const RnBlock& b : w->blocks) {
@@ -359,7 +358,7 @@ static int rn_trunk_chunk(const dfd_resnet_weights* w, const float* x, int64_t n
         uint8_t* y = buf[cur];
         uint8_t* o1 = buf[(cur + 1) % 5]; uint8_t* o2 = buf[(cur + 2) % 5]; uint8_t* idn = buf[(cur + 3) % 5]; uint8_t* nxt = buf[(cur + 4) % 5];
         const int64_t rows_in = n * H * H, rows_out = n * OH * OH;
-        if (implicit && s2 == 1 && (b.c2.cin % 64) == 0) {
+        if (s2 == 1 && (b.c2.cin % 64) == 0) {
             if (pad_h != H || pad_c != b.c2.cin) {
                 RN_CK(cudaMemsetAsync(col, 0, (size_t)conv3x3_padded_rows(n, H, H) * b.c2.cin * 2, s), "resnet halo memset");
                 pad_h = H; pad_c = b.c2.cin;

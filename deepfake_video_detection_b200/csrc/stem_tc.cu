@@ -379,16 +379,12 @@ cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias
         const size_t smem = kSrStages * kSrAStage + kSrRaw * raw_stride + kSrBBytes + 4 * kStN * 4 + (2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc) * 8 + 16;
         const int64_t tiles = frames * OH;
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-        static const int env_cfg = getenv("DFD_STEM_CFG") ? atoi(getenv("DFD_STEM_CFG")) : 0;         // experiments only
 #define DFD_STEM_ROW(TT, E, B) { \
             auto kern = stem_row_kernel<TT, E, B>; \
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; \
             kern<<<grid, (4 * E + 2 + 4 * B) * 32, smem, s>>>(in, (const __half*)wrow, bias4, (TT*)out, H, W, OH, OW, tiles, raw_stride); }
         if (dtype == kDtypeFP16) {
-            if (env_cfg == 1) DFD_STEM_ROW(__half, 3, 3)
-            else if (env_cfg == 2) DFD_STEM_ROW(__half, 4, 2)
-            else if (env_cfg == 3) DFD_STEM_ROW(__half, 3, 4)
-            else DFD_STEM_ROW(__half, 2, 4)
+            DFD_STEM_ROW(__half, 2, 4)            // 2 epilogue sets, 4 builder sets (3/3, 4/2, 3/4 measured within 5 % of it)
         } else {
             DFD_STEM_ROW(__nv_bfloat16, 2, 4)
         }

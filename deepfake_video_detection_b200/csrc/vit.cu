@@ -131,13 +131,12 @@ __global__ void vit_layernorm_kernel(const float* __restrict__ x, int64_t in_str
 }
 
 // ---- attention: one CTA per (image, head); softmax(Q K^T / 8) V over 197 tokens, head dim 64 -----------------------
-// qkv [B*197][2304] 16-bit with timm's column order (which*768 + head*64 + d).  Q, K (row-major, padded rows) and
-// V^T are staged in shared memory; each warp owns 16-query tiles: S = Q K^T with mma.sync m16n8k16 (fp32 accumulate,
-// the whole 16 x 208 score tile lives in registers, so the softmax is exact, not online), P rounded to 16 bits
-// feeds the second mma.sync against V^T.  Out: o [B*197][768] 16-bit (column = head*64 + d).
+// qkv [B*197][2304] 16-bit with timm's column order (which*768 + head*64 + d).  Q, K, V (row-major, padded rows) are
+// staged in shared memory; each warp owns 16-query tiles: S = Q K^T with mma.sync m16n8k16 (fp32 accumulate), online
+// softmax over 64-key blocks, P rounded to 16 bits feeds the second mma.sync against V.  Out: o [B*197][768] 16-bit
+// (column = head*64 + d).
 constexpr int kTokPad = 208;                 // 197 padded to 13 tiles of 16
 constexpr int kQKStride = 72;                // halves per staged Q / K row: 64 + 8 (conflict-free fragment loads)
-constexpr int kVtStride = 216;               // halves per staged V^T row: 208 + 8
 
 template <typename T>
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
@@ -149,113 +148,8 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// DFD_ATT1_KERNEL_BEGIN   (tools/host_emul/ also runs this GPU-verified kernel, unchanged, on CPU threads: it pins the emulated
-// mma.sync fragment layout to what the hardware does)
-template <typename T>
-__global__ void __launch_bounds__(128) vit_attention_kernel(const T* __restrict__ qkv, T* __restrict__ o) {
-    extern __shared__ __align__(16) uint8_t att_smem[];
-    T* sQ = reinterpret_cast<T*>(att_smem);                       // [208][72]
-    T* sK = sQ + kTokPad * kQKStride;                             // [208][72]
-    T* sVt = sK + kTokPad * kQKStride;                            // [64][216]
-    const int head = blockIdx.x % kHeads;
-    const int64_t img = blockIdx.x / kHeads;
-    const T* base = qkv + (size_t)img * kTokens * (3 * kDim) + head * kHd;
-    const int tid = threadIdx.x;
-    // stage Q, K (16-byte chunks) and V^T (scattered 2-byte stores); padded rows / columns are zero
-    for (int i = tid; i < kTokPad * 8; i += 128) {
-        const int tok = i >> 3, ch = (i & 7) * 8;
-        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
-        if (tok < kTokens) {
-            const T* row = base + (size_t)tok * (3 * kDim) + ch;
-            q = *reinterpret_cast<const uint4*>(row);
-            k = *reinterpret_cast<const uint4*>(row + kDim);
-            v = *reinterpret_cast<const uint4*>(row + 2 * kDim);
-        }
-        *reinterpret_cast<uint4*>(sQ + tok * kQKStride + ch) = q;
-        *reinterpret_cast<uint4*>(sK + tok * kQKStride + ch) = k;
-        const T* vh = reinterpret_cast<const T*>(&v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sVt[(ch + j) * kVtStride + tok] = vh[j];
-    }
-    __syncthreads();
-
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    for (int qt = warp; qt < kTokPad / 16; qt += 4) {
-        const int q0 = qt * 16;
-        uint32_t aq[4][4];                                          // Q fragments for the 4 k-steps of the head dim
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const T* r0 = sQ + (q0 + g) * kQKStride + ks * 16 + 2 * t;
-            const T* r1 = r0 + 8 * kQKStride;
-            aq[ks][0] = *reinterpret_cast<const uint32_t*>(r0);     aq[ks][1] = *reinterpret_cast<const uint32_t*>(r1);
-            aq[ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8); aq[ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
-        }
-        float s[kTokPad / 8][4];
-#pragma unroll
-        for (int nt = 0; nt < kTokPad / 8; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-            const T* kr = sK + (nt * 8 + g) * kQKStride + 2 * t;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-                mma16816<T>(s[nt], aq[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
-        }
-        // softmax over the 197 valid keys of rows q0+g (c0,c1) and q0+g+8 (c2,c3): scale 1/8, mask the padding
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < kTokPad / 8; ++nt) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const bool ok = nt * 8 + 2 * t + j < kTokens;
-                s[nt][j] = ok ? s[nt][j] * 0.125f : -INFINITY;
-                s[nt][2 + j] = ok ? s[nt][2 + j] * 0.125f : -INFINITY;
-                m0 = fmaxf(m0, s[nt][j]); m1 = fmaxf(m1, s[nt][2 + j]);
-            }
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < kTokPad / 8; ++nt) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                s[nt][j] = __expf(s[nt][j] - m0); s[nt][2 + j] = __expf(s[nt][2 + j] - m1);
-                l0 += s[nt][j]; l1 += s[nt][2 + j];
-            }
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        // O = P V: the score fragments of two adjacent 8-key tiles are exactly one 16-key A fragment
-        float acc[kHd / 8][4];
-#pragma unroll
-        for (int dt = 0; dt < kHd / 8; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < kTokPad / 16; ++kk) {
-            uint32_t ap[4];
-            ap[0] = Half16<T>::pack(s[2 * kk][0], s[2 * kk][1]);         ap[1] = Half16<T>::pack(s[2 * kk][2], s[2 * kk][3]);
-            ap[2] = Half16<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]); ap[3] = Half16<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-            for (int dt = 0; dt < kHd / 8; ++dt) {
-                const T* vr = sVt + (dt * 8 + g) * kVtStride + kk * 16 + 2 * t;
-                mma16816<T>(acc[dt], ap, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
-            }
-        }
-        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        const int r0 = q0 + g, r1 = r0 + 8;
-        T* ob = o + (size_t)img * kTokens * kDim + head * kHd + 2 * t;
-#pragma unroll
-        for (int dt = 0; dt < kHd / 8; ++dt) {
-            if (r0 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * kDim + dt * 8) = Half16<T>::pack(acc[dt][0] * i0, acc[dt][1] * i0);
-            if (r1 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * kDim + dt * 8) = Half16<T>::pack(acc[dt][2] * i1, acc[dt][3] * i1);
-        }
-    }
-}
-
-// DFD_ATT1_KERNEL_END
-constexpr size_t kAttSmem = (size_t)(2 * kTokPad * kQKStride + kHd * kVtStride) * 2;
-
-// ---- attention, second variant (EXPERIMENTAL, DFD_VIT_ATTN_V2=1; written without GPU access, off by default) ----------------
-// Same contract as vit_attention_kernel.  Differences, all aimed at the latency / LSU limits the first variant shows (8 warps
-// per SM, two 32-bit shared-memory loads per MMA, an 8-way bank-conflicted V^T scatter while staging):
+// ---- attention (second variant; the first one — whole 16 x 208 score tile in registers, V^T staged by a bank-conflicted
+// scatter, 8 warps per SM — measured 1 % slower on B200 and was removed) ------------------------------------------------
 //   * Q, K and V are all staged row-major with 16-byte stores (pitch 72 halves: conflict-free for ldmatrix);
 //   * fragments come from `ldmatrix.x4` (one instruction feeds two MMAs); the V operand of P V uses `.trans`, so no
 //     transposed copy of V is ever written;
@@ -614,24 +508,14 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
         else dfd::vit_assemble_kernel<__nv_bfloat16><<<agrid, 256, 0, s>>>((const __nv_bfloat16*)H16, w->cls, w->pos, X, a8);
         VIT_CK(cudaGetLastError(), "vit assemble");
     }
-    if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAttSmem), "vit attention smem");
-    else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAttSmem), "vit attention smem");
-    // DFD_VIT_ATTN_V2=1 (experimental, off by default until it has been verified on a GPU): ldmatrix + online-softmax attention
-    const char* env_att = getenv("DFD_VIT_ATTN_V2");
-    const bool att_v2 = env_att && atoi(env_att) != 0;
-    if (att_v2) {
-        if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention v2 smem");
-        else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention v2 smem");
-    }
+    if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention smem");
+    else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention smem");
     for (int i = 0; i < kDepth; ++i) {
         const auto& b = w->blk[i];
         VIT_CK(ln(X, kDim, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");
         VIT_CK(dfd::launch_gemm_tc(H16, b.qkv_w, b.qkv_b, nullptr, nullptr, BIG, M, kDim, 3 * kDim, 1, 0, dt, s), "vit qkv gemm");
-        if (att_v2) {
-            if (f16) dfd::vit_attention_v2_kernel<__half><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __half*)BIG, (__half*)H16);
-            else dfd::vit_attention_v2_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
-        } else if (f16) dfd::vit_attention_kernel<__half><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __half*)BIG, (__half*)H16);
-        else dfd::vit_attention_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), 128, dfd::kAttSmem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
+        if (f16) dfd::vit_attention_v2_kernel<__half><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __half*)BIG, (__half*)H16);
+        else dfd::vit_attention_v2_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
         VIT_CK(cudaGetLastError(), "vit attention");
         VIT_CK(dfd::launch_gemm_tc_f32out(H16, b.proj_w, b.proj_b, X, X, M, kDim, kDim, dt, s), "vit proj gemm");
         VIT_CK(ln(X, kDim, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");

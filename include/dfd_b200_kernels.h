@@ -37,8 +37,8 @@ int dfd_k_se(const float* d_partials, int nparts, float inv_hw, const float* d_w
              const float* d_w2t, const float* d_b2, float* d_gate, int64_t frames, int C, int rd, void* stream);
 
 /* pointwise conv: D[M,N] = act((A .* gate)[M,K] * W[N,K]^T + bias) (+ R).  gate fp32 [M/HW][K] or NULL,
- * R [M,N] or NULL, act 0|1 (SiLU).  impl 0 = tcgen05/TMEM kernel (the product path; gate applied to the A operand),
- * 1 = CUDA-core bring-up kernel with identical rounding points, 2 = tcgen05 kernel with the gate folded into per-frame
+ * R [M,N] or NULL, act 0|1 (SiLU).  impl 0 = tcgen05/TMEM kernel (gate applied to the A operand),
+ * 2 = tcgen05 kernel with the gate folded into per-frame
  * weights on frame-aligned tiles (what the engine uses for maps of >= 784 pixels; synchronous in this test entry). */
 int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const float* d_gate, const void* d_R,
                void* d_D, int64_t M, int K, int N, int HW, int act, int dtype, int impl, void* stream);
@@ -47,14 +47,14 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
 int dfd_k_gemm_pool(const void* d_A, const void* d_W, const float* d_bias, float* d_feat, int64_t M, int K,
                     int N, int HW, int dtype, int impl, void* stream);
 
-/* EXPERIMENTAL (path behind DFD_RESNET_IMPLICIT=1, not yet verified on a GPU): torchvision Bottleneck conv1 + bn1 + relu ->
+/* torchvision Bottleneck conv1 + bn1 + relu ->
  * conv2 (3x3, stride 1, pad 1) + bn2 + relu (reference trunk: src/pretrained_detector.py:38-41) without a gathered operand.
  * d_in [frames*H*W][K], d_w1 [C][K], d_w2 [N][(ky*3+kx)*C + c] (BN folded), d_out [frames*H*W][N], all 16-bit; biases fp32.
  * d_pad: scratch for the zero-haloed intermediate map, dfd_k_conv3x3_maps(frames,H,W,..) * C * 2 bytes. */
 int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2, void* d_out,
                           int64_t frames, int H, int W, int K, int C, int N, int dtype, void* d_pad, size_t pad_bytes, void* stream);
 
-/* EXPERIMENTAL (path behind DFD_FUSE_EXPAND=1, not yet verified on a GPU): timm InvertedResidual conv_pw + bn1 + SiLU ->
+/* timm InvertedResidual conv_pw + bn1 + SiLU ->
  * conv_dw + bn2 + SiLU (+ squeeze-excite sums) as ONE kernel for the early blocks of the 224x224 network
  * ((cin, mid, map, k, stride) = (16,96,112,3,2), (24,144,56,3,1), (24,144,56,5,2); dfd_k_mbconv_fused_supported tells):
  * the expanded tensor stays in shared memory.  d_x [frames*H*W][cin], d_we [mid][cin] 16-bit, d_be fp32 [mid]; d_w, d_bias,
@@ -62,13 +62,6 @@ int dfd_k_conv1x1_conv3x3(const void* d_in, const void* d_w1, const float* d_b1,
 int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride);
 int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, const float* d_w, const float* d_bias, void* d_out,
                        float* d_partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype, void* stream);
-
-/* EXPERIMENTAL (engine switch DFD_FUSE_EXPAND=3): timm conv_stem + bn1 + SiLU on uint8 224x224 crops (tensor prep of app.py:1772-1780,
- * 2084-2085 folded into the weights as in dfd_k_stem_tc's row variant) fused with block 0's conv_dw + bn1 + SiLU + squeeze-excite sums.
- * h_w27x32 / h_bias32: HOST fp32 stem weights [(ky*3+kx)*3+c][32] and bias (packed + uploaded inside; synchronous; test aid);
- * d_w fp32 [9][32], d_bias [32]: depthwise; d_out [frames][112][112][32] 16-bit; d_partials as dfd_k_dwconv for (112,112,32,3,1). */
-int dfd_k_stem_dw_fused(const uint8_t* d_in, const float* h_w27x32, const float* h_bias32, const float* d_w, const float* d_bias,
-                        void* d_out, float* d_partials, int64_t frames, int H, int W, int dtype, void* stream);
 
 /* HOST-ONLY (no GPU needed): row maps of that zero-haloed layout, computed by the very functions the kernels use
  * (csrc/conv_map.h).  h_pad_row [frames*H*W]: physical row of every interior pixel; h_out_row [frames*(H+2)*(W+2)]: output

@@ -83,20 +83,23 @@ def test_module_forward_is_dropin(synth_sd, golden, golden_crops):
     assert torch.allclose(logits2, logits + 1.0, atol=1e-5)
 
 
-def test_bf16_matches_its_emulation(synth_sd, golden_crops):
-    from deepfake_video_detection_b200 import FrameScorer
+def test_bf16_storage_against_the_oracle_with_its_measured_tolerance(synth_sd, golden, golden_crops):
+    """bf16 storage (precision="bf16") does NOT meet north_star's 2e-2: 8-bit significands cost 8x the fp16 error on this
+    checkpoint (profiles/r02_parity_diag.json: max 5.8e-2 on the 64 x 32 batch, 0.36 on single-frame videos).  It is kept
+    selectable and held to what it measures against the ORACLE (no self-comparison): features within 5 %, golden logits
+    within 0.15, verdicts equal outside the band that tolerance implies."""
+    from deepfake_video_detection_b200 import FrameScorer, decide, make_offsets
     from oracle import effnet_b0_oracle as O
-    from bf16_emulation import trunk_features_bf16
-    crops, _ = golden_crops
+    crops, offsets = golden_crops
+    lens = np.diff(offsets)
     sc = FrameScorer(synth_sd, "bf16", "cuda")
-    feat = sc.features(sc.preprocess(torch.from_numpy(crops[:4]).cuda())).cpu()
-    with torch.no_grad():
-        emu = trunk_features_bf16(synth_sd, O.prep_u8_hwc(crops[:4]))
-        ref = O.trunk_features(synth_sd, O.prep_u8_hwc(crops[:4]))
-    # rounding-order differences are amplified by the chaotic synthetic trunk; still far closer to the emulation
-    e_emu = ((feat - emu).norm() / emu.norm()).item()
-    e_ref = ((feat - ref).norm() / ref.norm()).item()
-    assert e_emu < 6e-2 and e_ref < 8e-2, (e_emu, e_ref)
+    logits, scores, feat = sc.score(torch.from_numpy(crops).cuda(), make_offsets(lens, "cuda"), return_features=True)
+    ref_feat, ref_logits = torch.from_numpy(golden["features"]), torch.from_numpy(golden["logits"])
+    assert ((feat.cpu() - ref_feat).norm() / ref_feat.norm()).item() < 5e-2
+    err = (logits.cpu() - ref_logits).abs().max().item()
+    assert 2e-2 < err <= 0.15 or err <= 2e-2, err
+    for o, r in zip(decide(logits), O.decide(ref_logits)):
+        assert o["is_fake"] == r["is_fake"] or abs(r["prob_fake"] - 0.5) < 2 * 0.15
 
 
 def test_determinism_and_chunking(scorer, golden_crops, monkeypatch):
@@ -195,11 +198,11 @@ def test_full_c2_batch_properties(scorer, synth_sd):
     crops_p = crops.view(V, T, 224, 224, 3)[perm.cuda()].reshape(V * T, 224, 224, 3).contiguous()
     lg_p, _ = scorer.score(crops_p, off)
     assert torch.equal(lg_p, logits[perm.cuda()])
-    # spot parity against the fp32 oracle on two videos
+    # spot parity against the fp32 oracle on two videos (tests/test_gpu_parity_large.py compares all 64 of a seeded batch)
     for v in (3, 40):
         ref, _ = O.score_ragged(synth_sd, crops[v * T:(v + 1) * T].cpu().numpy(), np.array([0, T]))
-        assert (logits[v].cpu() - ref[0]).abs().max().item() <= 2e-2 * max(1.0, ref.abs().max().item())
-        assert decide(logits[v:v + 1])[0]["is_fake"] == O.decide(ref)[0]["is_fake"] or abs(O.decide(ref)[0]["prob_fake"] - 0.5) < 1e-2
+        assert (logits[v].cpu() - ref[0]).abs().max().item() <= 2e-2
+        assert decide(logits[v:v + 1])[0]["is_fake"] == O.decide(ref)[0]["is_fake"] or abs(O.decide(ref)[0]["prob_fake"] - 0.5) < 2 * 2e-2
 
 
 def test_ragged_extremes(scorer):
@@ -251,21 +254,9 @@ def test_npz_batch_scorer_cli(tmp_path, synth_sd, golden, golden_crops):
         assert int(r["pred"]) == int(probs[v].item() >= 0.5)
 
 
-@pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
-@pytest.mark.parametrize("level,folded", [(1, 3), (2, 8), (3, 9)])
-def test_fused_expand_path_matches_default_path_and_goldens(synth_sd, golden, golden_crops, monkeypatch, level, folded):
-    """DFD_FUSE_EXPAND=1 (expand 1x1 fused into the depthwise kernel on the three early blocks) against the verified default
-    path and the reference goldens: same rounding points, so features agree to MMA accumulation-order noise."""
-    from deepfake_video_detection_b200 import FrameScorer, make_offsets
+def test_fused_early_blocks_are_on_the_default_path(scorer, golden_crops):
+    """Blocks 2.1.0, 2.1.1 and 2.2.0 run expand 1x1 + depthwise as one kernel (mbconv_fused.cu): 71 - 3 launches per pass."""
+    from deepfake_video_detection_b200 import make_offsets
     crops, offsets = golden_crops
-    lens = np.diff(offsets).tolist()
-    scorer = FrameScorer(synth_sd, "fp16", "cuda")
-    d = torch.from_numpy(crops).cuda()
-    base, _ = scorer.score(d, make_offsets(lens, "cuda"))
-    n_base = scorer.last_launch_count
-    monkeypatch.setenv("DFD_FUSE_EXPAND", str(level))
-    logits, scores = scorer.score(d, make_offsets(lens, "cuda"))
-    assert scorer.last_launch_count == n_base - folded                              # expand GEMMs folded away (level 1: 3, level 2: 8; level 3 also merges the stem into block 0's depthwise kernel)
-    err = (logits.cpu() - torch.from_numpy(golden["logits"])).abs().max().item()
-    print(f"fused expand: max |dlogit| vs goldens {err:.3e}, vs default path {(logits - base).abs().max().item():.3e}")
-    assert err <= TOL_LOGITS_FP16 and (logits - base).abs().max().item() <= 1e-2
+    scorer.score(torch.from_numpy(crops[:4]).cuda(), make_offsets([4], "cuda"))
+    assert scorer.last_launch_count == 68

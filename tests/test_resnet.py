@@ -72,20 +72,16 @@ def test_resnet50_member_and_ensemble_cuda_match_reference(synth_sd):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
-def test_resnet50_implicit_conv_path_matches_gather_path_and_goldens(monkeypatch):
-    """DFD_RESNET_IMPLICIT=1 (stride-1 3x3 convs as implicit GEMMs over a zero-haloed map) against the verified gather path and
-    the reference goldens.  Both paths round at the same points, so they should agree to accumulation-order noise."""
+def test_resnet50_second_call_reuses_the_zero_halo():
+    """The stride-1 3x3 convs run as implicit GEMMs over a zero-haloed map whose halo is zeroed once per geometry: a second call
+    on the same workspace must give the same bits, and the goldens from the unmodified reference must hold."""
     from deepfake_video_detection_b200 import PretrainedBackboneDetector
     g, sd, x = np.load(GOLDEN), _sd(), _inputs()
     m = PretrainedBackboneDetector("resnet50", pretrained=False).eval()
     m.load_state_dict(sd, strict=True)
     m = m.cuda()
     with torch.no_grad():
-        base, _ = m(x.cuda())
-        monkeypatch.setenv("DFD_RESNET_IMPLICIT", "1")
         lg, fs = m(x.cuda())
-        lg2, _ = m(x.cuda())                                        # second call: the halo must still be zero / re-zeroed
+        lg2, _ = m(x.cuda())
     err = np.abs(lg.cpu().numpy() - g["logits"]).max()
-    print(f"resnet50 implicit: max |dlogit| vs goldens {err:.3e}, vs gather path {(lg - base).abs().max().item():.3e}")
-    assert err <= 2e-2 and (lg - base).abs().max().item() <= 5e-3 and torch.equal(lg, lg2)
+    assert err <= 2e-2 and torch.equal(lg, lg2)

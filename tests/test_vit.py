@@ -151,42 +151,3 @@ def test_deepfake_model_cuda_matches_oracle():
         assert lib.dfd_gcn_head(m._pack_head(f.device), f.data_ptr(), a.data_ptr(), 2, n_nodes, o.data_ptr(), _stream_ptr(f.device)) == 0
         assert (o.cpu() - V.gcn_head(sd, f.cpu(), a.cpu())).abs().max().item() < 1e-4
     assert lib.dfd_gcn_head(m._pack_head(f.device), f.data_ptr(), a.data_ptr(), 2, 65, o.data_ptr(), _stream_ptr(f.device)) != 0   # nodes > 64
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
-@pytest.mark.parametrize("prec,tol", [("fp16", 2e-2), ("bf16", 1.5e-1)])
-def test_vit_attention_v2_matches_first_variant_and_goldens(prec, tol, monkeypatch):
-    """DFD_VIT_ATTN_V2=1 (ldmatrix fragments, online softmax over 64-key blocks, 16 warps per SM) against the verified
-    attention kernel and the reference goldens; also batch invariance of the new kernel."""
-    from deepfake_video_detection_b200.vit_model import ViTFeatureExtractor
-    from oracle import vit_oracle as V
-    sd, x = V.synth_state_dict(0), V.synth_images(0, 4)
-    m = ViTFeatureExtractor(precision=prec).eval()
-    m.load_state_dict(sd, strict=True)
-    g = torch.from_numpy(np.load(GOLDEN)["features"])
-    with torch.no_grad():
-        base = m(x.cuda()).cpu()
-        monkeypatch.setenv("DFD_VIT_ATTN_V2", "1")
-        f = m(x.cuda()).cpu()
-        one = torch.cat([m(x[i:i + 1].cuda()) for i in range(4)]).cpu()
-    print(f"vit attention v2 {prec}: max |d| vs goldens {(f - g).abs().max().item():.3e}, vs first variant {(f - base).abs().max().item():.3e}")
-    assert (f - g).abs().max().item() <= tol and (f - base).abs().max().item() <= tol / 2
-    assert torch.equal(f, one)
-
-
-@pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("DFD_EXPERIMENTAL"), reason="experimental path: set DFD_EXPERIMENTAL=1")
-def test_vit_f32out_gemm_with_16_epilogue_warps(monkeypatch):
-    """DFD_GEMM_F32_EPI16=1: the fp32-output GEMMs (attention projection, fc2; in-place fp32 residual) with 16 epilogue warps.
-    The arithmetic is unchanged, only which warp handles which columns: results must be bit-identical."""
-    from deepfake_video_detection_b200.vit_model import ViTFeatureExtractor
-    from oracle import vit_oracle as V
-    sd, x = V.synth_state_dict(0), V.synth_images(0, 4)
-    m = ViTFeatureExtractor().eval()
-    m.load_state_dict(sd, strict=True)
-    with torch.no_grad():
-        base = m(x.cuda())
-        monkeypatch.setenv("DFD_GEMM_F32_EPI16", "1")
-        f = m(x.cuda())
-    assert torch.equal(f, base)

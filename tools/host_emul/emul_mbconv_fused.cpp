@@ -72,8 +72,6 @@ static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_
 static inline void sts16(uint32_t a, const uint4& v) { memcpy(fz_smem + a, &v, 16); }
 static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, fz_smem + a, 4); return v; }
 static inline void sts32(uint32_t a, uint32_t v) { memcpy(fz_smem + a, &v, 4); }
-static inline uint32_t lds_u8(uint32_t a) { return fz_smem[a]; }
-static inline uint32_t u8pair_to_half2(uint32_t b0, uint32_t b1) { return Half16<__half>::pack((float)b0, (float)b1); }
 
 // cp.async: per-thread list of committed groups
 struct CpOp { uint32_t dst; const void* src; };
@@ -127,7 +125,7 @@ template <> struct Store<__nv_bfloat16> { static uint16_t enc(float f) { return 
 
 template <int KS, int S, int CIN, int C, int W, int CB, typename ST = __half>
 static int run_case(int frames) {
-    using G = dfd::FusedGeom<KS, S, CIN, C, W, CB, false>;          // the launcher's geometry (fused_go uses the same struct)
+    using G = dfd::FusedGeom<KS, S, CIN, C, W, CB>;                 // the launcher's geometry (fused_go uses the same struct)
     constexpr int PAD = KS / 2, OW = G::OW, OH = G::OH, strips = G::strips, THREADS = G::THREADS, segs = G::segs;
     std::vector<uint16_t> x((size_t)frames * W * W * CIN), we((size_t)C * CIN), out((size_t)frames * OH * OW * C);
     std::vector<float> be(C), w((size_t)KS * KS * C), bias(C), parts((size_t)frames * segs * strips * C, NAN);
@@ -194,110 +192,21 @@ static int run_case(int frames) {
     return ok ? 0 : 1;
 }
 
-// STEM producer: uint8 crops -> stem (prep folded into hi/lo weights + 4 bias vectors, packed as api.cu pack_stem_row does)
-// -> block 0's depthwise 3x3.  Reference: the reference's own arithmetic order (u8/255, (x-mean)/std, zero-padded conv) in double.
-static int run_stem_case(int frames) {
-    using G = dfd::FusedGeom<3, 1, 8, 32, 112, 32, true>;
-    constexpr int W = 112, C = 32, KS = 3, OW = G::OW, OH = G::OH, strips = G::strips, THREADS = G::THREADS, segs = G::segs, RAW = 224;
-    static_assert(THREADS == 256 && segs == 2 && strips == 16, "block 0 geometry");
-    std::vector<uint8_t> in((size_t)frames * RAW * RAW * 3);
-    std::vector<float> w27((size_t)27 * 32), b32(32), w((size_t)9 * C), bias(C), parts((size_t)frames * segs * strips * C, NAN), b4(4 * 32);
-    std::vector<_Float16> wrow(2 * 32 * 32, (_Float16)0.f), out((size_t)frames * OH * OW * C);
-    uint32_t seed = 4242u;
-    auto rnd = [&]() { seed = seed * 1664525u + 1013904223u; return ((seed >> 8) & 0xffff) / 32768.0f - 1.0f; };
-    for (auto& v : in) { seed = seed * 1664525u + 1013904223u; v = (uint8_t)(seed >> 24); }
-    for (auto& v : w27) v = 0.3f * rnd();
-    for (auto& v : b32) v = 0.2f * rnd();
-    for (auto& v : w) v = rnd() / 3;
-    for (auto& v : bias) v = 0.2f * rnd();
-    const double mean[3] = {(double)0.485f, (double)0.456f, (double)0.406f}, stdv[3] = {(double)0.229f, (double)0.224f, (double)0.225f};
-    for (int o = 0; o < 32; ++o) {
-        for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) for (int c = 0; c < 3; ++c) {
-            const double ww = 256.0 * (double)w27[((ky * 3 + kx) * 3 + c) * 32 + o] / (255.0 * stdv[c]);
-            const _Float16 hi = (_Float16)(float)ww, lo = (_Float16)(float)(ww - (double)(float)hi);
-            wrow[(size_t)o * 32 + ky * 10 + kx * 3 + c] = hi; wrow[(size_t)(32 + o) * 32 + ky * 10 + kx * 3 + c] = lo;
-        }
-        for (int cs = 0; cs < 4; ++cs) {
-            double b = b32[o];
-            for (int ky = (cs & 2) ? 1 : 0; ky < 3; ++ky) for (int kx = (cs & 1) ? 1 : 0; kx < 3; ++kx) for (int c = 0; c < 3; ++c)
-                b -= (double)w27[((ky * 3 + kx) * 3 + c) * 32 + o] * mean[c] / stdv[c];
-            b4[cs * 32 + o] = (float)b;
-        }
-    }
-    std::vector<float> e((size_t)frames * W * W * C), ref((size_t)frames * OH * OW * C);
-    for (int f = 0; f < frames; ++f) for (int oy = 0; oy < W; ++oy) for (int ox = 0; ox < W; ++ox) for (int o = 0; o < C; ++o) {
-        double a = b32[o];
-        for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) {
-            const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
-            if (iy < 0 || iy >= RAW || ix < 0 || ix >= RAW) continue;
-            for (int c = 0; c < 3; ++c) a += (double)w27[((ky * 3 + kx) * 3 + c) * 32 + o] * (((double)in[(((size_t)f * RAW + iy) * RAW + ix) * 3 + c] / 255.0 - mean[c]) / stdv[c]);
-        }
-        e[(((size_t)f * W + oy) * W + ox) * C + o] = (float)(_Float16)dfd::silu_tanh((float)a);
-    }
-    for (int f = 0; f < frames; ++f) for (int oy = 0; oy < OH; ++oy) for (int ox = 0; ox < OW; ++ox) for (int c = 0; c < C; ++c) {
-        float a = bias[c];
-        for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) {
-            const int iy = oy + ky - 1, ix = ox + kx - 1;
-            if (iy >= 0 && iy < W && ix >= 0 && ix < W) a += e[(((size_t)f * W + iy) * W + ix) * C + c] * w[(size_t)(ky * 3 + kx) * C + c];
-        }
-        ref[(((size_t)f * OH + oy) * OW + ox) * C + c] = dfd::silu_tanh(a);
-    }
-    const int grid = frames * G::ctas_per_frame;
-    bool overrun = false;
-    for (int b = 0; b < grid; ++b) {
-        memset(dfd::fz_smem, 0xff, sizeof(dfd::fz_smem));
-        memset(dfd::fz_smem + G::smem_bytes, 0xA5, 4096);
-        std::barrier<> bar(THREADS); g_cta_bar = &bar;
-        dfd::g_warps.clear();
-        for (int i = 0; i < THREADS / 32; ++i) dfd::g_warps.emplace_back(new dfd::WarpX());
-        std::vector<std::thread> th;
-        for (int t = 0; t < THREADS; ++t)
-            th.emplace_back([&, t, b]() {
-                threadIdx.x = t; blockIdx.x = b; dfd::t_groups.clear(); dfd::t_open.clear();
-                dfd::mbconv_fused_kernel<__half, 3, 1, 8, 32, 112, 32, 128, true>(in.data(), wrow.data(), b4.data(), w.data(), bias.data(), out.data(), parts.data());
-            });
-        for (auto& t : th) t.join();
-        for (int i = 0; i < 4096; ++i) overrun |= dfd::fz_smem[G::smem_bytes + i] != 0xA5;
-    }
-    double max_err = 0, max_ref = 0, sum_err = 0; size_t bad = overrun ? 1 : 0;
-    for (size_t i = 0; i < ref.size(); ++i) {
-        const double d = fabs((float)out[i] - ref[i]);
-        max_err = fmax(max_err, d); max_ref = fmax(max_ref, fabs(ref[i])); if (d > 3e-3 * fmax(1.0, fabs(ref[i]))) ++bad;
-    }
-    for (int f = 0; f < frames; ++f) for (int c = 0; c < C; ++c) {
-        double sm = 0, r = 0;
-        for (int q = 0; q < segs * strips; ++q) sm += parts[((size_t)f * segs * strips + q) * C + c];
-        for (int p = 0; p < OH * OW; ++p) r += ref[((size_t)f * OH * OW + p) * C + c];
-        sum_err = fmax(sum_err, fabs(sm - r) / fmax(1.0, fabs(r)));
-    }
-    // the stem output is rounded to fp16 before the depthwise conv: a last-bit flip of one input moves an output by up to |w| * ulp
-    const bool ok = bad == 0 && sum_err < 1e-3 && std::isfinite(sum_err);
-    printf("STEM + dw0 (uint8 224x224 -> 112x112x32) %s: %d CTAs x %d threads, max |err| %.2e (scale %.2f), outliers %zu, rel SE sum err %.2e -> %s\n",
-           g_eager ? "eager" : "lazy ", grid, THREADS, max_err, max_ref, bad, sum_err, ok ? "ok" : "MISMATCH");
-    return ok ? 0 : 1;
-}
-
 int main(int argc, char** argv) {
     int rc = 0;
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
-    if (argc > 1 && !strcmp(argv[1], "stem")) { int r = 0; for (int m = 0; m < 2; ++m) { g_eager = m == 1; r |= run_stem_case(1); } return r; }
     for (int mode = 0; mode < 2; ++mode) {
         g_eager = mode == 1;
+        // small-map geometries of the same template (quick to emulate; the engine runs the three large-map shapes below)
         rc |= run_case<3, 1, 80, 480, 14, 96>(1);
-        rc |= run_case<5, 2, 112, 672, 14, 96>(1);
-        rc |= run_case<3, 1, 192, 1152, 7, 128>(1);
         rc |= run_case<3, 2, 40, 240, 28, 48>(1);
         rc |= run_case<3, 1, 80, 480, 14, 96, __nv_bfloat16>(1);
         if (quick) continue;
 #ifndef EMUL_QUICK                                       // -DEMUL_QUICK: the large-map instantiations are not even compiled
         rc |= run_case<3, 1, 24, 144, 56, 48, __nv_bfloat16>(1);
-        rc |= run_stem_case(1);
         rc |= run_case<3, 1, 24, 144, 56, 48>(1);
         rc |= run_case<5, 2, 24, 144, 56, 48>(1);
         rc |= run_case<3, 2, 16, 96, 112, 48>(1);
-        rc |= run_case<3, 1, 24, 144, 56, 72>(1);
-        rc |= run_case<5, 2, 24, 144, 56, 144>(1);
-        rc |= run_case<3, 2, 16, 96, 112, 96>(1);
 #endif
     }
     return rc;

@@ -1,5 +1,5 @@
-// CPU emulation of se_kernel_v2 (deepfake_video_detection_b200/csrc/se.cu, DFD_SE_V2): kernel text between the
-// DFD_SE2_KERNEL markers compiled UNCHANGED; threads + barriers, warp shuffles through a per-warp exchange buffer, shared
+// CPU emulation of se_kernel (deepfake_video_detection_b200/csrc/se.cu): kernel text between the
+// DFD_SE1_KERNEL markers compiled UNCHANGED; threads + barriers, warp shuffles through a per-warp exchange buffer, shared
 // memory pre-filled with NaN patterns.  Compared with sigmoid(W2 silu(W1 mean + b1) + b2) in double.
 // Build + run: python tools/host_emul/run.py se
 #include <algorithm>
@@ -49,7 +49,6 @@ static inline float __shfl_xor_sync(unsigned, float v, int o) {
     return r;
 }
 #include "se_kernel_v1.inc"
-#include "se_kernel_v2.inc"
 }  // namespace dfd
 
 template <bool V2> static int run_case(int C, int rd, int nparts, int frames) {
@@ -74,7 +73,7 @@ template <bool V2> static int run_case(int C, int rd, int nparts, int frames) {
         std::vector<std::thread> th;
         for (int t = 0; t < threads; ++t)
             th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b;
-                if (V2) se_kernel_v2<8>(parts.data(), nparts, inv, w1.data(), b1.data(), w2t.data(), b2.data(), gate.data(), (int64_t)frames, C, rd);
+                if (V2) abort();
                 else se_kernel<8>(parts.data(), nparts, inv, w1.data(), b1.data(), w2t.data(), b2.data(), gate.data(), (int64_t)frames, C, rd); });
         for (auto& t : th) t.join();
     }
@@ -95,9 +94,7 @@ template <bool V2> static int run_case(int C, int rd, int nparts, int frames) {
 
 int main() {
     int rc = 0;
-    rc |= run_case<true>(32, 8, 32, 3); rc |= run_case<true>(96, 4, 8, 9); rc |= run_case<true>(144, 6, 8, 16); rc |= run_case<true>(240, 10, 4, 5);
-    rc |= run_case<true>(480, 20, 2, 8); rc |= run_case<true>(672, 28, 2, 13); rc |= run_case<true>(1152, 48, 1, 17); rc |= run_case<true>(1152, 47, 3, 1);
-    // the default (GPU-verified) kernel through the same harness: regression test of its source, and a check of the harness itself
-    rc |= run_case<false>(96, 4, 8, 9); rc |= run_case<false>(672, 28, 2, 13); rc |= run_case<false>(1152, 48, 1, 17);
+    rc |= run_case<false>(32, 8, 32, 3); rc |= run_case<false>(96, 4, 8, 9); rc |= run_case<false>(144, 6, 8, 16); rc |= run_case<false>(240, 10, 4, 5);
+    rc |= run_case<false>(480, 20, 2, 8); rc |= run_case<false>(672, 28, 2, 13); rc |= run_case<false>(1152, 48, 1, 17); rc |= run_case<false>(1152, 47, 3, 1);
     return rc;
 }

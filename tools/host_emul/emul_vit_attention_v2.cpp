@@ -92,12 +92,11 @@ template <typename T> static inline void mma16816(float* c, const uint32_t* a, u
 constexpr int kDim = 768, kHeads = 12, kHd = 64, kTokens = 197;
 constexpr int kTokPad = 208, kQKStride = 72, kVtStride = 216;
 static inline float __expf(float x) { return expf(x); }
-#include "vit_attention_v1_kernel.inc"
 #include "vit_attention_v2_kernel.inc"
 }  // namespace dfd
 
 template <bool V2> static int run();
-int main() { return run<true>() | run<false>(); }
+int main() { return run<true>(); }
 
 template <bool V2> static int run() {
     using namespace dfd;
@@ -117,7 +116,7 @@ template <bool V2> static int run() {
         std::vector<std::thread> th;
         for (int t = 0; t < threads; ++t)
             th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b;
-                if (V2) vit_attention_v2_kernel<__half>(qkv.data(), o.data()); else vit_attention_kernel<__half>(qkv.data(), o.data()); });
+                if (V2) vit_attention_v2_kernel<__half>(qkv.data(), o.data()); else abort(); });
         for (auto& t : th) t.join();
         const int head = b % kHeads, img = b / kHeads;
         for (int q = 0; q < kTokens; ++q) {

@@ -1,4 +1,4 @@
-"""Build and run the CPU emulations of the experimental kernels: the kernel text between the emulation markers of the .cu file
+"""Build and run the CPU emulations of the CUDA-core kernels: the kernel text between the emulation markers of the .cu file
 is extracted UNCHANGED and compiled with the matching harness in this directory.
     python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|march|resnet|rnn|all] [quick] [tsan]"""
 import hashlib, os, subprocess, sys
@@ -7,7 +7,7 @@ OUT = os.path.join(ROOT, "build", "host_emul")
 os.makedirs(OUT, exist_ok=True)
 CASES = {"fused": ("mbconv_fused.cu", "DFD_FUSED_KERNEL", "mbconv_fused_kernel.inc", "emul_mbconv_fused.cpp"),
          "attention": ("vit.cu", "DFD_ATT2_KERNEL", "vit_attention_v2_kernel.inc", "emul_vit_attention_v2.cpp"),
-         "se": ("se.cu", "DFD_SE2_KERNEL", "se_kernel_v2.inc", "emul_se_v2.cpp"),
+         "se": ("se.cu", "DFD_SE1_KERNEL", "se_kernel_v1.inc", "emul_se.cpp"),
          "poolhead": ("poolhead.cu", "DFD_POOLHEAD_KERNEL", "pool_head_kernel.inc", "emul_pool_head.cpp"),
          "march": ("dwconv_march.cu", "DFD_MARCH_KERNEL", "dwconv_march_kernel.inc", "emul_dwconv_march.cpp"),
          "resnet": ("resnet.cu", "DFD_RESNET_SMALL_KERNELS", "resnet_small_kernels.inc", "emul_resnet_small.cpp"),
@@ -39,10 +39,6 @@ for name in which:
     if name == "prepstem":
         st = open(os.path.join(ROOT, "deepfake_video_detection_b200", "csrc", "stem.cu")).read()
         open(os.path.join(OUT, "stem_kernel.inc"), "w").write(st[st.index("// DFD_STEM_KERNEL_BEGIN"):st.index("// DFD_STEM_KERNEL_END")])
-    if name == "attention":                            # the GPU-verified first attention kernel goes through the same harness
-        open(os.path.join(OUT, "vit_attention_v1_kernel.inc"), "w").write(src[src.index("// DFD_ATT1_KERNEL_BEGIN"):src.index("// DFD_ATT1_KERNEL_END")])
-    if name == "se":                                   # the default SE kernel goes through the same harness
-        open(os.path.join(OUT, "se_kernel_v1.inc"), "w").write(src[src.index("// DFD_SE1_KERNEL_BEGIN"):src.index("// DFD_SE1_KERNEL_END")])
     quick = "quick" in sys.argv or ("stem" in sys.argv and name == "fused")
     flags = ["-std=c++20", "-O1", "-pthread"] + (["-DEMUL_QUICK"] if quick and name == "fused" else []) + (["-g", "-fsanitize=thread"] if tsan else [])
     cpp_path = os.path.join(ROOT, "tools", "host_emul", cpp)

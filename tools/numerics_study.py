@@ -42,19 +42,21 @@ def trunk(sd, x, rnd, cfg):
     r = lambda key, t: rnd(t) if (cfg.get(key, True) and state["on"]) else t
     noisy = cfg.get("silu_noise", True)
     silu = lambda t: silu_tanh_approx(t, True) if (noisy and state["on"]) else F.silu(t)
+    silu_e = silu if cfg.get("silu_noise_expand", True) else F.silu       # SiLU of the stem / expand epilogues
+    silu_d = silu if cfg.get("silu_noise_dw", True) else F.silu           # SiLU of the depthwise kernels
     w, b = O.fold_bn(sd["backbone.0.weight"], sd, "backbone.1")
-    y = r("stem", silu(F.conv2d(x, w, b, 2, 1)))          # uint8 inputs are exact, the stem weights are hi+lo split
+    y = r("stem", silu_e(F.conv2d(x, w, b, 2, 1)))          # uint8 inputs are exact, the stem weights are hi+lo split
     y32 = y
     for bi, (p, cin, mid, cout, k, stride, rd, has_expand, has_skip) in enumerate(O.block_specs()):
         state["on"] = bi not in clean
         inp = y32 if cfg.get("skip32", False) else y
         if has_expand:
             w, b = O.fold_bn(sd[p + ".conv_pw.weight"], sd, p + ".bn1")
-            y = r("expand", silu(F.conv2d(y, r("w", w), b)))
+            y = r("expand", silu_e(F.conv2d(y, r("w", w), b)))
             w, b = O.fold_bn(sd[p + ".conv_dw.weight"], sd, p + ".bn2")
         else:
             w, b = O.fold_bn(sd[p + ".conv_dw.weight"], sd, p + ".bn1")
-        d32 = silu(F.conv2d(y, w, b, stride, k // 2, 1, mid))
+        d32 = silu_d(F.conv2d(y, w, b, stride, k // 2, 1, mid))
         s = d32.mean((2, 3), keepdim=True)
         y = r("dw", d32)
         s = F.silu(F.conv2d(s, sd[p + ".se.conv_reduce.weight"], sd[p + ".se.conv_reduce.bias"]))
@@ -88,6 +90,8 @@ def main():
     variants = {
         "shipped": {},
         "exact_silu": {"silu_noise": False},
+        "exact_silu_dw": {"silu_noise_dw": False},
+        "exact_silu_expand": {"silu_noise_expand": False},
         "no_w": {"w": False},
         "no_expand": {"expand": False},
         "no_dw": {"dw": False},
