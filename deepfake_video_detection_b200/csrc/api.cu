@@ -45,6 +45,12 @@ struct ProfScope {
 };
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+}  // namespace
+namespace dfd {
+void reset_launches() { g_launches = 0; }
+void note_launch(const char* what) { if (!strstr(what, "smem") && !strstr(what, "memset")) ++g_launches; }
+}  // namespace dfd
+namespace {
 int cuda_fail(cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return DFD_ECUDA;

@@ -6,6 +6,10 @@
 
 namespace dfd {
 
+// kernel-launch accounting shared by the engines (api.cu owns the thread-local counter behind dfd_last_launch_count)
+void reset_launches();
+void note_launch(const char* what);      // counts one launch unless `what` names a non-kernel call ("smem" attribute, "memset")
+
 // K1 (preprocess.cu): uint8 HWC -> 16-bit NCHW, ImageNet normalisation (app.py:1772-1780, 2084-2085)
 cudaError_t launch_preprocess(const uint8_t* in, void* out, int64_t frames, int H, int W, int dtype, cudaStream_t s);
 

@@ -324,7 +324,7 @@ static int rn_trunk_chunk(const dfd_resnet_weights* w, const float* x, int64_t n
     for (int i = 0; i < 5; ++i) { buf[i] = ws; ws += nup(kRnAct * 2) * (size_t)n; }
     uint8_t* col = ws;
     cudaError_t e;
-#define RN_CK(call, what) do { e = (call); if (e != cudaSuccess) return nfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
+#define RN_CK(call, what) do { e = (call); dfd::note_launch(what); if (e != cudaSuccess) return nfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
     auto im2col = [&](const void* in, void* a, int H, int W, int C, int OH, int OW, int k, int stride) {
         const int64_t total = n * OH * OW * (int64_t)(k * k) * (C / 8);
         const unsigned grid = (unsigned)((total + 255) / 256);
@@ -405,6 +405,7 @@ int dfd_resnet50_score_videos(const dfd_resnet_weights_t* w, const float* d_in, 
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255));
     const size_t chunk = (size_t)(frames < kRnMaxChunk ? frames : kRnMaxChunk);
     float* feat = d_features_out ? d_features_out : reinterpret_cast<float*>(ws + rn_frame_bytes() * chunk);
+    dfd::reset_launches();
     for (int64_t f0 = 0; f0 < frames; f0 += kRnMaxChunk) {
         const int64_t nfr = frames - f0 < kRnMaxChunk ? frames - f0 : kRnMaxChunk;
         rc = rn_trunk_chunk(w, d_in + (size_t)f0 * 3 * kRnImg * kRnImg, nfr, feat + (size_t)f0 * kRnFeat, ws, s);
@@ -416,6 +417,7 @@ int dfd_resnet50_score_videos(const dfd_resnet_weights_t* w, const float* d_in, 
     if (e != cudaSuccess) return nfail(DFD_ECUDA, std::string("resnet head smem: ") + cudaGetErrorString(e));
     dfd::rn_pool_head_kernel<<<(unsigned)videos, 256, smem, s>>>(hw, feat, d_offsets, kRnFeat, use_attention, d_logits, d_frame_scores);
     e = cudaGetLastError();
+    dfd::note_launch("resnet pool head");
     if (e != cudaSuccess) return nfail(DFD_ECUDA, std::string("resnet pool head: ") + cudaGetErrorString(e));
     return DFD_OK;
 }

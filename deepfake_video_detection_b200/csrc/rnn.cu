@@ -250,7 +250,8 @@ int dfd_rnn_forward(const dfd_rnn_weights_t* w, const float* d_x, const int32_t*
     float* outs = reinterpret_cast<float*>(ws);
     const bool f16 = w->dtype == DFD_DTYPE_FP16;
     cudaError_t e;
-#define RNN_CK(call, what) do { e = (call); if (e != cudaSuccess) return rfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
+    dfd::reset_launches();
+#define RNN_CK(call, what) do { e = (call); dfd::note_launch(what); if (e != cudaSuccess) return rfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
     {
         const int64_t n = (int64_t)B * T * IN + (int64_t)B * H;
         const unsigned grid = (unsigned)((n + 255) / 256);

@@ -487,7 +487,8 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
     const int dt = w->dtype;
     const bool f16 = dt == DFD_DTYPE_FP16;
     cudaError_t e;
-#define VIT_CK(call, what) do { e = (call); if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
+    dfd::reset_launches();
+#define VIT_CK(call, what) do { e = (call); dfd::note_launch(what); if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
     auto ln = [&](const float* in, int64_t stride, const float* g, const float* b, void* out, bool out_f32, int64_t rows) {
         const unsigned grid = (unsigned)((rows + 7) / 8);
         if (out_f32) dfd::vit_layernorm_kernel<float><<<grid, 256, 0, s>>>(in, stride, g, b, (float*)out, rows);

@@ -6,9 +6,16 @@ Reads  gpurun_out/launches_<tag>.csv (ncu --metrics gpu__time_duration.sum,dram_
 Writes profiles/<round>_launches.csv, profiles/<round>_ncu_full_summary.txt, profiles/<round>_bench.json,
        profiles/<round>_traffic.json (per kernel class: launches, ms, DRAM bytes — read by bench.py for roofline.traffic)
 """
-import csv, json, os, re, subprocess, sys
+import csv, hashlib, json, os, re, subprocess, sys
 tag, rnd = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+def source_digest():                       # = bench.py's: the traffic record is only quoted for the sources it was captured on
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "deepfake_video_detection_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:12]
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 
@@ -50,7 +57,7 @@ with open(os.path.join(P, f"{rnd}_launches.csv"), "w", newline="") as f:
 tot = sum(a["us"] for a in cls.values())
 for a in cls.values(): a["share"] = round(a["us"] / tot, 4); a["dram_bytes_per_launch"] = a["dram_bytes"] / a["launches"]
 json.dump({"source": f"ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, python tools/prof_step.py --videos 64 --frames 32 (2048 frames, one forward)",
-           "total_us": tot, "classes": cls}, open(os.path.join(P, f"{rnd}_traffic.json"), "w"), indent=1)
+           "source_digest": source_digest(), "total_us": tot, "classes": cls}, open(os.path.join(P, f"{rnd}_traffic.json"), "w"), indent=1)
 txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_table.py"), os.path.join(G, f"full_{tag}_raw.csv")], capture_output=True, text=True).stdout
 open(os.path.join(P, f"{rnd}_ncu_full_summary.txt"), "w").write(
     "ncu --set full --clock-control none, python tools/prof_step.py --videos 16 --frames 32 (512 frames), second forward pass, one line per launch\n"
