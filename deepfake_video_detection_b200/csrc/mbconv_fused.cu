@@ -29,9 +29,26 @@
 
 namespace dfd {
 
+// tuning constants (the defaults are the measured choice; `tools/build_variant.py` builds alternatives for a sweep)
+#ifndef DFD_FUSED_XR
+#define DFD_FUSED_XR 6               // x-row ring depth
+#endif
+#ifndef DFD_FUSED_REG_A
+#define DFD_FUSED_REG_A 128          // register cap, block 2.1.0 (16 -> 96 @112, k3 s2)
+#endif
+#ifndef DFD_FUSED_REG_B
+#define DFD_FUSED_REG_B 128          // block 2.1.1 (24 -> 144 @56, k3 s1)
+#endif
+#ifndef DFD_FUSED_REG_C
+#define DFD_FUSED_REG_C 168          // block 2.2.0 (24 -> 144 @56, k5 s2)
+#endif
+#ifndef DFD_FUSED_BLOCKS
+#define DFD_FUSED_BLOCKS 7           // bit i: fuse block 2.1.0 / 2.1.1 / 2.2.0
+#endif
+
 namespace {
 constexpr int kFTW = 7;              // output columns per thread (as dwconv_march.cu)
-constexpr int kXR = 6;               // x-row ring depth
+constexpr int kXR = DFD_FUSED_XR;
 
 #ifndef DFD_HOST_EMUL
 template <typename T>
@@ -307,9 +324,9 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 // smaller maps, the stem + block 0) were measured SLOWER fused (their kernels are issue-bound, not HBM-bound) and stay apart.
 bool mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stride) {
     if (H != W) return false;
-    return (cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
-           (cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
-           (cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2);
+    return ((DFD_FUSED_BLOCKS & 1) && cin == 16 && mid == 96 && W == 112 && k == 3 && stride == 2) ||
+           ((DFD_FUSED_BLOCKS & 2) && cin == 24 && mid == 144 && W == 56 && k == 3 && stride == 1) ||
+           ((DFD_FUSED_BLOCKS & 4) && cin == 24 && mid == 144 && W == 56 && k == 5 && stride == 2);
 }
 
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
@@ -330,9 +347,9 @@ template <typename T>
 static cudaError_t launch_fused_t(const void* x, const void* we, const float* be, const float* w, const float* bias, void* out,
                                   float* partials, int64_t frames, int W, int cin, int k, int stride, cudaStream_t s) {
     // 48 expanded channels per CTA (the wider blocks measured slower: 4.53 vs 3.57 ms for the three launches)
-    if (cin == 16 && W == 112) return fused_go<T, 3, 2, 16, 96, 112, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
-    if (cin == 24 && k == 3) return fused_go<T, 3, 1, 24, 144, 56, 48, 128>(x, we, be, w, bias, out, partials, frames, s);
-    return fused_go<T, 5, 2, 24, 144, 56, 48, 168>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 16 && W == 112) return fused_go<T, 3, 2, 16, 96, 112, 48, DFD_FUSED_REG_A>(x, we, be, w, bias, out, partials, frames, s);
+    if (cin == 24 && k == 3) return fused_go<T, 3, 1, 24, 144, 56, 48, DFD_FUSED_REG_B>(x, we, be, w, bias, out, partials, frames, s);
+    return fused_go<T, 5, 2, 24, 144, 56, 48, DFD_FUSED_REG_C>(x, we, be, w, bias, out, partials, frames, s);
 }
 
 // x [frames][H][W][cin], we [mid][cin] + be [mid] (expand conv, BN folded), w [k*k][mid] fp32 + bias [mid] (depthwise, BN

@@ -34,6 +34,15 @@ def silu_tanh_approx(x, noise):
     return x * (0.5 * t + 0.5)
 
 
+def silu_tanh_f16x2(x):
+    """tanh.approx.f16x2 form of the SiLU: h = x/2 rounded to fp16, t = tanh(h) with a maximum ABSOLUTE error of 2^-10.987 (PTX ISA,
+    modelled uniform) rounded to fp16, result h + h t in one fp16 FMA."""
+    h = (0.5 * x).half().float()
+    t = torch.tanh(h) + (torch.rand_like(h) * 2 - 1) * 2.0 ** -10.987
+    t = t.half().float()
+    return (h + h * t).half().float()
+
+
 def trunk(sd, x, rnd, cfg):
     """cfg keys (all default True = the shipped path's rounding): w (pointwise weights), stem, expand, dw, gate (gated A
     re-rounded), out (block outputs), skip32 (False; True keeps the skip operand in fp32), silu_noise, head_in."""
@@ -43,6 +52,7 @@ def trunk(sd, x, rnd, cfg):
     noisy = cfg.get("silu_noise", True)
     silu = lambda t: silu_tanh_approx(t, True) if (noisy and state["on"]) else F.silu(t)
     silu_e = silu if cfg.get("silu_noise_expand", True) else F.silu       # SiLU of the stem / expand epilogues
+    silu_x = silu_tanh_f16x2 if cfg.get("expand_f16tanh", False) else silu_e   # SiLU of the expand epilogues only
     silu_d = silu if cfg.get("silu_noise_dw", True) else F.silu           # SiLU of the depthwise kernels
     w, b = O.fold_bn(sd["backbone.0.weight"], sd, "backbone.1")
     y = r("stem", silu_e(F.conv2d(x, w, b, 2, 1)))          # uint8 inputs are exact, the stem weights are hi+lo split
@@ -52,7 +62,7 @@ def trunk(sd, x, rnd, cfg):
         inp = y32 if cfg.get("skip32", False) else y
         if has_expand:
             w, b = O.fold_bn(sd[p + ".conv_pw.weight"], sd, p + ".bn1")
-            y = r("expand", silu_e(F.conv2d(y, r("w", w), b)))
+            y = r("expand", (silu_x if bi in cfg.get("f16tanh_blocks", range(16)) else silu_e)(F.conv2d(y, r("w", w), b)))
             w, b = O.fold_bn(sd[p + ".conv_dw.weight"], sd, p + ".bn2")
         else:
             w, b = O.fold_bn(sd[p + ".conv_dw.weight"], sd, p + ".bn1")
@@ -92,6 +102,8 @@ def main():
         "exact_silu": {"silu_noise": False},
         "exact_silu_dw": {"silu_noise_dw": False},
         "exact_silu_expand": {"silu_noise_expand": False},
+        "expand_f16tanh_all": {"expand_f16tanh": True},
+        "expand_f16tanh_b123": {"expand_f16tanh": True, "f16tanh_blocks": (1, 2, 3)},
         "no_w": {"w": False},
         "no_expand": {"expand": False},
         "no_dw": {"dw": False},
