@@ -562,7 +562,7 @@ int dfd_attn_pool_head(const dfd_weights_t* w, const float* d_features, const in
     if (videos < 0 || frames < 0 || frames > INT32_MAX) return fail(DFD_EINVAL, "dfd_attn_pool_head: bad video / frame count");
     g_launches = 0;
     prof_next(KC_POOL_HEAD, (double)frames * 1280 * 4 * 2, 2.0 * frames * 1280 * 64 + 2.0 * videos * 1280 * 256, (cudaStream_t)stream);
-    DFD_LAUNCH(dfd::launch_pool_head(w->hw, d_features, d_offsets, videos, frames, use_attention, d_logits, d_frame_scores,
+    DFD_LAUNCH(dfd::launch_pool_head(w->hw, d_features, d_offsets, videos, frames, DFD_FEATURE_DIM, use_attention, d_logits, d_frame_scores,
                                      (cudaStream_t)stream), "pool+head kernel");
     return DFD_OK;
 }

@@ -196,20 +196,15 @@ int dw_march_slots(int OH, int OW) {
 }
 
 // (k, stride, max regs, C, W, CB) instantiations with compile-time geometry: the twelve depthwise shapes of the
-// 224x224 network with their candidate channel blocks (tools/sweep_dw.py picks; march_cb() holds the choice)
+// 224x224 network with the channel block tools/sweep_dw.py measured fastest (march_cb() holds the same choice)
+#ifndef DFD_MARCH_REG_5S1
+#define DFD_MARCH_REG_5S1 168        // register cap of the 5x5 stride-1 instantiations (tools/build_variant.py sweeps it)
+#endif
 #define DFD_MARCH_SPEC_LIST \
-    DFD_MARCH_SPEC(3, 1, 128, 32, 112, 16) DFD_MARCH_SPEC(3, 1, 128, 32, 112, 32) \
-    DFD_MARCH_SPEC(3, 2, 128, 96, 112, 16) DFD_MARCH_SPEC(3, 2, 128, 96, 112, 32) DFD_MARCH_SPEC(3, 2, 128, 96, 112, 48) \
-    DFD_MARCH_SPEC(3, 1, 128, 144, 56, 16) DFD_MARCH_SPEC(3, 1, 128, 144, 56, 48) \
-    DFD_MARCH_SPEC(5, 2, 168, 144, 56, 16) DFD_MARCH_SPEC(5, 2, 168, 144, 56, 48) DFD_MARCH_SPEC(5, 2, 168, 144, 56, 72) \
-    DFD_MARCH_SPEC(5, 1, 168, 240, 28, 16) DFD_MARCH_SPEC(5, 1, 168, 240, 28, 48) DFD_MARCH_SPEC(5, 1, 168, 240, 28, 80) DFD_MARCH_SPEC(5, 1, 168, 240, 28, 120) \
-    DFD_MARCH_SPEC(3, 2, 128, 240, 28, 48) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 80) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 120) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 240) \
-    DFD_MARCH_SPEC(3, 1, 128, 480, 14, 32) DFD_MARCH_SPEC(3, 1, 128, 480, 14, 96) DFD_MARCH_SPEC(3, 1, 128, 480, 14, 160) DFD_MARCH_SPEC(3, 1, 128, 480, 14, 240) \
-    DFD_MARCH_SPEC(5, 1, 168, 480, 14, 32) DFD_MARCH_SPEC(5, 1, 168, 480, 14, 96) DFD_MARCH_SPEC(5, 1, 168, 480, 14, 160) DFD_MARCH_SPEC(5, 1, 168, 480, 14, 240) \
-    DFD_MARCH_SPEC(5, 1, 168, 672, 14, 32) DFD_MARCH_SPEC(5, 1, 168, 672, 14, 96) DFD_MARCH_SPEC(5, 1, 168, 672, 14, 112) DFD_MARCH_SPEC(5, 1, 168, 672, 14, 224) \
-    DFD_MARCH_SPEC(5, 2, 168, 672, 14, 96) DFD_MARCH_SPEC(5, 2, 168, 672, 14, 224) DFD_MARCH_SPEC(5, 2, 168, 672, 14, 336) \
-    DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 64) DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 128) DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 192) DFD_MARCH_SPEC(5, 1, 168, 1152, 7, 384) \
-    DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 64) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 128) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 192) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 384)
+    DFD_MARCH_SPEC(3, 1, 128, 32, 112, 16) DFD_MARCH_SPEC(3, 2, 128, 96, 112, 48) DFD_MARCH_SPEC(3, 1, 128, 144, 56, 16) \
+    DFD_MARCH_SPEC(5, 2, 168, 144, 56, 16) DFD_MARCH_SPEC(5, 1, DFD_MARCH_REG_5S1, 240, 28, 16) DFD_MARCH_SPEC(3, 2, 128, 240, 28, 48) \
+    DFD_MARCH_SPEC(3, 1, 128, 480, 14, 32) DFD_MARCH_SPEC(5, 1, DFD_MARCH_REG_5S1, 480, 14, 32) DFD_MARCH_SPEC(5, 1, DFD_MARCH_REG_5S1, 672, 14, 32) \
+    DFD_MARCH_SPEC(5, 2, 168, 672, 14, 224) DFD_MARCH_SPEC(5, 1, DFD_MARCH_REG_5S1, 1152, 7, 64) DFD_MARCH_SPEC(3, 1, 128, 1152, 7, 64)
 
 static int g_march_cb_override = 0;      // tuning aid (dfd_k_set_dw_channel_block): 0 = the table in march_cb()
 void dw_march_set_cb(int cb) { g_march_cb_override = cb; }

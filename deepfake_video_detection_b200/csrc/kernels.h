@@ -75,11 +75,12 @@ cudaError_t launch_gemm_tc_conv3x3(const void* Apad, const void* W, const float*
                                    int C, int N, int dtype, cudaStream_t s);
 // K4 (poolhead.cu): temporal attention pool + fc1/ReLU/fc2 per video (pretrained_detector.py:123-141)
 struct HeadWeights {
-    const float *att_w1, *att_b1, *att_w2, *att_b2;   // [64][1280], [64], [64], [1]
-    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;       // [256][1280], [256], [2][256], [2]
+    const float *att_w1, *att_b1, *att_w2, *att_b2;   // [64][D], [64], [64], [1]
+    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b;       // [256][D], [256], [2][256], [2]
 };
-// a video that is empty or longer than 1024 frames gets NaN logits
+// feature_dim D = 1280 (efficientnet_b0) or 2048 (resnet50); a video that is empty, longer than 1024 frames or whose offsets leave
+// the feature matrix gets NaN logits
 cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,
-                             int use_attention, float* logits, float* frame_scores, cudaStream_t s);
+                             int feature_dim, int use_attention, float* logits, float* frame_scores, cudaStream_t s);
 
 }  // namespace dfd

@@ -42,6 +42,9 @@ namespace dfd {
 #ifndef DFD_FUSED_REG_C
 #define DFD_FUSED_REG_C 168          // block 2.2.0 (24 -> 144 @56, k5 s2)
 #endif
+#ifndef DFD_FUSED_CARVEOUT
+#define DFD_FUSED_CARVEOUT 0         // 1: ask for the maximum shared-memory carve-out (the driver's default picked 132 KB: 2 CTAs per SM)
+#endif
 #ifndef DFD_FUSED_BLOCKS
 #define DFD_FUSED_BLOCKS 7           // bit i: fuse block 2.1.0 / 2.1.1 / 2.2.0
 #endif
@@ -337,6 +340,9 @@ static cudaError_t fused_go(const void* x, const void* we, const float* be, cons
     constexpr size_t smem = G::smem_bytes;
     auto kern = mbconv_fused_kernel<T, KS, S, CIN, C, W, CB, MAXREG>;
     if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+#if DFD_FUSED_CARVEOUT
+    { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared); if (e != cudaSuccess) return e; }
+#endif
     const int64_t grid = frames * G::ctas_per_frame;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
     kern<<<(unsigned)grid, THREADS, smem, s>>>(x, we, be, w, bias, (T*)out, partials);

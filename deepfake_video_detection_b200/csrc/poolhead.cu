@@ -1,6 +1,7 @@
 // K4 — per-video temporal attention pool + classification head, fp32 throughout.
 // Reference: pretrained_detector.py:123-131 (sigmoid-MLP score -> softmax over T -> weighted FEATURE sum),
 // :132-135 (mean mode), :138-141 (fc1 / ReLU / fc2; dropout is the identity in eval).
+// One kernel for both members of the reference's ensemble: feature width 1280 (efficientnet_b0) and 2048 (resnet50).
 // One CTA per video (ragged T via offsets).  Segmented warp-level reductions: a warp owns whole frames for
 // the score MLP (1280-long dot products reduced with shuffles), then the softmax over the video's frames,
 // then the weighted sum and the two FCs.  No atomics: results are bit-reproducible.
@@ -11,7 +12,7 @@ namespace dfd {
 
 // DFD_POOLHEAD_KERNEL_BEGIN   (tools/host_emul/ runs the kernel below, unchanged, on CPU threads)
 constexpr int kPhThreads = 512;
-constexpr int kFeat = 1280, kAttHidden = 64, kFc1 = 256;
+constexpr int kFeat = 1280, kAttHidden = 64, kFc1 = 256;   // kFeat: efficientnet_b0's width (the default instantiation)
 constexpr int kMaxT = 1024;
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -27,13 +28,15 @@ __device__ __forceinline__ float warp_max(float x) {
 
 constexpr int kPhChunk = 32;          // frames staged in shared memory at a time (32 x 1280 fp32 = 160 KB)
 
+// FEAT: feature width (multiple of 32); CHUNK: frames staged at a time (CHUNK x FEAT fp32 of dynamic shared memory)
+template <int FEAT = kFeat, int CHUNK = kPhChunk>
 __global__ void __launch_bounds__(kPhThreads)
 pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int32_t* __restrict__ offsets,
                  int frames, int use_attention, float* __restrict__ logits, float* __restrict__ frame_scores) {
-    extern __shared__ float s_f[];                 // [kPhChunk][kFeat] features of the current frame chunk
+    extern __shared__ float s_f[];                 // [CHUNK][FEAT] features of the current frame chunk
     __shared__ float s_w[kMaxT];
-    __shared__ float s_hid[kPhChunk][kAttHidden + 1];
-    __shared__ float s_pooled[kFeat];
+    __shared__ float s_hid[CHUNK][kAttHidden + 1];
+    __shared__ float s_pooled[FEAT];
     __shared__ float s_h1[kFc1];
     const int v = blockIdx.x;
     const int f0 = offsets[v];
@@ -46,25 +49,25 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
             for (int t = threadIdx.x; t < T && f0 + t < frames; t += kPhThreads) frame_scores[f0 + t] = __int_as_float(0x7fc00000);
         return;
     }
-    const float* fv = feat + (size_t)f0 * kFeat;
+    const float* fv = feat + (size_t)f0 * FEAT;
 
     if (use_attention) {
         // scores: every W1 row is read ONCE per chunk of frames and applied to all frames staged in shared memory
         const float b2 = __ldg(hw.att_b2);
-        for (int c0 = 0; c0 < T; c0 += kPhChunk) {
-            const int tc = min(kPhChunk, T - c0);
+        for (int c0 = 0; c0 < T; c0 += CHUNK) {
+            const int tc = min(CHUNK, T - c0);
             __syncthreads();
-            for (int i = threadIdx.x; i < tc * kFeat; i += kPhThreads) s_f[i] = fv[(size_t)c0 * kFeat + i];
+            for (int i = threadIdx.x; i < tc * FEAT; i += kPhThreads) s_f[i] = fv[(size_t)c0 * FEAT + i];
             __syncthreads();
             for (int h = warp; h < kAttHidden; h += NW) {
-                float wr[kFeat / 32];
+                float wr[FEAT / 32];
 #pragma unroll
-                for (int i = 0; i < kFeat / 32; ++i) wr[i] = __ldg(hw.att_w1 + (size_t)h * kFeat + lane + 32 * i);
+                for (int i = 0; i < FEAT / 32; ++i) wr[i] = __ldg(hw.att_w1 + (size_t)h * FEAT + lane + 32 * i);
                 const float b1 = __ldg(hw.att_b1 + h), w2 = __ldg(hw.att_w2 + h);
                 for (int t = 0; t < tc; ++t) {
                     float acc = 0.f;
 #pragma unroll
-                    for (int i = 0; i < kFeat / 32; ++i) acc = fmaf(s_f[t * kFeat + lane + 32 * i], wr[i], acc);
+                    for (int i = 0; i < FEAT / 32; ++i) acc = fmaf(s_f[t * FEAT + lane + 32 * i], wr[i], acc);
                     acc = warp_sum(acc);
                     if (lane == 0) s_hid[t][h] = fmaxf(acc + b1, 0.f) * w2;          // ReLU then Linear(64,1) term
                 }
@@ -87,17 +90,17 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
             for (int t = lane; t < T; t += 32) s_w[t] = s_w[t] / sum;
         }
         __syncthreads();
-        for (int c = threadIdx.x; c < kFeat; c += kPhThreads) {               // (features * w).sum(dim=1), :131
+        for (int c = threadIdx.x; c < FEAT; c += kPhThreads) {               // (features * w).sum(dim=1), :131
             float acc = 0.f;
-            if (T <= kPhChunk) { for (int t = 0; t < T; ++t) acc += s_f[t * kFeat + c] * s_w[t]; }   // chunk still staged
-            else { for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c] * s_w[t]; }
+            if (T <= CHUNK) { for (int t = 0; t < T; ++t) acc += s_f[t * FEAT + c] * s_w[t]; }   // chunk still staged
+            else { for (int t = 0; t < T; ++t) acc += fv[(size_t)t * FEAT + c] * s_w[t]; }
             s_pooled[c] = acc;
         }
     } else {
         for (int t = threadIdx.x; t < T; t += kPhThreads) s_w[t] = 1.0f / (float)T;   // :135
-        for (int c = threadIdx.x; c < kFeat; c += kPhThreads) {               // features.mean(dim=1), :134
+        for (int c = threadIdx.x; c < FEAT; c += kPhThreads) {               // features.mean(dim=1), :134
             float acc = 0.f;
-            for (int t = 0; t < T; ++t) acc += fv[(size_t)t * kFeat + c];
+            for (int t = 0; t < T; ++t) acc += fv[(size_t)t * FEAT + c];
             s_pooled[c] = acc / (float)T;
         }
     }
@@ -105,15 +108,15 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
     if (frame_scores) for (int t = threadIdx.x; t < T; t += kPhThreads) frame_scores[f0 + t] = s_w[t];
 
     for (int j = warp * 4; j < kFc1; j += NW * 4) {                           // relu(fc1(.)), :139 — 4 outputs per pass
-        const float* wr = hw.fc1_w + (size_t)j * kFeat + lane;
+        const float* wr = hw.fc1_w + (size_t)j * FEAT + lane;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-        for (int i = 0; i < kFeat / 32; ++i) {
+        for (int i = 0; i < FEAT / 32; ++i) {
             const float xv = s_pooled[lane + 32 * i];
             a0 = fmaf(xv, __ldg(wr + 32 * i), a0);
-            a1 = fmaf(xv, __ldg(wr + kFeat + 32 * i), a1);
-            a2 = fmaf(xv, __ldg(wr + 2 * kFeat + 32 * i), a2);
-            a3 = fmaf(xv, __ldg(wr + 3 * kFeat + 32 * i), a3);
+            a1 = fmaf(xv, __ldg(wr + FEAT + 32 * i), a1);
+            a2 = fmaf(xv, __ldg(wr + 2 * FEAT + 32 * i), a2);
+            a3 = fmaf(xv, __ldg(wr + 3 * FEAT + 32 * i), a3);
         }
         a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
         if (lane == 0) {
@@ -132,14 +135,22 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
 
 // DFD_POOLHEAD_KERNEL_END
 
-cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,
-                             int use_attention, float* logits, float* frame_scores, cudaStream_t s) {
-    if (videos <= 0) return cudaSuccess;
-    const size_t smem = (size_t)kPhChunk * kFeat * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int FEAT, int CHUNK>
+static cudaError_t launch_pool_head_t(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,
+                                      int use_attention, float* logits, float* frame_scores, cudaStream_t s) {
+    const size_t smem = (size_t)CHUNK * FEAT * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(pool_head_kernel<FEAT, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pool_head_kernel<<<(unsigned)videos, kPhThreads, smem, s>>>(hw, feat, offsets, (int)frames, use_attention, logits, frame_scores);
+    pool_head_kernel<FEAT, CHUNK><<<(unsigned)videos, kPhThreads, smem, s>>>(hw, feat, offsets, (int)frames, use_attention, logits, frame_scores);
     return cudaGetLastError();
+}
+
+cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,
+                             int feature_dim, int use_attention, float* logits, float* frame_scores, cudaStream_t s) {
+    if (videos <= 0) return cudaSuccess;
+    if (feature_dim == 1280) return launch_pool_head_t<1280, 32>(hw, feat, offsets, videos, frames, use_attention, logits, frame_scores, s);   // 160 KB
+    if (feature_dim == 2048) return launch_pool_head_t<2048, 16>(hw, feat, offsets, videos, frames, use_attention, logits, frame_scores, s);   // 128 KB
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace dfd

@@ -139,70 +139,6 @@ __global__ void rn_avgpool_kernel(const T* __restrict__ in, float* __restrict__ 
     *reinterpret_cast<float2*>(feat + (size_t)f * C + 2 * c2) = make_float2(s0 * inv, s1 * inv);
 }
 
-// attention pool + head for a generic feature width D (pretrained_detector.py:123-141), one CTA of 256 threads per video:
-//   a_t = sigmoid(w2 . relu(W1 f_t + b1) + b2);  w = softmax_T(a);  g = sum_t w_t f_t;  logits = W4 relu(W3 g + b3) + b4
-struct RnHead { const float *att_w1, *att_b1, *att_w2, *att_b2, *fc1_w, *fc1_b, *fc2_w, *fc2_b; };
-__global__ void __launch_bounds__(256) rn_pool_head_kernel(RnHead hw, const float* __restrict__ feat, const int32_t* __restrict__ offsets,
-                                                           int D, int use_attention, float* __restrict__ logits, float* __restrict__ frame_scores) {
-    extern __shared__ float sm[];
-    const int v = blockIdx.x, t0 = offsets[v], T = offsets[v + 1] - t0;
-    float* s_score = sm;                 // [T]
-    float* s_pool = sm + T;              // [D]
-    float* s_hid = s_pool + D;           // [256]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (T <= 0) { if (tid < 2) logits[(size_t)v * 2 + tid] = NAN; return; }
-    if (use_attention) {
-        for (int t = 0; t < T; ++t) {
-            const float* f = feat + (size_t)(t0 + t) * D;
-            for (int j = warp; j < 64; j += 8) {                              // hidden unit j: dot over D, lanes strided
-                const float* wr = hw.att_w1 + (size_t)j * D;
-                float a = 0.f;
-                for (int d = lane; d < D; d += 32) a = fmaf(__ldg(wr + d), f[d], a);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-                if (lane == 0) s_hid[j] = fmaxf(a + hw.att_b1[j], 0.f);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                float a = hw.att_b2[0];
-                for (int j = 0; j < 64; ++j) a = fmaf(hw.att_w2[j], s_hid[j], a);
-                s_score[t] = 1.0f / (1.0f + expf(-a));
-            }
-            __syncthreads();
-        }
-        if (tid == 0) {                                                       // softmax over T (fixed order)
-            float m = -INFINITY, s = 0.f;
-            for (int t = 0; t < T; ++t) m = fmaxf(m, s_score[t]);
-            for (int t = 0; t < T; ++t) { s_score[t] = expf(s_score[t] - m); s += s_score[t]; }
-            for (int t = 0; t < T; ++t) s_score[t] /= s;
-        }
-    } else {
-        for (int t = tid; t < T; t += 256) s_score[t] = 1.0f / (float)T;
-    }
-    __syncthreads();
-    for (int d = tid; d < D; d += 256) {
-        float g = 0.f;
-        for (int t = 0; t < T; ++t) g = fmaf(s_score[t], feat[(size_t)(t0 + t) * D + d], g);
-        s_pool[d] = g;
-    }
-    if (frame_scores) for (int t = tid; t < T; t += 256) frame_scores[t0 + t] = s_score[t];
-    __syncthreads();
-    for (int j = warp; j < 256; j += 8) {
-        const float* wr = hw.fc1_w + (size_t)j * D;
-        float a = 0.f;
-        for (int d = lane; d < D; d += 32) a = fmaf(__ldg(wr + d), s_pool[d], a);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) s_hid[j] = fmaxf(a + hw.fc1_b[j], 0.f);
-    }
-    __syncthreads();
-    if (tid < 2) {
-        float a = hw.fc2_b[tid];
-        for (int j = 0; j < 256; ++j) a = fmaf(hw.fc2_w[tid * 256 + j], s_hid[j], a);
-        logits[(size_t)v * 2 + tid] = a;
-    }
-}
-
 // DFD_RESNET_SMALL_KERNELS_END
 
 }  // namespace dfd
@@ -396,7 +332,7 @@ int dfd_resnet50_score_videos(const dfd_resnet_weights_t* w, const float* d_in, 
                               int max_frames_per_video, int use_attention, float* d_logits, float* d_frame_scores, float* d_features_out,
                               void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!w || !d_in || !d_offsets || !d_logits || !d_workspace) return nfail(DFD_EINVAL, "dfd_resnet50_score_videos: null pointer");
-    if (videos <= 0 || frames <= 0 || max_frames_per_video <= 0 || max_frames_per_video > 4096) return nfail(DFD_EINVAL, "dfd_resnet50_score_videos: bad counts");
+    if (videos <= 0 || frames <= 0 || max_frames_per_video <= 0 || max_frames_per_video > 1024) return nfail(DFD_EINVAL, "dfd_resnet50_score_videos: bad counts (1..1024 frames per video)");
     size_t need = 0;
     int rc = dfd_resnet50_workspace_bytes(frames, &need);
     if (rc) return rc;
@@ -411,12 +347,9 @@ int dfd_resnet50_score_videos(const dfd_resnet_weights_t* w, const float* d_in, 
         rc = rn_trunk_chunk(w, d_in + (size_t)f0 * 3 * kRnImg * kRnImg, nfr, feat + (size_t)f0 * kRnFeat, ws, s);
         if (rc) return rc;
     }
-    const dfd::RnHead hw{w->att_w1, w->att_b1, w->att_w2, w->att_b2, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b};
-    const size_t smem = ((size_t)max_frames_per_video + kRnFeat + 256) * 4;
-    cudaError_t e = cudaFuncSetAttribute(dfd::rn_pool_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return nfail(DFD_ECUDA, std::string("resnet head smem: ") + cudaGetErrorString(e));
-    dfd::rn_pool_head_kernel<<<(unsigned)videos, 256, smem, s>>>(hw, feat, d_offsets, kRnFeat, use_attention, d_logits, d_frame_scores);
-    e = cudaGetLastError();
+    // the same attention pool + head kernel as the efficientnet_b0 member (poolhead.cu), instantiated for 2048 features
+    const dfd::HeadWeights hw{w->att_w1, w->att_b1, w->att_w2, w->att_b2, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b};
+    cudaError_t e = dfd::launch_pool_head(hw, feat, d_offsets, videos, frames, kRnFeat, use_attention, d_logits, d_frame_scores, s);
     dfd::note_launch("resnet pool head");
     if (e != cudaSuccess) return nfail(DFD_ECUDA, std::string("resnet pool head: ") + cudaGetErrorString(e));
     return DFD_OK;

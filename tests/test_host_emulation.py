@@ -37,8 +37,9 @@ def test_se_gate_kernel_source_on_cpu():
 
 def test_pool_head_kernel_source_on_cpu():
     """Rows a6 / a7 (attention pool + head, pretrained_detector.py:123-141): the default kernel's source against the reference
-    arithmetic in double, ragged videos incl. an empty one, both pooling modes."""
-    assert _run("poolhead").count("-> ok") == 2
+    arithmetic in double, ragged videos incl. an empty one, both pooling modes, both feature widths (1280: efficientnet_b0,
+    2048: the resnet50 member, row a9)."""
+    assert _run("poolhead").count("-> ok") == 4
 
 
 def test_preprocess_and_stem_kernel_sources_on_cpu():
@@ -55,8 +56,9 @@ def test_depthwise_march_kernel_source_on_cpu():
 
 
 def test_resnet_member_small_kernel_sources_on_cpu():
-    """Row a9 (`resnet50` ensemble member): its max-pool, average-pool and 2048-wide attention pool + head kernels on CPU threads."""
-    assert _run("resnet").count("-> ok") == 4
+    """Row a9 (`resnet50` ensemble member): its max-pool and average-pool kernels on CPU threads (its attention pool + head is
+    the shared kernel of poolhead.cu, emulated above)."""
+    assert _run("resnet").count("-> ok") == 2
 
 
 def test_rnn_head_kernel_sources_on_cpu():

@@ -45,8 +45,9 @@ static inline float __shfl_xor_sync(unsigned, float v, int o) {
 #include "pool_head_kernel.inc"
 }  // namespace dfd
 
-int main() {
+template <int FEAT, int CHUNK> static int run() {
     using namespace dfd;
+    constexpr int kFeat = FEAT;                                        // shadows the namespace constant inside this function
     const std::vector<int> lens = {8, 1, 3, 0, 40, 33, 2};              // ragged, one empty, two longer than one staged chunk
     std::vector<int32_t> off(1, 0);
     for (int t : lens) off.push_back(off.back() + t);
@@ -73,7 +74,7 @@ int main() {
             for (int i = 0; i < kPhThreads / 32; ++i) g_warps.emplace_back(new WarpX());
             std::vector<std::thread> th;
             for (int t = 0; t < kPhThreads; ++t)
-                th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b; pool_head_kernel(hw, feat.data(), off.data(), (int)(feat.size() / 1280), att, logits.data(), scores.data()); });
+                th.emplace_back([&, t, b]() { threadIdx.x = t; blockIdx.x = b; pool_head_kernel<FEAT, CHUNK>(hw, feat.data(), off.data(), (int)(feat.size() / FEAT), att, logits.data(), scores.data()); });
             for (auto& t : th) t.join();
         }
         double max_l = 0, max_s = 0; bool nan_ok = true;
@@ -97,9 +98,11 @@ int main() {
             for (int t = 0; t < T; ++t) max_s = fmax(max_s, fabs(wgt[t] - scores[f0 + t]));
         }
         const bool ok = max_l < 2e-5 && max_s < 1e-6 && nan_ok && std::isfinite(max_l);
-        printf("pool_head_kernel (%s): %d ragged videos, max |dlogit| %.2e, max |dscore| %.2e, empty video -> NaN %s -> %s\n",
-               att ? "temporal attention" : "mean pool", V, max_l, max_s, nan_ok ? "yes" : "NO", ok ? "ok" : "MISMATCH");
+        printf("pool_head_kernel<%d, %d> (%s): %d ragged videos, max |dlogit| %.2e, max |dscore| %.2e, empty video -> NaN %s -> %s\n",
+               FEAT, CHUNK, att ? "temporal attention" : "mean pool", V, max_l, max_s, nan_ok ? "yes" : "NO", ok ? "ok" : "MISMATCH");
         rc |= ok ? 0 : 1;
     }
     return rc;
 }
+
+int main() { return run<1280, 32>() | run<2048, 16>(); }

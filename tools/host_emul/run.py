@@ -29,9 +29,6 @@ for name in which:
     if name == "rnn":
         assert text.count("extern __shared__ float sm[];") == 1
         text = text.replace("extern __shared__ float sm[];", "")
-    if name == "resnet":                               # the pool head's dynamic shared memory is the harness's `sm` array
-        assert text.count("extern __shared__ float sm[];") == 1
-        text = text.replace("extern __shared__ float sm[];", "")
     if name == "poolhead":                             # the one dynamic shared-memory array becomes a host buffer
         assert "extern __shared__ float s_f[];" in text
         text = text.replace("extern __shared__ float s_f[];", "float* s_f = g_dyn_smem;")
