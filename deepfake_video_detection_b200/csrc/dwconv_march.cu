@@ -117,8 +117,8 @@ dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const
 #pragma unroll
         for (int j = 0; j < TW; ++j) acc[s][j] = 0ull;
     uint64_t sums = 0ull;
-    T* obase = out + (((size_t)frame * OH) * OW + ox0) * C + c0;
-    uint32_t ro = (uint32_t)(oy0 * OW) * (uint32_t)C;                 // element offset of the next output row inside the frame
+    // pointer to this thread's first output of the next output row: ONE 64-bit add per row, the 7 stores use constant offsets
+    T* orow = out + (((size_t)frame * OH + oy0) * OW + ox0) * C + c0;
     const uint32_t ro_step = (uint32_t)OW * (uint32_t)C;
     const uint32_t pix_b = (uint32_t)CB * 2;
     uint32_t sb_c = sm0 + (uint32_t)(ox0 * S * CB + 2 * cpl) * 2;    // window column 0 of this thread in the current ring slot
@@ -171,10 +171,10 @@ dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const
                                 const float2 a = f2_unpack(acc[slot][j]);
                                 const float y0 = fmaf(a.x, tanh_approx(a.x), a.x), y1 = fmaf(a.y, tanh_approx(a.y), a.y);
                                 sums = add2(sums, f2_pack(y0, y1));
-                                *reinterpret_cast<uint32_t*>(obase + (ro + (uint32_t)(j * C))) = Half16<T>::pack(y0, y1);
+                                *reinterpret_cast<uint32_t*>(orow + j * C) = Half16<T>::pack(y0, y1);
                             }
                         }
-                        ro += ro_step;
+                        orow += ro_step;
                     }
                 }
             }

@@ -34,13 +34,13 @@ namespace dfd {
 #define DFD_FUSED_XR 6               // x-row ring depth
 #endif
 #ifndef DFD_FUSED_REG_A
-#define DFD_FUSED_REG_A 128          // register cap, block 2.1.0 (16 -> 96 @112, k3 s2)
+#define DFD_FUSED_REG_A 160          // register cap, block 2.1.0 (16 -> 96 @112, k3 s2)
 #endif
 #ifndef DFD_FUSED_REG_B
-#define DFD_FUSED_REG_B 128          // block 2.1.1 (24 -> 144 @56, k3 s1)
+#define DFD_FUSED_REG_B 160          // block 2.1.1 (24 -> 144 @56, k3 s1)
 #endif
 #ifndef DFD_FUSED_REG_C
-#define DFD_FUSED_REG_C 168          // block 2.2.0 (24 -> 144 @56, k5 s2)
+#define DFD_FUSED_REG_C 200          // block 2.2.0 (24 -> 144 @56, k5 s2)
 #endif
 #ifndef DFD_FUSED_CARVEOUT
 #define DFD_FUSED_CARVEOUT 0         // 1: ask for the maximum shared-memory carve-out (the driver's default picked 132 KB: 2 CTAs per SM)
@@ -67,6 +67,25 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v;
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+// four 8x8 16-bit matrices = the A fragment (a0..a3) of one m16n8k16 step in ONE shared-memory instruction
+__device__ __forceinline__ void ldsm_x4_f(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// 8 packed 16-bit values times 0.5 (exact: a power of two)
+template <typename T> __device__ __forceinline__ uint4 halve8(uint4 v) {
+    if constexpr (Half16<T>::kCode == kDtypeFP16) {
+        __half2* p = reinterpret_cast<__half2*>(&v);
+        const __half2 h = __floats2half2_rn(0.5f, 0.5f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = __hmul2(p[i], h);
+    } else {
+        __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&v);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(0.5f, 0.5f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = __hmul2(p[i], h);
+    }
+    return v;
+}
 #endif
 }  // namespace
 
@@ -84,7 +103,10 @@ struct FusedGeom {
     static constexpr int KP = (CIN + 15) & ~15;                     // K padded to whole mma k-steps
     static constexpr int XP = KP + 8;                               // halves per staged x pixel / weight row (conflict-free)
     static constexpr int PXT = (W + 15) / 16;                       // 16-pixel tiles per row
-    static constexpr uint32_t rsb = (uint32_t)pixw * CB * 2;        // bytes per expanded row slot
+    // halves per pixel of the expanded ring: CB rounded up so that the pitch in 32-bit words is 4 (mod 8) — the 8 pixels x 4
+    // channel pairs a warp stores per MMA tile then tile all 32 banks (CB = 48: 56 halves; the unpadded pitch is a 2-way conflict)
+    static constexpr int EP = 2 * ((CB / 2 + 3) / 8 * 8 + 4) >= CB ? 2 * ((CB / 2 + 3) / 8 * 8 + 4) : CB + 8;
+    static constexpr uint32_t rsb = (uint32_t)pixw * EP * 2;        // bytes per expanded row slot
     static constexpr uint32_t xsb = (uint32_t)PXT * 16 * XP * 2;    // x row slot: [PXT*16 pixels][XP]
     static constexpr uint32_t wsb = (uint32_t)CB * XP * 2;          // bytes of the weight slice
     static constexpr uint32_t bias_floats = (uint32_t)CB;
@@ -95,6 +117,7 @@ struct FusedGeom {
     static_assert(OW % kFTW == 0, "whole strips only");
     static_assert(CB % 8 == 0 && C % CB == 0 && CIN % 8 == 0, "channel blocks");
     static_assert(THREADS - DWT < DWT, "shadow threads map onto real ones");
+    static_assert(EP >= CB && EP % 2 == 0 && (EP / 2) % 8 == 4, "conflict-free pixel pitch of the expanded ring");
 };
 
 template <typename T, int KS, int S, int CIN, int C, int W, int CB, int MAXREG>
@@ -110,7 +133,7 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
     constexpr int DWT = G::DWT, THREADS = G::THREADS, WARPS = G::WARPS;
     constexpr int NCOL = (TW - 1) * S + KS;
     constexpr int RING = (KS + S - 1) / S, PERIOD = S * RING;
-    constexpr int pixw = G::pixw, KP = G::KP, KSTEPS = KP / 16, XP = G::XP, PXT = G::PXT;
+    constexpr int KP = G::KP, KSTEPS = KP / 16, XP = G::XP, PXT = G::PXT, EP = G::EP;
     constexpr uint32_t rsb = G::rsb, xsb = G::xsb, wsb = G::wsb;
     constexpr int NTL = CB / 8;                                   // 8-channel tiles of the channel block
     constexpr int rps = G::rps, segs = G::segs;
@@ -146,9 +169,10 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
     // expand weights [CB][CIN] (BN folded, 16-bit, K-major) and bias of this channel block
     for (int i = threadIdx.x; i < CB * (CIN / 8); i += THREADS) {
         const int r = i / (CIN / 8), q = i - r * (CIN / 8);
-        sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8));
+        // weights and bias are staged HALVED: the MMA then accumulates h = (x W^T + b) / 2 directly, SiLU(x) = h + h tanh(h)
+        sts16(sm_w + (uint32_t)(r * XP + q * 8) * 2, halve8<T>(ldg16(we + (size_t)(cb * CB + r) * CIN + q * 8)));
     }
-    for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = be[cb * CB + i];
+    for (int i = threadIdx.x; i < CB; i += THREADS) s_be[i] = 0.5f * be[cb * CB + i];
 
     uint64_t wr[KS * KS];
     const uint64_t half2 = f2_pack(0.5f, 0.5f);
@@ -181,16 +205,20 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
         xs_i += xsb; if (xs_i == sm_x + kXR * xsb) xs_i = sm_x;
     };
 
-    // expand one input row (index k of this CTA's walk, image row iy) from its x slot into expanded slot k & 1
-    auto expand_row = [&](int k, int iy) {
-        if (k >= rend || (unsigned)iy >= (unsigned)H) return;            // CTA-uniform
+    // Expand one input row (index k of this CTA's walk, image row iy) from its x slot into expanded slot k & 1, in two halves so
+    // that the depthwise FMAs of the row being consumed can be scheduled between them (MUFU pipe and FMA pipe busy together):
+    //   expand_compute  every fragment load (ldmatrix), every MMA, the SiLU of all accumulators -> packed 16-bit pairs in registers
+    //   expand_store    the stores into the expanded ring
+    // A warp owns NTL / WARPS channel tiles (always whole) and all pixel tiles of the row (compile-time unrolled); the
+    // asm-volatile shared-memory accesses and MMAs keep their program order, so writing the phases out is what lets the
+    // scheduler overlap the tiles' MMA -> MUFU chains (tile-by-tile code spent a third of its issue slots on fixed-latency waits).
+    static_assert(NTL % WARPS == 0, "whole channel tiles per warp");
+    constexpr int NPW = NTL / WARPS;
+    auto expand_compute = [&](int k, int iy, uint32_t (&o)[NPW][PXT][2]) -> bool {
+        if (k >= rend || (unsigned)iy >= (unsigned)H) return false;      // CTA-uniform
         const uint32_t xs = sm_x + (uint32_t)(k % kXR) * xsb;
-        const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
-        // A warp owns NTL / WARPS channel tiles (8 / strips of them: always whole) and walks the pixel tiles of the row: the
-        // weight fragments are loaded once per row, every offset below is a compile-time constant, and the unrolled pixel
-        // tiles give the scheduler independent load -> MMA -> SiLU -> store chains.
-        static_assert(NTL % WARPS == 0, "whole channel tiles per warp");
-        constexpr int NPW = NTL / WARPS;
+        // ldmatrix row of this lane: pixel (lane & 7) + 8 * ((lane >> 3) & 1) of the tile, K columns 8 * (lane >> 4) ...
+        const uint32_t ar0 = xs + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * XP + (lane >> 4) * 8) * 2;
 #pragma unroll
         for (int q = 0; q < NPW; ++q) {
             const int nt = warp * NPW + q;
@@ -198,44 +226,37 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
             uint32_t bf[KSTEPS][2];
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) { bf[ks][0] = lds32(br + ks * 32); bf[ks][1] = lds32(br + ks * 32 + 16); }
-            // h = (acc + bias) / 2 in one FMA; SiLU(x) = h + h tanh(h)
-            const float hbx = 0.5f * s_be[nt * 8 + 2 * t], hby = 0.5f * s_be[nt * 8 + 2 * t + 1];
-            const uint32_t ar0 = xs + (uint32_t)(g * XP + 2 * t) * 2;
-            const uint32_t ea0 = es + (uint32_t)((g + PAD) * CB + nt * 8 + 2 * t) * 2;
-            // the fragment loads of pixel tile pt+1 are issued before the MMA -> SiLU -> store chain of tile pt (the volatile
-            // shared-memory accesses keep their program order, so the overlap has to be written out)
-            constexpr bool PREF = KSTEPS <= 3;
-            uint32_t an[PREF ? KSTEPS : 1][4];
-            auto load_a = [&](int pt, uint32_t (*dst)[4]) {
-                const uint32_t ar = ar0 + (uint32_t)(pt * 16 * XP) * 2;
+            const float hbx = s_be[nt * 8 + 2 * t], hby = s_be[nt * 8 + 2 * t + 1];      // accumulators start from the halved bias
+            uint32_t a[PXT][KSTEPS][4];
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    dst[ks][0] = lds32(ar + ks * 32);                 dst[ks][1] = lds32(ar + ks * 32 + 8 * XP * 2);
-                    dst[ks][2] = lds32(ar + ks * 32 + 16);            dst[ks][3] = lds32(ar + ks * 32 + 8 * XP * 2 + 16);
-                }
-            };
-            if (PREF) load_a(0, an);
+            for (int pt = 0; pt < PXT; ++pt)
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) ldsm_x4_f(a[pt][ks], ar0 + (uint32_t)(pt * 16 * XP) * 2 + ks * 32);
+            float c[PXT][4];
 #pragma unroll
             for (int pt = 0; pt < PXT; ++pt) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
-                uint32_t a[KSTEPS][4];
-                if (PREF) {
+                c[pt][0] = hbx; c[pt][1] = hby; c[pt][2] = hbx; c[pt][3] = hby;
 #pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks)
+                for (int ks = 0; ks < KSTEPS; ++ks) mma16816_f<T>(c[pt], a[pt][ks], bf[ks][0], bf[ks][1]);
+            }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) a[ks][i] = an[ks][i];
-                    if (pt + 1 < PXT) load_a(pt + 1, an);
-                } else {
-                    load_a(pt, a);
-                }
+            for (int pt = 0; pt < PXT; ++pt) {
+                o[q][pt][0] = Half16<T>::pack(fmaf(c[pt][0], tanh_approx(c[pt][0]), c[pt][0]), fmaf(c[pt][1], tanh_approx(c[pt][1]), c[pt][1]));
+                o[q][pt][1] = Half16<T>::pack(fmaf(c[pt][2], tanh_approx(c[pt][2]), c[pt][2]), fmaf(c[pt][3], tanh_approx(c[pt][3]), c[pt][3]));
+            }
+        }
+        return true;
+    };
+    auto expand_store = [&](int k, const uint32_t (&o)[NPW][PXT][2]) {
+        const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) mma16816_f<T>(c, a[ks], bf[ks][0], bf[ks][1]);
-                const float h0 = fmaf(c[0], 0.5f, hbx), h1 = fmaf(c[1], 0.5f, hby), h2 = fmaf(c[2], 0.5f, hbx), h3 = fmaf(c[3], 0.5f, hby);
-                const uint32_t ea = ea0 + (uint32_t)(pt * 16 * CB) * 2;
-                if (pt * 16 + 8 <= W || pt * 16 + g < W)
-                    sts32(ea, Half16<T>::pack(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1)));
-                if (pt * 16 + 16 <= W || pt * 16 + 8 + g < W)
-                    sts32(ea + 8 * CB * 2, Half16<T>::pack(fmaf(h2, tanh_approx(h2), h2), fmaf(h3, tanh_approx(h3), h3)));
+        for (int q = 0; q < NPW; ++q) {
+            const uint32_t ea0 = es + (uint32_t)((g + PAD) * EP + (warp * NPW + q) * 8 + 2 * t) * 2;
+#pragma unroll
+            for (int pt = 0; pt < PXT; ++pt) {
+                const uint32_t ea = ea0 + (uint32_t)(pt * 16 * EP) * 2;
+                if (pt * 16 + 8 <= W || pt * 16 + g < W) sts32(ea, o[q][pt][0]);
+                if (pt * 16 + 16 <= W || pt * 16 + 8 + g < W) sts32(ea + 8 * EP * 2, o[q][pt][1]);
             }
         }
     };
@@ -245,7 +266,10 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
     cp_async_wait<kXR - 2>();                // x row 0 has landed (this thread's copies) ...
     __syncthreads();                         // ... and everybody's; weights and bias are visible too
     issue_row();                             // row kXR-1 into the free slot
-    expand_row(0, iy_start);
+    {
+        uint32_t eo[NPW][PXT][2];
+        if (expand_compute(0, iy_start, eo)) expand_store(0, eo);
+    }
 
     uint64_t acc[RING][TW];
 #pragma unroll
@@ -253,11 +277,10 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 #pragma unroll
         for (int j = 0; j < TW; ++j) acc[s][j] = 0ull;
     uint64_t sums = 0ull;
-    T* obase = out + (((size_t)frame * OH) * OW + ox0) * C + c0;
-    uint32_t ro = (uint32_t)(oy0 * OW) * (uint32_t)C;
+    T* orow = out + (((size_t)frame * OH + oy0) * OW + ox0) * C + c0;     // one 64-bit add per output row, constant store offsets
     constexpr uint32_t ro_step = (uint32_t)OW * (uint32_t)C;
-    constexpr uint32_t pix_b = (uint32_t)CB * 2;
-    const uint32_t sb_c0 = sm_e + (uint32_t)(ox0 * S * CB + 2 * cpl) * 2;   // window column 0 of this thread in slot 0
+    constexpr uint32_t pix_b = (uint32_t)EP * 2;
+    const uint32_t sb_c0 = sm_e + (uint32_t)(ox0 * S * EP + 2 * cpl) * 2;   // window column 0 of this thread in slot 0
     int iy = iy_start;
 
     for (int rb = 0; rb < rend; rb += PERIOD) {
@@ -268,7 +291,8 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
                 cp_async_wait<kXR - 2>();                // x row r+1 has landed (this thread's copies) ...
                 __syncthreads();                         // ... and everybody's; expanded row r is complete; row r-1 consumed
                 issue_row();                             // x row r+kXR into the slot of x row r (expanded in step r-1)
-                expand_row(r + 1, iy + 1);
+                uint32_t eo[NPW][PXT][2];
+                const bool expanded = expand_compute(r + 1, iy + 1, eo);
                 const uint32_t sb_c = sb_c0 + (uint32_t)(r & 1) * rsb;
                 if ((unsigned)iy < (unsigned)H) {
 #pragma unroll
@@ -296,6 +320,7 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 #pragma unroll
                     for (int j = 0; j < TW; ++j) acc[slot][j] = b2;
                 }
+                if (expanded) expand_store(r + 1, eo);
                 ++iy;
                 if ((p - (KS - 1) + 2 * PERIOD) % S == 0) {
                     const int slot = ((p - (KS - 1) + 2 * PERIOD) / S) % RING;
@@ -305,9 +330,9 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
                             const float2 a = f2_unpack(acc[slot][j]);
                             const float y0 = fmaf(a.x, tanh_approx(a.x), a.x), y1 = fmaf(a.y, tanh_approx(a.y), a.y);
                             sums = add2(sums, f2_pack(y0, y1));
-                            if (dw_active) *reinterpret_cast<uint32_t*>(obase + (ro + (uint32_t)(j * C))) = Half16<T>::pack(y0, y1);
+                            if (dw_active) *reinterpret_cast<uint32_t*>(orow + j * C) = Half16<T>::pack(y0, y1);
                         }
-                        ro += ro_step;
+                        orow += ro_step;
                     }
                 }
             }

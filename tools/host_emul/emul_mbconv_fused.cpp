@@ -90,7 +90,7 @@ template <int N> static inline void cp_async_wait() {
 }
 
 // mma.sync m16n8k16 (row.col, fp16 x fp16 -> fp32): fragments exchanged through a per-warp buffer
-struct WarpX { uint32_t a[32][4], b[32][2]; float c[32][4]; std::barrier<> bar{32}; };
+struct WarpX { uint32_t a[32][4], b[32][2]; float c[32][4]; uint32_t addr[32]; std::barrier<> bar{32}; };
 static std::vector<std::unique_ptr<WarpX>> g_warps;
 template <typename T> static inline void mma16816_f(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -111,6 +111,20 @@ template <typename T> static inline void mma16816_f(float* c, const uint32_t* a,
             c[half * 2 + j] = acc;
         }
     w.bar.arrive_and_wait();
+}
+
+// ldmatrix.m8n8.x4.b16 by its PTX definition (the model the GPU-verified attention kernel's emulation uses): lane l supplies the
+// address of row l % 8 of matrix l / 8; lane i receives, per matrix, the 32-bit word (row i / 4, columns 2 (i % 4), 2 (i % 4) + 1)
+static inline void ldsm_x4_f(uint32_t (&r)[4], uint32_t addr) {
+    WarpX& w = *g_warps[threadIdx.x >> 5]; const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    w.addr[lane] = addr; w.bar.arrive_and_wait();
+    for (int m = 0; m < 4; ++m) memcpy(&r[m], fz_smem + w.addr[m * 8 + g] + (2 * t) * 2, 4);
+    w.bar.arrive_and_wait();
+}
+template <typename T> static inline uint4 halve8(uint4 v) {
+    uint32_t* p = &v.x;
+    for (int i = 0; i < 4; ++i) { const float2 f = Half16<T>::unpack(p[i]); p[i] = Half16<T>::pack(0.5f * f.x, 0.5f * f.y); }
+    return v;
 }
 
 namespace { constexpr int kFTW = 7; constexpr int kXR = 6; }
