@@ -554,10 +554,13 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     // Weights stay resident only up to 60 KB: beyond that the shared memory is worth more as pipeline stages (W blocks then
     // stream from L2 by TMA).  Measured: 672->112 gated 233 -> 178 us, 112->672 expand 88 -> 78 us per 2048 / 1024 frames.
     const size_t res_limit = 60 * 1024;
+#ifndef DFD_GEMM_CHUNK_RESLIM
+#define DFD_GEMM_CHUNK_RESLIM (60 * 1024)      // limit for keeping ONE column chunk per CTA (tools/build_variant.py sweeps it)
+#endif
     a.b_resident = 0;
     if (a.tpf == 0) {
         if (bres <= res_limit) a.b_resident = 1;
-        else if (a.n_chunks > 1 && a.n_chunks <= g_num_sms && a.b_chunk_bytes <= res_limit) a.b_resident = 2;
+        else if (a.n_chunks > 1 && a.n_chunks <= g_num_sms && a.b_chunk_bytes <= (size_t)DFD_GEMM_CHUNK_RESLIM) a.b_resident = 2;
     }
     a.b_res_bytes = a.b_resident == 1 ? (uint32_t)bres : (a.b_resident == 2 ? a.b_chunk_bytes : 0u);
     const size_t stage_bytes = ((size_t)kAStageBytes + (a.b_resident ? 0 : a.b_stage_bytes) + a.g_stage_bytes + 1023) & ~size_t(1023);

@@ -34,13 +34,13 @@ namespace dfd {
 #define DFD_FUSED_XR 6               // x-row ring depth
 #endif
 #ifndef DFD_FUSED_REG_A
-#define DFD_FUSED_REG_A 160          // register cap, block 2.1.0 (16 -> 96 @112, k3 s2)
+#define DFD_FUSED_REG_A 128          // register cap, block 2.1.0 (16 -> 96 @112, k3 s2)
 #endif
 #ifndef DFD_FUSED_REG_B
-#define DFD_FUSED_REG_B 160          // block 2.1.1 (24 -> 144 @56, k3 s1)
+#define DFD_FUSED_REG_B 128          // block 2.1.1 (24 -> 144 @56, k3 s1)
 #endif
 #ifndef DFD_FUSED_REG_C
-#define DFD_FUSED_REG_C 200          // block 2.2.0 (24 -> 144 @56, k5 s2)
+#define DFD_FUSED_REG_C 168          // block 2.2.0 (24 -> 144 @56, k5 s2)
 #endif
 #ifndef DFD_FUSED_CARVEOUT
 #define DFD_FUSED_CARVEOUT 0         // 1: ask for the maximum shared-memory carve-out (the driver's default picked 132 KB: 2 CTAs per SM)
@@ -205,18 +205,19 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
         xs_i += xsb; if (xs_i == sm_x + kXR * xsb) xs_i = sm_x;
     };
 
-    // Expand one input row (index k of this CTA's walk, image row iy) from its x slot into expanded slot k & 1, in two halves so
-    // that the depthwise FMAs of the row being consumed can be scheduled between them (MUFU pipe and FMA pipe busy together):
-    //   expand_compute  every fragment load (ldmatrix), every MMA, the SiLU of all accumulators -> packed 16-bit pairs in registers
-    //   expand_store    the stores into the expanded ring
-    // A warp owns NTL / WARPS channel tiles (always whole) and all pixel tiles of the row (compile-time unrolled); the
+    // Expand one input row (index k of this CTA's walk, image row iy) from its x slot into expanded slot k & 1.
+    // A warp owns NTL / WARPS channel tiles (always whole) and all pixel tiles of the row (compile-time unrolled), in PHASES:
+    // every fragment load (ldmatrix) first, then every MMA, then the SiLU of all accumulators, then every store.  The
     // asm-volatile shared-memory accesses and MMAs keep their program order, so writing the phases out is what lets the
-    // scheduler overlap the tiles' MMA -> MUFU chains (tile-by-tile code spent a third of its issue slots on fixed-latency waits).
+    // scheduler overlap the tiles' MMA -> MUFU -> store chains (tile-by-tile code spent a third of its issue slots on
+    // fixed-latency waits: 1.54 -> 1.35 ms for block 2.1.0 at 2048 frames).  Holding the packed results back until after the
+    // depthwise FMAs of the same step (to overlap the MUFU and FMA pipes) measured SLOWER (register pressure): 1.42 ms.
     static_assert(NTL % WARPS == 0, "whole channel tiles per warp");
     constexpr int NPW = NTL / WARPS;
-    auto expand_compute = [&](int k, int iy, uint32_t (&o)[NPW][PXT][2]) -> bool {
-        if (k >= rend || (unsigned)iy >= (unsigned)H) return false;      // CTA-uniform
+    auto expand_row = [&](int k, int iy) {
+        if (k >= rend || (unsigned)iy >= (unsigned)H) return;            // CTA-uniform
         const uint32_t xs = sm_x + (uint32_t)(k % kXR) * xsb;
+        const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
         // ldmatrix row of this lane: pixel (lane & 7) + 8 * ((lane >> 3) & 1) of the tile, K columns 8 * (lane >> 4) ...
         const uint32_t ar0 = xs + (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * XP + (lane >> 4) * 8) * 2;
 #pragma unroll
@@ -227,6 +228,7 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) { bf[ks][0] = lds32(br + ks * 32); bf[ks][1] = lds32(br + ks * 32 + 16); }
             const float hbx = s_be[nt * 8 + 2 * t], hby = s_be[nt * 8 + 2 * t + 1];      // accumulators start from the halved bias
+            const uint32_t ea0 = es + (uint32_t)((g + PAD) * EP + nt * 8 + 2 * t) * 2;
             uint32_t a[PXT][KSTEPS][4];
 #pragma unroll
             for (int pt = 0; pt < PXT; ++pt)
@@ -239,24 +241,17 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) mma16816_f<T>(c[pt], a[pt][ks], bf[ks][0], bf[ks][1]);
             }
+            uint32_t o[PXT][2];
 #pragma unroll
             for (int pt = 0; pt < PXT; ++pt) {
-                o[q][pt][0] = Half16<T>::pack(fmaf(c[pt][0], tanh_approx(c[pt][0]), c[pt][0]), fmaf(c[pt][1], tanh_approx(c[pt][1]), c[pt][1]));
-                o[q][pt][1] = Half16<T>::pack(fmaf(c[pt][2], tanh_approx(c[pt][2]), c[pt][2]), fmaf(c[pt][3], tanh_approx(c[pt][3]), c[pt][3]));
+                o[pt][0] = Half16<T>::pack(fmaf(c[pt][0], tanh_approx(c[pt][0]), c[pt][0]), fmaf(c[pt][1], tanh_approx(c[pt][1]), c[pt][1]));
+                o[pt][1] = Half16<T>::pack(fmaf(c[pt][2], tanh_approx(c[pt][2]), c[pt][2]), fmaf(c[pt][3], tanh_approx(c[pt][3]), c[pt][3]));
             }
-        }
-        return true;
-    };
-    auto expand_store = [&](int k, const uint32_t (&o)[NPW][PXT][2]) {
-        const uint32_t es = sm_e + (uint32_t)(k & 1) * rsb;
-#pragma unroll
-        for (int q = 0; q < NPW; ++q) {
-            const uint32_t ea0 = es + (uint32_t)((g + PAD) * EP + (warp * NPW + q) * 8 + 2 * t) * 2;
 #pragma unroll
             for (int pt = 0; pt < PXT; ++pt) {
                 const uint32_t ea = ea0 + (uint32_t)(pt * 16 * EP) * 2;
-                if (pt * 16 + 8 <= W || pt * 16 + g < W) sts32(ea, o[q][pt][0]);
-                if (pt * 16 + 16 <= W || pt * 16 + 8 + g < W) sts32(ea + 8 * EP * 2, o[q][pt][1]);
+                if (pt * 16 + 8 <= W || pt * 16 + g < W) sts32(ea, o[pt][0]);
+                if (pt * 16 + 16 <= W || pt * 16 + 8 + g < W) sts32(ea + 8 * EP * 2, o[pt][1]);
             }
         }
     };
@@ -266,10 +261,7 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
     cp_async_wait<kXR - 2>();                // x row 0 has landed (this thread's copies) ...
     __syncthreads();                         // ... and everybody's; weights and bias are visible too
     issue_row();                             // row kXR-1 into the free slot
-    {
-        uint32_t eo[NPW][PXT][2];
-        if (expand_compute(0, iy_start, eo)) expand_store(0, eo);
-    }
+    expand_row(0, iy_start);
 
     uint64_t acc[RING][TW];
 #pragma unroll
@@ -291,8 +283,7 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
                 cp_async_wait<kXR - 2>();                // x row r+1 has landed (this thread's copies) ...
                 __syncthreads();                         // ... and everybody's; expanded row r is complete; row r-1 consumed
                 issue_row();                             // x row r+kXR into the slot of x row r (expanded in step r-1)
-                uint32_t eo[NPW][PXT][2];
-                const bool expanded = expand_compute(r + 1, iy + 1, eo);
+                expand_row(r + 1, iy + 1);
                 const uint32_t sb_c = sb_c0 + (uint32_t)(r & 1) * rsb;
                 if ((unsigned)iy < (unsigned)H) {
 #pragma unroll
@@ -320,7 +311,6 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
 #pragma unroll
                     for (int j = 0; j < TW; ++j) acc[slot][j] = b2;
                 }
-                if (expanded) expand_store(r + 1, eo);
                 ++iy;
                 if ((p - (KS - 1) + 2 * PERIOD) % S == 0) {
                     const int slot = ((p - (KS - 1) + 2 * PERIOD) / S) % RING;
