@@ -61,6 +61,7 @@ _SIGNATURES = {
     "dfd_k_dwconv": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp]),
     "dfd_k_se": (_int, [_vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _vp]),
     "dfd_k_gemm": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp]),
+    "dfd_k_vit_attention": (_int, [_vp, _vp, _i64, _int, _vp]),
     "dfd_k_conv1x1_conv3x3": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp, C.c_size_t, _vp]),
     "dfd_k_mbconv_fused_supported": (_int, [_int, _int, _int, _int, _int, _int]),
     "dfd_k_mbconv_fused": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _int, _vp]),

@@ -517,6 +517,10 @@ static cudaError_t make_tmap(const void* A, int64_t M, int K, int box_rows, CUte
     return cudaSuccess;
 }
 
+cudaError_t make_tmap_2d(const void* base, int64_t rows, int cols, int box_rows, void* out_tmap) {
+    return make_tmap(base, rows, cols, box_rows, reinterpret_cast<CUtensorMap*>(out_tmap));
+}
+
 template <typename KernelT>
 static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, int xform_warps, cudaStream_t s) {
     if (g_num_sms == 0) {

@@ -73,6 +73,12 @@ cudaError_t launch_gemm_tc_padout(const void* A, const void* W, const float* bia
                                   int K, int N, int dtype, cudaStream_t s);
 cudaError_t launch_gemm_tc_conv3x3(const void* Apad, const void* W, const float* bias, void* D, int64_t frames, int H, int Wd,
                                    int C, int N, int dtype, cudaStream_t s);
+// 2-D tensor map (CUtensorMap written to *out_tmap) over a row-major 16-bit matrix [rows][cols]: boxes of 64 columns x box_rows
+// rows, 128-byte swizzle, zero fill outside the tensor (gemm_tc.cu; cached per (pointer, shape))
+cudaError_t make_tmap_2d(const void* base, int64_t rows, int cols, int box_rows, void* out_tmap);
+// ViT attention on tcgen05 (vit_attn_tc.cu): qkv [images*197][2304] 16-bit -> o [images*197][768], softmax(Q K^T / 8) V per (image, head)
+cudaError_t launch_vit_attention_tc(const void* qkv, void* o, int64_t images, int dtype, cudaStream_t s);
+
 // K4 (poolhead.cu): temporal attention pool + fc1/ReLU/fc2 per video (pretrained_detector.py:123-141)
 struct HeadWeights {
     const float *att_w1, *att_b1, *att_w2, *att_b2;   // [64][D], [64], [64], [1]

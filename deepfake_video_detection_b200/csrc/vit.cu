@@ -27,7 +27,7 @@
 #include "kernels.h"
 
 namespace {
-constexpr int kDim = 768, kDepth = 12, kHeads = 12, kHd = 64, kPatch = 16, kImg = 224, kGridP = 14;
+constexpr int kDim = 768, kDepth = 12, kPatch = 16, kImg = 224, kGridP = 14;
 constexpr int kPatches = kGridP * kGridP, kTokens = kPatches + 1, kMlp = 3072, kPatchK = 3 * kPatch * kPatch;
 }
 
@@ -130,180 +130,8 @@ __global__ void vit_layernorm_kernel(const float* __restrict__ x, int64_t in_str
     }
 }
 
-// ---- attention: one CTA per (image, head); softmax(Q K^T / 8) V over 197 tokens, head dim 64 -----------------------
-// qkv [B*197][2304] 16-bit with timm's column order (which*768 + head*64 + d).  Q, K, V (row-major, padded rows) are
-// staged in shared memory; each warp owns 16-query tiles: S = Q K^T with mma.sync m16n8k16 (fp32 accumulate), online
-// softmax over 64-key blocks, P rounded to 16 bits feeds the second mma.sync against V.  Out: o [B*197][768] 16-bit
-// (column = head*64 + d).
-constexpr int kTokPad = 208;                 // 197 padded to 13 tiles of 16
-constexpr int kQKStride = 72;                // halves per staged Q / K row: 64 + 8 (conflict-free fragment loads)
-
-template <typename T>
-__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    if constexpr (Half16<T>::kCode == kDtypeFP16)
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-    else
-        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// ---- attention (second variant; the first one — whole 16 x 208 score tile in registers, V^T staged by a bank-conflicted
-// scatter, 8 warps per SM — measured 1 % slower on B200 and was removed) ------------------------------------------------
-//   * Q, K and V are all staged row-major with 16-byte stores (pitch 72 halves: conflict-free for ldmatrix);
-//   * fragments come from `ldmatrix.x4` (one instruction feeds two MMAs); the V operand of P V uses `.trans`, so no
-//     transposed copy of V is ever written;
-//   * keys are processed in blocks of 64 with the online-softmax recurrence (fp32 running max / sum, accumulator rescaled
-//     when the max moves), so a thread holds 32 score registers instead of 104: 256 threads per CTA and 2 CTAs per SM
-//     (16 warps per SM instead of 8).  Scores are pre-multiplied by log2(e)/8 and exponentiated with ex2.approx.
-// (tools/host_emul/ compiles the kernel between the DFD_ATT2_KERNEL markers unchanged for the CPU, with its own ldmatrix / mma.)
-template <typename T>
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-template <typename T>
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-
-// DFD_ATT2_KERNEL_BEGIN
-constexpr int kAtt2Warps = 8;
-constexpr int kAtt2KeyBlock = 64;
-
-template <typename T>
-__global__ void __launch_bounds__(kAtt2Warps * 32, 2) vit_attention_v2_kernel(const T* __restrict__ qkv, T* __restrict__ o) {
-    extern __shared__ __align__(16) uint8_t att_smem[];
-    T* sQ = reinterpret_cast<T*>(att_smem);                       // [208][72]
-    T* sK = sQ + kTokPad * kQKStride;                             // [208][72]
-    T* sV = sK + kTokPad * kQKStride;                             // [208][72]  row-major (read through ldmatrix.trans)
-    const int head = blockIdx.x % kHeads;
-    const int64_t img = blockIdx.x / kHeads;
-    const T* base = qkv + (size_t)img * kTokens * (3 * kDim) + head * kHd;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < kTokPad * 8; i += kAtt2Warps * 32) {
-        const int tok = i >> 3, ch = (i & 7) * 8;
-        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
-        if (tok < kTokens) {
-            const T* row = base + (size_t)tok * (3 * kDim) + ch;
-            q = *reinterpret_cast<const uint4*>(row);
-            k = *reinterpret_cast<const uint4*>(row + kDim);
-            v = *reinterpret_cast<const uint4*>(row + 2 * kDim);
-        }
-        *reinterpret_cast<uint4*>(sQ + tok * kQKStride + ch) = q;
-        *reinterpret_cast<uint4*>(sK + tok * kQKStride + ch) = k;
-        *reinterpret_cast<uint4*>(sV + tok * kQKStride + ch) = v;
-    }
-    __syncthreads();
-
-    const int warp = tid >> 5, lane = tid & 31, t = lane & 3;
-    const uint32_t sq = smem_u32(sQ), sk = smem_u32(sK), sv = smem_u32(sV);
-    constexpr uint32_t kRowB = kQKStride * 2;                                     // bytes per staged row
-    // per-lane row / column offsets of the three ldmatrix address patterns (see the fragment layouts of mma.m16n8k16):
-    //   A (Q):        matrices (rows 0-7, k 0-7) (rows 8-15, k 0-7) (rows 0-7, k 8-15) (rows 8-15, k 8-15)
-    //   B (K, S=QK^T): matrices (keys 0-7, d 0-7) (keys 0-7, d 8-15) (keys 0-7, d 16-23) (keys 0-7, d 24-31)
-    //   B (V, O=PV):   .trans of (keys 0-7, d 0-7) (keys 8-15, d 0-7) (keys 0-7, d 8-15) (keys 8-15, d 8-15)
-    const uint32_t a_off = (uint32_t)(lane & 15) * kRowB + (uint32_t)(lane >> 4) * 16;
-    const uint32_t k_off = (uint32_t)(lane & 7) * kRowB + (uint32_t)(lane >> 3) * 16;
-    const uint32_t v_off = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8) * kRowB + (uint32_t)(lane >> 4) * 16;
-    const float kScale = 0.125f * 1.4426950408889634f;                            // 1/sqrt(64) * log2(e)
-
-    for (int qt = warp; qt < kTokPad / 16; qt += kAtt2Warps) {
-        const int q0 = qt * 16;
-        uint32_t aq[4][4];
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) ldsm_x4<T>(aq[ks], sq + (uint32_t)q0 * kRowB + a_off + ks * 32);
-        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-        float acc[kHd / 8][4];
-#pragma unroll
-        for (int dt = 0; dt < kHd / 8; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
-#pragma unroll 1
-        for (int kb0 = 0; kb0 < kTokPad; kb0 += kAtt2KeyBlock) {
-            const int nkt = min(kAtt2KeyBlock, kTokPad - kb0) / 8;                // 8-key tiles in this block: 8, 8, 8, 2
-            float s[kAtt2KeyBlock / 8][4];
-            // the K fragments of key tile nt+1 are requested before the MMAs of tile nt (the asm statements keep their program
-            // order, so the load / MMA overlap inside a warp has to be written out)
-            uint32_t kn0[4], kn1[4];
-            ldsm_x4<T>(kn0, sk + (uint32_t)kb0 * kRowB + k_off); ldsm_x4<T>(kn1, sk + (uint32_t)kb0 * kRowB + k_off + 64);   // head dims 0-31, 32-63
-#pragma unroll
-            for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
-                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-                if (nt < nkt) {
-                    uint32_t b0[4], b1[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { b0[i] = kn0[i]; b1[i] = kn1[i]; }
-                    if (nt + 1 < nkt) {
-                        const uint32_t ka = sk + (uint32_t)(kb0 + (nt + 1) * 8) * kRowB + k_off;
-                        ldsm_x4<T>(kn0, ka); ldsm_x4<T>(kn1, ka + 64);
-                    }
-                    mma16816<T>(s[nt], aq[0], b0[0], b0[1]); mma16816<T>(s[nt], aq[1], b0[2], b0[3]);
-                    mma16816<T>(s[nt], aq[2], b1[0], b1[1]); mma16816<T>(s[nt], aq[3], b1[2], b1[3]);
-                }
-            }
-            // scale, mask the padding keys, block maxima of rows g (c0,c1) and g+8 (c2,c3)
-            float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-            for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const bool ok = nt < nkt && kb0 + nt * 8 + 2 * t + j < kTokens;
-                    s[nt][j] = ok ? s[nt][j] * kScale : -INFINITY;
-                    s[nt][2 + j] = ok ? s[nt][2 + j] * kScale : -INFINITY;
-                    bm0 = fmaxf(bm0, s[nt][j]); bm1 = fmaxf(bm1, s[nt][2 + j]);
-                }
-            }
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-            const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);                 // finite: every block holds a valid key
-            const float al0 = ex2_approx(m0 - n0), al1 = ex2_approx(m1 - n1);     // first block: ex2(-inf) = 0
-            m0 = n0; m1 = n1;
-            float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-            for (int nt = 0; nt < kAtt2KeyBlock / 8; ++nt) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    s[nt][j] = ex2_approx(s[nt][j] - n0); s[nt][2 + j] = ex2_approx(s[nt][2 + j] - n1);
-                    r0 += s[nt][j]; r1 += s[nt][2 + j];
-                }
-            }
-            l0 = l0 * al0 + r0; l1 = l1 * al1 + r1;                               // per-lane partial sums; quad-reduced at the end
-#pragma unroll
-            for (int dt = 0; dt < kHd / 8; ++dt) { acc[dt][0] *= al0; acc[dt][1] *= al0; acc[dt][2] *= al1; acc[dt][3] *= al1; }
-            // O += P V: two adjacent 8-key score tiles are one 16-key A fragment
-#pragma unroll
-            for (int kk = 0; kk < kAtt2KeyBlock / 16; ++kk) {
-                if (2 * kk < nkt) {
-                    uint32_t ap[4];
-                    ap[0] = Half16<T>::pack(s[2 * kk][0], s[2 * kk][1]);         ap[1] = Half16<T>::pack(s[2 * kk][2], s[2 * kk][3]);
-                    ap[2] = Half16<T>::pack(s[2 * kk + 1][0], s[2 * kk + 1][1]); ap[3] = Half16<T>::pack(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-                    const uint32_t va = sv + (uint32_t)(kb0 + kk * 16) * kRowB + v_off;
-                    uint32_t vn[4];
-                    ldsm_x4_trans<T>(vn, va);
-#pragma unroll
-                    for (int dp = 0; dp < kHd / 16; ++dp) {
-                        uint32_t bv[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) bv[i] = vn[i];
-                        if (dp + 1 < kHd / 16) ldsm_x4_trans<T>(vn, va + (dp + 1) * 32);      // next pair of head-dim tiles
-                        mma16816<T>(acc[2 * dp], ap, bv[0], bv[1]);
-                        mma16816<T>(acc[2 * dp + 1], ap, bv[2], bv[3]);
-                    }
-                }
-            }
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        const int r0 = q0 + (lane >> 2), r1 = r0 + 8;
-        T* ob = o + (size_t)img * kTokens * kDim + head * kHd + 2 * t;
-#pragma unroll
-        for (int dt = 0; dt < kHd / 8; ++dt) {
-            if (r0 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * kDim + dt * 8) = Half16<T>::pack(acc[dt][0] * i0, acc[dt][1] * i0);
-            if (r1 < kTokens) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * kDim + dt * 8) = Half16<T>::pack(acc[dt][2] * i1, acc[dt][3] * i1);
-        }
-    }
-}
-// DFD_ATT2_KERNEL_END
-constexpr size_t kAtt2Smem = (size_t)(3 * kTokPad * kQKStride) * 2;
+// ---- attention: csrc/vit_attn_tc.cu (tcgen05 / TMEM; the mma.sync + ldmatrix kernel it replaced measured 152 TFLOP/s against
+// 270 TFLOP/s at batch 512 on B200 and was removed) ----------------------------------------------------------------------
 
 // ---- DeepfakeModel head (src/models.py:199-291): SimpleGCN over the frame graph + mean pool + classifier ------------
 //   g = relu(fc2(relu(fc1(A_norm @ H))));  logits = Linear(64 -> C)(relu(Linear(128 -> 64)(mean_n g)))      (:186-197, :283-291)
@@ -470,6 +298,15 @@ int dfd_vit_workspace_bytes(int64_t images, size_t* bytes) {
     return DFD_OK;
 }
 
+// kernel-level entry (include/dfd_b200_kernels.h): the attention of one ViT block (the kernel the encoder runs)
+int dfd_k_vit_attention(const void* d_qkv, void* d_o, int64_t images, int dtype, void* stream) {
+    if (!d_qkv || !d_o || images <= 0) return vfail(DFD_EINVAL, "dfd_k_vit_attention: bad argument");
+    if (dtype != DFD_DTYPE_FP16 && dtype != DFD_DTYPE_BF16) return vfail(DFD_EINVAL, "dfd_k_vit_attention: unknown dtype");
+    cudaError_t e = dfd::launch_vit_attention_tc(d_qkv, d_o, images, dtype, (cudaStream_t)stream);
+    if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string("vit attention: ") + cudaGetErrorString(e));
+    return DFD_OK;
+}
+
 int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t images, float* d_features,
                      void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!w || !d_in || !d_features || !d_workspace) return vfail(DFD_EINVAL, "dfd_vit_features: null pointer");
@@ -509,15 +346,11 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
         else dfd::vit_assemble_kernel<__nv_bfloat16><<<agrid, 256, 0, s>>>((const __nv_bfloat16*)H16, w->cls, w->pos, X, a8);
         VIT_CK(cudaGetLastError(), "vit assemble");
     }
-    if (f16) VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention smem");
-    else VIT_CK(cudaFuncSetAttribute(dfd::vit_attention_v2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dfd::kAtt2Smem), "vit attention smem");
     for (int i = 0; i < kDepth; ++i) {
         const auto& b = w->blk[i];
         VIT_CK(ln(X, kDim, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");
         VIT_CK(dfd::launch_gemm_tc(H16, b.qkv_w, b.qkv_b, nullptr, nullptr, BIG, M, kDim, 3 * kDim, 1, 0, dt, s), "vit qkv gemm");
-        if (f16) dfd::vit_attention_v2_kernel<__half><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __half*)BIG, (__half*)H16);
-        else dfd::vit_attention_v2_kernel<__nv_bfloat16><<<(unsigned)(images * kHeads), dfd::kAtt2Warps * 32, dfd::kAtt2Smem, s>>>((const __nv_bfloat16*)BIG, (__nv_bfloat16*)H16);
-        VIT_CK(cudaGetLastError(), "vit attention");
+        VIT_CK(dfd::launch_vit_attention_tc(BIG, H16, images, dt, s), "vit attention");
         VIT_CK(dfd::launch_gemm_tc_f32out(H16, b.proj_w, b.proj_b, X, X, M, kDim, kDim, dt, s), "vit proj gemm");
         VIT_CK(ln(X, kDim, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");
         VIT_CK(dfd::launch_gemm_tc(H16, b.fc1_w, b.fc1_b, nullptr, nullptr, BIG, M, kDim, kMlp, 1, 2, dt, s), "vit fc1 gemm");

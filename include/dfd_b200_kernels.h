@@ -63,6 +63,11 @@ int dfd_k_mbconv_fused_supported(int H, int W, int cin, int mid, int k, int stri
 int dfd_k_mbconv_fused(const void* d_x, const void* d_we, const float* d_be, const float* d_w, const float* d_bias, void* d_out,
                        float* d_partials, int64_t frames, int H, int W, int cin, int mid, int k, int stride, int dtype, void* stream);
 
+/* timm vit_base_patch16_224 attention of one block (reference: src/models.py:88-107): d_qkv [images*197][2304] 16-bit in timm's
+ * column order (which*768 + head*64 + d) -> d_o [images*197][768] = softmax(Q K^T / 8) V per (image, head); the tcgen05 / TMEM
+ * kernel the encoder runs (csrc/vit_attn_tc.cu). */
+int dfd_k_vit_attention(const void* d_qkv, void* d_o, int64_t images, int dtype, void* stream);
+
 /* HOST-ONLY (no GPU needed): row maps of that zero-haloed layout, computed by the very functions the kernels use
  * (csrc/conv_map.h).  h_pad_row [frames*H*W]: physical row of every interior pixel; h_out_row [frames*(H+2)*(W+2)]: output
  * row of every padded pixel, -1 for halo pixels; h_tap_row / h_tap_col [9*cpk]: row offset and channel column of the A box

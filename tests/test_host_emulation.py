@@ -27,10 +27,6 @@ def test_fused_expand_depthwise_kernel_source_on_cpu():
     assert out.count("-> ok") == 6
 
 
-def test_attention_kernel_source_on_cpu():
-    assert _run("attention").count("-> ok") == 1        # ViT attention (ldmatrix + online softmax) against fp32 softmax(QK^T/8)V
-
-
 def test_se_gate_kernel_source_on_cpu():
     assert _run("se").count("-> ok") == 8               # squeeze-excite gate: 8 shapes incl. a partial last CTA and an odd rd
 

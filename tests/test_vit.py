@@ -151,3 +151,30 @@ def test_deepfake_model_cuda_matches_oracle():
         assert lib.dfd_gcn_head(m._pack_head(f.device), f.data_ptr(), a.data_ptr(), 2, n_nodes, o.data_ptr(), _stream_ptr(f.device)) == 0
         assert (o.cpu() - V.gcn_head(sd, f.cpu(), a.cpu())).abs().max().item() < 1e-4
     assert lib.dfd_gcn_head(m._pack_head(f.device), f.data_ptr(), a.data_ptr(), 2, 65, o.data_ptr(), _stream_ptr(f.device)) != 0   # nodes > 64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("fp16", 2.5e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("images", [1, 3, 37, 160])
+def test_vit_attention_tcgen05_kernel(prec, tol, images):
+    """The tcgen05 / TMEM attention kernel (csrc/vit_attn_tc.cu) on random qkv against fp32 softmax(Q K^T / 8) V of the same
+    16-bit-rounded operands (tolerance = rounding of P and of the output to the storage type: the mma.sync kernel this one
+    replaced measured the same 1.9e-3 / 1.6e-2 on B200).  37 images = 888 tiles: several per CTA (both TMEM buffers, both stages,
+    the P buffer reused), the last image's tiles read past the end of the tensor (zero fill); 160 images: > 12 tiles per CTA."""
+    from deepfake_video_detection_b200 import _lib
+    from deepfake_video_detection_b200.engine import PRECISIONS, TORCH_DTYPE, _stream_ptr
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(images)
+    qkv = (torch.randn(images * 197, 2304, generator=g) * 1.5).to(TORCH_DTYPE[prec]).cuda()
+    o = torch.full((images * 197, 768), float("nan"), dtype=TORCH_DTYPE[prec], device="cuda")
+    rc = lib.dfd_k_vit_attention(qkv.data_ptr(), o.data_ptr(), images, PRECISIONS[prec], _stream_ptr(qkv.device))
+    assert rc == 0, lib.dfd_vit_last_error()
+    torch.cuda.synchronize()
+    out = o.float().cpu()
+    x = qkv.float().cpu().view(images, 197, 3, 12, 64).permute(2, 0, 3, 1, 4)          # (3, B, heads, tokens, d)
+    ref = torch.softmax(x[0] @ x[1].transpose(-1, -2) * 0.125, dim=-1) @ x[2]          # (B, heads, tokens, d)
+    ref = ref.permute(0, 2, 1, 3).reshape(images * 197, 768)
+    assert torch.isfinite(out).all()
+    err = (out - ref).abs().max().item()
+    print(f"vit attention {prec} images {images}: max |err| {err:.2e}")
+    assert err <= tol, err

@@ -1,12 +1,11 @@
 """Build and run the CPU emulations of the CUDA-core kernels: the kernel text between the emulation markers of the .cu file
 is extracted UNCHANGED and compiled with the matching harness in this directory.
-    python tools/host_emul/run.py [fused|attention|se|poolhead|prepstem|march|resnet|rnn|all] [quick] [tsan]"""
+    python tools/host_emul/run.py [fused|se|poolhead|prepstem|march|resnet|rnn|all] [quick] [tsan]"""
 import hashlib, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "build", "host_emul")
 os.makedirs(OUT, exist_ok=True)
 CASES = {"fused": ("mbconv_fused.cu", "DFD_FUSED_KERNEL", "mbconv_fused_kernel.inc", "emul_mbconv_fused.cpp"),
-         "attention": ("vit.cu", "DFD_ATT2_KERNEL", "vit_attention_v2_kernel.inc", "emul_vit_attention_v2.cpp"),
          "se": ("se.cu", "DFD_SE1_KERNEL", "se_kernel_v1.inc", "emul_se.cpp"),
          "poolhead": ("poolhead.cu", "DFD_POOLHEAD_KERNEL", "pool_head_kernel.inc", "emul_pool_head.cpp"),
          "march": ("dwconv_march.cu", "DFD_MARCH_KERNEL", "dwconv_march_kernel.inc", "emul_dwconv_march.cpp"),
