@@ -487,7 +487,7 @@ def bench_config5(args, rank, world, dev, timer, sampler_cls, local_rank):
     hbm_gbs, tf_peak, peak_kind = measured_peaks()
     flops = 35.1e9 * B                                   # 17.56 GMAC per image
     tfl = flops / (steady["median_ms"] / 1e3) / 1e12
-    roofline = {"kernel": "whole ViT-B/16 forward (12 x [qkv, attention, proj, fc1, fc2] tcgen05 GEMMs + mma.sync attention)", "bound": "tensor",
+    roofline = {"kernel": "whole ViT-B/16 forward (12 x [qkv, attention, proj, fc1, fc2] CTA-pair tcgen05 GEMMs + tcgen05 attention)", "bound": "tensor",
                 "achieved": round(tfl, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(tfl / tf_peak, 4), "traffic": None,
                 "peak_kind": f"sustained bf16, {peak_kind}", "flops_per_step": flops, "timed_on": "median step of the steady run"}
     cfg = {"workload": "ViT frame encoder (ViT-B/16, 224x224) forward at batch 512 (BASELINE configs[4])", "images_per_gpu": B,

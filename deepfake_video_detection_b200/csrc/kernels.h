@@ -62,6 +62,10 @@ cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bi
 // (rnn.cu) and the fp32 residual stream of the ViT encoder (vit.cu)
 cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, const float* R, float* D,
                                   int64_t M, int K, int N, int dtype, cudaStream_t s);
+// K3b (gemm_pair.cu): D[M,N] = act(A[M,K] * W[N,K]^T + bias) on CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, TMA-store
+// epilogue); act 0 none | 2 exact GELU; N a multiple of 256.  The ViT-B/16 contractions.
+bool gemm_pair_supported(int64_t M, int K, int N);
+cudaError_t launch_gemm_pair(const void* A, const void* W, const float* bias, void* D, int64_t M, int K, int N, int act, int dtype, cudaStream_t s);
 // conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
                                 int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);

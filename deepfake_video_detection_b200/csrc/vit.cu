@@ -2,16 +2,17 @@
 // timm `vit_base_patch16_224(num_classes=0)` (un-vendored dependency, requirements.txt:12): x (B,3,224,224) fp32 ->
 // CLS feature (B,768) fp32.
 //
-// Every dense contraction (patch embedding, qkv, attention projection, the two MLP layers: 99 % of the 35 GFLOP per
-// image) runs on the tcgen05/TMEM GEMM of gemm_tc.cu with 16-bit operands and fp32 accumulation:
+// Every dense contraction (patch embedding, qkv, attention projection, the two MLP layers: 96 % of the 35 GFLOP per
+// image) runs on the CTA-pair tcgen05/TMEM GEMM of gemm_pair.cu with 16-bit operands and fp32 accumulation:
 //   patchify (fp32 NCHW -> 16-bit [B*196, 768], column = c*256 + ky*16 + kx, the Conv2d weight order)
 //   -> GEMM(+bias) -> assemble tokens: [cls | patches] + pos_embed -> residual stream X fp32 [B*197, 768]
-//   12 x { LN1(X) -> 16-bit ; qkv GEMM ; attention (softmax(QK^T/8)V per image and head, mma.sync m16n8k16, fp32
-//          softmax) ; proj GEMM with fp32 residual epilogue (X += ..., in place) ; LN2 ; fc1 GEMM + exact-erf GELU ;
-//          fc2 GEMM with fp32 residual epilogue }
-//   final LayerNorm on the CLS rows only -> fp32 features.
-// The residual stream stays fp32 end to end (only GEMM operands are rounded to 16 bits), LayerNorm statistics
-// and the softmax are fp32.  Every reduction has a fixed order: results do not depend on the batch.
+//   12 x { X += fc2 output of the previous block ; LN1(X) -> 16-bit ; qkv GEMM ; attention (softmax(QK^T/8)V per image and
+//          head on tcgen05, vit_attn_tc.cu) ; proj GEMM -> 16-bit ; X += proj output ; LN2(X) ; fc1 GEMM + exact GELU ; fc2 GEMM }
+//   X[cls] += last fc2 output ; final LayerNorm on the CLS rows only -> fp32 features.
+// The residual stream stays fp32 end to end; the branch outputs are rounded to 16 bits once (GEMM output) and added to it
+// inside the LayerNorm kernel that needs the sum anyway (one read-modify-write of X per branch instead of a second one in a
+// GEMM epilogue).  LayerNorm statistics and the softmax are fp32.  Every reduction has a fixed order: results do not
+// depend on the batch.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -91,18 +92,32 @@ __global__ void vit_assemble_kernel(const T* __restrict__ p, const float* __rest
 }
 
 // LayerNorm over 768 channels, eps 1e-6, one warp per row: fp32 statistics (mean, then centred variance).
-// Input row r lives at x + r * in_stride floats.  OUT = 16-bit GEMM operand or fp32 (final norm).
-template <typename OUT>
-__global__ void vit_layernorm_kernel(const float* __restrict__ x, int64_t in_stride, const float* __restrict__ w,
+// Row r of the residual stream lives at x + r * in_stride floats.  With `delta` (the 16-bit output of the previous branch,
+// row r at delta + r * in_stride elements) the row becomes x + delta first and is written back (the residual add).
+// OUT = 16-bit GEMM operand or fp32 (final norm).
+template <typename OUT, typename DT>
+__global__ void vit_layernorm_kernel(float* __restrict__ x, int64_t in_stride, const DT* __restrict__ delta, const float* __restrict__ w,
                                      const float* __restrict__ b, OUT* __restrict__ y, int64_t rows) {
     const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= rows) return;
     const int lane = threadIdx.x & 31;
-    const float4* src = reinterpret_cast<const float4*>(x + (size_t)r * in_stride);
+    float4* src = reinterpret_cast<float4*>(x + (size_t)r * in_stride);
     float4 v[6];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) { v[j] = src[lane + 32 * j]; s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+    for (int j = 0; j < 6; ++j) v[j] = src[lane + 32 * j];
+    if (delta) {
+        const uint2* dp = reinterpret_cast<const uint2*>(delta + (size_t)r * in_stride);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const uint2 d = __ldg(dp + lane + 32 * j);
+            const float2 d0 = Half16<DT>::unpack(d.x), d1 = Half16<DT>::unpack(d.y);
+            v[j].x += d0.x; v[j].y += d0.y; v[j].z += d1.x; v[j].w += d1.y;
+            src[lane + 32 * j] = v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * (1.0f / kDim);
@@ -294,7 +309,7 @@ void dfd_vit_free_weights(dfd_vit_weights_t* w) { if (w) { if (w->arena) cudaFre
 int dfd_vit_workspace_bytes(int64_t images, size_t* bytes) {
     if (!bytes || images <= 0) return vfail(DFD_EINVAL, "dfd_vit_workspace_bytes: bad argument");
     const size_t M = (size_t)images * kTokens;
-    *bytes = vup(M * kDim * 4) + vup(M * kDim * 2) + vup(M * kMlp * 2) + 1024;
+    *bytes = vup(M * kDim * 4) + 2 * vup(M * kDim * 2) + vup(M * kMlp * 2) + 1024;
     return DFD_OK;
 }
 
@@ -320,17 +335,23 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
     uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d_workspace) + 255) & ~uintptr_t(255));
     float* X = reinterpret_cast<float*>(ws);   ws += vup((size_t)M * kDim * 4);     // fp32 residual stream
     void* H16 = ws;                            ws += vup((size_t)M * kDim * 2);     // LN output / attention output / patch GEMM output
+    void* P16 = ws;                            ws += vup((size_t)M * kDim * 2);     // branch output (proj / fc2) waiting to be added to X
     void* BIG = ws;                                                                  // patches / qkv / MLP hidden
     const int dt = w->dtype;
     const bool f16 = dt == DFD_DTYPE_FP16;
     cudaError_t e;
     dfd::reset_launches();
 #define VIT_CK(call, what) do { e = (call); dfd::note_launch(what); if (e != cudaSuccess) return vfail(DFD_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); } while (0)
-    auto ln = [&](const float* in, int64_t stride, const float* g, const float* b, void* out, bool out_f32, int64_t rows) {
+    // y = LN(x (+= delta)) over `rows` rows `stride` elements apart
+    auto ln = [&](float* x, int64_t stride, const void* delta, const float* g, const float* b, void* out, bool out_f32, int64_t rows) {
         const unsigned grid = (unsigned)((rows + 7) / 8);
-        if (out_f32) dfd::vit_layernorm_kernel<float><<<grid, 256, 0, s>>>(in, stride, g, b, (float*)out, rows);
-        else if (f16) dfd::vit_layernorm_kernel<__half><<<grid, 256, 0, s>>>(in, stride, g, b, (__half*)out, rows);
-        else dfd::vit_layernorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(in, stride, g, b, (__nv_bfloat16*)out, rows);
+        if (f16) {
+            if (out_f32) dfd::vit_layernorm_kernel<float, __half><<<grid, 256, 0, s>>>(x, stride, (const __half*)delta, g, b, (float*)out, rows);
+            else dfd::vit_layernorm_kernel<__half, __half><<<grid, 256, 0, s>>>(x, stride, (const __half*)delta, g, b, (__half*)out, rows);
+        } else {
+            if (out_f32) dfd::vit_layernorm_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>(x, stride, (const __nv_bfloat16*)delta, g, b, (float*)out, rows);
+            else dfd::vit_layernorm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>(x, stride, (const __nv_bfloat16*)delta, g, b, (__nv_bfloat16*)out, rows);
+        }
         return cudaGetLastError();
     };
     {
@@ -339,7 +360,7 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
         if (f16) dfd::vit_patchify_kernel<__half><<<grid, 256, 0, s>>>(d_in, (__half*)BIG, n8);
         else dfd::vit_patchify_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(d_in, (__nv_bfloat16*)BIG, n8);
         VIT_CK(cudaGetLastError(), "vit patchify");
-        VIT_CK(dfd::launch_gemm_tc(BIG, w->patch_w, w->patch_b, nullptr, nullptr, H16, MP, kPatchK, kDim, 1, 0, dt, s), "vit patch-embed gemm");
+        VIT_CK(dfd::launch_gemm_pair(BIG, w->patch_w, w->patch_b, H16, MP, kPatchK, kDim, 0, dt, s), "vit patch-embed gemm");
         const int64_t a8 = M * (kDim / 8);
         const unsigned agrid = (unsigned)((a8 + 255) / 256);
         if (f16) dfd::vit_assemble_kernel<__half><<<agrid, 256, 0, s>>>((const __half*)H16, w->cls, w->pos, X, a8);
@@ -348,15 +369,15 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
     }
     for (int i = 0; i < kDepth; ++i) {
         const auto& b = w->blk[i];
-        VIT_CK(ln(X, kDim, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");
-        VIT_CK(dfd::launch_gemm_tc(H16, b.qkv_w, b.qkv_b, nullptr, nullptr, BIG, M, kDim, 3 * kDim, 1, 0, dt, s), "vit qkv gemm");
+        VIT_CK(ln(X, kDim, i ? P16 : nullptr, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");            // X += fc2 output of block i-1
+        VIT_CK(dfd::launch_gemm_pair(H16, b.qkv_w, b.qkv_b, BIG, M, kDim, 3 * kDim, 0, dt, s), "vit qkv gemm");
         VIT_CK(dfd::launch_vit_attention_tc(BIG, H16, images, dt, s), "vit attention");
-        VIT_CK(dfd::launch_gemm_tc_f32out(H16, b.proj_w, b.proj_b, X, X, M, kDim, kDim, dt, s), "vit proj gemm");
-        VIT_CK(ln(X, kDim, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");
-        VIT_CK(dfd::launch_gemm_tc(H16, b.fc1_w, b.fc1_b, nullptr, nullptr, BIG, M, kDim, kMlp, 1, 2, dt, s), "vit fc1 gemm");
-        VIT_CK(dfd::launch_gemm_tc_f32out(BIG, b.fc2_w, b.fc2_b, X, X, M, kMlp, kDim, dt, s), "vit fc2 gemm");
+        VIT_CK(dfd::launch_gemm_pair(H16, b.proj_w, b.proj_b, P16, M, kDim, kDim, 0, dt, s), "vit proj gemm");
+        VIT_CK(ln(X, kDim, P16, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");                          // X += attention branch
+        VIT_CK(dfd::launch_gemm_pair(H16, b.fc1_w, b.fc1_b, BIG, M, kDim, kMlp, 2, dt, s), "vit fc1 gemm");
+        VIT_CK(dfd::launch_gemm_pair(BIG, b.fc2_w, b.fc2_b, P16, M, kMlp, kDim, 0, dt, s), "vit fc2 gemm");
     }
-    VIT_CK(ln(X, (int64_t)kTokens * kDim, w->norm_w, w->norm_b, d_features, true, images), "vit final norm");
+    VIT_CK(ln(X, (int64_t)kTokens * kDim, P16, w->norm_w, w->norm_b, d_features, true, images), "vit final norm");   // CLS rows only
 #undef VIT_CK
     return DFD_OK;
 }

@@ -292,3 +292,33 @@ def test_mbconv_fused_expand_depthwise(lib, prec, cin, mid, H, k, s):
     chk(lib, lib.dfd_k_dwconv(E.data_ptr(), wp.data_ptr(), bd.data_ptr(), out2.data_ptr(), parts2.data_ptr(), frames, H, H, mid, k, s, code, stream()))
     close(out.cpu(), out2.cpu(), rel)                                               # same rounding points; only the MMA accumulation order differs
     close(parts.cpu(), parts2.cpu(), 1e-3, abs_=5e-2)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("M,K,N,act", [
+    (591, 768, 768, 0),          # 3 row tiles of 256, the last one partial (TMA zero fill on load, clipped store)
+    (100, 768, 256, 2),          # fewer rows than one CTA of the pair holds: the peer CTA's rows are all out of range
+    (256 * 80 + 37, 768, 2304, 0),   # 729 tiles on 74 pairs: both accumulator buffers, every stage, the staging panels reused
+    (4096, 3072, 768, 0),        # 48 k-blocks per tile (fc2 shape)
+    (3000, 768, 3072, 2),        # fc1 shape with the GELU epilogue
+    (1500, 72, 512, 2),          # K tail inside a 64-wide k-block
+])
+def test_gemm_cta_pairs(lib, prec, M, K, N, act):
+    """The CTA-pair GEMM (csrc/gemm_pair.cu, `tcgen05.mma.cta_group::2`, TMA-store epilogue) against an fp64 matmul of the same
+    16-bit-rounded operands; GELU is the exact erf form (timm's nn.GELU, reference src/models.py:93)."""
+    code, tdt, rel = DT[prec]
+    g = torch.Generator().manual_seed(M + K + N)
+    A = (torch.randn(M, K, generator=g)).to(tdt)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(tdt)
+    b = torch.randn(N, generator=g) * 0.5
+    Ad, Wd, bd = A.cuda(), W.cuda(), b.cuda()
+    D = torch.full((M, N), float("nan"), dtype=tdt, device="cuda")
+    guard = torch.full((4096,), 7.0, dtype=tdt, device="cuda")          # allocated right behind D on a fresh allocator segment or not: checked either way
+    chk(lib, lib.dfd_k_gemm(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, None, D.data_ptr(), M, K, N, 1, act, code, 3, stream()))
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    if act == 2:
+        ref = F.gelu(ref)
+    assert torch.isfinite(D).all()
+    close(D.cpu(), ref, rel)
+    assert (guard == 7.0).all()

@@ -8,9 +8,9 @@ timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$tag.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke_$tag.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; cat gpurun_out/bench_$tag.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>/dev/null; cat gpurun_out/bench_ref_$tag.json
-timeout 300 python tools/bench_vit.py --batch 512 --iters 5 > gpurun_out/bench_vit_$tag.json 2>&1; cat gpurun_out/bench_vit_$tag.json
-timeout 300 python tools/bench_rnn.py > gpurun_out/bench_rnn_$tag.json 2>&1; cat gpurun_out/bench_rnn_$tag.json
-timeout 300 python tools/bench_resnet.py > gpurun_out/bench_resnet_$tag.json 2>&1; cat gpurun_out/bench_resnet_$tag.json
+timeout 400 python bench.py --config 5 --no-cpu-baseline > gpurun_out/bench_vit_$tag.json 2> gpurun_out/bench_vit_$tag.err; cat gpurun_out/bench_vit_$tag.json
+timeout 400 python bench.py --config 3 --no-cpu-baseline > gpurun_out/bench_rnn_$tag.json 2> gpurun_out/bench_rnn_$tag.err; cat gpurun_out/bench_rnn_$tag.json
+timeout 400 python bench.py --config ensemble --no-cpu-baseline > gpurun_out/bench_ens_$tag.json 2> gpurun_out/bench_ens_$tag.err; cat gpurun_out/bench_ens_$tag.json
 CMD="python tools/prof_step.py --videos 64 --frames 32 --iters 2"
 timeout 300 $CMD > gpurun_out/prof_plain_$tag.log 2>&1
 L=$(grep -o '[0-9]* launches' gpurun_out/prof_plain_$tag.log | tail -1 | cut -d' ' -f1); L=${L:-71}     # launches per forward pass (71 by default, fewer with DFD_FUSE_EXPAND)
