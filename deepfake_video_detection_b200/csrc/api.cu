@@ -687,9 +687,12 @@ int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const floa
         if (e2 != cudaSuccess) return cuda_fail(e2, "gemm (tcgen05, per-frame weights) sync");
         return DFD_OK;
     }
-    if (impl == 3) {                 // CTA-pair GEMM (gemm_pair.cu, the ViT contractions): no gate, no residual, act 0 or 2 (GELU), N % 256 == 0
-        if (d_gate || d_R || (act != 0 && act != 2) || !dfd::gemm_pair_supported(M, K, N)) return fail(DFD_EINVAL, "dfd_k_gemm impl 3: no gate / residual, act 0 or 2, N a multiple of 256");
-        DFD_LAUNCH(dfd::launch_gemm_pair(d_A, d_W, d_bias, d_D, M, K, N, act, dtype, (cudaStream_t)stream), "gemm (tcgen05, CTA pairs)");
+    if (impl == 3) {                 // CTA-pair GEMM (gemm_pair.cu, the ViT contractions): no gate, act 0 or 2 (GELU), N % 256 == 0;
+                                     // d_R == d_D: fp32 residual stream updated in place (X += A W^T + bias, act 0)
+        if (d_gate || (d_R && (d_R != d_D || act)) || (act != 0 && act != 2) || !dfd::gemm_pair_supported(M, K, N))
+            return fail(DFD_EINVAL, "dfd_k_gemm impl 3: no gate, act 0 or 2, N a multiple of 256, residual only in place (d_R == d_D, fp32, act 0)");
+        if (d_R) DFD_LAUNCH(dfd::launch_gemm_pair_residual(d_A, d_W, d_bias, (float*)d_D, M, K, N, dtype, (cudaStream_t)stream), "gemm (tcgen05, CTA pairs, fp32 residual)");
+        else DFD_LAUNCH(dfd::launch_gemm_pair(d_A, d_W, d_bias, d_D, M, K, N, act, dtype, (cudaStream_t)stream), "gemm (tcgen05, CTA pairs)");
         return DFD_OK;
     }
     if (impl != 0) return fail(DFD_EINVAL, "dfd_k_gemm: impl must be 0 (tcgen05 GEMM), 2 (per-frame weights) or 3 (CTA pairs)");

@@ -170,6 +170,12 @@ __device__ __forceinline__ U32x8 ldg32_coherent(const void* p) {   // 256-bit lo
     return r;
 }
 
+__device__ __forceinline__ uint4 ldg16_coherent(const void* p) {   // 128-bit load of data this kernel also writes
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

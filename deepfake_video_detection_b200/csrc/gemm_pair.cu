@@ -34,10 +34,12 @@ constexpr size_t kPSmem = 1024 + (size_t)kPStages * kPStage + 4 * kPPanel + 256;
 static_assert(kPSmem <= 227 * 1024, "shared memory budget");
 }  // namespace
 
-template <typename T, int ACT>
+// RES: the output is the fp32 residual stream X [M][N], updated in place: X += A W^T + bias (no activation, no tensor map for D)
+template <typename T, int ACT, bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                 const float* __restrict__ bias, int K, int m_tiles, int n_tiles) {
+                 const float* __restrict__ bias, float* __restrict__ X, int64_t M, int N, int K, int m_tiles, int n_tiles) {
+    static_assert(!RES || ACT == 0, "the residual variant has no activation");
     extern __shared__ __align__(128) uint8_t pr_smem[];
     const uint32_t base = (smem_u32(pr_smem) + 1023u) & ~1023u;
     const uint32_t sm_out = base + kPStages * kPStage;
@@ -121,6 +123,57 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after_sync();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kPN + g * 64);
             const float4* bp = reinterpret_cast<const float4*>(bias + nt * kPN + g * 64);
+            if constexpr (RES) {
+                // fp32 read-modify-write of the residual stream.  A thread owns an accumulator ROW, so direct global accesses would
+                // touch 32 cache lines per warp instruction: the 128 x 32 fp32 half-panel goes through the (swizzled) staging
+                // buffer and is added to X with 8 lanes per 128-byte row segment (4 rows per warp instruction, 8 loads in flight).
+                const int t128 = q * 32 + lane, cj = t128 & 7, r0 = t128 >> 3;
+                const int64_t m0 = (int64_t)mt * (2 * kPM) + (int64_t)rank * kPM;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r[2][16];
+                    tmem_ld16(t_addr + h * 32, r[0]);
+                    tmem_ld16(t_addr + h * 32 + 16, r[1]);
+                    tmem_ld_wait();
+                    if (h == 1) {                                               // all TMEM reads of this warp are done
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b4 = __ldg(bp + h * 8 + i);
+                        const uint32_t* rr = &r[i >> 2][(i & 3) * 4];
+                        uint4 v;
+                        v.x = __float_as_uint(__uint_as_float(rr[0]) + b4.x); v.y = __float_as_uint(__uint_as_float(rr[1]) + b4.y);
+                        v.z = __float_as_uint(__uint_as_float(rr[2]) + b4.z); v.w = __float_as_uint(__uint_as_float(rr[3]) + b4.w);
+                        sts16(out_row + (((uint32_t)i ^ sw) << 4), v);
+                    }
+                    named_bar_sync(1 + g, 128);
+                    float* xp = X + (m0 + r0) * N + (nt * kPN + g * 64 + h * 32 + cj * 4);
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk += 4) {
+                        uint4 xv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (m0 + r0 + 16 * (kk + k) < M) xv[k] = ldg16_coherent(xp + (size_t)(16 * (kk + k)) * N);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr_ = r0 + 16 * (kk + k);
+                            if (m0 + rr_ < M) {
+                                const uint4 a = lds16(panel + (uint32_t)rr_ * 128 + (((uint32_t)cj ^ (uint32_t)(rr_ & 7)) << 4));
+                                float4 o4;
+                                o4.x = __uint_as_float(xv[k].x) + __uint_as_float(a.x); o4.y = __uint_as_float(xv[k].y) + __uint_as_float(a.y);
+                                o4.z = __uint_as_float(xv[k].z) + __uint_as_float(a.z); o4.w = __uint_as_float(xv[k].w) + __uint_as_float(a.w);
+                                *reinterpret_cast<float4*>(xp + (size_t)(16 * (kk + k)) * N) = o4;
+                            }
+                        }
+                    }
+                    named_bar_sync(1 + g, 128);                                 // staging reusable
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             if (issuer) bulk_wait_group_read0();                              // the previous store has read the panel
             named_bar_sync(1 + g, 128);
             uint32_t r[2][16];
@@ -155,7 +208,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (issuer) bulk_wait_group_read0();
+        if (!RES && issuer) bulk_wait_group_read0();
     }
     tc_fence_before_sync();
     cluster_sync_all();                                  // the peer may still count on this CTA's barriers / read its operands
@@ -164,20 +217,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 bool gemm_pair_supported(int64_t M, int K, int N) { return M > 0 && N % kPN == 0 && K % 8 == 0 && K >= 8 && M < (1ll << 31) - 256; }
 
-cudaError_t launch_gemm_pair(const void* A, const void* W, const float* bias, void* D, int64_t M, int K, int N, int act, int dtype, cudaStream_t s) {
+static cudaError_t launch_pair(const void* A, const void* W, const float* bias, void* D, float* X, int64_t M, int K, int N, int act, int dtype, cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
-    if (!gemm_pair_supported(M, K, N) || (act != 0 && act != 2)) return cudaErrorInvalidValue;
+    if (!gemm_pair_supported(M, K, N) || (act != 0 && act != 2) || (X && act)) return cudaErrorInvalidValue;
     CUtensorMap tmA, tmB, tmD;
     cudaError_t e = make_tmap_2d(A, M, K, kPM, &tmA);
     if (e != cudaSuccess) return e;
     e = make_tmap_2d(W, N, K, kPN / 2, &tmB);
     if (e != cudaSuccess) return e;
-    e = make_tmap_2d(D, M, N, kPM, &tmD);
-    if (e != cudaSuccess) return e;
-    const int m_tiles = (int)((M + 2 * kPM - 1) / (2 * kPM)), n_tiles = N / kPN;
+    if (X) tmD = tmA;
+    else { e = make_tmap_2d(D, M, N, kPM, &tmD); if (e != cudaSuccess) return e; }
+    int m_tiles = (int)((M + 2 * kPM - 1) / (2 * kPM)), n_tiles = N / kPN;
     const void* fn;
-    if (dtype == kDtypeFP16) fn = act == 2 ? (const void*)gemm_pair_kernel<__half, 2> : (const void*)gemm_pair_kernel<__half, 0>;
-    else fn = act == 2 ? (const void*)gemm_pair_kernel<__nv_bfloat16, 2> : (const void*)gemm_pair_kernel<__nv_bfloat16, 0>;
+    const bool f16 = dtype == kDtypeFP16;
+    if (X) fn = f16 ? (const void*)gemm_pair_kernel<__half, 0, true> : (const void*)gemm_pair_kernel<__nv_bfloat16, 0, true>;
+    else if (act == 2) fn = f16 ? (const void*)gemm_pair_kernel<__half, 2, false> : (const void*)gemm_pair_kernel<__nv_bfloat16, 2, false>;
+    else fn = f16 ? (const void*)gemm_pair_kernel<__half, 0, false> : (const void*)gemm_pair_kernel<__nv_bfloat16, 0, false>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmem);
     if (e != cudaSuccess) return e;
     static int max_pairs = 0;                            // co-resident pairs (one CTA per SM; a GPC with an odd SM count leaves one idle)
@@ -197,8 +252,17 @@ cudaError_t launch_gemm_pair(const void* A, const void* W, const float* bias, vo
     }
     const int64_t units = (int64_t)m_tiles * n_tiles;
     const unsigned grid = 2u * (unsigned)(units < max_pairs ? units : max_pairs);
-    void* args[] = {(void*)&tmA, (void*)&tmB, (void*)&tmD, (void*)&bias, (void*)&K, (void*)&m_tiles, (void*)&n_tiles};
+    void* args[] = {(void*)&tmA, (void*)&tmB, (void*)&tmD, (void*)&bias, (void*)&X, (void*)&M, (void*)&N, (void*)&K, (void*)&m_tiles, (void*)&n_tiles};
     return cudaLaunchKernel(fn, dim3(grid, 1, 1), dim3(kPThreads, 1, 1), args, kPSmem, s);
+}
+
+cudaError_t launch_gemm_pair(const void* A, const void* W, const float* bias, void* D, int64_t M, int K, int N, int act, int dtype, cudaStream_t s) {
+    return launch_pair(A, W, bias, D, nullptr, M, K, N, act, dtype, s);
+}
+// X[M,N] (fp32, in place) += A[M,K] * W[N,K]^T + bias: the residual stream of the ViT encoder
+cudaError_t launch_gemm_pair_residual(const void* A, const void* W, const float* bias, float* X, int64_t M, int K, int N, int dtype, cudaStream_t s) {
+    if (!X) return cudaErrorInvalidValue;
+    return launch_pair(A, W, bias, nullptr, X, M, K, N, 0, dtype, s);
 }
 
 }  // namespace dfd

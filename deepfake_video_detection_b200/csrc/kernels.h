@@ -66,6 +66,8 @@ cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bia
 // epilogue); act 0 none | 2 exact GELU; N a multiple of 256.  The ViT-B/16 contractions.
 bool gemm_pair_supported(int64_t M, int K, int N);
 cudaError_t launch_gemm_pair(const void* A, const void* W, const float* bias, void* D, int64_t M, int K, int N, int act, int dtype, cudaStream_t s);
+// X[M,N] (fp32, updated in place) += A[M,K] * W[N,K]^T + bias — the fp32 residual stream of the ViT encoder
+cudaError_t launch_gemm_pair_residual(const void* A, const void* W, const float* bias, float* X, int64_t M, int K, int N, int dtype, cudaStream_t s);
 // conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
                                 int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);

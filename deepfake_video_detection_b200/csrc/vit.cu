@@ -367,8 +367,20 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
         else dfd::vit_assemble_kernel<__nv_bfloat16><<<agrid, 256, 0, s>>>((const __nv_bfloat16*)H16, w->cls, w->pos, X, a8);
         VIT_CK(cudaGetLastError(), "vit assemble");
     }
+#ifndef DFD_VIT_RES_IN_GEMM
+#define DFD_VIT_RES_IN_GEMM 1      // 1: proj / fc2 add their output to the fp32 residual stream in the GEMM epilogue (HBM traffic in the
+#endif                             //    shadow of a tensor-bound kernel); 0: 16-bit branch outputs, added inside the next LayerNorm kernel
     for (int i = 0; i < kDepth; ++i) {
         const auto& b = w->blk[i];
+#if DFD_VIT_RES_IN_GEMM
+        VIT_CK(ln(X, kDim, nullptr, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");
+        VIT_CK(dfd::launch_gemm_pair(H16, b.qkv_w, b.qkv_b, BIG, M, kDim, 3 * kDim, 0, dt, s), "vit qkv gemm");
+        VIT_CK(dfd::launch_vit_attention_tc(BIG, H16, images, dt, s), "vit attention");
+        VIT_CK(dfd::launch_gemm_pair_residual(H16, b.proj_w, b.proj_b, X, M, kDim, kDim, dt, s), "vit proj gemm");
+        VIT_CK(ln(X, kDim, nullptr, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");
+        VIT_CK(dfd::launch_gemm_pair(H16, b.fc1_w, b.fc1_b, BIG, M, kDim, kMlp, 2, dt, s), "vit fc1 gemm");
+        VIT_CK(dfd::launch_gemm_pair_residual(BIG, b.fc2_w, b.fc2_b, X, M, kMlp, kDim, dt, s), "vit fc2 gemm");
+#else
         VIT_CK(ln(X, kDim, i ? P16 : nullptr, b.ln1_w, b.ln1_b, H16, false, M), "vit norm1");            // X += fc2 output of block i-1
         VIT_CK(dfd::launch_gemm_pair(H16, b.qkv_w, b.qkv_b, BIG, M, kDim, 3 * kDim, 0, dt, s), "vit qkv gemm");
         VIT_CK(dfd::launch_vit_attention_tc(BIG, H16, images, dt, s), "vit attention");
@@ -376,8 +388,14 @@ int dfd_vit_features(const dfd_vit_weights_t* w, const float* d_in, int64_t imag
         VIT_CK(ln(X, kDim, P16, b.ln2_w, b.ln2_b, H16, false, M), "vit norm2");                          // X += attention branch
         VIT_CK(dfd::launch_gemm_pair(H16, b.fc1_w, b.fc1_b, BIG, M, kDim, kMlp, 2, dt, s), "vit fc1 gemm");
         VIT_CK(dfd::launch_gemm_pair(BIG, b.fc2_w, b.fc2_b, P16, M, kMlp, kDim, 0, dt, s), "vit fc2 gemm");
+#endif
     }
+#if DFD_VIT_RES_IN_GEMM
+    (void)P16;
+    VIT_CK(ln(X, (int64_t)kTokens * kDim, nullptr, w->norm_w, w->norm_b, d_features, true, images), "vit final norm");   // CLS rows only
+#else
     VIT_CK(ln(X, (int64_t)kTokens * kDim, P16, w->norm_w, w->norm_b, d_features, true, images), "vit final norm");   // CLS rows only
+#endif
 #undef VIT_CK
     return DFD_OK;
 }

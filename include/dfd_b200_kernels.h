@@ -41,7 +41,8 @@ int dfd_k_se(const float* d_partials, int nparts, float inv_hw, const float* d_w
  * 2 = tcgen05 kernel with the gate folded into per-frame
  * weights on frame-aligned tiles (what the engine uses for maps of >= 784 pixels; synchronous in this test entry),
  * 3 = CTA-pair kernel (tcgen05 cta_group::2, 256 x 256 tiles, TMA-store epilogue: the ViT-B/16 contractions; no gate, no
- * residual, act 0 | 2 (exact GELU), N a multiple of 256). */
+ * 16-bit residual, act 0 | 2 (exact GELU), N a multiple of 256; with d_R == d_D the output is an fp32 matrix updated in place,
+ * X += A W^T + bias: the encoder's residual stream). */
 int dfd_k_gemm(const void* d_A, const void* d_W, const float* d_bias, const float* d_gate, const void* d_R,
                void* d_D, int64_t M, int K, int N, int HW, int act, int dtype, int impl, void* stream);
 

@@ -322,3 +322,23 @@ def test_gemm_cta_pairs(lib, prec, M, K, N, act):
     assert torch.isfinite(D).all()
     close(D.cpu(), ref, rel)
     assert (guard == 7.0).all()
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("M,K,N", [(591, 768, 768), (256 * 80 + 37, 768, 768), (4096, 3072, 768), (100, 72, 256)])
+def test_gemm_cta_pairs_fp32_residual(lib, prec, M, K, N):
+    """X += A W^T + bias on the fp32 residual stream, in place (the ViT attention-projection / fc2 epilogue of csrc/gemm_pair.cu):
+    the accumulator tile goes through shared memory so that the read-modify-write of X is coalesced."""
+    code, tdt, _ = DT[prec]
+    g = torch.Generator().manual_seed(M + K + N + 1)
+    A = torch.randn(M, K, generator=g).to(tdt)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(tdt)
+    b = torch.randn(N, generator=g) * 0.5
+    X0 = torch.randn(M + 1, N, generator=g) * 3.0                                    # one guard row behind the matrix
+    Ad, Wd, bd, X = A.cuda(), W.cuda(), b.cuda(), X0.cuda()
+    chk(lib, lib.dfd_k_gemm(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), None, X.data_ptr(), X.data_ptr(), M, K, N, 1, 0, code, 3, stream()))
+    torch.cuda.synchronize()
+    ref = X0[:M].double() + A.double() @ W.double().t() + b.double()
+    err = (X[:M].cpu().double() - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), err                       # fp32 accumulation and adds only
+    assert torch.equal(X[M].cpu(), X0[M])
