@@ -123,7 +123,8 @@ def test_dwconv_and_squeeze(lib, prec, C_, k, s, H):
     close(sums, ref.sum((2, 3)), 1e-5, abs_=1e-3)
 
 
-@pytest.mark.parametrize("C_,rd,nparts,frames", [(32, 8, 49, 3), (96, 4, 37, 9), (1152, 48, 8, 17), (672, 28, 19, 8)])
+@pytest.mark.parametrize("C_,rd,nparts,frames", [(32, 8, 49, 3), (96, 4, 37, 9), (1152, 48, 8, 17), (672, 28, 19, 8), (240, 10, 7, 5),
+                                                  (480, 20, 2, 33), (672, 28, 1, 16), (1152, 48, 2, 40), (1152, 48, 1, 1)])
 def test_se_gate(lib, C_, rd, nparts, frames):
     g = torch.Generator().manual_seed(C_)
     parts = torch.randn(frames, nparts, C_, generator=g)
