@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "libdfd_b200.so")
-SOURCES = ["api.cu", "preprocess.cu", "stem.cu", "stem_tc.cu", "dwconv_march.cu", "mbconv_fused.cu", "se.cu", "gemm_tc.cu", "gemm_pair.cu", "poolhead.cu", "rnn.cu", "vit.cu", "vit_attn_tc.cu", "resize.cu", "resnet.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "stem.cu", "stem_tc.cu", "dwconv_march.cu", "mbconv_fused.cu", "se.cu", "gemm_tc.cu", "gemm_pair.cu", "head_pool_tc.cu", "poolhead.cu", "rnn.cu", "vit.cu", "vit_attn_tc.cu", "resize.cu", "resnet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

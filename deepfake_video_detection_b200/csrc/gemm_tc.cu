@@ -685,22 +685,26 @@ cudaError_t launch_gemm_tc_framew(const void* A, const void* Wf, const float* bi
 
 template <typename T>
 __global__ void scale_weights_kernel(const T* __restrict__ W, const float* __restrict__ gate, T* __restrict__ Wf, int N, int K, int Kg, int64_t total) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 2 consecutive k
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one thread = 8 consecutive k (16 bytes in, 16 bytes out)
     if (i >= total) return;
-    const int k2 = (int)(i % (K / 2));
-    const int64_t fn = i / (K / 2);
+    const int k8 = (int)(i % (K / 8));
+    const int64_t fn = i / (K / 8);
     const int n = (int)(fn % N);
     const int64_t f = fn / N;
-    const uint32_t w = reinterpret_cast<const uint32_t*>(W)[(size_t)n * (K / 2) + k2];
-    const float2 g = *reinterpret_cast<const float2*>(gate + (size_t)f * Kg + (2 * k2) % Kg);
-    const float2 x = Half16<T>::unpack(w);
-    reinterpret_cast<uint32_t*>(Wf)[i] = Half16<T>::pack(x.x * g.x, x.y * g.y);
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(W) + (size_t)n * (K / 8) + k8);
+    const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)f * Kg + (8 * k8) % Kg);      // Kg % 8 == 0: the group does not wrap
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
+    const float2 x0 = Half16<T>::unpack(w.x), x1 = Half16<T>::unpack(w.y), x2 = Half16<T>::unpack(w.z), x3 = Half16<T>::unpack(w.w);
+    uint4 o;
+    o.x = Half16<T>::pack(x0.x * g0.x, x0.y * g0.y); o.y = Half16<T>::pack(x1.x * g0.z, x1.y * g0.w);
+    o.z = Half16<T>::pack(x2.x * g1.x, x2.y * g1.y); o.w = Half16<T>::pack(x3.x * g1.z, x3.y * g1.w);
+    reinterpret_cast<uint4*>(Wf)[i] = o;
 }
 // Wf[f][n][k] = W[n][k] * gate[f][k % Kg]   (Kg < K: pixel-packed block-diagonal weights, the gate repeats per pixel)
 cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int64_t frames, int N, int K, int Kg, int dtype, cudaStream_t s) {
-    const int64_t total = frames * N * (K / 2);
+    const int64_t total = frames * N * (K / 8);
     if (total <= 0) return cudaSuccess;
-    if (Kg <= 0 || (Kg & 1) || K % Kg) return cudaErrorInvalidValue;
+    if (Kg <= 0 || (Kg & 7) || (K & 7) || K % Kg) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (dtype == kDtypeFP16) scale_weights_kernel<__half><<<grid, 256, 0, s>>>((const __half*)W, gate, (__half*)Wf, N, K, Kg, total);
     else scale_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, gate, (__nv_bfloat16*)Wf, N, K, Kg, total);
@@ -728,6 +732,10 @@ cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bia
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
                                 int64_t M, int K, int N, int HW, int dtype, cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
+#ifndef DFD_HEAD_TRANSPOSED
+#define DFD_HEAD_TRANSPOSED 1      // 0: always the row-major POOL epilogue below (A/B builds)
+#endif
+    if (DFD_HEAD_TRANSPOSED && head_pool_tc_supported(M, K, N, HW)) return launch_head_pool_tc(A, W, bias, feat, M, K, N, HW, dtype, s);
     if ((K & 7) || (N & 7) || HW <= 0 || HW > kBM || (M % HW) != 0 || kBM / HW > 4) return cudaErrorInvalidValue;
     GemmArgs a{};
     a.A = A; a.W = W; a.bias = bias; a.gate = nullptr; a.R = nullptr; a.D = nullptr; a.feat = feat;

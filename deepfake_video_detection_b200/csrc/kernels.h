@@ -71,6 +71,10 @@ cudaError_t launch_gemm_pair_residual(const void* A, const void* W, const float*
 // conv_head + BN + SiLU + global average pool (pretrained_detector.py:116 tail): feat fp32 [M/HW][N]
 cudaError_t launch_gemm_tc_pool(const void* A, const void* W, const float* bias, float* feat,
                                 int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
+// K3h (head_pool_tc.cu): the same op as a transposed GEMM (channels on the TMEM lanes, a frame's pixels along a thread's row: the pool is a
+// serial sum in the thread) for maps of up to 64 pixels, K <= 320, N a multiple of 128; launch_gemm_tc_pool dispatches to it
+bool head_pool_tc_supported(int64_t M, int K, int N, int HW);
+cudaError_t launch_head_pool_tc(const void* A, const void* W, const float* bias, float* feat, int64_t M, int K, int N, int HW, int dtype, cudaStream_t s);
 // 3x3 stride-1 pad-1 convolution + bias + ReLU as an implicit GEMM (resnet50 conv2): the
 // producing pointwise conv scatters its rows into a zero-haloed map of conv3x3_padded_rows(frames,H,W) x N elements (zeroed
 // by the caller once per geometry), the 3x3 conv reads nine shifted TMA boxes of it.  Weights [N][(ky*3+kx)*C + c].

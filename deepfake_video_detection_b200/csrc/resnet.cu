@@ -31,7 +31,7 @@ namespace {
 constexpr int kRnFeat = 2048, kRnImg = 224, kRnStemK = 152;       // 7*7*3 = 147 padded to a multiple of 8
 struct RnLayer { int blocks, width, stride; };
 constexpr RnLayer kRnLayers[4] = {{3, 64, 1}, {4, 128, 2}, {6, 256, 2}, {3, 512, 2}};
-constexpr int kRnMaxChunk = 128;                                   // frames per trunk pass (workspace = 11.9 MB per frame)
+constexpr int kRnMaxChunk = 256;                                   // frames per trunk pass (workspace = 11.9 MB per frame)
 }
 
 struct RnConv { void* w; float* b; int cin, cout, k, stride; };

@@ -214,11 +214,13 @@ def test_gemm_tcgen05_ragged_m(lib, M_frames, HW):
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("frames", [1, 2, 7])
-def test_head_gemm_pool(lib, prec, frames, impl=0):
+@pytest.mark.parametrize("frames,HW", [(1, 49), (2, 49), (7, 49), (301, 49), (9, 64), (5, 36), (6, 100)])
+def test_head_gemm_pool(lib, prec, frames, HW, impl=0):
+    """conv_head + BN + SiLU + average pool: the transposed tcgen05 kernel (csrc/head_pool_tc.cu; maps of up to 64 pixels; 301 frames =
+    more work units than SMs, a partial last tile) and the row-major fallback (100 pixels)."""
     code, tdt, rel = DT[prec]
     g = torch.Generator().manual_seed(frames)
-    K, N, HW = 320, 1280, 49
+    K, N = 320, 1280
     A = torch.randn(frames * HW, K, generator=g).to(tdt)
     Wt = (torch.randn(N, K, generator=g) * (1.0 / K ** 0.5)).to(tdt)
     bias = torch.randn(N, generator=g) * 0.3
