@@ -273,8 +273,8 @@ def hbm_roofline(kernels, traffic, traffic_src, hbm_gbs, peak_kind, frames=None)
         out["fused_class"] = {"limiter": "MUFU + issue (one tanh.approx per SiLU), not HBM",
                               "silu_per_s": round(FUSED_SILU_PER_FRAME * frames / (f["ms"] / 1e3), 0), "mufu_peak_per_s": round(MUFU_PER_S, 0),
                               "frac_of_mufu": round(FUSED_SILU_PER_FRAME * frames / (f["ms"] / 1e3) / MUFU_PER_S, 4),
-                              "replaces_unfused_MB": round(unfused_mb, 1), "unfused_hbm_floor_ms": round(unfused_mb / hbm_gbs / 1e3, 4),
-                              "unfused_equivalent_GBps": round(unfused_mb / f["ms"] / 1e3, 1)}
+                              "replaces_unfused_MB": round(unfused_mb, 1), "unfused_hbm_floor_ms": round(unfused_mb / hbm_gbs, 4),
+                              "unfused_equivalent_GBps": round(unfused_mb / f["ms"], 1)}
     return out
 
 
