@@ -371,6 +371,11 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(tmap), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
 }
+// TMA reduction shared -> global: global[box] += shared[box] (fp32 add performed at the L2; rows / columns outside the tensor are dropped)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(tmap), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }

@@ -38,11 +38,11 @@ constexpr size_t kPSmem = 1024 + (size_t)kPStages * kPStage + 4 * kPPanel + 256;
 static_assert(kPSmem <= 227 * 1024, "shared memory budget");
 }  // namespace
 
-// RES: the output is the fp32 residual stream X [M][N], updated in place: X += A W^T + bias (no activation, no tensor map for D)
+// RES: the output is the fp32 residual stream X [M][N], updated in place: X += A W^T + bias (no activation; tmD is an fp32 map of X)
 template <typename T, int ACT, bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-                 const float* __restrict__ bias, float* __restrict__ X, int64_t M, int N, int K, int m_tiles, int n_tiles) {
+                 const float* __restrict__ bias, int K, int m_tiles, int n_tiles) {
     static_assert(!RES || ACT == 0, "the residual variant has no activation");
     extern __shared__ __align__(128) uint8_t pr_smem[];
     const uint32_t base = (smem_u32(pr_smem) + 1023u) & ~1023u;
@@ -127,13 +127,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kPN + g * 64);
             const float4* bp = reinterpret_cast<const float4*>(bias + nt * kPN + g * 64);
             if constexpr (RES) {
-                // fp32 read-modify-write of the residual stream.  A thread owns an accumulator ROW, so direct global accesses would
-                // touch 32 cache lines per warp instruction: the 128 x 32 fp32 half-panel goes through the (swizzled) staging
-                // buffer and is added to X with 8 lanes per 128-byte row segment (4 rows per warp instruction, 8 loads in flight).
-                const int t128 = q * 32 + lane, cj = t128 & 7, r0 = t128 >> 3;
-                const int64_t m0 = (int64_t)mt * (2 * kPM) + (int64_t)rank * kPM;
+                // X += tile: the fp32 accumulator (+ bias) goes to the warp's staging slab (32 rows x 32 columns x 4 B, swizzled) and
+                // from there into the residual stream with a TMA REDUCTION (fp32 add at the L2): the SM never reads X and issues
+                // no per-thread global access (a thread owns an accumulator ROW: direct accesses would touch 32 lines per instruction)
+                const uint32_t slab = panel + (uint32_t)q * 4096u;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (lane == 0) bulk_wait_group_read0();                     // the previous reduction has read the slab
+                    __syncwarp();
                     uint32_t r[2][16];
                     tmem_ld16(t_addr + h * 32, r[0]);
                     tmem_ld16(t_addr + h * 32 + 16, r[1]);
@@ -150,29 +151,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         uint4 v;
                         v.x = __float_as_uint(__uint_as_float(rr[0]) + b4.x); v.y = __float_as_uint(__uint_as_float(rr[1]) + b4.y);
                         v.z = __float_as_uint(__uint_as_float(rr[2]) + b4.z); v.w = __float_as_uint(__uint_as_float(rr[3]) + b4.w);
-                        sts16(out_row + (((uint32_t)i ^ sw) << 4), v);
+                        sts16(slab + (uint32_t)lane * 128u + (((uint32_t)i ^ (uint32_t)(lane & 7)) << 4), v);
                     }
-                    named_bar_sync(1 + g, 128);
-                    float* xp = X + (m0 + r0) * N + (nt * kPN + g * 64 + h * 32 + cj * 4);
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk += 4) {
-                        uint4 xv[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (m0 + r0 + 16 * (kk + k) < M) xv[k] = ldg16_coherent(xp + (size_t)(16 * (kk + k)) * N);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int rr_ = r0 + 16 * (kk + k);
-                            if (m0 + rr_ < M) {
-                                const uint4 a = lds16(panel + (uint32_t)rr_ * 128 + (((uint32_t)cj ^ (uint32_t)(rr_ & 7)) << 4));
-                                float4 o4;
-                                o4.x = __uint_as_float(xv[k].x) + __uint_as_float(a.x); o4.y = __uint_as_float(xv[k].y) + __uint_as_float(a.y);
-                                o4.z = __uint_as_float(xv[k].z) + __uint_as_float(a.z); o4.w = __uint_as_float(xv[k].w) + __uint_as_float(a.w);
-                                *reinterpret_cast<float4*>(xp + (size_t)(16 * (kk + k)) * N) = o4;
-                            }
-                        }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_reduce_add_2d(&tmD, slab, nt * kPN + g * 64 + h * 32, mt * (2 * kPM) + (int)rank * kPM + q * 32);
+                        bulk_commit_group();
                     }
-                    named_bar_sync(1 + g, 128);                                 // staging reusable
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 continue;
@@ -213,7 +199,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (!RES && lane == 0) bulk_wait_group_read0();
+        if (lane == 0) bulk_wait_group_read0();
     }
     tc_fence_before_sync();
     cluster_sync_all();                                  // the peer may still count on this CTA's barriers / read its operands
@@ -230,8 +216,8 @@ static cudaError_t launch_pair(const void* A, const void* W, const float* bias, 
     if (e != cudaSuccess) return e;
     e = make_tmap_2d(W, N, K, kPN / 2, &tmB);
     if (e != cudaSuccess) return e;
-    if (X) tmD = tmA;
-    else { e = make_tmap_2d(D, M, N, 32, &tmD); if (e != cudaSuccess) return e; }
+    e = X ? make_tmap_2d_f32(X, M, N, 32, &tmD) : make_tmap_2d(D, M, N, 32, &tmD);
+    if (e != cudaSuccess) return e;
     int m_tiles = (int)((M + 2 * kPM - 1) / (2 * kPM)), n_tiles = N / kPN;
     const void* fn;
     const bool f16 = dtype == kDtypeFP16;
@@ -257,7 +243,7 @@ static cudaError_t launch_pair(const void* A, const void* W, const float* bias, 
     }
     const int64_t units = (int64_t)m_tiles * n_tiles;
     const unsigned grid = 2u * (unsigned)(units < max_pairs ? units : max_pairs);
-    void* args[] = {(void*)&tmA, (void*)&tmB, (void*)&tmD, (void*)&bias, (void*)&X, (void*)&M, (void*)&N, (void*)&K, (void*)&m_tiles, (void*)&n_tiles};
+    void* args[] = {(void*)&tmA, (void*)&tmB, (void*)&tmD, (void*)&bias, (void*)&K, (void*)&m_tiles, (void*)&n_tiles};
     return cudaLaunchKernel(fn, dim3(grid, 1, 1), dim3(kPThreads, 1, 1), args, kPSmem, s);
 }
 

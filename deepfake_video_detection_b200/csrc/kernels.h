@@ -86,6 +86,8 @@ cudaError_t launch_gemm_tc_conv3x3(const void* Apad, const void* W, const float*
 // 2-D tensor map (CUtensorMap written to *out_tmap) over a row-major 16-bit matrix [rows][cols]: boxes of 64 columns x box_rows
 // rows, 128-byte swizzle, zero fill outside the tensor (gemm_tc.cu; cached per (pointer, shape))
 cudaError_t make_tmap_2d(const void* base, int64_t rows, int cols, int box_rows, void* out_tmap);
+// the same over an fp32 matrix: boxes of 32 columns x box_rows rows (gemm_pair.cu adds its tiles into the residual stream through it)
+cudaError_t make_tmap_2d_f32(const float* base, int64_t rows, int cols, int box_rows, void* out_tmap);
 // ViT attention on tcgen05 (vit_attn_tc.cu): qkv [images*197][2304] 16-bit -> o [images*197][768], softmax(Q K^T / 8) V per (image, head)
 cudaError_t launch_vit_attention_tc(const void* qkv, void* o, int64_t images, int dtype, cudaStream_t s);
 
