@@ -22,7 +22,8 @@ os.makedirs(P, exist_ok=True)
 def klass(name):
     if "mbconv_fused" in name: return "expand_dwconv_fused"   # bench.py's class name for the fused producer + depthwise kernel
     if "dwconv" in name: return "dwconv_se_squeeze"
-    if "se_kernel" in name: return "se_gate"
+    if "se_kernel" in name or "se_wide" in name: return "se_gate"
+    if "head_pool_tc" in name: return "gemm_head_pool"
     if "stem" in name: return "stem"
     if "pool_head" in name: return "attn_pool_head"
     if "preprocess" in name: return "preprocess"
