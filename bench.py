@@ -380,6 +380,7 @@ def bench_config2(args, rank, world, dev, timer, sampler_cls, local_rank):
         "config": {"workload": WORKLOAD, "videos_per_gpu": V, "frames_per_video": T, "crop": SIZE, "l2": "inputs (308 MB/GPU) and every activation tensor exceed the 126 MB L2",
                    "weights": "calibrated synthetic checkpoint, reference state_dict schema (366 tensors)",
                    "chunk_frames": int(os.environ.get("DFD_CHUNK_FRAMES", "2048")), "parallelism": f"videos sharded over {world} GPU(s), one all-gather of logits",
+                   "host_affinity": getattr(args, "host_affinity", None),
                    "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("DFD_")}},
         "clocks": sampler.result(), "steady": steady, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step, "roofline": roofline, "kernels": kernels,
@@ -605,6 +606,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
     stdout_to_stderr()
     torch.cuda.set_device(local_rank)
+    from deepfake_video_detection_b200.sharding import bind_host_to_gpu
+    args.host_affinity = bind_host_to_gpu(local_rank) if world > 1 else None     # one process per GPU: pinned buffers on the GPU's own NUMA node
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
