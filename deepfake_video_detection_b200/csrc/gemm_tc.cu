@@ -579,7 +579,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     const size_t bres = (size_t)a.n_chunks * a.b_chunk_bytes;
     // Weights stay resident only up to 60 KB: beyond that the shared memory is worth more as pipeline stages (W blocks then
     // stream from L2 by TMA).  Measured: 672->112 gated 233 -> 178 us, 112->672 expand 88 -> 78 us per 2048 / 1024 frames.
-    const size_t res_limit = 60 * 1024;
+    const size_t res_limit = 60 * 1024;      // (keeping the 73 KB of the 64 -> 64 implicit 3x3 layer resident changed nothing: 213 vs 209 us)
 #ifndef DFD_GEMM_CHUNK_RESLIM
 #define DFD_GEMM_CHUNK_RESLIM (60 * 1024)      // limit for keeping ONE column chunk per CTA (tools/build_variant.py sweeps it)
 #endif
