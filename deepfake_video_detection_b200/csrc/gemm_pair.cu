@@ -67,8 +67,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == kPTmaWarp) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+        {   // the whole warp, converged: `elect.sync` inside the helpers picks the issuing lane
+            if (lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
             const uint32_t full0 = mapa_u32(b_full, 0);
             int stage = 0; uint32_t phase = 0;
             for (int u = pair; u < units; u += pairs) {
@@ -76,35 +76,33 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int row_a = mt * (2 * kPM) + (int)rank * kPM, row_b = nt * kPN + (int)rank * (kPN / 2);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(b_empty + 8 * stage, phase ^ 1);
-                    if (rank == 0) mbar_arrive_expect_tx(b_full + 8 * stage, 2 * kPStage);
+                    if (rank == 0) mbar_arrive_expect_tx_elect(b_full + 8 * stage, 2 * kPStage);
                     const uint32_t dst = base + stage * kPStage;
-                    tma_load_2d_pair(dst, &tmA, kb * kPK, row_a, full0 + 8 * stage);
-                    tma_load_2d_pair(dst + kPABytes, &tmB, kb * kPK, row_b, full0 + 8 * stage);
+                    tma_load_2d_pair_elect(dst, &tmA, kb * kPK, row_a, full0 + 8 * stage);
+                    tma_load_2d_pair_elect(dst + kPABytes, &tmB, kb * kPK, row_b, full0 + 8 * stage);
                     if (++stage == kPStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-        __syncwarp();                                    // the cluster barrier below is warp-aligned
     } else if (warp == kPMmaWarp) {
         if (rank == 0) {
+            // the whole warp runs this loop converged; `elect.sync` inside the helpers picks the issuing lane (uniform operands)
             const uint32_t idesc = umma_idesc(Half16<T>::kUmmaFormat, 2 * kPM, kPN);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int u = pair; u < units; u += pairs) {
                 mbar_wait_cluster(b_tempty + 8 * acc, acc_phase ^ 1);        // both CTAs' epilogues have drained this buffer
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kPN);
+                const uint32_t d_tmem = tmem_u + (uint32_t)(acc * kPN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(b_full + 8 * stage, phase);
                     tc_fence_after_sync();
-                    if (lane == 0) {
-                        const uint64_t ad = umma_smem_desc_sw128(base + stage * kPStage);
-                        const uint64_t bd = umma_smem_desc_sw128(base + stage * kPStage + kPABytes);
+                    const uint64_t ad = umma_smem_desc_sw128(base + stage * kPStage);
+                    const uint64_t bd = umma_smem_desc_sw128(base + stage * kPStage + kPABytes);
 #pragma unroll
-                        for (int j = 0; j < kPK / 16; ++j) umma_f16_pair(d_tmem, ad + 2u * j, bd + 2u * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                        umma_commit_pair(b_empty + 8 * stage);
-                        if (kb == num_kb - 1) umma_commit_pair(b_tfull + 8 * acc);
-                    }
-                    __syncwarp();
+                    for (int j = 0; j < kPK / 16; ++j) umma_f16_pair_elect(d_tmem, ad + 2u * j, bd + 2u * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    umma_commit_pair_elect(b_empty + 8 * stage);
+                    if (kb == num_kb - 1) umma_commit_pair_elect(b_tfull + 8 * acc);
                     if (++stage == kPStages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -10,7 +10,7 @@
 //   pool variant: conv_head + BN + SiLU + global average pool -> features fp32 [frames][N]
 //
 // Structure (one persistent CTA per SM, warp-specialised; roles are template parameters):
-//   TMA issuer   ONE thread issues the copies of a pipeline stage with cp.async.bulk.tensor.2d: the A tile (64 K-elements
+//   TMA issuer   ONE elected lane of a converged warp issues the copies of a pipeline stage with cp.async.bulk.tensor.2d: the A tile (64 K-elements
 //                x 128 rows) and, when the weights are not resident, the W block (64 x N) — both land in the 128-byte
 //                swizzled K-major UMMA layout, out-of-range K / M is zero-filled by the copy engine, completion is counted
 //                in bytes on the stage mbarrier (`mbarrier.arrive.expect_tx`).  Up to 13 stages are in flight.
@@ -18,7 +18,7 @@
 //   transformers (gated project layers on small maps) wait for a landed stage, multiply the A tile in place by the
 //                per-frame squeeze-excite gate (gate slice staged beside the tile by two loader warps), issue
 //                `fence.proxy.async` and hand the stage to the MMA warp; the warps form groups that take alternate stages.
-//   MMA issuer   one elected thread issues tcgen05.mma (M=128, N<=256, K=16) per 16-wide K step with descriptors that only
+//   MMA issuer   one elected lane of a converged warp (`elect.sync`: operands stay in uniform registers) issues tcgen05.mma (M=128, N<=256, K=16) per 16-wide K step with descriptors that only
 //                add to the 14-bit start-address field; accumulators in TMEM (ring of up to 8), tcgen05.commit releases
 //                smem stages / signals the epilogue.
 //   epilogue     8-16 warps in sets that take alternate tiles: tcgen05.ld (32 lanes x 16 columns), +bias, SiLU / exact GELU,
@@ -191,9 +191,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         // for weights too large to stay resident, the W block (box 64 x NBp) — both into the 128-byte-swizzled UMMA
         // layout, completion counted in bytes on the stage barrier.  No other loader thread has work in the main loop.
         const int tp = threadIdx.x - (kMmaWarp + 1) * 32;
-        if (tp == 0) {
-            tma_prefetch_desc(&tmA);
-            if (!p.b_resident) tma_prefetch_desc(&tmB);
+        if (tp < 32) {                                                     // the whole first loader warp, converged (elect.sync inside)
+            if (tp == 0) { tma_prefetch_desc(&tmA); if (!p.b_resident) tma_prefetch_desc(&tmB); }
             const uint32_t tx_bytes = kAStageBytes + (p.b_resident ? 0u : p.b_stage_bytes);
             int stage = 0; uint32_t phase = 0;
             TileIter it; it.init(p, blockIdx.x);
@@ -205,11 +204,11 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
                     DFD_TWAIT(w0, bar_empty + 8 * stage, phase ^ 1)
                     const uint32_t a_base = smem_base + stage * stage_bytes;
                     const uint32_t bar = (GATE ? bar_raw : bar_full) + 8 * stage;
-                    mbar_arrive_expect_tx(bar, (p.dbg & 1) ? 0u : tx_bytes);
+                    mbar_arrive_expect_tx_elect(bar, (p.dbg & 1) ? 0u : tx_bytes);
                     if (!(p.dbg & 1)) {
-                        if (CONV == 2) tma_load_2d(a_base, &tmA, tap.ck * kKB, tap.row, bar);
-                        else tma_load_2d(a_base, &tmA, kb * kKB, m0, bar);
-                        if (!p.b_resident) tma_load_2d(a_base + kAStageBytes, &tmB, kb * kKB, wrow, bar);
+                        if (CONV == 2) tma_load_2d_elect(a_base, &tmA, tap.ck * kKB, tap.row, bar);
+                        else tma_load_2d_elect(a_base, &tmA, kb * kKB, m0, bar);
+                        if (!p.b_resident) tma_load_2d_elect(a_base + kAStageBytes, &tmB, kb * kKB, wrow, bar);
                     }
                     if (CONV == 2) tap.next(p.conv_cpk, p.conv_w);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -302,19 +301,23 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         const uint32_t b_lo_res = (uint32_t)b_d0, b_lo_str = (uint32_t)b_d0;
         const uint32_t stage_step = stage_bytes >> 4, b_chunk_step = p.b_chunk_bytes >> 4, b_kb_step = (8 * p.lbo_b) >> 4;
         const uint32_t b_jstep = p.b_resident ? (2 * p.lbo_b) >> 4 : 2u;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         TileIter it; it.init(p, blockIdx.x);
         for (; it.u < units; it.next1(p)) {
             const int nc = it.nc;
             DFD_TWAIT(w0, bar_tempty + 8 * acc, acc_phase ^ 1)
             tc_fence_after_sync();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NBp);
+            const uint32_t d_tmem = tmem_u + (uint32_t)(acc * p.NBp);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int kc = min(8, (p.K - kb * kKB) >> 3);
                 const int steps = (kc + 1) >> 1;
                 DFD_TWAIT(w1, bar_full + 8 * stage, phase)
-                tc_fence_after_sync();
-                if (lane == 0) {
+                if (!(p.dbg & 512)) tc_fence_after_sync();
+                {
+                    // The whole warp runs this block converged; `elect.sync` inside the helpers picks the issuing lane, so the
+                    // operands stay warp-uniform (behind `if (lane == 0)` every UTCHMMA operand went through an ELECT + R2UR loop:
+                    // ~0.5 us per k-block in this warp whatever the tile did — measured with loads, MMAs and stores all skipped).
                     // descriptors differ only in the 14-bit start-address field: add to the low word
                     const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step;
                     const uint32_t b_lo = p.b_resident ? b_lo_res + (uint32_t)(p.b_resident == 2 ? 0 : nc) * b_chunk_step + (uint32_t)kb * b_kb_step
@@ -322,13 +325,19 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (j < steps && !(p.dbg & 2))
-                            umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2u * j), ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)j * b_jstep),
-                                     idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                            umma_f16_elect(d_tmem, ((uint64_t)a_hi << 32) | (a_lo + 2u * j), ((uint64_t)b_hi << 32) | (b_lo + (uint32_t)j * b_jstep),
+                                           idesc, (kb > 0 || j > 0) ? 1u : 0u);
                     }
-                    umma_commit(bar_empty + 8 * stage);                 // smem stage reusable once the MMAs retire
-                    if (kb == num_kb - 1) umma_commit(bar_tfull + 8 * acc);
+                    if (p.dbg & 256) {                                  // timing experiment (with dbg & 2): plain arrives instead of commits
+                        if (lane == 0) {
+                            mbar_arrive(bar_empty + 8 * stage);
+                            if (kb == num_kb - 1) mbar_arrive(bar_tfull + 8 * acc);
+                        }
+                    } else {
+                        umma_commit_elect(bar_empty + 8 * stage);       // smem stage reusable once the MMAs retire
+                        if (kb == num_kb - 1) umma_commit_elect(bar_tfull + 8 * acc);
+                    }
                 }
-                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             if (++acc == p.nacc) { acc = 0; acc_phase ^= 1; }
@@ -594,6 +603,9 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     const size_t bres_pad = ((size_t)a.b_res_bytes + 1023) & ~size_t(1023);      // + worst-case alignment of the stage ring
     int stages = (int)((budget - fixed - bres_pad - 1024) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
+#ifdef DFD_GEMM_STAGE_CAP
+    if (stages > DFD_GEMM_STAGE_CAP) stages = DFD_GEMM_STAGE_CAP;
+#endif
     if (stages < 3) return cudaErrorInvalidValue;
     a.stages = stages;
     while (a.xg > 1 && (a.xg > stages || a.xg > 4)) a.xg >>= 1;      // groups take alternate stages: never more groups than stages

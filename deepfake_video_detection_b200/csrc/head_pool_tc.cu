@@ -92,6 +92,7 @@ head_pool_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     } else if (warp == 16) {
         // ---------------------------------------------------------------- MMA issue
         const uint32_t idesc = umma_idesc(Half16<T>::kUmmaFormat, kHM, (uint32_t)np16);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int ws = 0; uint32_t wph = 0, xph = 0; int acc = 0; uint32_t aph = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, xph ^= 1u) {
             for (int ct = 0; ct < cpu; ++ct) {
@@ -101,16 +102,15 @@ head_pool_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     mbar_wait(b_xfull + 8 * kb, xph);
                     mbar_wait(b_wfull + 8 * ws, wph);
                     tc_fence_after_sync();
-                    if (lane == 0) {
+                    {   // whole warp converged, `elect.sync` picks the issuing lane (uniform operands; see umma_f16_elect)
                         const uint64_t ad = umma_smem_desc_sw128(sm_w + ws * kHWBytes);
                         const uint64_t bd = umma_smem_desc_sw128(base + kb * x_bytes);
                         const int steps = min(kHK, K - kb * kHK) >> 4;
-                        for (int j = 0; j < steps; ++j) umma_f16(tmem_base + (uint32_t)(acc * 256), ad + 2u * j, bd + 2u * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-                        umma_commit(b_wempty + 8 * ws);
-                        if (ct == cpu - 1) umma_commit(b_xempty + 8 * kb);          // the tile's last use of this K block
-                        if (kb == num_kb - 1) umma_commit(b_tfull + 8 * acc);
+                        for (int j = 0; j < steps; ++j) umma_f16_elect(tmem_u + (uint32_t)(acc * 256), ad + 2u * j, bd + 2u * j, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        umma_commit_elect(b_wempty + 8 * ws);
+                        if (ct == cpu - 1) umma_commit_elect(b_xempty + 8 * kb);    // the tile's last use of this K block
+                        if (kb == num_kb - 1) umma_commit_elect(b_tfull + 8 * acc);
                     }
-                    __syncwarp();
                     if (++ws == wstages) { ws = 0; wph ^= 1u; }
                 }
                 if (++acc == 2) { acc = 0; aph ^= 1u; }

@@ -8,7 +8,7 @@
 //   warp 0   TMA: one stage = Q tile (box 64 x 128 rows), K and V (boxes 64 x 208 rows) straight out of the qkv matrix,
 //            128-byte swizzle; rows past the image's 197 tokens belong to the next image (or are zero-filled at the end of
 //            the tensor): the key columns 197..207 are masked in the softmax, the query rows past 196 are never stored.
-//   warp 1   MMA issue (one lane): S = Q K^T as 4 `tcgen05.mma` (M 128, N 208, K 16) into one of two TMEM buffers; after the
+//   warp 1   MMA issue (the warp stays converged, `elect.sync` picks the lane): S = Q K^T as 4 `tcgen05.mma` (M 128, N 208, K 16) into one of two TMEM buffers; after the
 //            softmax of the tile, O = P V as 13 `tcgen05.mma` (M 128, N 64, K 16) with P as the TMEM A OPERAND (the softmax warps
 //            write it over the S columns they have consumed: P never touches shared memory) and V as an MN-MAJOR shared-memory
 //            operand (the rows TMA delivered: no transpose anywhere); O lands in columns 128..191 of the same buffer.  S of tile
@@ -49,9 +49,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128_mn(uint32_t saddr) {
     return d;
 }
 // D[tmem] (+)= A[tmem: lane = row, 32-bit column = two consecutive K elements] · B[smem]
+// (executed by the whole converged MMA warp: `elect.sync` picks the issuing lane, operands stay warp-uniform — see umma_f16_elect)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // registers -> TMEM: this thread's lane, 8 consecutive 32-bit columns
@@ -109,20 +110,20 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         // ---------------------------------------------------------------- MMA issue
         const uint32_t idesc_qk = umma_idesc(Half16<T>::kUmmaFormat, 128, kTKeys);
         const uint32_t idesc_pv = umma_idesc_bmn(Half16<T>::kUmmaFormat, 128, kTHd);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int qst = 0; uint32_t qph = 0;                               // stage cursor of the S = Q K^T issues (one tile ahead)
         auto issue_qk = [&](int i) {
             const int b = i & 1;
             mbar_wait(b_full + 8 * qst, qph);
             mbar_wait(b_tempty + 8 * b, ((uint32_t)(i >> 1) & 1u) ^ 1u);
             tc_fence_after_sync();
-            if (lane == 0) {
+            {
                 const uint64_t qd = umma_smem_desc_sw128(base + qst * kTStageBytes);
                 const uint64_t kd = umma_smem_desc_sw128(base + qst * kTStageBytes + kTQBytes);
 #pragma unroll
-                for (int j = 0; j < kTHd / 16; ++j) umma_f16(tmem_base + (uint32_t)(b * 256), qd + 2u * j, kd + 2u * j, idesc_qk, j > 0 ? 1u : 0u);
-                umma_commit(b_sfull + 8 * b);
+                for (int j = 0; j < kTHd / 16; ++j) umma_f16_elect(tmem_u + (uint32_t)(b * 256), qd + 2u * j, kd + 2u * j, idesc_qk, j > 0 ? 1u : 0u);
+                umma_commit_elect(b_sfull + 8 * b);
             }
-            __syncwarp();
             if (++qst == kTStages) { qst = 0; qph ^= 1u; }
         };
         if (n_local > 0) issue_qk(0);
@@ -132,16 +133,15 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             if (i + 1 < n_local) issue_qk(i + 1);
             mbar_wait(b_pfull + 8 * b, (uint32_t)(i >> 1) & 1u);
             tc_fence_after_sync();
-            if (lane == 0) {
+            {
                 const uint64_t vd = umma_smem_desc_sw128_mn(base + st * kTStageBytes + kTQBytes + kTKVBytes);
-                const uint32_t tb = tmem_base + (uint32_t)(b * 256);
+                const uint32_t tb = tmem_u + (uint32_t)(b * 256);
 #pragma unroll
                 for (int j = 0; j < kTKeys / 16; ++j)
                     umma_f16_ts(tb + kTOCol, tb + 8u * j, vd + (uint64_t)(2048 >> 4) * j, idesc_pv, j > 0 ? 1u : 0u);
-                umma_commit(b_ofull + 8 * b);
-                umma_commit(b_empty + 8 * st);
+                umma_commit_elect(b_ofull + 8 * b);
+                umma_commit_elect(b_empty + 8 * st);
             }
-            __syncwarp();
             if (++st == kTStages) st = 0;
         }
     } else {
