@@ -313,20 +313,21 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         const uint64_t a_d0 = umma_smem_desc(a_base0, kStLboA, 128);
         const uint64_t b_d0 = umma_smem_desc(b_base, kSrLboB, 128), b_d1 = umma_smem_desc(b_base + 2 * kSrLboB, kSrLboB, 128);
         const uint32_t a_hi = (uint32_t)(a_d0 >> 32), a_lo0 = (uint32_t)a_d0;
-        int64_t li = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++li) {
-            const int stage = (int)(li % kSrStages), acc = (int)(li % kSrAcc);
-            mbar_wait(bar_tempty + 8 * acc, ((uint32_t)(li / kSrAcc) & 1u) ^ 1u);
-            mbar_wait(bar_afull + 8 * stage, (uint32_t)(li / kSrStages) & 1u);
+        // the whole warp runs the loop converged, `elect.sync` picks the issuing lane (uniform operands; see umma_f16_elect);
+        // ring positions and parities are counters (the 64-bit % and / per tile cost more than the two MMAs)
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        int stage = 0, acc = 0; uint32_t sph = 0, aph = 0;
+        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+            mbar_wait(bar_afull + 8 * stage, sph);
             tc_fence_after_sync();
-            if (lane == 0) {
-                const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kSrAStage >> 4);
-                umma_f16(tmem_base + acc * kSrN, ((uint64_t)a_hi << 32) | a_lo, b_d0, idesc, 0u);
-                umma_f16(tmem_base + acc * kSrN, ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4)), b_d1, idesc, 1u);
-                umma_commit(bar_aempty + 8 * stage);
-                umma_commit(bar_tfull + 8 * acc);
-            }
-            __syncwarp();
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kSrAStage >> 4);
+            umma_f16_elect(tmem_u + acc * kSrN, ((uint64_t)a_hi << 32) | a_lo, b_d0, idesc, 0u);
+            umma_f16_elect(tmem_u + acc * kSrN, ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4)), b_d1, idesc, 1u);
+            umma_commit_elect(bar_aempty + 8 * stage);
+            umma_commit_elect(bar_tfull + 8 * acc);
+            if (++stage == kSrStages) { stage = 0; sph ^= 1u; }
+            if (++acc == kSrAcc) { acc = 0; aph ^= 1u; }
         }
     } else {
         // ================================ EPILOGUE ==============================================
