@@ -6,8 +6,38 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 
 namespace dfd {
+
+// ------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the scoring step is launched with the programmatic-stream-serialisation
+// attribute (`launch_pdl`), so the 68 dependent launches of a step overlap their launch latency and constant-only prologues
+// (barrier init, TMEM allocation, weight staging, shared-memory zeroing) with the tail of the kernel before them — in a plain
+// stream and, as programmatic edges, in a captured CUDA graph.  The contract every kernel keeps:
+//   * `griddep_wait()` is executed by every CTA BEFORE its first read of anything another kernel produced and BEFORE its first
+//     global write (the buffers of the step are reused, so a write may race with the previous kernel's reads otherwise); it returns
+//     when the preceding kernel has completed and its writes are visible.  Completion is transitive: the preceding kernel itself
+//     waited for its predecessor.
+//   * no kernel triggers its dependents early (`griddepcontrol.launch_dependents`): the next kernel's CTAs become resident as this
+//     kernel's CTAs exit.  An explicit trigger at the top of every kernel measured the same at 2048 frames and SLOWER for small
+//     batches (8 frames: 0.95 vs 0.84 ms in a stream, 0.93 vs 0.84 ms under graph replay) — profiles/r02_experimental.md.
+// DFD_PDL=0 builds plain launches (the instructions are no-ops then): `tools/build_variant.py` uses it for A/B timing.
+// ------------------------------------------------------------------------------------------
+#ifndef DFD_PDL
+#define DFD_PDL 1
+#endif
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = DFD_PDL ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // ------------------------------------------------------------------------------------------
 // 16-bit storage types.  Activations and GEMM operands are stored as fp16 (default) or bf16;

@@ -93,6 +93,7 @@ dwconv_march_kernel(const T* __restrict__ in, const float* __restrict__ w, const
     }
     const size_t rowpitch_b = (size_t)W * C * 2;
     __syncthreads();
+    griddep_wait();                                      // everything above touched only weights and shared memory
 
     // running state of the stager: next input row to issue, its global address and ring slot
     int iy_i = iy_start, left_i = rend;
@@ -258,8 +259,7 @@ static cudaError_t launch_march_t(const void* in, const float* w, const float* b
     if (chunks > kMarchMaxK * threads || smem > 200 * 1024 || grid > 0x7fffffffLL) return cudaErrorInvalidValue;
 #define DFD_MARCH_GO(kern) { \
         if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; } \
-        kern<<<(unsigned)grid, threads, smem, s>>>((const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, CB, strips, rps, segs, pixw); \
-        return cudaGetLastError(); }
+        return launch_pdl(kern, dim3((unsigned)grid), dim3(threads), smem, s, (const T*)in, w, bias, (T*)out, partials, H, W, C, OH, OW, CB, strips, rps, segs, pixw); }
     // the network's own layer shapes at 224x224, fp16: compile-time geometry
 #define DFD_MARCH_SPEC(KS, ST, MR, CC_, WW_, CB_) \
     if constexpr (std::is_same<T, __half>::value) if (k == KS && stride == ST && C == CC_ && W == WW_ && H == WW_ && CB == CB_) { \

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
+    // programmatic dependent launch: the set-up above read only the bias and (resident case, never per-frame weights) W
+    griddep_wait();
 
     const int num_kb = (p.K + kKB - 1) / kKB;
     const int64_t units = p.m_tiles * p.n_chunks;
@@ -638,8 +640,7 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     } else {
         tmB = tmA;
     }
-    kernel<<<grid, (epi_warps + 1 + prod_warps + xform_warps) * 32, smem, s>>>(a, tmA, tmB);
-    return cudaGetLastError();
+    return launch_pdl(kernel, dim3(grid), dim3((epi_warps + 1 + prod_warps + xform_warps) * 32), smem, s, a, tmA, tmB);
 }
 
 template <typename T>
@@ -726,6 +727,7 @@ __global__ void scale_weights_kernel(const T* __restrict__ W, const float* __res
     const int n = (int)(fn % N);
     const int64_t f = fn / N;
     const uint4 w = __ldg(reinterpret_cast<const uint4*>(W) + (size_t)n * (K / 8) + k8);
+    griddep_wait();                                                             // the gate comes from the SE kernel before this one
     const float4* gp = reinterpret_cast<const float4*>(gate + (size_t)f * Kg + (8 * k8) % Kg);      // Kg % 8 == 0: the group does not wrap
     const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1);
     const float2 x0 = Half16<T>::unpack(w.x), x1 = Half16<T>::unpack(w.y), x2 = Half16<T>::unpack(w.z), x3 = Half16<T>::unpack(w.w);
@@ -740,9 +742,8 @@ cudaError_t launch_scale_weights(const void* W, const float* gate, void* Wf, int
     if (total <= 0) return cudaSuccess;
     if (Kg <= 0 || (Kg & 7) || (K & 7) || K % Kg) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)((total + 255) / 256);
-    if (dtype == kDtypeFP16) scale_weights_kernel<__half><<<grid, 256, 0, s>>>((const __half*)W, gate, (__half*)Wf, N, K, Kg, total);
-    else scale_weights_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)W, gate, (__nv_bfloat16*)Wf, N, K, Kg, total);
-    return cudaGetLastError();
+    if (dtype == kDtypeFP16) return launch_pdl(scale_weights_kernel<__half>, dim3(grid), dim3(256), 0, s, (const __half*)W, gate, (__half*)Wf, N, K, Kg, total);
+    return launch_pdl(scale_weights_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, (const __nv_bfloat16*)W, gate, (__nv_bfloat16*)Wf, N, K, Kg, total);
 }
 
 cudaError_t launch_gemm_tc_f32out(const void* A, const void* W, const float* bias, const float* R, float* D,

@@ -56,6 +56,7 @@ head_pool_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
+    griddep_wait();                         // barriers and TMEM are set up; the activations come from the kernel before this one
 
     if (warp == 17) {
         // ---------------------------------------------------------------- TMA: activations of the pixel tile
@@ -192,13 +193,12 @@ cudaError_t launch_head_pool_tc(const void* A, const void* W, const float* bias,
     if (dtype == kDtypeFP16) {
         e = cudaFuncSetAttribute(head_pool_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        head_pool_tc_kernel<__half><<<grid, kHThreads, smem, s>>>(tmX, tmW, bias, feat, frames, HW, N, K, np16, wstages, cgroups, ptiles, inv_hw);
+        return launch_pdl(head_pool_tc_kernel<__half>, dim3(grid), dim3(kHThreads), smem, s, tmX, tmW, bias, feat, frames, HW, N, K, np16, wstages, cgroups, ptiles, inv_hw);
     } else {
         e = cudaFuncSetAttribute(head_pool_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        head_pool_tc_kernel<__nv_bfloat16><<<grid, kHThreads, smem, s>>>(tmX, tmW, bias, feat, frames, HW, N, K, np16, wstages, cgroups, ptiles, inv_hw);
+        return launch_pdl(head_pool_tc_kernel<__nv_bfloat16>, dim3(grid), dim3(kHThreads), smem, s, tmX, tmW, bias, feat, frames, HW, N, K, np16, wstages, cgroups, ptiles, inv_hw);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace dfd

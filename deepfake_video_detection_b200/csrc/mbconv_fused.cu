@@ -256,6 +256,7 @@ mbconv_fused_kernel(const void* __restrict__ xv, const void* __restrict__ wev, c
         }
     };
 
+    griddep_wait();                          // everything above touched only weights and shared memory
 #pragma unroll
     for (int r = 0; r < kXR - 1; ++r) issue_row();
     cp_async_wait<kXR - 2>();                // x row 0 has landed (this thread's copies) ...
@@ -360,8 +361,7 @@ static cudaError_t fused_go(const void* x, const void* we, const float* be, cons
 #endif
     const int64_t grid = frames * G::ctas_per_frame;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidValue;
-    kern<<<(unsigned)grid, THREADS, smem, s>>>(x, we, be, w, bias, (T*)out, partials);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((unsigned)grid), dim3(THREADS), smem, s, x, we, be, w, bias, (T*)out, partials);
 }
 
 template <typename T>

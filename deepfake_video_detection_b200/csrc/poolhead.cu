@@ -39,6 +39,7 @@ pool_head_kernel(const HeadWeights hw, const float* __restrict__ feat, const int
     __shared__ float s_pooled[FEAT];
     __shared__ float s_h1[kFc1];
     const int v = blockIdx.x;
+    griddep_wait();                                // features (and possibly the offsets) come from kernels before this one
     const int f0 = offsets[v];
     const int T = offsets[v + 1] - f0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,8 +142,7 @@ static cudaError_t launch_pool_head_t(const HeadWeights& hw, const float* feat, 
     const size_t smem = (size_t)CHUNK * FEAT * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(pool_head_kernel<FEAT, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pool_head_kernel<FEAT, CHUNK><<<(unsigned)videos, kPhThreads, smem, s>>>(hw, feat, offsets, (int)frames, use_attention, logits, frame_scores);
-    return cudaGetLastError();
+    return launch_pdl(pool_head_kernel<FEAT, CHUNK>, dim3((unsigned)videos), dim3(kPhThreads), smem, s, hw, feat, offsets, (int)frames, use_attention, logits, frame_scores);
 }
 
 cudaError_t launch_pool_head(const HeadWeights& hw, const float* feat, const int32_t* offsets, int64_t videos, int64_t frames,

@@ -26,6 +26,7 @@ se_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
     const int kSeThreads = blockDim.x;
     const int64_t f0 = (int64_t)blockIdx.x * kSeFrames;
     const int nf = (int)min((int64_t)kSeFrames, frames - f0);
+    griddep_wait();                               // the partial sums come from the depthwise kernel before this one
 
 #pragma unroll 4
     for (int i = threadIdx.x; i < kSeFrames * C; i += kSeThreads) {
@@ -152,6 +153,7 @@ se_wide_kernel(const float* __restrict__ partials, int nparts, float inv_hw,
     };
     load_chunk(0);
     load_chunk(1);
+    griddep_wait();                                             // weights are in flight; the partial sums come from the depthwise kernel
 
     // means of the 16 frames, frame-minor.  Thread = channel (coalesced over the warp), the 16 frames' loads of one partial row
     // are independent and issued back to back (a load -> shared-memory store loop per element is one memory latency per
@@ -275,8 +277,7 @@ static cudaError_t launch_se_wide_t(const float* partials, int nparts, float inv
     cudaError_t e = cudaFuncSetAttribute(se_wide_kernel<JPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((frames + kSe3Frames - 1) / kSe3Frames);
-    se_wide_kernel<JPL><<<grid, kSe3Threads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, CC, JC, (uint32_t)buf_floats);
-    return cudaGetLastError();
+    return launch_pdl(se_wide_kernel<JPL>, dim3(grid), dim3(kSe3Threads), smem, s, partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd, CC, JC, (uint32_t)buf_floats);
 }
 
 template <int FPB>
@@ -289,8 +290,7 @@ static cudaError_t launch_se_t(const float* partials, int nparts, float inv_hw, 
     const unsigned grid = (unsigned)((frames + FPB - 1) / FPB);
     // the kernel is instruction-latency-bound (IPC 0.66 at 8 warps per SM): wide layers get 32 warps per CTA
     const int threads = C >= 480 ? 1024 : (C >= 144 ? 512 : 256);
-    se_kernel<FPB><<<grid, threads, smem, s>>>(partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
-    return cudaGetLastError();
+    return launch_pdl(se_kernel<FPB>, dim3(grid), dim3(threads), smem, s, partials, nparts, inv_hw, w1, b1, w2t, b2, gate, frames, C, rd);
 }
 
 cudaError_t launch_se(const float* partials, int nparts, float inv_hw, const float* w1, const float* b1,

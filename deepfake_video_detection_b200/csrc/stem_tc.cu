@@ -67,6 +67,7 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
+    griddep_wait();                                 // the crops may come from a kernel (crop + resize); the output buffer is reused
     const int64_t tiles = (total + kStBM - 1) / kStBM;
     const int ohw = OH * OW;
 
@@ -190,8 +191,8 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
 // K layout: k = ky*10 + kx*3 + c (9 taps + 1 zero per input row, 32 in all).
 constexpr int kSrK = 32, kSrChunks = kSrK / 8;
 constexpr uint32_t kSrAStage = kSrChunks * kStLboA;      // 8256 B
-constexpr int kSrN = 2 * kStN;                           // MMA N: W_hi and W_lo stacked (the epilogue adds the two halves)
-constexpr uint32_t kSrLboB = kSrN * 16 + 16;
+constexpr int kSrN = kStN;                               // MMA N = 32: the W_hi and W_lo MMAs accumulate into the SAME TMEM columns
+constexpr uint32_t kSrLboB = 2 * kStN * 16 + 16;         // W_hi rows 0-31, W_lo rows 32-63 of one canonical tile
 constexpr uint32_t kSrBBytes = kSrChunks * kSrLboB;
 constexpr int kSrStages = 8, kSrRaw = 8, kSrAcc = 8;
 // kSrEpiSets epilogue sets and kSrSets builder sets (4 warps each) take alternate tiles: both roles are latency-bound per tile
@@ -204,7 +205,9 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc
 template <typename T, int kSrEpiSets, int kSrSets>
 __global__ void __launch_bounds__((4 * kSrEpiSets + 2 + 4 * kSrSets) * 32, 1)
 stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow, const float* __restrict__ bias4,
-                T* __restrict__ out, int H, int W, int OH, int OW, int64_t tiles, uint32_t raw_stride) {
+                T* __restrict__ out, int H, int W, int OH, int OW, int tiles, uint32_t raw_stride) {
+    // tile = frame * OH + oy as a 32-bit counter; the row inside the frame is carried along (oy += stride % OH, one conditional
+    // subtract) — the 64-bit `tile % OH` / `tile / OH` this replaces were a ~100-instruction subroutine call per tile and thread
     constexpr int kSrEpiWarps = 4 * kSrEpiSets, kSrMmaWarp = kSrEpiWarps, kSrRawWarp = kSrEpiWarps + 1;
     constexpr int kSrThreads = (kSrEpiWarps + 2 + 4 * kSrSets) * 32;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -222,7 +225,7 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t RB = (uint32_t)W * 3;
 
-    for (int i = threadIdx.x; i < 4 * kStN; i += kSrThreads) s_bias[i] = bias4[i];
+    for (int i = threadIdx.x; i < 4 * kStN; i += kSrThreads) s_bias[i] = 0.5f * bias4[i];   // halved: the epilogue forms h = x / 2 directly
     for (int i = threadIdx.x; i < 2 * kStN * kSrChunks; i += kSrThreads) {        // [hi|lo][32 oc][32 k] -> canonical layout
         const int h = i / (kStN * kSrChunks), r = (i / kSrChunks) % kStN, q = i % kSrChunks;
         *reinterpret_cast<uint4*>(s_b + q * kSrLboB + (h * kStN + r) * 16) = __ldg(reinterpret_cast<const uint4*>(wrow + (h * kStN + r) * kSrK + q * 8));
@@ -241,16 +244,17 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
+    griddep_wait();                                 // the crops may come from a kernel (crop + resize); the output buffer is reused
 
     if (warp == kSrRawWarp) {
         // ================================ RAW LOADER ============================================
         if (lane == 0) {
-            int64_t li = 0;
-            for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++li) {
+            uint32_t li = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++li) {
                 const int stage = (int)(li % kSrRaw);
-                mbar_wait(bar_rempty + 8 * stage, ((uint32_t)(li / kSrRaw) & 1u) ^ 1u);
-                const int64_t frame = tile / OH;
-                const int oy = (int)(tile - frame * OH);
+                mbar_wait(bar_rempty + 8 * stage, ((li / kSrRaw) & 1u) ^ 1u);
+                const int frame = tile / OH;
+                const int oy = tile - frame * OH;
                 const uint8_t* src = in + ((size_t)frame * H + (2 * oy - 1)) * RB;        // input rows 2oy-1 .. 2oy+1
                 uint32_t dst = raw_base0 + stage * raw_stride + 16, bytes = 3 * RB;
                 if (oy == 0) { src += RB; dst += RB; bytes = 2 * RB; }                     // row -1 is padding (masked by the builders)
@@ -264,14 +268,17 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         const int set = bt >> 7, row = bt & 127;
         const uint32_t magic = 0x00000064u;                       // byte 4 = 0x64, bytes 5..7 = 0
         const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
-        int64_t li = set;
-        for (int64_t tile = blockIdx.x + (int64_t)set * gridDim.x; tile < tiles; tile += kSrSets * (int64_t)gridDim.x, li += kSrSets) {
+        uint32_t li = set;
+        const int tstep = kSrSets * (int)gridDim.x, oystep = tstep % OH;
+        int oy = (int)((blockIdx.x + (uint32_t)set * gridDim.x) % (uint32_t)OH);
+        for (int tile = blockIdx.x + set * (int)gridDim.x; tile < tiles; tile += tstep, li += kSrSets) {
             const int rstage = (int)(li % kSrRaw), astage = (int)(li % kSrStages);
-            const bool top = (tile % OH) == 0;
+            const bool top = oy == 0;
+            oy += oystep; if (oy >= OH) oy -= OH;
             uint32_t h2[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) h2[i] = 0u;
-            mbar_wait(bar_rfull + 8 * rstage, (uint32_t)(li / kSrRaw) & 1u);
+            mbar_wait(bar_rfull + 8 * rstage, (li / kSrRaw) & 1u);
             if (row < OW) {
                 const uint32_t rb = raw_base0 + rstage * raw_stride;
 #pragma unroll
@@ -297,7 +304,7 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
                 }
             }
             mbar_arrive(bar_rempty + 8 * rstage);
-            mbar_wait(bar_aempty + 8 * astage, ((uint32_t)(li / kSrStages) & 1u) ^ 1u);
+            mbar_wait(bar_aempty + 8 * astage, ((li / kSrStages) & 1u) ^ 1u);
             if (row < OW) {
                 const uint32_t dst = a_base0 + astage * kSrAStage + row * 16;
 #pragma unroll
@@ -308,22 +315,27 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         }
     } else if (warp == kSrMmaWarp) {
         // ================================ MMA ISSUER ============================================
-        // two MMAs per tile (K = 32) against [W_hi ; W_lo] (N = 64); descriptors differ only in the start-address field
+        // four MMAs per tile (K = 32 = two k-steps, against W_hi and against W_lo, N = 32) accumulate x * (w_hi + w_lo) in ONE set of
+        // TMEM columns: the epilogue reads 32 columns, not 64, and adds nothing; descriptors differ only in the start-address field
         const uint32_t idesc = umma_idesc(0u /* fp16 operands whatever the output type */, kStBM, kSrN);
         const uint64_t a_d0 = umma_smem_desc(a_base0, kStLboA, 128);
         const uint64_t b_d0 = umma_smem_desc(b_base, kSrLboB, 128), b_d1 = umma_smem_desc(b_base + 2 * kSrLboB, kSrLboB, 128);
+        const uint64_t b_l0 = umma_smem_desc(b_base + kStN * 16, kSrLboB, 128), b_l1 = umma_smem_desc(b_base + 2 * kSrLboB + kStN * 16, kSrLboB, 128);
         const uint32_t a_hi = (uint32_t)(a_d0 >> 32), a_lo0 = (uint32_t)a_d0;
         // the whole warp runs the loop converged, `elect.sync` picks the issuing lane (uniform operands; see umma_f16_elect);
         // ring positions and parities are counters (the 64-bit % and / per tile cost more than the two MMAs)
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0, acc = 0; uint32_t sph = 0, aph = 0;
-        for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
             mbar_wait(bar_afull + 8 * stage, sph);
             tc_fence_after_sync();
             const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kSrAStage >> 4);
-            umma_f16_elect(tmem_u + acc * kSrN, ((uint64_t)a_hi << 32) | a_lo, b_d0, idesc, 0u);
-            umma_f16_elect(tmem_u + acc * kSrN, ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4)), b_d1, idesc, 1u);
+            const uint64_t a_k0 = ((uint64_t)a_hi << 32) | a_lo, a_k1 = ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4));
+            umma_f16_elect(tmem_u + acc * kSrN, a_k0, b_d0, idesc, 0u);
+            umma_f16_elect(tmem_u + acc * kSrN, a_k1, b_d1, idesc, 1u);
+            umma_f16_elect(tmem_u + acc * kSrN, a_k0, b_l0, idesc, 1u);
+            umma_f16_elect(tmem_u + acc * kSrN, a_k1, b_l1, idesc, 1u);
             umma_commit_elect(bar_aempty + 8 * stage);
             umma_commit_elect(bar_tfull + 8 * acc);
             if (++stage == kSrStages) { stage = 0; sph ^= 1u; }
@@ -333,27 +345,29 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         // ================================ EPILOGUE ==============================================
         const int q = warp & 3, eset = warp >> 2;          // TMEM lane quarter, epilogue set
         const int row = 32 * q + lane;
-        int64_t li = eset;
-        for (int64_t tile = blockIdx.x + (int64_t)eset * gridDim.x; tile < tiles; tile += kSrEpiSets * (int64_t)gridDim.x, li += kSrEpiSets) {
+        uint32_t li = eset;
+        const int tstep = kSrEpiSets * (int)gridDim.x, oystep = tstep % OH;
+        int oy = (int)((blockIdx.x + (uint32_t)eset * gridDim.x) % (uint32_t)OH);
+        for (int tile = blockIdx.x + eset * (int)gridDim.x; tile < tiles; tile += tstep, li += kSrEpiSets) {
             const int acc = (int)(li % kSrAcc);
-            mbar_wait(bar_tfull + 8 * acc, (uint32_t)(li / kSrAcc) & 1u);
+            mbar_wait(bar_tfull + 8 * acc, (li / kSrAcc) & 1u);
             tc_fence_after_sync();
-            const float* bs = s_bias + (((tile % OH) == 0 ? 2 : 0) + (row == 0 ? 1 : 0)) * kStN;
+            const float* bs = s_bias + ((oy == 0 ? 2 : 0) + (row == 0 ? 1 : 0)) * kStN;
+            oy += oystep; if (oy >= OH) oy -= OH;
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * kSrN;
-            uint32_t r[4][16];                                  // columns 0-31: A * W_hi, 32-63: A * W_lo
+            uint32_t r[2][16];                                  // A * (W_hi + W_lo), scaled by 256
             tmem_ld16(t_row, r[0]);
             tmem_ld16(t_row + 16, r[1]);
-            tmem_ld16(t_row + 32, r[2]);
-            tmem_ld16(t_row + 48, r[3]);
             tmem_ld_wait();
 #pragma unroll
             for (int c16 = 0; c16 < 2; ++c16) {
                 U32x8 o;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float a = fmaf(__uint_as_float(r[c16][2 * i]) + __uint_as_float(r[2 + c16][2 * i]), 0.00390625f, bs[c16 * 16 + 2 * i]);
-                    const float b = fmaf(__uint_as_float(r[c16][2 * i + 1]) + __uint_as_float(r[2 + c16][2 * i + 1]), 0.00390625f, bs[c16 * 16 + 2 * i + 1]);
-                    o.v[i] = Half16<T>::pack(silu_tanh(a), silu_tanh(b));
+                    // h = x / 2 = acc * 2^-9 + bias / 2 (exact scaling), SiLU(x) = h + h tanh(h)
+                    const float a = fmaf(__uint_as_float(r[c16][2 * i]), 0.001953125f, bs[c16 * 16 + 2 * i]);
+                    const float b = fmaf(__uint_as_float(r[c16][2 * i + 1]), 0.001953125f, bs[c16 * 16 + 2 * i + 1]);
+                    o.v[i] = Half16<T>::pack(fmaf(a, tanh_approx(a), a), fmaf(b, tanh_approx(b), b));
                 }
                 if (row < OW) stg32(out + ((size_t)tile * OW + row) * kStN + c16 * 16, o);
             }
@@ -378,31 +392,31 @@ cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias
         // row variant: one tile per output row
         const uint32_t raw_stride = (16u + 3u * (uint32_t)W * 3u + 127u) & ~127u;
         const size_t smem = kSrStages * kSrAStage + kSrRaw * raw_stride + kSrBBytes + 4 * kStN * 4 + (2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc) * 8 + 16;
-        const int64_t tiles = frames * OH;
+        if (frames * OH > 0x7fffffffLL / 4) return cudaErrorInvalidValue;             // 32-bit tile counters in the kernel
+        const int tiles = (int)(frames * OH);
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
 #define DFD_STEM_ROW(TT, E, B) { \
             auto kern = stem_row_kernel<TT, E, B>; \
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; \
-            kern<<<grid, (4 * E + 2 + 4 * B) * 32, smem, s>>>(in, (const __half*)wrow, bias4, (TT*)out, H, W, OH, OW, tiles, raw_stride); }
+            e = launch_pdl(kern, dim3(grid), dim3((4 * E + 2 + 4 * B) * 32), smem, s, in, (const __half*)wrow, bias4, (TT*)out, H, W, OH, OW, tiles, raw_stride); }
         if (dtype == kDtypeFP16) {
             DFD_STEM_ROW(__half, 2, 4)            // 2 epilogue sets, 4 builder sets (3/3, 4/2, 3/4 measured within 5 % of it)
         } else {
             DFD_STEM_ROW(__nv_bfloat16, 2, 4)
         }
 #undef DFD_STEM_ROW
-        return cudaGetLastError();
+        return e;
     }
     const size_t smem = kStStages * kStAStage + kStChunks * kStLboB + 768 * 4 + kStN * 4 + (2 * kStStages + 2 * kStAcc) * 8 + 16;
     const int64_t tiles = (total + kStBM - 1) / kStBM;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     if (dtype == kDtypeFP16) {
         e = cudaFuncSetAttribute(stem_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
-        stem_tc_kernel<__half><<<grid, kStThreads, smem, s>>>(in, (const __half*)w16, bias, (__half*)out, H, W, OH, OW, total);
+        return launch_pdl(stem_tc_kernel<__half>, dim3(grid), dim3(kStThreads), smem, s, in, (const __half*)w16, bias, (__half*)out, H, W, OH, OW, total);
     } else {
         e = cudaFuncSetAttribute(stem_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
-        stem_tc_kernel<__nv_bfloat16><<<grid, kStThreads, smem, s>>>(in, (const __nv_bfloat16*)w16, bias, (__nv_bfloat16*)out, H, W, OH, OW, total);
+        return launch_pdl(stem_tc_kernel<__nv_bfloat16>, dim3(grid), dim3(kStThreads), smem, s, in, (const __nv_bfloat16*)w16, bias, (__nv_bfloat16*)out, H, W, OH, OW, total);
     }
-    return cudaGetLastError();
 }
 
 }  // namespace dfd

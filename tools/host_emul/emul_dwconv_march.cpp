@@ -46,6 +46,7 @@ static inline uint64_t mul2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y
 static inline uint64_t add2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y = f2_unpack(b); return f2_pack(x.x + y.x, x.y + y.y); }
 static inline float tanh_approx(float x) { return tanhf(x); }
 template <typename P> static inline P __ldg(const P* p) { return *p; }
+static inline void griddep_wait() {}      // programmatic dependent launch: nothing to wait for on the host
 static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - dw_smem); }
 static inline void sts16(uint32_t a, const uint4& v) { memcpy(dw_smem + a, &v, 16); }
 static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, dw_smem + a, 4); return v; }

@@ -67,6 +67,7 @@ static inline uint64_t add2(uint64_t a, uint64_t b) { float2 x = f2_unpack(a), y
 static inline float tanh_approx(float x) { return tanhf(x); }
 static inline float silu_tanh(float x) { const float h = 0.5f * x; return fmaf(h, tanhf(h), h); }
 template <typename P> static inline P __ldg(const P* p) { return *p; }
+static inline void griddep_wait() {}      // programmatic dependent launch: nothing to wait for on the host
 static inline uint4 ldg16(const void* p) { uint4 v; memcpy(&v, p, 16); return v; }
 static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const uint8_t*)p - fz_smem); }
 static inline void sts16(uint32_t a, const uint4& v) { memcpy(fz_smem + a, &v, 16); }

@@ -33,6 +33,7 @@ namespace dfd {
 struct HeadWeights { const float *att_w1, *att_b1, *att_w2, *att_b2, *fc1_w, *fc1_b, *fc2_w, *fc2_b; };
 static float g_dyn_smem[32 * 1280];
 template <typename P> static inline P __ldg(const P* p) { return *p; }
+static inline void griddep_wait() {}      // programmatic dependent launch: nothing to wait for on the host
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 struct WarpX { float f[32]; std::barrier<> bar{32}; };
 static std::vector<std::unique_ptr<WarpX>> g_warps;

@@ -40,6 +40,7 @@ static inline uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { float2 x = f2_
 static inline float silu_f(float x) { return x / (1.0f + expf(-x)); }
 static inline float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 template <typename P> static inline P __ldg(const P* p) { return *p; }
+static inline void griddep_wait() {}      // programmatic dependent launch: nothing to wait for on the host
 struct WarpX { float f[32]; std::barrier<> bar{32}; };
 static std::vector<std::unique_ptr<WarpX>> g_warps;
 static inline float __shfl_xor_sync(unsigned, float v, int o) {
