@@ -194,28 +194,42 @@ constexpr uint32_t kSrAStage = kSrChunks * kStLboA;      // 8256 B
 constexpr int kSrN = kStN;                               // MMA N = 32: the W_hi and W_lo MMAs accumulate into the SAME TMEM columns
 constexpr uint32_t kSrLboB = 2 * kStN * 16 + 16;         // W_hi rows 0-31, W_lo rows 32-63 of one canonical tile
 constexpr uint32_t kSrBBytes = kSrChunks * kSrLboB;
-constexpr int kSrStages = 8, kSrRaw = 8, kSrAcc = 8;
-// kSrEpiSets epilogue sets and kSrSets builder sets (4 warps each) take alternate tiles: both roles are latency-bound per tile
+#ifndef DFD_STEM_STAGES
+#define DFD_STEM_STAGES 8      // A-tile ring, raw-byte ring (tools/build_variant.py sweeps them: 8/8 0.476 ms, 8/12 0.53, 6/12 0.53, 8/16 0.46)
+#define DFD_STEM_RAW 16
+#endif
+constexpr int kSrStages = DFD_STEM_STAGES, kSrRaw = DFD_STEM_RAW, kSrAcc = 8;
+#ifndef DFD_STEM_DBG
+#define DFD_STEM_DBG 0      // timing experiments only (wrong results): 1 builders skip their work, 2 epilogue skips its work, 4 no MMAs, 8 no raw loads
+#endif
+// kSrEpiSets epilogue sets and kSrSets builder sets (4 warps each) take alternate tiles: both roles are latency-bound per tile.
+// A tile is R consecutive output rows of one frame (R = 2 when OH is even): with every role's work skipped the barrier hand-offs
+// alone cost 0.18 us per tile (0.28 ms per 2048 frames at one row per tile, profiles/r02_experimental.md), so a tile carries two
+// rows' worth of work per hand-off; the 2R+1 input rows it needs are still ONE bulk copy.
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <typename T, int kSrEpiSets, int kSrSets>
+template <typename T, int kSrEpiSets, int kSrSets, int R>
 __global__ void __launch_bounds__((4 * kSrEpiSets + 2 + 4 * kSrSets) * 32, 1)
 stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow, const float* __restrict__ bias4,
                 T* __restrict__ out, int H, int W, int OH, int OW, int tiles, uint32_t raw_stride) {
-    // tile = frame * OH + oy as a 32-bit counter; the row inside the frame is carried along (oy += stride % OH, one conditional
-    // subtract) — the 64-bit `tile % OH` / `tile / OH` this replaces were a ~100-instruction subroutine call per tile and thread
+    // tile = frame * (OH / R) + ty as a 32-bit counter; ty (the tile's position inside its frame) is carried along (ty += stride %
+    // (OH / R), one conditional subtract) — the 64-bit `tile % OH` / `tile / OH` this replaces were a ~100-instruction subroutine
+    // call per tile and thread
     constexpr int kSrEpiWarps = 4 * kSrEpiSets, kSrMmaWarp = kSrEpiWarps, kSrRawWarp = kSrEpiWarps + 1;
     constexpr int kSrThreads = (kSrEpiWarps + 2 + 4 * kSrSets) * 32;
+    constexpr uint32_t kTileA = R * kSrAStage;             // A operand of a tile: R row tiles of [128 pixels][32 k]
+    constexpr int kAccCols = R * kSrN;                     // TMEM columns of a tile's accumulators
+    static_assert(kSrAcc * kAccCols <= 512 && ((kSrAcc * kAccCols) & (kSrAcc * kAccCols - 1)) == 0, "TMEM allocation: a power of two up to 512 columns");
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t* sp = smem_raw + kSrStages * kSrAStage;
+    uint8_t* sp = smem_raw + kSrStages * kTileA;
     uint8_t* s_rawb = sp;                           sp += kSrRaw * raw_stride;
     uint8_t* s_b = sp;                              sp += kSrBBytes;
     float* s_bias = reinterpret_cast<float*>(sp);   sp += 4 * kStN * 4;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);      // afull[S], aempty[S], rfull[R], rempty[R], tfull[ACC], tempty[ACC]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sp);      // afull[S], aempty[S], rfull[RAW], rempty[RAW], tfull[ACC], tempty[ACC]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc);
 
     const uint32_t a_base0 = smem_u32(smem_raw), raw_base0 = smem_u32(s_rawb), b_base = smem_u32(s_b);
@@ -224,6 +238,7 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
     const uint32_t bar_tfull = smem_u32(bars + 2 * kSrStages + 2 * kSrRaw), bar_tempty = bar_tfull + 8 * kSrAcc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t RB = (uint32_t)W * 3;
+    const int OHT = OH / R;                                // tiles per frame
 
     for (int i = threadIdx.x; i < 4 * kStN; i += kSrThreads) s_bias[i] = 0.5f * bias4[i];   // halved: the epilogue forms h = x / 2 directly
     for (int i = threadIdx.x; i < 2 * kStN * kSrChunks; i += kSrThreads) {        // [hi|lo][32 oc][32 k] -> canonical layout
@@ -238,7 +253,7 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         for (int a = 0; a < kSrAcc; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 128); }
         fence_barrier_init();
     }
-    if (warp == kSrMmaWarp) tmem_alloc(smem_u32(s_tmem), kSrAcc * kSrN);
+    if (warp == kSrMmaWarp) tmem_alloc(smem_u32(s_tmem), kSrAcc * kAccCols);
     fence_proxy_async_smem();                       // W tiles were written with st.shared
     tc_fence_before_sync();
     __syncthreads();
@@ -249,17 +264,20 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
     if (warp == kSrRawWarp) {
         // ================================ RAW LOADER ============================================
         if (lane == 0) {
-            uint32_t li = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++li) {
-                const int stage = (int)(li % kSrRaw);
-                mbar_wait(bar_rempty + 8 * stage, ((li / kSrRaw) & 1u) ^ 1u);
-                const int frame = tile / OH;
-                const int oy = tile - frame * OH;
-                const uint8_t* src = in + ((size_t)frame * H + (2 * oy - 1)) * RB;        // input rows 2oy-1 .. 2oy+1
-                uint32_t dst = raw_base0 + stage * raw_stride + 16, bytes = 3 * RB;
-                if (oy == 0) { src += RB; dst += RB; bytes = 2 * RB; }                     // row -1 is padding (masked by the builders)
-                mbar_arrive_expect_tx(bar_rfull + 8 * stage, bytes);
-                bulk_load_1d(dst, src, bytes, bar_rfull + 8 * stage);
+            int stage = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                mbar_wait(bar_rempty + 8 * stage, ph ^ 1u);
+                const int frame = tile / OHT;
+                const int ty = tile - frame * OHT;
+                const uint8_t* src = in + ((size_t)frame * H + (2 * R * ty - 1)) * RB;    // input rows 2R ty - 1 .. 2R ty + 2R - 1
+                uint32_t dst = raw_base0 + stage * raw_stride + 16, bytes = (2 * R + 1) * RB;
+                if (ty == 0) { src += RB; dst += RB; bytes -= RB; }                        // row -1 is padding (masked by the builders)
+                if (DFD_STEM_DBG & 8) mbar_arrive(bar_rfull + 8 * stage);
+                else {
+                    mbar_arrive_expect_tx(bar_rfull + 8 * stage, bytes);
+                    bulk_load_1d(dst, src, bytes, bar_rfull + 8 * stage);
+                }
+                if (++stage == kSrRaw) { stage = 0; ph ^= 1u; }
             }
         }
     } else if (warp > kSrRawWarp) {
@@ -269,73 +287,87 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         const uint32_t magic = 0x00000064u;                       // byte 4 = 0x64, bytes 5..7 = 0
         const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
         uint32_t li = set;
-        const int tstep = kSrSets * (int)gridDim.x, oystep = tstep % OH;
-        int oy = (int)((blockIdx.x + (uint32_t)set * gridDim.x) % (uint32_t)OH);
+        const int tstep = kSrSets * (int)gridDim.x, tystep = tstep % OHT;
+        int ty = (int)((blockIdx.x + (uint32_t)set * gridDim.x) % (uint32_t)OHT);
         for (int tile = blockIdx.x + set * (int)gridDim.x; tile < tiles; tile += tstep, li += kSrSets) {
             const int rstage = (int)(li % kSrRaw), astage = (int)(li % kSrStages);
-            const bool top = oy == 0;
-            oy += oystep; if (oy >= OH) oy -= OH;
-            uint32_t h2[16];
+            const bool top = ty == 0;
+            ty += tystep; if (ty >= OHT) ty -= OHT;
+            uint32_t h2[R][16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) h2[i] = 0u;
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) h2[j][i] = 0u;
             mbar_wait(bar_rfull + 8 * rstage, (li / kSrRaw) & 1u);
-            if (row < OW) {
+            if (row < OW && !(DFD_STEM_DBG & 1)) {
                 const uint32_t rb = raw_base0 + rstage * raw_stride;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    if (r == 0 && top) continue;                                           // padding row: zeros
-                    const uint32_t s0 = 16u + r * RB + 6u * row - 3u;                      // first byte of the 9-byte window
-                    const uint32_t wa = rb + (s0 & ~3u), sh = (s0 & 3u) * 8u;
-                    uint32_t x0, x1, x2;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(wa));
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(wa + 4));
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x2) : "r"(wa + 8));
-                    uint32_t a0 = __funnelshift_r(x0, x1, sh), a1 = __funnelshift_r(x1, x2, sh), a2 = x2 >> sh;
-                    if (row == 0) a0 &= 0xff000000u;                                       // left padding column: taps kx = 0
-                    uint32_t p[5];
-                    p[0] = __byte_perm(a0, magic, 0x4140); p[1] = __byte_perm(a0, magic, 0x4342);
-                    p[2] = __byte_perm(a1, magic, 0x4140); p[3] = __byte_perm(a1, magic, 0x4342);
-                    p[4] = __byte_perm(a2, magic, 0x4540);
+                for (int j = 0; j < R; ++j) {
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) {
-                        __half2 v = __hsub2(*reinterpret_cast<__half2*>(&p[i]), k1024);      // exact: 1024 + u -> u
-                        h2[r * 5 + i] = *reinterpret_cast<uint32_t*>(&v);
+                    for (int r = 0; r < 3; ++r) {
+                        if (j == 0 && r == 0 && top) continue;                             // padding row: zeros
+                        const uint32_t s0 = 16u + (2 * j + r) * RB + 6u * row - 3u;        // first byte of the 9-byte window
+                        const uint32_t wa = rb + (s0 & ~3u), sh = (s0 & 3u) * 8u;
+                        uint32_t x0, x1, x2;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x0) : "r"(wa));
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x1) : "r"(wa + 4));
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x2) : "r"(wa + 8));
+                        uint32_t a0 = __funnelshift_r(x0, x1, sh), a1 = __funnelshift_r(x1, x2, sh), a2 = x2 >> sh;
+                        if (row == 0) a0 &= 0xff000000u;                                   // left padding column: taps kx = 0
+                        uint32_t p[5];
+                        p[0] = __byte_perm(a0, magic, 0x4140); p[1] = __byte_perm(a0, magic, 0x4342);
+                        p[2] = __byte_perm(a1, magic, 0x4140); p[3] = __byte_perm(a1, magic, 0x4342);
+                        p[4] = __byte_perm(a2, magic, 0x4540);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            __half2 v = __hsub2(*reinterpret_cast<__half2*>(&p[i]), k1024);  // exact: 1024 + u -> u
+                            h2[j][r * 5 + i] = *reinterpret_cast<uint32_t*>(&v);
+                        }
                     }
                 }
             }
             mbar_arrive(bar_rempty + 8 * rstage);
             mbar_wait(bar_aempty + 8 * astage, ((li / kSrStages) & 1u) ^ 1u);
-            if (row < OW) {
-                const uint32_t dst = a_base0 + astage * kSrAStage + row * 16;
+            if (row < OW && !(DFD_STEM_DBG & 1)) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) sts16(dst + q * kStLboA, make_uint4(h2[4 * q], h2[4 * q + 1], h2[4 * q + 2], h2[4 * q + 3]));
+                for (int j = 0; j < R; ++j) {
+                    const uint32_t dst = a_base0 + astage * kTileA + j * kSrAStage + row * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sts16(dst + q * kStLboA, make_uint4(h2[j][4 * q], h2[j][4 * q + 1], h2[j][4 * q + 2], h2[j][4 * q + 3]));
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(bar_afull + 8 * astage);
         }
     } else if (warp == kSrMmaWarp) {
         // ================================ MMA ISSUER ============================================
-        // four MMAs per tile (K = 32 = two k-steps, against W_hi and against W_lo, N = 32) accumulate x * (w_hi + w_lo) in ONE set of
-        // TMEM columns: the epilogue reads 32 columns, not 64, and adds nothing; descriptors differ only in the start-address field
+        // four MMAs per output row (K = 32 = two k-steps, against W_hi and against W_lo, N = 32) accumulate x * (w_hi + w_lo) in ONE
+        // set of TMEM columns: the epilogue reads 32 columns per row and adds nothing; descriptors differ only in the start address
         const uint32_t idesc = umma_idesc(0u /* fp16 operands whatever the output type */, kStBM, kSrN);
         const uint64_t a_d0 = umma_smem_desc(a_base0, kStLboA, 128);
         const uint64_t b_d0 = umma_smem_desc(b_base, kSrLboB, 128), b_d1 = umma_smem_desc(b_base + 2 * kSrLboB, kSrLboB, 128);
         const uint64_t b_l0 = umma_smem_desc(b_base + kStN * 16, kSrLboB, 128), b_l1 = umma_smem_desc(b_base + 2 * kSrLboB + kStN * 16, kSrLboB, 128);
         const uint32_t a_hi = (uint32_t)(a_d0 >> 32), a_lo0 = (uint32_t)a_d0;
         // the whole warp runs the loop converged, `elect.sync` picks the issuing lane (uniform operands; see umma_f16_elect);
-        // ring positions and parities are counters (the 64-bit % and / per tile cost more than the two MMAs)
+        // ring positions and parities are counters
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         int stage = 0, acc = 0; uint32_t sph = 0, aph = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
             mbar_wait(bar_afull + 8 * stage, sph);
             tc_fence_after_sync();
-            const uint32_t a_lo = a_lo0 + (uint32_t)stage * (kSrAStage >> 4);
-            const uint64_t a_k0 = ((uint64_t)a_hi << 32) | a_lo, a_k1 = ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4));
-            umma_f16_elect(tmem_u + acc * kSrN, a_k0, b_d0, idesc, 0u);
-            umma_f16_elect(tmem_u + acc * kSrN, a_k1, b_d1, idesc, 1u);
-            umma_f16_elect(tmem_u + acc * kSrN, a_k0, b_l0, idesc, 1u);
-            umma_f16_elect(tmem_u + acc * kSrN, a_k1, b_l1, idesc, 1u);
+            if (!(DFD_STEM_DBG & 4)) {
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)(stage * R + j) * (kSrAStage >> 4);
+                    const uint64_t a_k0 = ((uint64_t)a_hi << 32) | a_lo, a_k1 = ((uint64_t)a_hi << 32) | (a_lo + ((2 * kStLboA) >> 4));
+                    const uint32_t d = tmem_u + acc * kAccCols + j * kSrN;
+                    umma_f16_elect(d, a_k0, b_d0, idesc, 0u);
+                    umma_f16_elect(d, a_k1, b_d1, idesc, 1u);
+                    umma_f16_elect(d, a_k0, b_l0, idesc, 1u);
+                    umma_f16_elect(d, a_k1, b_l1, idesc, 1u);
+                }
+            }
             umma_commit_elect(bar_aempty + 8 * stage);
             umma_commit_elect(bar_tfull + 8 * acc);
             if (++stage == kSrStages) { stage = 0; sph ^= 1u; }
@@ -346,30 +378,37 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
         const int q = warp & 3, eset = warp >> 2;          // TMEM lane quarter, epilogue set
         const int row = 32 * q + lane;
         uint32_t li = eset;
-        const int tstep = kSrEpiSets * (int)gridDim.x, oystep = tstep % OH;
-        int oy = (int)((blockIdx.x + (uint32_t)eset * gridDim.x) % (uint32_t)OH);
+        const int tstep = kSrEpiSets * (int)gridDim.x, tystep = tstep % OHT;
+        int ty = (int)((blockIdx.x + (uint32_t)eset * gridDim.x) % (uint32_t)OHT);
         for (int tile = blockIdx.x + eset * (int)gridDim.x; tile < tiles; tile += tstep, li += kSrEpiSets) {
             const int acc = (int)(li % kSrAcc);
             mbar_wait(bar_tfull + 8 * acc, (li / kSrAcc) & 1u);
             tc_fence_after_sync();
-            const float* bs = s_bias + ((oy == 0 ? 2 : 0) + (row == 0 ? 1 : 0)) * kStN;
-            oy += oystep; if (oy >= OH) oy -= OH;
-            const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * kSrN;
-            uint32_t r[2][16];                                  // A * (W_hi + W_lo), scaled by 256
-            tmem_ld16(t_row, r[0]);
-            tmem_ld16(t_row + 16, r[1]);
-            tmem_ld_wait();
+            const bool top = ty == 0;
+            ty += tystep; if (ty >= OHT) ty -= OHT;
+            if (!(DFD_STEM_DBG & 2)) {
 #pragma unroll
-            for (int c16 = 0; c16 < 2; ++c16) {
-                U32x8 o;
+                for (int j = 0; j < R; ++j) {
+                    const float* bs = s_bias + ((top && j == 0 ? 2 : 0) + (row == 0 ? 1 : 0)) * kStN;
+                    const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + acc * kAccCols + j * kSrN;
+                    uint32_t r[2][16];                                  // A * (W_hi + W_lo), scaled by 256
+                    tmem_ld16(t_row, r[0]);
+                    tmem_ld16(t_row + 16, r[1]);
+                    tmem_ld_wait();
+                    T* orow = out + (((size_t)tile * R + j) * OW + row) * kStN;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    // h = x / 2 = acc * 2^-9 + bias / 2 (exact scaling), SiLU(x) = h + h tanh(h)
-                    const float a = fmaf(__uint_as_float(r[c16][2 * i]), 0.001953125f, bs[c16 * 16 + 2 * i]);
-                    const float b = fmaf(__uint_as_float(r[c16][2 * i + 1]), 0.001953125f, bs[c16 * 16 + 2 * i + 1]);
-                    o.v[i] = Half16<T>::pack(fmaf(a, tanh_approx(a), a), fmaf(b, tanh_approx(b), b));
+                    for (int c16 = 0; c16 < 2; ++c16) {
+                        U32x8 o;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            // h = x / 2 = acc * 2^-9 + bias / 2 (exact scaling), SiLU(x) = h + h tanh(h)
+                            const float a = fmaf(__uint_as_float(r[c16][2 * i]), 0.001953125f, bs[c16 * 16 + 2 * i]);
+                            const float b = fmaf(__uint_as_float(r[c16][2 * i + 1]), 0.001953125f, bs[c16 * 16 + 2 * i + 1]);
+                            o.v[i] = Half16<T>::pack(fmaf(a, tanh_approx(a), a), fmaf(b, tanh_approx(b), b));
+                        }
+                        if (row < OW) stg32(orow + c16 * 16, o);
+                    }
                 }
-                if (row < OW) stg32(out + ((size_t)tile * OW + row) * kStN + c16 * 16, o);
             }
             tc_fence_before_sync();
             mbar_arrive(bar_tempty + 8 * acc);
@@ -377,7 +416,7 @@ stem_row_kernel(const uint8_t* __restrict__ in, const __half* __restrict__ wrow,
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kSrMmaWarp) { tc_fence_after_sync(); tmem_dealloc(tmem_base, kSrAcc * kSrN); }
+    if (warp == kSrMmaWarp) { tc_fence_after_sync(); tmem_dealloc(tmem_base, kSrAcc * kAccCols); }
 }
 
 cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias, const void* wrow, const float* bias4, void* out,
@@ -389,20 +428,25 @@ cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias
     cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
     if (wrow && bias4 && OW <= kStBM && (W & 15) == 0 && (H & 1) == 0) {
-        // row variant: one tile per output row
-        const uint32_t raw_stride = (16u + 3u * (uint32_t)W * 3u + 127u) & ~127u;
-        const size_t smem = kSrStages * kSrAStage + kSrRaw * raw_stride + kSrBBytes + 4 * kStN * 4 + (2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc) * 8 + 16;
+        // row variant: one tile = two output rows of a frame (one when OH is odd)
+        const int R = (OH & 1) ? 1 : 2;
+        const uint32_t raw_stride = (16u + (2u * R + 1u) * (uint32_t)W * 3u + 127u) & ~127u;
+        const size_t smem = (size_t)kSrStages * R * kSrAStage + kSrRaw * raw_stride + kSrBBytes + 4 * kStN * 4 + (2 * kSrStages + 2 * kSrRaw + 2 * kSrAcc) * 8 + 16;
         if (frames * OH > 0x7fffffffLL / 4) return cudaErrorInvalidValue;             // 32-bit tile counters in the kernel
-        const int tiles = (int)(frames * OH);
+        const int tiles = (int)(frames * (OH / R));
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-#define DFD_STEM_ROW(TT, E, B) { \
-            auto kern = stem_row_kernel<TT, E, B>; \
+#define DFD_STEM_ROW(TT, E, B, RR) { \
+            auto kern = stem_row_kernel<TT, E, B, RR>; \
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; \
             e = launch_pdl(kern, dim3(grid), dim3((4 * E + 2 + 4 * B) * 32), smem, s, in, (const __half*)wrow, bias4, (TT*)out, H, W, OH, OW, tiles, raw_stride); }
+#ifndef DFD_STEM_ESETS
+#define DFD_STEM_ESETS 3                          // epilogue sets / builder sets (tools/build_variant.py sweeps them): 3/3 0.446 ms,
+#define DFD_STEM_BSETS 3                          // 4/2 0.452, 2/4 0.464, 2/3 0.464, 4/3 0.476, 3/4 0.483 per 2048 frames
+#endif
         if (dtype == kDtypeFP16) {
-            DFD_STEM_ROW(__half, 2, 4)            // 2 epilogue sets, 4 builder sets (3/3, 4/2, 3/4 measured within 5 % of it)
+            if (R == 2) DFD_STEM_ROW(__half, DFD_STEM_ESETS, DFD_STEM_BSETS, 2) else DFD_STEM_ROW(__half, DFD_STEM_ESETS, DFD_STEM_BSETS, 1)
         } else {
-            DFD_STEM_ROW(__nv_bfloat16, 2, 4)
+            if (R == 2) DFD_STEM_ROW(__nv_bfloat16, DFD_STEM_ESETS, DFD_STEM_BSETS, 2) else DFD_STEM_ROW(__nv_bfloat16, DFD_STEM_ESETS, DFD_STEM_BSETS, 1)
         }
 #undef DFD_STEM_ROW
         return e;

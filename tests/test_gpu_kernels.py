@@ -76,7 +76,7 @@ def test_stem(lib, prec, kind):
 
 
 @pytest.mark.parametrize("prec", ["fp16", "bf16"])
-@pytest.mark.parametrize("frames,H,W", [(3, 64, 96), (2, 224, 224), (1, 32, 32), (1, 32, 288)])   # 288: wider than one row tile
+@pytest.mark.parametrize("frames,H,W", [(3, 64, 96), (2, 224, 224), (1, 32, 32), (1, 32, 288), (2, 34, 48)])   # 288: wider than one row tile; 34: odd OH (one row per tile)
 def test_stem_tcgen05(lib, prec, frames, H, W):
     """uint8 stem as tcgen05 implicit GEMM with hi/lo split operands: must agree with the fp32 conv to ~1 output rounding."""
     from oracle import effnet_b0_oracle as O
