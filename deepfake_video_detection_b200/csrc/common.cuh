@@ -455,6 +455,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t sme
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 
 // exact GELU x * Phi(x) without erff: erfc(t / sqrt 2) = 2^-q(t) with a degree-6 polynomial q fitted on [0, 6] (beyond 6 the

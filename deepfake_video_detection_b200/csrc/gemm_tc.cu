@@ -113,9 +113,14 @@ struct TileIter {
 //   2  implicit GEMM over it: k-block kb = (tap, 64-channel slice), A box at row m0 + ky*(W+2) + kx; M runs over the padded
 //      pixels, halo rows are computed and dropped, interior rows are stored to the ordinary [frames*H*W][N] layout
 // ACT: 0 none, 1 SiLU, 2 exact-erf GELU (ViT MLP), 3 ReLU applied AFTER the residual add (ResNet bottleneck: relu(bn(conv) + identity)).  F32OUT: fp32 D (and fp32 R when RES: the ViT residual stream, in place).
-template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false, int CONV = 0>
-__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+// TSTORE = 32 / 16 (expand layers whose column chunk is a multiple of 32 / 16): the epilogue stages 32 rows x TSTORE columns per warp
+// in shared memory and writes them with ONE TMA store — a thread owns an accumulator ROW, so its direct 32-byte stores touch 32
+// different lines per warp instruction; with the stores skipped the 192 -> 1152 layer at 7x7 ran in 54 instead of 91 us
+// (profiles/r02_experimental.md).
+template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false, int CONV = 0, int TSTORE = 0>
+__global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");
+    static_assert(TSTORE == 0 || ((TSTORE == 16 || TSTORE == 32) && !GATE && !RES && !POOL && !F32OUT && CONV == 0), "TMA-store epilogue: plain 16-bit outputs only");
     static_assert(CONV == 0 || (!GATE && !RES && !POOL && !F32OUT), "CONV variants: plain 16-bit epilogue only");
     constexpr int kProdThreads = kProdWarps * 32;
     constexpr int kXformThreads = kXformWarps * 32;
@@ -130,6 +135,8 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
     const uint32_t bres_base = smem_u32(smem_raw);
     const uint32_t smem_base = (bres_base + p.b_res_bytes + 1023u) & ~1023u;
     uint8_t* sp = smem_raw + (smem_base - bres_base) + (size_t)p.stages * stage_bytes;
+    const uint32_t sm_out = smem_u32(sp);                         // TSTORE: one 2 KB staging slab per epilogue warp (1024-aligned)
+    if (TSTORE != 0) sp += kEpiWarps * 2048;
     float* s_bias = reinterpret_cast<float*>(sp);                 sp += (size_t)((p.N + 3) & ~3) * 4;
     float* s_pool = reinterpret_cast<float*>(sp);                 if (POOL) sp += kColGroups * kBM * 17 * 4;
     sp = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sp) + 7) & ~uintptr_t(7));
@@ -374,6 +381,43 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             tc_fence_after_sync();
             const uint32_t t_row = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * p.NBp);
             const int slots = POOL ? rows_valid / p.HW : 0;
+            if constexpr (TSTORE != 0) {
+                // TSTORE columns at a time: TMEM -> + bias -> SiLU -> 16-bit -> the warp's slab [32 rows][2 TSTORE bytes] in the swizzle
+                // of the output tensor map (64-byte rows: 16-byte chunk ^= row / 2 % 4; 32-byte rows: chunk ^= row / 4 % 2) -> one
+                // TMA store of the 32 x TSTORE box (rows past M are clipped by the map)
+                constexpr int NH = TSTORE / 16;
+                const uint32_t slab = sm_out + (uint32_t)warp * 2048u;
+                const uint32_t srow = slab + (uint32_t)lane * (2u * TSTORE);
+                const uint32_t sw = TSTORE == 32 ? ((uint32_t)lane >> 1) & 3u : ((uint32_t)lane >> 2) & 1u;
+                (void)valid; (void)m;
+                for (int cg = sub; cg * TSTORE < p.NB; cg += gpt) {
+                    uint32_t r[NH][16];
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) tmem_ld16(t_row + cg * TSTORE + h * 16, r[h]);
+                    tmem_ld_wait();
+                    uint32_t pk[NH * 8];
+#pragma unroll
+                    for (int h = 0; h < NH; ++h)
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            uint64_t x = add2(f2_pack(__uint_as_float(r[h][i]), __uint_as_float(r[h][i + 1])),
+                                              *reinterpret_cast<const uint64_t*>(&s_bias[n0 + cg * TSTORE + h * 16 + i]));
+                            if (ACT == 1) x = neg_silu2(x);                   // -silu(x)
+                            const float2 xf = f2_unpack(x);
+                            pk[h * 8 + (i >> 1)] = ACT == 1 ? Half16<T>::pack(-xf.x, -xf.y) : Half16<T>::pack(xf.x, xf.y);
+                        }
+                    if (lane == 0) bulk_wait_group_read0();                     // the warp's previous store has read the slab
+                    __syncwarp();
+#pragma unroll
+                    for (uint32_t j = 0; j < 2 * NH; ++j) sts16(srow + ((j ^ sw) << 4), make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(p.dbg & 4)) {
+                        tma_store_2d(&tmD, slab, n0 + cg * TSTORE, (int)m0 + 32 * q);
+                        bulk_commit_group();
+                    }
+                }
+            } else
             for (int c16 = sub; c16 * 16 < p.NBp; c16 += gpt) {
                 uint32_t r[16];
                 tmem_ld16(t_row + c16 * 16, r);
@@ -476,6 +520,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
             else { __syncwarp(); if (lane == 0) mbar_arrive(bar_tempty + 8 * acc); }     // one arrival per warp
             acc += p.na; if (acc >= p.nacc) { acc -= p.nacc; acc_phase ^= 1; }
         }
+        if (TSTORE != 0 && lane == 0) bulk_wait_group0();                     // the slabs must outlive their stores
     }
 
     if (prof && blockIdx.x == 0 && lane == 0)
@@ -528,6 +573,27 @@ static cudaError_t make_tmap(const void* A, int64_t M, int K, int box_rows, CUte
     return cudaSuccess;
 }
 
+// 16-bit output matrix [M][N] row-major: boxes of 32 (16) columns x 32 rows, 64-byte (32-byte) swizzle (the TSTORE epilogue's slabs)
+static cudaError_t make_tmap_out(const void* D, int64_t M, int N, int box_cols, CUtensorMap* out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32u};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(D), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t make_tmap_2d(const void* base, int64_t rows, int cols, int box_rows, void* out_tmap) {
     return make_tmap(base, rows, cols, box_rows, reinterpret_cast<CUtensorMap*>(out_tmap));
 }
@@ -554,15 +620,22 @@ cudaError_t make_tmap_2d_f32(const float* base, int64_t rows, int cols, int box_
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// columns per work unit: N split into equal chunks of <= 256 columns (multiple of 8)
+static int gemm_n_chunks(int N) {
+    int n_chunks = (N + 255) / 256;
+    while ((N % n_chunks) != 0 || ((N / n_chunks) & 7)) ++n_chunks;
+    return n_chunks;
+}
+
+static cudaError_t make_tmap_out(const void* D, int64_t M, int N, int box_cols, CUtensorMap* out);
+
 template <typename KernelT>
-static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, int xform_warps, cudaStream_t s) {
+static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warps, int xform_warps, cudaStream_t s, int tstore = 0) {
     if (g_num_sms == 0) {
         int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
     }
-    // split N into equal chunks of <= 256 columns (multiple of 8)
-    int n_chunks = (a.N + 255) / 256;
-    while ((a.N % n_chunks) != 0 || ((a.N / n_chunks) & 7)) ++n_chunks;
+    const int n_chunks = gemm_n_chunks(a.N);
     a.n_chunks = n_chunks;
     a.NB = a.N / n_chunks;
     a.NBp = (a.NB + 15) & ~15;
@@ -582,7 +655,8 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     }
     uint32_t cols = 32; while (cols < (uint32_t)(a.nacc * a.NBp)) cols <<= 1;
     a.tmem_cols = cols;
-    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (3 * kMaxStages + 16) * 8 + 16;
+    const size_t fixed = (size_t)((a.N + 3) & ~3) * 4 + (a.feat ? (size_t)(epi_warps / 4) * kBM * 17 * 4 : 0) + 8 + (3 * kMaxStages + 16) * 8 + 16
+                         + (tstore ? (size_t)epi_warps * 2048 : 0);
     a.nf_max = a.gate ? (kBM - 1) / a.HW + 2 : 0;
     a.total_frames = (int)((a.M + a.HW - 1) / a.HW);
     a.g_stage_bytes = (uint32_t)a.nf_max * 256u;
@@ -640,7 +714,13 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     } else {
         tmB = tmA;
     }
-    return launch_pdl(kernel, dim3(grid), dim3((epi_warps + 1 + prod_warps + xform_warps) * 32), smem, s, a, tmA, tmB);
+    CUtensorMap tmD = tmA;
+    if (tstore) {
+        if (a.tpf != 0 || (a.NB % tstore)) return cudaErrorInvalidValue;
+        e = make_tmap_out(a.D, a.M, a.N, tstore, &tmD);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_pdl(kernel, dim3(grid), dim3((epi_warps + 1 + prod_warps + xform_warps) * 32), smem, s, a, tmA, tmB, tmD);
 }
 
 template <typename T>
@@ -650,7 +730,17 @@ static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     if (a.feat) return run(gemm_tc_kernel<T, false, 1, false, true, 16, 4, 0>, a, 16, 4, 0, s);
     if (gate && res && !act) return run(gemm_tc_kernel<T, true, 0, true, false, 8, 4, 8>, a, 8, 4, 8, s);
     if (gate && !res && !act) return run(gemm_tc_kernel<T, true, 0, false, false, 8, 4, 8>, a, 8, 4, 8, s);
-    if (!gate && !res && act == 1) return run(gemm_tc_kernel<T, false, 1, false, false, 16, 4, 0>, a, 16, 4, 0, s);
+    if (!gate && !res && act == 1) {
+#ifndef DFD_GEMM_TSTORE
+#define DFD_GEMM_TSTORE 1      // 0: direct stores everywhere (A/B builds)
+#endif
+        const int nb = a.N / gemm_n_chunks(a.N);
+        if (DFD_GEMM_TSTORE && a.tpf == 0 && (nb & 31) == 0)
+            return run(gemm_tc_kernel<T, false, 1, false, false, 16, 4, 0, false, 0, 32>, a, 16, 4, 0, s, 32);
+        // (16-column boxes for N = 240 / 480 measured exactly the time of the direct 32-byte stores — 183.3 / 107.5 us: it is the 32-byte
+        // row segment, not the instruction that writes it, that is slow — so those layers keep the direct stores)
+        return run(gemm_tc_kernel<T, false, 1, false, false, 16, 4, 0>, a, 16, 4, 0, s);
+    }
     if (!gate && !res && act == 2) return run(gemm_tc_kernel<T, false, 2, false, false, 16, 4, 0>, a, 16, 4, 0, s);
     if (!gate && !res && act == 3) return run(gemm_tc_kernel<T, false, 3, false, false, 8, 4, 0>, a, 8, 4, 0, s);
     if (!gate && res && act == 3) return run(gemm_tc_kernel<T, false, 3, true, false, 8, 4, 0>, a, 8, 4, 0, s);

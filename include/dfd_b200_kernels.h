@@ -3,6 +3,12 @@
  * a binding for the reference only needs dfd_b200.h.  Layouts:
  *   activations   NHWC, 16-bit (DFD_DTYPE_*), i.e. a [frames*H*W, C] row-major matrix
  *   BatchNorm     already folded into weight/bias by the caller (dfd_pack_weights does this)
+ * Stream ordering: the EfficientNet kernels are launched with programmatic dependent launch.  Each of them reads its WEIGHT and
+ * BIAS operands (d_w, d_bias, d_W, SE matrices ...) in a prologue that may run before the kernel enqueued ahead of it on `stream`
+ * has finished; activations, gates, partial sums and offsets are read (and every output is written) only after that kernel has
+ * completed.  So weights must be complete in device memory when the call is enqueued (a cudaMemcpy, or an earlier
+ * synchronisation) — never the product of the kernel immediately ahead on the same stream.  dfd_pack_weights guarantees this
+ * for the handle-based entry points of dfd_b200.h.
  */
 #ifndef DFD_B200_KERNELS_H
 #define DFD_B200_KERNELS_H

@@ -1,0 +1,15 @@
+#!/bin/bash
+# call 39: TMA-store epilogue of the expand GEMMs (column chunks that are multiples of 32): parity and A/B against direct stores
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm" > gpurun_out/c39_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/c39_pytest.log
+for v in default notstore; do
+  if [ $v = default ]; then unset DFD_LIB_PATH; else export DFD_LIB_PATH=build/variants/libdfd_$v.so; fi
+  echo "== $v"
+  timeout 100 python tools/prof_gemm.py --K 192 --N 1152 --HW 49 --frames 2048 --gate 0 --res 0 --act 1 --iters 3 2>&1 | tail -1
+  timeout 100 python tools/prof_gemm.py --K 112 --N 672 --HW 196 --frames 2048 --gate 0 --res 0 --act 1 --iters 3 2>&1 | tail -1
+  timeout 100 python tools/prof_gemm.py --K 16 --N 96 --HW 12544 --frames 512 --gate 0 --res 0 --act 1 --iters 3 2>&1 | tail -1
+done
+unset DFD_LIB_PATH
+timeout 120 python tools/time_classes.py --iters 3 2>&1 | tail -1
