@@ -1,5 +1,5 @@
 #!/bin/bash
-# call 40: TMA-store epilogue with 16-column groups (N = 240, 480): parity and A/B against direct stores
+# call 40-41: TMA-store epilogue for N = 240, 480 (16-column boxes alone; then 32-column boxes + a 16-column tail): parity and A/B against direct stores
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
