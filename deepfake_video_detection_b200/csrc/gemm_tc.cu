@@ -252,7 +252,7 @@ __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 3
         const int tx = threadIdx.x - (kMmaWarp + 1 + kProdWarps) * 32;
         const int gthreads = kXformThreads / p.xg;
         const int grp = tx / gthreads, tg = tx - grp * gthreads;
-        const int q = tg & 7, rb = tg >> 3, xstep = gthreads >> 3, xpasses = kBM / xstep;
+        const int q = tg & 7, rb = tg >> 3, xstep = gthreads >> 3, xpasses = (kBM + xstep - 1) / xstep;      // (rows past rows_valid are skipped in the loop)
         int stage = 0; uint32_t phase = 0; int turn = 0;
         TileIter it; it.init(p, blockIdx.x);
         for (; it.u < units; it.next1(p)) {
@@ -642,7 +642,10 @@ static cudaError_t run(KernelT kernel, GemmArgs& a, int epi_warps, int prod_warp
     a.lbo_b = (uint32_t)a.NBp * 16 + 16;
     a.kchunks_pad = ((a.K >> 3) + 1) & ~1;
     { static const int env_dbg = getenv("DFD_GEMM_DBG") ? atoi(getenv("DFD_GEMM_DBG")) : 0; a.dbg = env_dbg; }
-    a.xg = xform_warps > 0 ? 4 : 1;                                // transformer warp groups (take alternate stages)
+#ifndef DFD_GEMM_XG
+#define DFD_GEMM_XG 4
+#endif
+    a.xg = xform_warps > 0 ? DFD_GEMM_XG : 1;                      // transformer warp groups (take alternate stages)
     if (a.xg > xform_warps || (xform_warps % a.xg)) a.xg = 1;
     a.b_stage_bytes = (uint32_t)a.NBp * 128u;                      // streamed W block: NBp rows x 64 elements, 128-byte swizzle
     a.b_chunk_bytes = (uint32_t)a.kchunks_pad * a.lbo_b;
@@ -728,8 +731,18 @@ static cudaError_t launch_t(GemmArgs& a, int act, cudaStream_t s) {
     const bool gate = a.gate != nullptr, res = a.R != nullptr;
     // <T, GATE, ACT, RES, POOL, epilogue warps, loader warps, transformer warps>
     if (a.feat) return run(gemm_tc_kernel<T, false, 1, false, true, 16, 4, 0>, a, 16, 4, 0, s);
-    if (gate && res && !act) return run(gemm_tc_kernel<T, true, 0, true, false, 8, 4, 8>, a, 8, 4, 8, s);
-    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, 0, false, false, 8, 4, 8>, a, 8, 4, 8, s);
+    // gated layers: the transformers' lds -> multiply -> sts -> fence chain per stage is latency-bound (they were busy 80 % of the
+    // kernel with 8 warps while the MMA warp waited 60 % for transformed stages): 12 warps in 4 groups of 3 are 6-11 % faster on
+    // every gated layer (1152 -> 192 @7x7: 109.5 -> 101.3 us; 672 -> 112 @14x14: 179.2 -> 159.7 us); 16 warps spill (64 registers)
+#ifndef DFD_GEMM_XFORM_WARPS
+#define DFD_GEMM_XFORM_WARPS 12     // transformer warps / epilogue warps of the gated layers (tools/build_variant.py sweeps them)
+#endif
+#ifndef DFD_GEMM_GATED_EPI
+#define DFD_GEMM_GATED_EPI 8
+#endif
+    constexpr int XW = DFD_GEMM_XFORM_WARPS, GE = DFD_GEMM_GATED_EPI;
+    if (gate && res && !act) return run(gemm_tc_kernel<T, true, 0, true, false, GE, 4, XW>, a, GE, 4, XW, s);
+    if (gate && !res && !act) return run(gemm_tc_kernel<T, true, 0, false, false, GE, 4, XW>, a, GE, 4, XW, s);
     if (!gate && !res && act == 1) {
 #ifndef DFD_GEMM_TSTORE
 #define DFD_GEMM_TSTORE 1      // 0: direct stores everywhere (A/B builds)
