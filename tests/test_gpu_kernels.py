@@ -345,3 +345,46 @@ def test_gemm_cta_pairs_fp32_residual(lib, prec, M, K, N):
     err = (X[:M].cpu().double() - ref).abs().max().item()
     assert err <= 2e-5 * max(1.0, ref.abs().max().item()), err                       # fp32 accumulation and adds only
     assert torch.equal(X[M].cpu(), X0[M])
+
+
+@pytest.mark.parametrize("C_,k,HW_,N", [(672, 5, 14, 112), (240, 3, 28, 40)])
+def test_dependent_launches_without_synchronisation(lib, C_, k, HW_, N):
+    """Programmatic dependent launch (csrc/common.cuh): every kernel is launched with the programmatic-stream-serialisation
+    attribute and waits (`griddepcontrol.wait`) before it touches what the kernel ahead of it produced.  One MBConv tail —
+    depthwise + SE sums -> SE gate -> gated project GEMM, each consuming the output of the launch before it — enqueued back to back WITHOUT any host synchronisation, 30 times over the same buffers (so a missing
+    wait shows up as a write racing with the previous round's reads, too), must give the bits of the fully synchronised sequence."""
+    code, tdt, _ = DT["fp16"]
+    g = torch.Generator().manual_seed(C_ + N)
+    frames, rd = 24, max(8, C_ // 24)
+    x = torch.randn(frames, HW_, HW_, C_, generator=g).to(tdt).cuda()
+    w = (torch.randn(C_, 1, k, k, generator=g) / k).reshape(C_, k * k).t().contiguous().cuda()
+    b = (torch.randn(C_, generator=g) * 0.2).cuda()
+    w1 = (torch.randn(rd, C_, generator=g) * 0.1).cuda(); b1 = (torch.randn(rd, generator=g) * 0.1).cuda()
+    w2t = (torch.randn(rd, C_, generator=g) * 0.3).cuda(); b2 = (torch.randn(C_, generator=g) * 0.3).cuda()
+    Wp = (torch.randn(N, C_, generator=g) / C_ ** 0.5).to(tdt).cuda(); bp = (torch.randn(N, generator=g) * 0.3).cuda()
+    nparts = lib.dfd_k_dw_num_partials(HW_, HW_, C_, k, 1)
+    torch.cuda.synchronize()
+
+    def tail(sync):
+        out = torch.empty((frames, HW_, HW_, C_), dtype=tdt, device="cuda")
+        parts = torch.empty((frames, nparts, C_), device="cuda")
+        gate = torch.empty((frames, C_), device="cuda")
+        D = torch.empty((frames * HW_ * HW_, N), dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        rounds = 1 if sync else 30
+        for _ in range(rounds):
+            chk(lib, lib.dfd_k_dwconv(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), parts.data_ptr(), frames, HW_, HW_, C_, k, 1, code, stream()))
+            if sync: torch.cuda.synchronize()
+            chk(lib, lib.dfd_k_se(parts.data_ptr(), nparts, C.c_float(1.0 / (HW_ * HW_)), w1.data_ptr(), b1.data_ptr(), w2t.data_ptr(), b2.data_ptr(),
+                                  gate.data_ptr(), frames, C_, rd, stream()))
+            if sync: torch.cuda.synchronize()
+            chk(lib, lib.dfd_k_gemm(out.data_ptr(), Wp.data_ptr(), bp.data_ptr(), gate.data_ptr(), None, D.data_ptr(), frames * HW_ * HW_, C_, N, HW_ * HW_,
+                                    0, code, 0, stream()))
+            if sync: torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return out, gate, D
+
+    ref = tail(True)
+    got = tail(False)
+    for a_, b_ in zip(ref, got):
+        assert torch.isfinite(a_.float()).all() and torch.equal(a_, b_)
