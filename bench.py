@@ -270,7 +270,12 @@ def hbm_roofline(kernels, traffic, traffic_src, hbm_gbs, peak_kind, frames=None)
     f = kernels.get("expand_dwconv_fused")
     if f and frames:
         unfused_mb = FUSED_UNFUSED_MB_PER_FRAME * frames
-        out["fused_class"] = {"limiter": "MUFU + issue (one tanh.approx per SiLU), not HBM",
+        own_mb = sum(k["MB"] for k in kernels.values())
+        # the same step on the bytes of the REFERENCE's op graph (every op reads and writes its tensors once): the fused
+        # kernels counted as the expand GEMM + depthwise pair they replace.  `frac` above stays on the bytes the kernels really need.
+        out["whole_step"]["reference_graph_GB"] = round((own_mb - f["MB"] + unfused_mb) / 1e3, 3)
+        out["whole_step"]["reference_graph_frac"] = round((own_mb - f["MB"] + unfused_mb) / total / hbm_gbs, 4)
+        out["fused_class"] = {"limiter": "latency (12 warps per SM behind a per-row barrier; fewer instructions or fewer barriers measured no gain) with MUFU at 0.4 of its rate; not HBM",
                               "silu_per_s": round(FUSED_SILU_PER_FRAME * frames / (f["ms"] / 1e3), 0), "mufu_peak_per_s": round(MUFU_PER_S, 0),
                               "frac_of_mufu": round(FUSED_SILU_PER_FRAME * frames / (f["ms"] / 1e3) / MUFU_PER_S, 4),
                               "replaces_unfused_MB": round(unfused_mb, 1), "unfused_hbm_floor_ms": round(unfused_mb / hbm_gbs, 4),
