@@ -116,7 +116,8 @@ struct TileIter {
 // TSTORE = 32 / 16 (expand layers whose column chunk is a multiple of 32 / 16): the epilogue stages 32 rows x TSTORE columns per warp
 // in shared memory and writes them with ONE TMA store — a thread owns an accumulator ROW, so its direct 32-byte stores touch 32
 // different lines per warp instruction; with the stores skipped the 192 -> 1152 layer at 7x7 ran in 54 instead of 91 us
-// (profiles/r02_experimental.md).
+// (profiles/r02_experimental.md).  The launcher selects 32-column boxes on 64-byte-aligned rows only (N = 96, 672, 1152): 16-column
+// boxes write the same 32-byte row segments as the direct stores and measured exactly their time.
 template <typename T, bool GATE, int ACT, bool RES, bool POOL, int kEpiWarps, int kProdWarps, int kXformWarps, bool F32OUT = false, int CONV = 0, int TSTORE = 0>
 __global__ void __launch_bounds__((kEpiWarps + 1 + kProdWarps + kXformWarps) * 32, 1) gemm_tc_kernel(const GemmArgs p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD) {
     static_assert(GATE == (kXformWarps > 0), "transformer warps exist exactly for gated layers");

@@ -177,15 +177,16 @@ stem_tc_kernel(const uint8_t* __restrict__ in, const T* __restrict__ w16, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Row variant (maps up to 128 output columns, i.e. the 224x224 crops): one tile = ONE OUTPUT ROW of one frame.
-//  * the three input rows a tile needs are 3*W*3 contiguous bytes: one thread fetches them with a single 1-D bulk
+// Row variant (maps up to 128 output columns, i.e. the 224x224 crops): one tile = R consecutive OUTPUT ROWS of one frame
+// (R = 2 when the map height is even, else 1; see the note on hand-off cost below).
+//  * the 2R+1 input rows a tile needs are (2R+1)*W*3 contiguous bytes: one thread fetches them with a single 1-D bulk
 //    copy (cp.async.bulk, completion in bytes on an mbarrier) into a ring of raw-byte stages — no per-byte global
-//    loads, every input byte crosses the SM boundary once per output row (1.5x in total);
+//    loads, every input byte crosses the SM boundary 1.25x (R = 2) in total;
 //  * the raw uint8 values ARE the A operand: an integer 0..255 is exact in fp16 (PRMT with the 0x64 magic byte gives
 //    1024 + u, one HSUB2 removes the 1024), so the tensor prep of app.py:2084-2085 moves into the weights:
 //        y = sum_inb w * ((u/255 - mean_c)/std_c) + b = sum_inb (w / (255 std_c)) * u + [b - sum_inb w * mean_c/std_c]
-//    with w' = 256 * w / (255 std_c) split into fp16 hi + lo (two MMAs against the same A tile, ~22 significant bits,
-//    the 2^-8 is applied with the bias in the epilogue) and FOUR bias vectors for the in-bounds tap sets of the
+//    with w' = 256 * w / (255 std_c) split into fp16 hi + lo (MMAs against the same A tile accumulating into the same TMEM
+//    columns, ~22 significant bits; the 2^-8 is applied with the bias in the epilogue) and FOUR bias vectors for the in-bounds tap sets of the
 //    interior / left column / top row / top-left corner (zero padding happens after normalisation, as F.conv2d does);
 //  * a builder thread (= one output pixel) reads its 3 x 9 window bytes as 9 aligned 32-bit shared-memory words.
 // K layout: k = ky*10 + kx*3 + c (9 taps + 1 zero per input row, 32 in all).
@@ -196,6 +197,8 @@ constexpr uint32_t kSrLboB = 2 * kStN * 16 + 16;         // W_hi rows 0-31, W_lo
 constexpr uint32_t kSrBBytes = kSrChunks * kSrLboB;
 #ifndef DFD_STEM_STAGES
 #define DFD_STEM_STAGES 8      // A-tile ring, raw-byte ring (tools/build_variant.py sweeps them: 8/8 0.476 ms, 8/12 0.53, 6/12 0.53, 8/16 0.46)
+#endif
+#ifndef DFD_STEM_RAW
 #define DFD_STEM_RAW 16
 #endif
 constexpr int kSrStages = DFD_STEM_STAGES, kSrRaw = DFD_STEM_RAW, kSrAcc = 8;
@@ -441,6 +444,8 @@ cudaError_t launch_stem_tc(const uint8_t* in, const void* w16, const float* bias
             e = launch_pdl(kern, dim3(grid), dim3((4 * E + 2 + 4 * B) * 32), smem, s, in, (const __half*)wrow, bias4, (TT*)out, H, W, OH, OW, tiles, raw_stride); }
 #ifndef DFD_STEM_ESETS
 #define DFD_STEM_ESETS 3                          // epilogue sets / builder sets (tools/build_variant.py sweeps them): 3/3 0.446 ms,
+#endif
+#ifndef DFD_STEM_BSETS
 #define DFD_STEM_BSETS 3                          // 4/2 0.452, 2/4 0.464, 2/3 0.464, 4/3 0.476, 3/4 0.483 per 2048 frames
 #endif
         if (dtype == kDtypeFP16) {
